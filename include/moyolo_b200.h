@@ -1,0 +1,210 @@
+/*
+ * moyolo_b200.h — C ABI of libmoyolo_b200.so: the B200 (sm_100a) decoder hot path of
+ * DecoderTracker / MO-YOLO.
+ *
+ * Every entry point takes raw DEVICE pointers (unless the parameter name ends in `_host`),
+ * plain sizes and a CUDA stream handle. The library never allocates or frees device memory,
+ * never synchronises the device, and enqueues all work on the caller's stream, so every call
+ * is CUDA-graph capturable. Functions return MOYOLO_OK (0) or a non-zero status;
+ * `moyolo_last_error()` then returns a thread-local, human-readable message.
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root):
+ *   - moyolo_msda_sampled_forward  <-  pybind `ms_deform_attn_forward`
+ *         MOTR/models/ops/src/vision.cpp:13-16, MOTR/models/ops/src/ms_deform_attn.h:20-40,
+ *         MOTR/models/ops/src/cuda/ms_deform_attn_cuda.cu:20-80 (the legacy FFI), and the
+ *         Python core `multi_scale_deformable_attn_pytorch`, ultralytics/nn/modules/utils.py:41-78
+ *   - moyolo_msda_fused_forward    <-  ultralytics/nn/modules/transformer.py:268-285
+ *         (softmax over L*P, sampling-location arithmetic, grid_sample gather, weighted sum)
+ *   - moyolo_linear                <-  nn.Linear call sites transformer.py:264,268,269,286
+ *         (value_proj / sampling_offsets / attention_weights / output_proj) and :576-580 (FFN)
+ *   - moyolo_self_attention        <-  nn.MultiheadAttention call, transformer.py:637-641
+ *   - moyolo_add_layernorm         <-  residual + nn.LayerNorm, transformer.py:640-641,646-647,578-579
+ *   - moyolo_box_refine            <-  transformer.py:709 + ultralytics/nn/modules/utils.py:34-38
+ *   - moyolo_score_head            <-  transformer.py:717-721, head.py:310
+ *   - moyolo_pos2posemb            <-  transformer.py:183-190
+ *   - moyolo_track_assign          <-  RuntimeTrackerBase.update, ultralytics/nn/modules/head.py:1201-1283
+ *   - moyolo_track_compact         <-  QueryInteractionModule._select_active_tracks, MOTR/models/qim.py:184-187
+ *                                      + Instances.__getitem__, MOTR/models/structures/instances.py:152-178
+ */
+#ifndef MOYOLO_B200_H_
+#define MOYOLO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+#define MOYOLO_VERSION 100 /* 0.1.0 */
+#define MOYOLO_MAX_LEVELS 8
+
+/* status codes */
+#define MOYOLO_OK 0
+#define MOYOLO_ERR_BAD_ARG 1      /* null pointer, negative size, bad enum             -> ValueError   */
+#define MOYOLO_ERR_BAD_SHAPE 2    /* sum(H_l*W_l) != Lv, ref last dim not 2|4, ...     -> ValueError   */
+#define MOYOLO_ERR_UNSUPPORTED 3  /* dtype / head-dim combination with no kernel       -> RuntimeError */
+#define MOYOLO_ERR_CUDA 4         /* launch or driver error                            -> RuntimeError */
+#define MOYOLO_ERR_ALIGNMENT 5    /* pointer / stride not 16-byte aligned where needed -> ValueError   */
+
+/* element types */
+#define MOYOLO_F32 0
+#define MOYOLO_BF16 1
+#define MOYOLO_F64 2 /* generic gather only (the legacy FFI is dispatched on float/double) */
+
+/* attention-weight normalisation of the fused gather */
+#define MOYOLO_SOFTMAX 0      /* F.softmax over the joint L*P axis, transformer.py:271            */
+#define MOYOLO_SOFTMAX_PLUS1 1 /* exp/(1+sum exp), MOTRMSDeformAttn `my_softmax`, transformer.py:239-244 */
+
+/* epilogue flags of moyolo_linear */
+#define MOYOLO_EPI_NONE 0
+#define MOYOLO_EPI_RELU 1
+
+/* GEMM engine selector of moyolo_linear */
+#define MOYOLO_GEMM_AUTO 0    /* bf16 -> tcgen05, f32 -> SIMT */
+#define MOYOLO_GEMM_SIMT 1    /* fp32-accumulate CUDA-core kernel (exact-parity path)              */
+#define MOYOLO_GEMM_TCGEN05 2 /* TMA + tcgen05.mma + TMEM kernel (bf16 operands only)              */
+
+typedef void* moyolo_stream_t; /* a cudaStream_t */
+
+int moyolo_version(void);
+const char* moyolo_last_error(void);
+/* 1 if the current device is compute capability 10.x (the only supported target), else 0. */
+int moyolo_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-scale deformable attention gather.
+ *
+ * value        [B, Lv, n_heads, head_dim]; consecutive spatial positions are `value_pos_stride`
+ *              elements apart, consecutive batches `value_batch_stride` elements apart (so one
+ *              layer's slice of an all-layers value tensor [B, Lv, n_layers*C] can be addressed
+ *              without a copy). Head h of a position starts at element h*head_dim.
+ * shapes_hw_host  host int32 [n_levels*2] = (H_0, W_0, H_1, W_1, ...); sum(H_l*W_l) must equal Lv.
+ * rows         total query rows R. If `row_offsets` (device int32 [B+1]) is NULL the rows are
+ *              dense: batch b owns rows [b*R/B, (b+1)*R/B). Otherwise batch b owns rows
+ *              [row_offsets[b], row_offsets[b+1]) (ragged lock-step sequences).
+ * out          [R, n_heads*head_dim], row stride `out_row_stride` elements, same dtype as value.
+ * -------------------------------------------------------------------------------------------*/
+
+/* Pre-normalised mode (legacy FFI and `multi_scale_deformable_attn_pytorch`):
+ *   loc     [R, n_heads, n_levels, n_points, 2] normalised (x, y) in [0,1] (may fall outside),
+ *   weights [R, n_heads, n_levels, n_points]; both of dtype `aux_dtype` (F32, or F64 with F64 value). */
+int moyolo_msda_sampled_forward(const void* value, int value_dtype, int64_t value_batch_stride,
+                                int64_t value_pos_stride, const int32_t* shapes_hw_host,
+                                int n_levels, int batch, int64_t len_v, int n_heads, int head_dim,
+                                int n_points, const void* loc, const void* weights, int aux_dtype,
+                                int64_t rows, const int32_t* row_offsets, void* out,
+                                int64_t out_row_stride, moyolo_stream_t stream);
+
+/* Fused mode (transformer.py:268-285): raw Linear outputs in, no intermediate tensors.
+ *   offsets [R, n_heads, n_levels, n_points, 2] fp32, row stride `offsets_row_stride` elements,
+ *   logits  [R, n_heads, n_levels*n_points]     fp32, row stride `logits_row_stride` elements
+ *           (both may be column slices of one fused GEMM output),
+ *   refer   [R, ref_levels, ref_dim] fp32 with ref_levels in {1, n_levels}, ref_dim in {2, 4}:
+ *           ref_dim 4: loc = ref_xy + off / n_points * ref_wh * 0.5      (transformer.py:280-282)
+ *           ref_dim 2: loc = ref_xy + off / (W_l, H_l)                   (transformer.py:276-279) */
+int moyolo_msda_fused_forward(const void* value, int value_dtype, int64_t value_batch_stride,
+                              int64_t value_pos_stride, const int32_t* shapes_hw_host, int n_levels,
+                              int batch, int64_t len_v, int n_heads, int head_dim, int n_points,
+                              const float* offsets, int64_t offsets_row_stride, const float* logits,
+                              int64_t logits_row_stride, const float* refer, int ref_levels,
+                              int ref_dim, int softmax_mode, int64_t rows,
+                              const int32_t* row_offsets, void* out, int64_t out_row_stride,
+                              moyolo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * y[M, N] = act(x[M, K] . w[N, K]^T + bias[N]); x row stride ldx, y row stride ldy (elements).
+ * in_dtype applies to x and w (F32 or BF16); bias is fp32 (may be NULL); out_dtype F32 or BF16.
+ * Optional row mask: if `zero_rows` (device uint8 [M]) is non-NULL, rows with a non-zero entry
+ * are written as zeros (value_mask semantics of transformer.py:265-266).
+ * The tcgen05 engine needs K % 64 == 0, N % 16 == 0, 16-byte aligned x, w and ldx*2 % 16 == 0.
+ * -------------------------------------------------------------------------------------------*/
+int moyolo_linear(const void* x, int64_t ldx, const void* w, const float* bias, void* y,
+                  int64_t ldy, int64_t M, int N, int K, int in_dtype, int out_dtype, int epilogue,
+                  const uint8_t* zero_rows, int engine, moyolo_stream_t stream);
+
+/* Query self-attention over ragged sequences (transformer.py:637-641 with nn.MultiheadAttention
+ * semantics: scores = (q/sqrt(head_dim)) . k^T, softmax over all keys of the same sequence, . v).
+ * q, k, v: [R, n_heads*head_dim] slices with row strides ldq/ldk/ldv (elements) of dtype `dtype`;
+ * attn_mask: optional additive fp32 [Rq, Rk] mask for the dense single-batch case (NULL in eval).
+ * out: [R, n_heads*head_dim], row stride ldo, dtype `dtype`. row_offsets as above (host-side
+ * `row_offsets_host` [B+1] mirrors it for grid sizing). head_dim must be 32 or 64. */
+int moyolo_self_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                          int64_t ldv, void* out, int64_t ldo, int dtype, int batch,
+                          const int32_t* row_offsets, const int32_t* row_offsets_host, int n_heads,
+                          int head_dim, const float* attn_mask, moyolo_stream_t stream);
+
+/* out = LayerNorm(x + residual) * gamma + beta over the last dim C (eps as given), fp32 math.
+ * x: [R, C] fp32 (GEMM output), residual: [R, C] fp32 (may be NULL).
+ * Writes up to three results (any may be NULL): out_f32 [R, C] fp32; out_lp [R, C] of `lp_dtype`;
+ * out_pos_lp [R, C] of `lp_dtype` = (LayerNorm result + pos) with pos [R, C] fp32
+ * (the `with_pos_embed` operand of the next GEMM, transformer.py:637,644). */
+int moyolo_add_layernorm(const float* x, const float* residual, const float* gamma,
+                         const float* beta, float eps, int64_t rows, int C, float* out_f32,
+                         void* out_lp, const float* pos, void* out_pos_lp, int lp_dtype,
+                         moyolo_stream_t stream);
+
+/* out_lp = (a [+ b]) converted to lp_dtype; a, b: [R, C] fp32 (b may be NULL). */
+int moyolo_add_cast(const float* a, const float* b, void* out_lp, int lp_dtype, int64_t n_elems,
+                    moyolo_stream_t stream);
+
+/* new_ref[R,4] = sigmoid(h[R,K] . w3[4,K]^T + b3 + inverse_sigmoid(ref[R,4]))  (transformer.py:709;
+ * inverse_sigmoid = log(clamp(x,1e-5)/clamp(1-x,1e-5)) after clamp to [0,1], utils.py:34-38).
+ * h is the output of the first two MLP layers, dtype h_dtype. w3/b3/ref/new_ref are fp32. */
+int moyolo_box_refine(const void* h, int64_t ldh, int h_dtype, const float* w3, const float* b3,
+                      const float* ref, float* new_ref, int64_t rows, int K, moyolo_stream_t stream);
+
+/* logits[R,nc] = x[R,K] . w[nc,K]^T + b; scores[R] = max_c sigmoid(logits) (head.py:310),
+ * labels[R] = argmax_c logits (first maximum, torch.max semantics). scores/labels may be NULL. */
+int moyolo_score_head(const void* x, int64_t ldx, int x_dtype, const float* w, const float* b,
+                      float* logits, float* scores, int32_t* labels, int64_t rows, int K, int nc,
+                      moyolo_stream_t stream);
+
+/* refer_sig[R,4] = sigmoid(refer_logit[R,4]) (transformer.py:690) */
+int moyolo_sigmoid(const float* x, float* y, int64_t n, moyolo_stream_t stream);
+/* y = inverse_sigmoid(x), eps 1e-5 (MOTR/util/misc.py:532-536, qim.py:299) */
+int moyolo_inverse_sigmoid(const float* x, float* y, int64_t n, moyolo_stream_t stream);
+
+/* pos2posemb (transformer.py:183-190): pos [R, n_coord] fp32 -> emb [R, n_coord*num_pos_feats] fp32,
+ * emb[r, c*F + i] = (i even ? sin : cos)(pos[r,c]*2*pi / temperature^(2*(i/2)/F)). */
+int moyolo_pos2posemb(const float* pos, float* emb, int64_t rows, int n_coord, int num_pos_feats,
+                      float temperature, moyolo_stream_t stream);
+
+/* pos-MLP first layer (DeformableTransformerDecoder, transformer.py:491 with MLP(4, 2*hd, hd, 2)):
+ * y[R,N] = relu(x[R,4] . w[N,4]^T + b) written as `out_dtype`. */
+int moyolo_linear_k4_relu(const float* x, const float* w, const float* b, void* y, int out_dtype,
+                          int64_t rows, int N, moyolo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Track-query update (one sequence per call; all state on device, no host sync).
+ *
+ * moyolo_track_assign: RuntimeTrackerBase.update (head.py:1201-1283) restated as parallel scans.
+ *   scores [N] fp32, boxes [N,4] fp32 (decoder boxes), obj_idxes [N] int64 in/out,
+ *   disappear_time [N] int64 in/out, counters int64 [2] in/out = {max_obj_id, max_obj_id_pre},
+ *   workspace: moyolo_track_workspace_bytes(N) bytes.
+ *   In query order: id==-1 && score>=score_thresh -> id = max_obj_id++;
+ *   id>=0 && score<filter_thresh -> disappear_time++, and at >= miss_tolerance id = -1.
+ *   Then the greedy duplicate filter (IoU > iou_thresh, head.py:1155-1196) and the renumbering
+ *   (head.py:1268-1282) are evaluated on the active subset only for their side effect on counters.
+ * moyolo_track_compact: select rows with obj_idxes >= 0 preserving order; writes n_active (int32
+ *   device scalar) and, for each of the `n_fields` row-major arrays (src[i], dst[i], row_bytes[i]
+ *   given as HOST arrays of device pointers / sizes), dst[j] = src[index of j-th active row].
+ * -------------------------------------------------------------------------------------------*/
+int64_t moyolo_track_workspace_bytes(int64_t n);
+int moyolo_track_assign(const float* scores, const float* boxes, int64_t* obj_idxes,
+                        int64_t* disappear_time, int64_t* counters, int64_t n, float score_thresh,
+                        float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace,
+                        moyolo_stream_t stream);
+int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,
+                         int32_t* active_index, const void* const* src_host, void* const* dst_host,
+                         const int64_t* row_bytes_host, int n_fields, moyolo_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOYOLO_B200_H_ */

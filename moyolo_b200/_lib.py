@@ -1,0 +1,78 @@
+"""ctypes binding of libmoyolo_b200.so (the C ABI declared in include/moyolo_b200.h).
+
+There is no CPU or PyTorch fallback: if the shared object is missing the import of any op fails
+loudly with instructions to build it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libmoyolo_b200.so"
+_lib = None
+
+# status codes / enums (mirror include/moyolo_b200.h)
+OK, ERR_BAD_ARG, ERR_BAD_SHAPE, ERR_UNSUPPORTED, ERR_CUDA, ERR_ALIGNMENT = range(6)
+F32, BF16, F64 = 0, 1, 2
+SOFTMAX, SOFTMAX_PLUS1 = 0, 1
+EPI_NONE, EPI_RELU = 0, 1
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+
+_p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol include/moyolo_b200.h declares
+SIGNATURES = {
+    "moyolo_version": (_i, []),
+    "moyolo_last_error": (C.c_char_p, []),
+    "moyolo_device_supported": (_i, []),
+    "moyolo_msda_sampled_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _p, _i, _l, _p, _p, _l, _p]),
+    "moyolo_msda_fused_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _l, _p, _i, _i, _i,
+                                       _l, _p, _p, _l, _p]),
+    "moyolo_linear": (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "moyolo_self_attention": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "moyolo_add_layernorm": (_i, [_p, _p, _p, _p, _f, _l, _i, _p, _p, _p, _p, _i, _p]),
+    "moyolo_add_cast": (_i, [_p, _p, _p, _i, _l, _p]),
+    "moyolo_box_refine": (_i, [_p, _l, _i, _p, _p, _p, _p, _l, _i, _p]),
+    "moyolo_score_head": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _l, _i, _i, _p]),
+    "moyolo_sigmoid": (_i, [_p, _p, _l, _p]),
+    "moyolo_inverse_sigmoid": (_i, [_p, _p, _l, _p]),
+    "moyolo_pos2posemb": (_i, [_p, _p, _l, _i, _i, _f, _p]),
+    "moyolo_linear_k4_relu": (_i, [_p, _p, _p, _p, _i, _l, _i, _p]),
+    "moyolo_track_workspace_bytes": (_l, [_l]),
+    "moyolo_track_assign": (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _i, _f, _p, _p]),
+    "moyolo_track_compact": (_i, [_p, _l, _p, _p, _p, _p, _p, _i, _p]),
+}
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the shared library; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: the CUDA extension is the only implementation of this path "
+                "(no CPU/PyTorch fallback). Build it with `python -m moyolo_b200.build`.")
+        handle = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is not exported
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def last_error() -> str:
+    return lib().moyolo_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    """Map a C status to the exception type the reference raises for the same condition."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc in (ERR_BAD_ARG, ERR_BAD_SHAPE, ERR_ALIGNMENT):
+        raise ValueError(msg)
+    raise RuntimeError(f"moyolo_b200 status {rc}: {msg}")

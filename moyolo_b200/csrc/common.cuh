@@ -1,0 +1,85 @@
+// Shared helpers of libmoyolo_b200: status/error plumbing, vector load/store, warp reductions.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/moyolo_b200.h"
+
+namespace moyolo {
+
+// thread-local last-error text (moyolo_last_error)
+char* last_error_buf();
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);
+
+#define MOYOLO_REQUIRE(cond, code, ...)            \
+  do {                                             \
+    if (!(cond)) return ::moyolo::fail(code, __VA_ARGS__); \
+  } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct LevelTable {
+  int n;
+  int h[MOYOLO_MAX_LEVELS];
+  int w[MOYOLO_MAX_LEVELS];
+  int start[MOYOLO_MAX_LEVELS];
+};
+
+// Builds the level table and validates sum(H*W) == len_v (transformer.py:262 assert).
+int make_levels(const int32_t* shapes_hw_host, int n_levels, int64_t len_v, LevelTable* out);
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// 128-bit read-only global load.
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t u) {
+  // bf16 -> fp32 is a 16-bit left shift; low half is element 0.
+  float2 r;
+  r.x = __uint_as_float(u << 16);
+  r.y = __uint_as_float(u & 0xffff0000u);
+  return r;
+}
+__device__ __forceinline__ uint32_t float2_to_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <typename T>
+__device__ __forceinline__ float to_float(T v);
+template <>
+__device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+template <typename T>
+__device__ __forceinline__ T from_float(float v);
+template <>
+__device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// batch index of a row for dense (row_offsets == nullptr) or ragged batches.
+__device__ __forceinline__ int batch_of_row(int64_t row, const int32_t* __restrict__ row_offsets,
+                                            int batch, int64_t rows_per_batch) {
+  if (row_offsets == nullptr) return static_cast<int>(row / rows_per_batch);
+  int b = 0;
+  while (b + 1 < batch && row >= row_offsets[b + 1]) ++b;
+  return b;
+}
+
+}  // namespace moyolo

@@ -1,0 +1,288 @@
+// Row-wise fused epilogues of the decoder layer: residual + LayerNorm (+ with_pos_embed operand),
+// box refinement, score head, positional embedding. One warp per row, fp32 math throughout.
+// Reference arithmetic: ultralytics/nn/modules/transformer.py:183-190 (pos2posemb), :637-647 and
+// :576-580 (post-norm residual blocks), :709 (box refinement), :717-721 (score head);
+// ultralytics/nn/modules/utils.py:34-38 (inverse_sigmoid); ultralytics/nn/modules/head.py:310.
+#include "common.cuh"
+
+namespace moyolo {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float inverse_sigmoidf_(float x) {
+  x = fminf(fmaxf(x, 0.0f), 1.0f);
+  const float x1 = fmaxf(x, 1e-5f);
+  const float x2 = fmaxf(1.0f - x, 1e-5f);
+  return logf(x1 / x2);
+}
+
+constexpr int kRowWarps = 4;  // warps (rows) per block
+
+template <typename LP_T>
+__global__ void __launch_bounds__(kRowWarps * 32) add_layernorm_kernel(
+    const float* __restrict__ x, const float* __restrict__ residual, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, int64_t rows, int C, float* __restrict__ out_f32,
+    LP_T* __restrict__ out_lp, const float* __restrict__ pos, LP_T* __restrict__ out_pos_lp) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * C;
+  const float* rr = residual ? residual + row * C : nullptr;
+  // C <= 1024 is held in registers (32 per lane); larger rows re-read from L1/L2.
+  constexpr int kMaxPerLane = 32;
+  float v[kMaxPerLane];
+  const int per_lane = (C + 31) / 32;
+  const bool in_regs = per_lane <= kMaxPerLane;
+  float sum = 0.0f;
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int c = lane + i * 32;
+      v[i] = (i < per_lane && c < C) ? xr[c] + (rr ? rr[c] : 0.0f) : 0.0f;
+      sum += v[i];
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) sum += xr[c] + (rr ? rr[c] : 0.0f);
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(C);
+  float sq = 0.0f;
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int c = lane + i * 32;
+      const float d = (i < per_lane && c < C) ? v[i] - mean : 0.0f;
+      sq += d * d;
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) {
+      const float d = xr[c] + (rr ? rr[c] : 0.0f) - mean;
+      sq += d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(C) + eps);
+  auto emit = [&](int c, float val) {
+    const float o = (val - mean) * rstd * gamma[c] + beta[c];
+    if (out_f32) out_f32[row * C + c] = o;
+    if (out_lp) out_lp[row * C + c] = from_float<LP_T>(o);
+    if (out_pos_lp) out_pos_lp[row * C + c] = from_float<LP_T>(o + pos[row * C + c]);
+  };
+  if (in_regs) {
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+      const int c = lane + i * 32;
+      if (i < per_lane && c < C) emit(c, v[i]);
+    }
+  } else {
+    for (int c = lane; c < C; c += 32) emit(c, xr[c] + (rr ? rr[c] : 0.0f));
+  }
+}
+
+template <typename LP_T>
+__global__ void add_cast_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                LP_T* __restrict__ out, int64_t n) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[i] = from_float<LP_T>(a[i] + (b ? b[i] : 0.0f));
+}
+
+template <typename HT>
+__global__ void __launch_bounds__(kRowWarps * 32) box_refine_kernel(
+    const HT* __restrict__ h, int64_t ldh, const float* __restrict__ w3, const float* __restrict__ b3,
+    const float* __restrict__ ref, float* __restrict__ new_ref, int64_t rows, int K) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int k = lane; k < K; k += 32) {
+    const float hv = to_float<HT>(h[row * ldh + k]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d[j] = fmaf(hv, w3[j * K + k], d[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) d[j] = warp_sum(d[j]);
+  if (lane < 4) {
+    float t = lane == 0 ? d[0] : (lane == 1 ? d[1] : (lane == 2 ? d[2] : d[3]));
+    t += b3[lane] + inverse_sigmoidf_(ref[row * 4 + lane]);
+    new_ref[row * 4 + lane] = sigmoidf_(t);
+  }
+}
+
+template <typename XT>
+__global__ void __launch_bounds__(kRowWarps * 32) score_head_kernel(
+    const XT* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
+    float* __restrict__ logits, float* __restrict__ scores, int32_t* __restrict__ labels, int64_t rows,
+    int K, int nc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float best = -INFINITY;
+  int best_c = 0;
+  for (int c = 0; c < nc; ++c) {
+    float d = 0.0f;
+    for (int k = lane; k < K; k += 32) d = fmaf(to_float<XT>(x[row * ldx + k]), w[c * K + k], d);
+    d = warp_sum(d) + b[c];
+    if (lane == 0 && logits) logits[row * nc + c] = d;
+    if (d > best) { best = d; best_c = c; }  // first maximum wins, as torch.max
+  }
+  if (lane == 0) {
+    if (scores) scores[row] = sigmoidf_(best);
+    if (labels) labels[row] = best_c;
+  }
+}
+
+__global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int inverse) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    y[i] = inverse ? inverse_sigmoidf_(x[i]) : sigmoidf_(x[i]);
+}
+
+__global__ void pos2posemb_kernel(const float* __restrict__ pos, float* __restrict__ emb, int64_t rows,
+                                  int n_coord, int F, float temperature) {
+  const int64_t total = rows * n_coord * F;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(idx % F);
+    const int64_t rc = idx / F;  // row * n_coord + coord
+    const float p = pos[rc] * 6.283185307179586f;
+    const float dim_t = powf(temperature, static_cast<float>(2 * (i / 2)) / static_cast<float>(F));
+    const float e = p / dim_t;
+    emb[idx] = (i & 1) ? cosf(e) : sinf(e);
+  }
+}
+
+template <typename TO>
+__global__ void linear_k4_relu_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                      const float* __restrict__ b, TO* __restrict__ y, int64_t rows, int N) {
+  const int64_t total = rows * N;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int n = static_cast<int>(idx % N);
+    const int64_t r = idx / N;
+    float v = b ? b[n] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v = fmaf(x[r * 4 + k], w[n * 4 + k], v);
+    y[idx] = from_float<TO>(fmaxf(v, 0.0f));
+  }
+}
+
+static unsigned ew_blocks(int64_t n) {
+  return static_cast<unsigned>(n <= 0 ? 1 : ((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8));
+}
+static unsigned row_blocks(int64_t rows) { return static_cast<unsigned>((rows + kRowWarps - 1) / kRowWarps); }
+
+}  // namespace moyolo
+
+using namespace moyolo;
+
+extern "C" int moyolo_add_layernorm(const float* x, const float* residual, const float* gamma,
+                                    const float* beta, float eps, int64_t rows, int C, float* out_f32,
+                                    void* out_lp, const float* pos, void* out_pos_lp, int lp_dtype,
+                                    moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(x && gamma && beta, MOYOLO_ERR_BAD_ARG, "add_layernorm: null x/gamma/beta");
+  MOYOLO_REQUIRE(rows >= 0 && C > 0, MOYOLO_ERR_BAD_SHAPE, "add_layernorm: bad rows/C");
+  MOYOLO_REQUIRE(out_pos_lp == nullptr || pos != nullptr, MOYOLO_ERR_BAD_ARG,
+                 "add_layernorm: out_pos_lp requested without pos");
+  if (rows == 0) return MOYOLO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (lp_dtype == MOYOLO_BF16) {
+    add_layernorm_kernel<__nv_bfloat16><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+        x, residual, gamma, beta, eps, rows, C, out_f32, static_cast<__nv_bfloat16*>(out_lp), pos,
+        static_cast<__nv_bfloat16*>(out_pos_lp));
+  } else if (lp_dtype == MOYOLO_F32) {
+    add_layernorm_kernel<float><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+        x, residual, gamma, beta, eps, rows, C, out_f32, static_cast<float*>(out_lp), pos,
+        static_cast<float*>(out_pos_lp));
+  } else {
+    return fail(MOYOLO_ERR_UNSUPPORTED, "add_layernorm: unsupported lp_dtype %d", lp_dtype);
+  }
+  return check_launch("add_layernorm_kernel");
+}
+
+extern "C" int moyolo_add_cast(const float* a, const float* b, void* out_lp, int lp_dtype, int64_t n,
+                               moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(a && out_lp && n >= 0, MOYOLO_ERR_BAD_ARG, "add_cast: bad arguments");
+  if (n == 0) return MOYOLO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (lp_dtype == MOYOLO_BF16)
+    add_cast_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>(a, b, static_cast<__nv_bfloat16*>(out_lp), n);
+  else if (lp_dtype == MOYOLO_F32)
+    add_cast_kernel<float><<<ew_blocks(n), 256, 0, st>>>(a, b, static_cast<float*>(out_lp), n);
+  else
+    return fail(MOYOLO_ERR_UNSUPPORTED, "add_cast: unsupported lp_dtype %d", lp_dtype);
+  return check_launch("add_cast_kernel");
+}
+
+extern "C" int moyolo_box_refine(const void* h, int64_t ldh, int h_dtype, const float* w3, const float* b3,
+                                 const float* ref, float* new_ref, int64_t rows, int K,
+                                 moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(h && w3 && b3 && ref && new_ref, MOYOLO_ERR_BAD_ARG, "box_refine: null pointer");
+  MOYOLO_REQUIRE(rows >= 0 && K > 0 && ldh >= K, MOYOLO_ERR_BAD_SHAPE, "box_refine: bad sizes");
+  if (rows == 0) return MOYOLO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (h_dtype == MOYOLO_BF16)
+    box_refine_kernel<__nv_bfloat16><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(h), ldh, w3, b3, ref, new_ref, rows, K);
+  else if (h_dtype == MOYOLO_F32)
+    box_refine_kernel<float><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(static_cast<const float*>(h), ldh,
+                                                                        w3, b3, ref, new_ref, rows, K);
+  else
+    return fail(MOYOLO_ERR_UNSUPPORTED, "box_refine: unsupported h_dtype %d", h_dtype);
+  return check_launch("box_refine_kernel");
+}
+
+extern "C" int moyolo_score_head(const void* x, int64_t ldx, int x_dtype, const float* w, const float* b,
+                                 float* logits, float* scores, int32_t* labels, int64_t rows, int K, int nc,
+                                 moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(x && w && b, MOYOLO_ERR_BAD_ARG, "score_head: null pointer");
+  MOYOLO_REQUIRE(rows >= 0 && K > 0 && nc > 0 && ldx >= K, MOYOLO_ERR_BAD_SHAPE, "score_head: bad sizes");
+  if (rows == 0) return MOYOLO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_dtype == MOYOLO_BF16)
+    score_head_kernel<__nv_bfloat16><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), ldx, w, b, logits, scores, labels, rows, K, nc);
+  else if (x_dtype == MOYOLO_F32)
+    score_head_kernel<float><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+        static_cast<const float*>(x), ldx, w, b, logits, scores, labels, rows, K, nc);
+  else
+    return fail(MOYOLO_ERR_UNSUPPORTED, "score_head: unsupported x_dtype %d", x_dtype);
+  return check_launch("score_head_kernel");
+}
+
+extern "C" int moyolo_sigmoid(const float* x, float* y, int64_t n, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(x && y && n >= 0, MOYOLO_ERR_BAD_ARG, "sigmoid: bad arguments");
+  if (n == 0) return MOYOLO_OK;
+  sigmoid_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, 0);
+  return check_launch("sigmoid_kernel");
+}
+
+extern "C" int moyolo_inverse_sigmoid(const float* x, float* y, int64_t n, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(x && y && n >= 0, MOYOLO_ERR_BAD_ARG, "inverse_sigmoid: bad arguments");
+  if (n == 0) return MOYOLO_OK;
+  sigmoid_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, 1);
+  return check_launch("inverse_sigmoid_kernel");
+}
+
+extern "C" int moyolo_pos2posemb(const float* pos, float* emb, int64_t rows, int n_coord, int num_pos_feats,
+                                 float temperature, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(pos && emb, MOYOLO_ERR_BAD_ARG, "pos2posemb: null pointer");
+  MOYOLO_REQUIRE(rows >= 0 && n_coord > 0 && num_pos_feats > 0, MOYOLO_ERR_BAD_SHAPE, "pos2posemb: bad sizes");
+  if (rows == 0) return MOYOLO_OK;
+  pos2posemb_kernel<<<ew_blocks(rows * n_coord * num_pos_feats), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      pos, emb, rows, n_coord, num_pos_feats, temperature);
+  return check_launch("pos2posemb_kernel");
+}
+
+extern "C" int moyolo_linear_k4_relu(const float* x, const float* w, const float* b, void* y, int out_dtype,
+                                     int64_t rows, int N, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(x && w && y, MOYOLO_ERR_BAD_ARG, "linear_k4_relu: null pointer");
+  MOYOLO_REQUIRE(rows >= 0 && N > 0, MOYOLO_ERR_BAD_SHAPE, "linear_k4_relu: bad sizes");
+  if (rows == 0) return MOYOLO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (out_dtype == MOYOLO_BF16)
+    linear_k4_relu_kernel<__nv_bfloat16><<<ew_blocks(rows * N), 256, 0, st>>>(
+        x, w, b, static_cast<__nv_bfloat16*>(y), rows, N);
+  else if (out_dtype == MOYOLO_F32)
+    linear_k4_relu_kernel<float><<<ew_blocks(rows * N), 256, 0, st>>>(x, w, b, static_cast<float*>(y), rows, N);
+  else
+    return fail(MOYOLO_ERR_UNSUPPORTED, "linear_k4_relu: unsupported out_dtype %d", out_dtype);
+  return check_launch("linear_k4_relu_kernel");
+}

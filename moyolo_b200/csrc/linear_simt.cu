@@ -1,0 +1,133 @@
+// CUDA-core GEMM: y = act(x . w^T + bias), fp32 accumulate in strict K order.
+// This is the exact-parity engine (fp32 operands reproduce nn.Linear to ~1e-6 relative); the
+// throughput engine for bf16 operands is the tcgen05 kernel in gemm_tcgen05.cu.
+// Replaces nn.Linear call sites ultralytics/nn/modules/transformer.py:264,268,269,286,576-580.
+#include "common.cuh"
+
+namespace moyolo {
+
+constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) linear_simt_kernel(const TI* __restrict__ x, int64_t ldx,
+                                                          const TI* __restrict__ w,
+                                                          const float* __restrict__ bias,
+                                                          TO* __restrict__ y, int64_t ldy, int64_t M,
+                                                          int N, int K, int relu,
+                                                          const uint8_t* __restrict__ zero_rows) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * BM;
+  const int n0 = blockIdx.x * BN;
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+  // loader mapping: 256 threads cover a 64x16 tile, 4 elements each (one row, 4 consecutive k)
+  const int lr = tid / 4;        // 0..63
+  const int lk = (tid % 4) * 4;  // 0,4,8,12
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int kk = k0 + lk + i;
+      const int64_t gm = m0 + lr;
+      const int gn = n0 + lr;
+      As[lk + i][lr] = (gm < M && kk < K) ? to_float<TI>(x[gm * ldx + kk]) : 0.0f;
+      Ws[lk + i][lr] = (gn < N && kk < K) ? to_float<TI>(w[static_cast<int64_t>(gn) * K + kk]) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) a[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) b[j] = Ws[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t gm = m0 + ty * TM + i;
+    if (gm >= M) continue;
+    const bool zero = zero_rows != nullptr && zero_rows[gm] != 0;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int gn = n0 + tx * TN + j;
+      if (gn >= N) continue;
+      float v = acc[i][j] + (bias ? bias[gn] : 0.0f);
+      if (relu) v = fmaxf(v, 0.0f);
+      if (zero) v = 0.0f;
+      y[gm * ldy + gn] = from_float<TO>(v);
+    }
+  }
+}
+
+template <typename TI, typename TO>
+static int launch_simt(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy,
+                       int64_t M, int N, int K, int relu, const uint8_t* zero_rows, cudaStream_t st) {
+  dim3 grid((N + BN - 1) / BN, static_cast<unsigned>((M + BM - 1) / BM));
+  linear_simt_kernel<TI, TO><<<grid, 256, 0, st>>>(static_cast<const TI*>(x), ldx, static_cast<const TI*>(w),
+                                                   bias, static_cast<TO*>(y), ldy, M, N, K, relu, zero_rows);
+  return check_launch("linear_simt_kernel");
+}
+
+int linear_simt(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy,
+                int64_t M, int N, int K, int in_dtype, int out_dtype, int relu, const uint8_t* zero_rows,
+                cudaStream_t st) {
+  if (in_dtype == MOYOLO_F32 && out_dtype == MOYOLO_F32)
+    return launch_simt<float, float>(x, ldx, w, bias, y, ldy, M, N, K, relu, zero_rows, st);
+  if (in_dtype == MOYOLO_F32 && out_dtype == MOYOLO_BF16)
+    return launch_simt<float, __nv_bfloat16>(x, ldx, w, bias, y, ldy, M, N, K, relu, zero_rows, st);
+  if (in_dtype == MOYOLO_BF16 && out_dtype == MOYOLO_F32)
+    return launch_simt<__nv_bfloat16, float>(x, ldx, w, bias, y, ldy, M, N, K, relu, zero_rows, st);
+  if (in_dtype == MOYOLO_BF16 && out_dtype == MOYOLO_BF16)
+    return launch_simt<__nv_bfloat16, __nv_bfloat16>(x, ldx, w, bias, y, ldy, M, N, K, relu, zero_rows, st);
+  return fail(MOYOLO_ERR_UNSUPPORTED, "moyolo_linear: unsupported dtype pair (%d -> %d)", in_dtype, out_dtype);
+}
+
+// implemented in gemm_tcgen05.cu
+int linear_tcgen05(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy,
+                   int64_t M, int N, int K, int out_dtype, int relu, const uint8_t* zero_rows,
+                   cudaStream_t st);
+bool linear_tcgen05_supported(const void* x, int64_t ldx, const void* w, int64_t M, int N, int K);
+
+}  // namespace moyolo
+
+extern "C" int moyolo_linear(const void* x, int64_t ldx, const void* w, const float* bias, void* y,
+                             int64_t ldy, int64_t M, int N, int K, int in_dtype, int out_dtype,
+                             int epilogue, const uint8_t* zero_rows, int engine, moyolo_stream_t stream) {
+  using namespace moyolo;
+  MOYOLO_REQUIRE(x && w && y, MOYOLO_ERR_BAD_ARG, "moyolo_linear: null x/w/y pointer");
+  MOYOLO_REQUIRE(M >= 0 && N > 0 && K > 0 && ldx >= K && ldy >= N, MOYOLO_ERR_BAD_SHAPE,
+                 "moyolo_linear: bad sizes M=%lld N=%d K=%d ldx=%lld ldy=%lld", (long long)M, N, K,
+                 (long long)ldx, (long long)ldy);
+  MOYOLO_REQUIRE(epilogue == MOYOLO_EPI_NONE || epilogue == MOYOLO_EPI_RELU, MOYOLO_ERR_BAD_ARG,
+                 "moyolo_linear: bad epilogue %d", epilogue);
+  if (M == 0) return MOYOLO_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int relu = epilogue == MOYOLO_EPI_RELU;
+  if (engine == MOYOLO_GEMM_AUTO)
+    engine = (in_dtype == MOYOLO_BF16 && linear_tcgen05_supported(x, ldx, w, M, N, K)) ? MOYOLO_GEMM_TCGEN05
+                                                                                       : MOYOLO_GEMM_SIMT;
+  if (engine == MOYOLO_GEMM_TCGEN05) {
+    MOYOLO_REQUIRE(in_dtype == MOYOLO_BF16, MOYOLO_ERR_UNSUPPORTED,
+                   "moyolo_linear: the tcgen05 engine takes bf16 operands");
+    MOYOLO_REQUIRE(linear_tcgen05_supported(x, ldx, w, M, N, K), MOYOLO_ERR_ALIGNMENT,
+                   "moyolo_linear: tcgen05 engine needs K%%64==0, N%%16==0, 16B-aligned x/w/ldx");
+    return linear_tcgen05(x, ldx, w, bias, y, ldy, M, N, K, out_dtype, relu, zero_rows, st);
+  }
+  MOYOLO_REQUIRE(engine == MOYOLO_GEMM_SIMT, MOYOLO_ERR_BAD_ARG, "moyolo_linear: bad engine %d", engine);
+  return linear_simt(x, ldx, w, bias, y, ldy, M, N, K, in_dtype, out_dtype, relu, zero_rows, st);
+}

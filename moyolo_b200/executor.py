@@ -1,0 +1,206 @@
+"""Decoder-layer executor: the kernel schedule behind the drop-in modules.
+
+One decoder layer (ultralytics/nn/modules/transformer.py:627-652 / :431-450) is run as the chain
+
+    in-proj GEMMs (q,k from x+pos; v from x) -> self-attention -> out-proj GEMM -> add+LayerNorm
+    -> fused offsets|logits GEMM -> deformable gather -> output-proj GEMM -> add+LayerNorm
+    -> FFN GEMM(ReLU) -> FFN GEMM -> add+LayerNorm [-> + pos for the next layer]
+
+with `value_proj` hoisted out of the layer loop: `feats` is the same tensor in every layer
+(transformer.py:705 passes it unchanged), so all layers' values come from ONE GEMM
+[B*Lv, C] x [C, n_layers*C] and each layer's gather reads its own column slice in place.
+
+Two precisions: "fp32" (CUDA-core GEMMs, reference-grade parity) and "bf16" (bf16 GEMM operands and
+value tensor on tcgen05; residual stream, LayerNorm, softmax, sampling locations and accumulation
+stay fp32).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+
+_DEFAULT_PRECISION = "fp32"
+_GEMM_ENGINE = _lib.GEMM_AUTO
+
+
+def set_default_precision(p: str) -> None:
+    global _DEFAULT_PRECISION
+    if p not in ("fp32", "bf16"):
+        raise ValueError("precision must be 'fp32' or 'bf16'")
+    _DEFAULT_PRECISION = p
+
+
+def get_default_precision() -> str:
+    return _DEFAULT_PRECISION
+
+
+def set_gemm_engine(engine: int) -> None:
+    """Force the GEMM engine (GEMM_AUTO / GEMM_SIMT / GEMM_TCGEN05) — used by tests and profiling."""
+    global _GEMM_ENGINE
+    _GEMM_ENGINE = engine
+
+
+def lp_dtype(precision: str) -> torch.dtype:
+    return torch.bfloat16 if precision == "bf16" else torch.float32
+
+
+def _w(t: torch.Tensor, dt: torch.dtype) -> torch.Tensor:
+    return t.detach().to(dt).contiguous()
+
+
+def _f(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().float().contiguous()
+
+
+def _versions(module: torch.nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+class LinearPack:
+    __slots__ = ("w", "b")
+
+    def __init__(self, weight, bias, dt):
+        self.w = _w(weight, dt)
+        self.b = _f(bias) if bias is not None else None
+
+
+class MsdaPack:
+    """Weights of one MSDeformAttn (transformer.py:214-217); offsets and logits linears fused."""
+
+    def __init__(self, m, dt):
+        self.n_heads, self.n_levels, self.n_points, self.d_model = m.n_heads, m.n_levels, m.n_points, m.d_model
+        self.n_off = m.n_heads * m.n_levels * m.n_points * 2
+        self.offlog = LinearPack(torch.cat([m.sampling_offsets.weight, m.attention_weights.weight], 0),
+                                 torch.cat([m.sampling_offsets.bias, m.attention_weights.bias], 0), dt)
+        self.value = LinearPack(m.value_proj.weight, m.value_proj.bias, dt)
+        self.out = LinearPack(m.output_proj.weight, m.output_proj.bias, dt)
+        self.softmax_mode = _lib.SOFTMAX_PLUS1 if getattr(m, "my_softmax", False) and \
+            type(m).__name__ == "MOTRMSDeformAttn" else _lib.SOFTMAX
+
+
+class LayerPack:
+    def __init__(self, layer, dt):
+        sa = layer.self_attn
+        C = sa.embed_dim
+        self.C, self.n_heads = C, sa.num_heads
+        self.qk = LinearPack(sa.in_proj_weight[:2 * C], sa.in_proj_bias[:2 * C], dt)
+        self.v = LinearPack(sa.in_proj_weight[2 * C:], sa.in_proj_bias[2 * C:], dt)
+        self.o = LinearPack(sa.out_proj.weight, sa.out_proj.bias, dt)
+        self.msda = MsdaPack(layer.cross_attn, dt)
+        self.ffn1 = LinearPack(layer.linear1.weight, layer.linear1.bias, dt)
+        self.ffn2 = LinearPack(layer.linear2.weight, layer.linear2.bias, dt)
+        self.norms = [(_f(n.weight), _f(n.bias), n.eps) for n in (layer.norm1, layer.norm2, layer.norm3)]
+        if not isinstance(layer.act, torch.nn.ReLU):
+            raise NotImplementedError("moyolo_b200 decoder layer: only ReLU FFN activation is implemented")
+
+
+class MlpPack:
+    def __init__(self, mlp, dt):
+        ls = list(mlp.layers)
+        self.hidden = [LinearPack(l.weight, l.bias, dt) for l in ls[:-1]]
+        self.last_w, self.last_b = _f(ls[-1].weight), _f(ls[-1].bias)
+        self.last_lp = LinearPack(ls[-1].weight, ls[-1].bias, dt)
+        self.first_w_f32 = _f(ls[0].weight) if ls[0].in_features == 4 else None
+
+
+def cached_pack(module, key: str, builder, dt):
+    """Per-module weight pack, rebuilt when any parameter is modified in place or re-assigned."""
+    cache = module.__dict__.setdefault("_moyolo_packs", {})
+    ver = _versions(module)
+    hit = cache.get((key, dt))
+    if hit is None or hit[0] != ver:
+        hit = (ver, builder(module, dt))
+        cache[(key, dt)] = hit
+    return hit[1]
+
+
+def dense_row_offsets(B: int, Q: int, device) -> tuple:
+    host = [b * Q for b in range(B + 1)]
+    return torch.tensor(host, dtype=torch.int32, device=device), host
+
+
+_ro_cache = {}
+
+
+def cached_dense_row_offsets(B: int, Q: int, device):
+    key = (B, Q, str(device))
+    if key not in _ro_cache:
+        _ro_cache[key] = dense_row_offsets(B, Q, device)
+    return _ro_cache[key]
+
+
+def project_values(feats_lp: torch.Tensor, msda_packs: Sequence[MsdaPack], zero_rows, dt) -> torch.Tensor:
+    """One GEMM for every layer's value_proj: feats_lp [B*Lv, C] -> [B*Lv, n_layers*C]."""
+    if len(msda_packs) == 1:
+        w, b = msda_packs[0].value.w, msda_packs[0].value.b
+    else:
+        w = torch.cat([p.value.w for p in msda_packs], 0)
+        b = torch.cat([p.value.b for p in msda_packs], 0)
+    return ops.linear(feats_lp, w, b, out_dtype=dt, zero_rows=zero_rows, engine=_GEMM_ENGINE)
+
+
+class ValueProjPack:
+    def __init__(self, layers, dt):
+        self.w = torch.cat([_w(l.cross_attn.value_proj.weight, dt) for l in layers], 0).contiguous()
+        self.b = torch.cat([_f(l.cross_attn.value_proj.bias) for l in layers], 0).contiguous()
+
+
+def msda_forward(pack: MsdaPack, xq_lp: torch.Tensor, refer: torch.Tensor, value_view: torch.Tensor, shapes,
+                 batch: int, row_offsets, dt) -> torch.Tensor:
+    """offsets|logits GEMM -> fused gather -> output_proj GEMM. Returns fp32 [R, C]."""
+    ol = ops.linear(xq_lp, pack.offlog.w, pack.offlog.b, out_dtype=torch.float32, engine=_GEMM_ENGINE)
+    g = ops.msda_fused(value_view, shapes, ol[:, :pack.n_off], ol[:, pack.n_off:], refer, pack.n_heads,
+                       pack.n_points, batch, pack.softmax_mode, row_offsets)
+    return ops.linear(g, pack.out.w, pack.out.b, out_dtype=torch.float32, engine=_GEMM_ENGINE)
+
+
+def run_layer(pk: LayerPack, x_f32, x_lp, xq_lp, refer, value_view, shapes, batch, row_offsets, row_offsets_host,
+              dense: bool, attn_mask, pos_cur, pos_next, dt):
+    """One post-norm decoder layer.
+
+    x_f32 residual stream, x_lp its GEMM-operand copy, xq_lp = (x + pos_cur) operand copy.
+    pos_cur / pos_next: fp32 [R, C] positional embeddings of this / the next layer (None = no pos).
+    Returns (x_f32, x_lp, xq_lp for the next layer or None when pos_next is None).
+    """
+    R, C = x_f32.shape
+    eng = _GEMM_ENGINE
+    qkv = torch.empty(R, 3 * C, dtype=dt, device=x_f32.device)
+    ops.linear(xq_lp, pk.qk.w, pk.qk.b, out=qkv[:, :2 * C], engine=eng)
+    ops.linear(x_lp, pk.v.w, pk.v.b, out=qkv[:, 2 * C:], engine=eng)
+    att = ops.self_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], row_offsets, row_offsets_host,
+                             pk.n_heads, attn_mask)
+    t = ops.linear(att, pk.o.w, pk.o.b, out_dtype=torch.float32, engine=eng)
+    g, b_, e = pk.norms[0]
+    # after norm1 only the residual (fp32) and the cross-attention query operand (x + pos) are needed
+    x1_f32, x1_lp, x1q_lp = ops.add_layernorm(t, x_f32, g, b_, e, want_f32=True, want_lp=pos_cur is None,
+                                              lp_dtype=dt, pos=pos_cur)
+    t2 = msda_forward(pk.msda, x1q_lp if pos_cur is not None else x1_lp, refer, value_view, shapes, batch,
+                      None if dense else row_offsets, dt)
+    g, b_, e = pk.norms[1]
+    x2_f32, x2_lp, _ = ops.add_layernorm(t2, x1_f32, g, b_, e, want_f32=True, want_lp=True, lp_dtype=dt)
+    h = ops.linear(x2_lp, pk.ffn1.w, pk.ffn1.b, relu=True, engine=eng)
+    t3 = ops.linear(h, pk.ffn2.w, pk.ffn2.b, out_dtype=torch.float32, engine=eng)
+    g, b_, e = pk.norms[2]
+    x3_f32, x3_lp, x3q_lp = ops.add_layernorm(t3, x2_f32, g, b_, e, want_f32=True, want_lp=True, lp_dtype=dt,
+                                              pos=pos_next)
+    return x3_f32, x3_lp, x3q_lp
+
+
+def bbox_head(mp: MlpPack, x_lp, refer, out=None):
+    """sigmoid(MLP(x) + inverse_sigmoid(refer)) (transformer.py:709); last MLP layer fused with the refine."""
+    h = x_lp
+    for lin in mp.hidden:
+        h = ops.linear(h, lin.w, lin.b, relu=True, engine=_GEMM_ENGINE)
+    return ops.box_refine(h, mp.last_w, mp.last_b, refer, out=out)
+
+
+def pos_mlp_forward(mp: MlpPack, refer, dt):
+    """pos_mlp(refer) for DeformableTransformerDecoder (transformer.py:491): MLP(4, 2*hd, hd, 2)."""
+    if len(mp.hidden) != 1 or mp.hidden[0].w.shape[1] != 4:
+        raise NotImplementedError("pos_mlp must be MLP(4, hidden, out, num_layers=2)")
+    first = mp.hidden[0]
+    h = ops.linear_k4_relu(refer, mp.first_w_f32, first.b, dt)
+    return ops.linear(h, mp.last_lp.w, mp.last_lp.b, out_dtype=torch.float32, engine=_GEMM_ENGINE)

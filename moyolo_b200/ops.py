@@ -1,0 +1,254 @@
+"""Tensor-level wrappers over the C ABI. PyTorch is used for device memory and streams only.
+
+Every function requires CUDA tensors and enqueues on `torch.cuda.current_stream()`; outputs are
+allocated here (the C library never allocates), see include/moyolo_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, F64
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16, torch.float64: F64}
+
+
+def _dt(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise RuntimeError(f"moyolo_b200: unsupported dtype {t.dtype}") from None
+
+
+def _cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            # same wording as the reference extension (MOTR/models/ops/src/ms_deform_attn.h:36)
+            raise RuntimeError("Not implemented on the CPU")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _shapes_arr(shapes: Sequence[Sequence[int]]):
+    flat = [int(v) for hw in shapes for v in hw]
+    return (C.c_int32 * len(flat))(*flat), len(flat) // 2
+
+
+def msda_sampled(value: torch.Tensor, shapes, loc: torch.Tensor, weights: torch.Tensor,
+                 row_offsets: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """multi_scale_deformable_attn_pytorch (utils.py:41-78) / legacy ms_deform_attn_forward.
+
+    value [B, Lv, H, Dh] (last two dims contiguous), loc [B, Q, H, L, P, 2], weights [B, Q, H, L, P]
+    -> [B, Q, H*Dh].
+    """
+    _cuda(value, loc, weights)
+    B, Lv, H, Dh = value.shape
+    if value.stride(3) != 1 or value.stride(2) != Dh:
+        value = value.contiguous()
+    loc, weights = loc.contiguous(), weights.contiguous()
+    _, Q, _, L, P, _ = loc.shape
+    arr, n_levels = _shapes_arr(shapes)
+    if n_levels != L:
+        raise ValueError(f"value_shapes has {n_levels} levels but sampling locations have {L}")
+    out = torch.empty(B, Q, H * Dh, dtype=value.dtype, device=value.device)
+    _lib.check(_lib.lib().moyolo_msda_sampled_forward(
+        value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, H, Dh, P,
+        loc.data_ptr(), weights.data_ptr(), _dt(loc), B * Q, _ptr(row_offsets), out.data_ptr(), H * Dh,
+        _stream()))
+    return out
+
+
+def msda_fused(value: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch.Tensor, refer: torch.Tensor,
+               n_heads: int, n_points: int, batch: int, softmax_mode: int = _lib.SOFTMAX,
+               row_offsets: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Fused softmax + location + bilinear gather (transformer.py:268-285).
+
+    value  [B, Lv, C] view (last dim contiguous; arbitrary batch/position strides)
+    offsets [R, H*L*P*2] fp32 view, logits [R, H*L*P] fp32 view (row-strided slices allowed)
+    refer  [R, ref_levels, 2|4] fp32 contiguous
+    -> [R, C] of value.dtype
+    """
+    _cuda(value, offsets, logits, refer)
+    B, Lv, Cc = value.shape
+    if B != batch or value.stride(2) != 1:
+        raise ValueError("value must be [B, Lv, C] with contiguous channels")
+    Dh = Cc // n_heads
+    R = offsets.shape[0]
+    arr, L = _shapes_arr(shapes)
+    if offsets.stride(1) != 1 or logits.stride(1) != 1 or offsets.dtype != torch.float32 or \
+            logits.dtype != torch.float32:
+        raise ValueError("offsets/logits must be fp32 with contiguous columns")
+    refer = refer.contiguous()
+    if refer.dtype != torch.float32:
+        raise ValueError("refer must be fp32")
+    if out is None:
+        out = torch.empty(R, Cc, dtype=value.dtype, device=value.device)
+    _lib.check(_lib.lib().moyolo_msda_fused_forward(
+        value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, n_heads, Dh, n_points,
+        offsets.data_ptr(), offsets.stride(0), logits.data_ptr(), logits.stride(0), refer.data_ptr(),
+        refer.shape[1], refer.shape[2], softmax_mode, R, _ptr(row_offsets), out.data_ptr(), out.stride(0),
+        _stream()))
+    return out
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out_dtype: torch.dtype = None,
+           relu: bool = False, zero_rows: Optional[torch.Tensor] = None, engine: int = _lib.GEMM_AUTO,
+           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = act(x . w^T + b); x [M, K] (row stride free), w [N, K] contiguous, b fp32 [N] or None."""
+    _cuda(x, w, b)
+    M, K = x.shape
+    N = w.shape[0]
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    if not w.is_contiguous() or w.shape[1] != K or w.dtype != x.dtype:
+        raise ValueError("linear: w must be contiguous [N, K] of x.dtype")
+    if b is not None and (b.dtype != torch.float32 or not b.is_contiguous()):
+        raise ValueError("linear: bias must be contiguous fp32")
+    out_dtype = out_dtype or x.dtype
+    if out is None:
+        out = torch.empty(M, N, dtype=out_dtype, device=x.device)
+    _lib.check(_lib.lib().moyolo_linear(
+        x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), out.data_ptr(), out.stride(0), M, N, K, _dt(x),
+        _dt(out), _lib.EPI_RELU if relu else _lib.EPI_NONE, _ptr(zero_rows), engine, _stream()))
+    return out
+
+
+def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, row_offsets: torch.Tensor,
+                   row_offsets_host: Sequence[int], n_heads: int, attn_mask: Optional[torch.Tensor] = None,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(q k^T / sqrt(Dh)) v per (sequence, head); q/k/v are [R, C] column slices."""
+    _cuda(q, k, v, row_offsets, attn_mask)
+    R, Cc = q.shape
+    if out is None:
+        out = torch.empty(R, Cc, dtype=q.dtype, device=q.device)
+    host = (C.c_int32 * len(row_offsets_host))(*[int(x) for x in row_offsets_host])
+    _lib.check(_lib.lib().moyolo_self_attention(
+        q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
+        out.stride(0), _dt(q), len(row_offsets_host) - 1, row_offsets.data_ptr(), host, n_heads, Cc // n_heads,
+        _ptr(attn_mask), _stream()))
+    return out
+
+
+def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
+                  eps: float, want_f32: bool = True, want_lp: bool = False,
+                  lp_dtype: Optional[torch.dtype] = None, pos: Optional[torch.Tensor] = None):
+    """LayerNorm(x + residual); returns (out_f32 | None, out_lp | None, out_plus_pos_lp | None)."""
+    _cuda(x, residual, gamma, beta, pos)
+    R, Cc = x.shape
+    lp_dtype = lp_dtype or torch.float32
+    out_f32 = torch.empty(R, Cc, dtype=torch.float32, device=x.device) if want_f32 else None
+    out_lp = torch.empty(R, Cc, dtype=lp_dtype, device=x.device) if want_lp else None
+    out_pos = torch.empty(R, Cc, dtype=lp_dtype, device=x.device) if pos is not None else None
+    _lib.check(_lib.lib().moyolo_add_layernorm(
+        x.data_ptr(), _ptr(residual), gamma.data_ptr(), beta.data_ptr(), float(eps), R, Cc, _ptr(out_f32),
+        _ptr(out_lp), _ptr(pos), _ptr(out_pos), _DT[lp_dtype], _stream()))
+    return out_f32, out_lp, out_pos
+
+
+def add_cast(a: torch.Tensor, b: Optional[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
+    _cuda(a, b)
+    out = torch.empty(a.shape, dtype=dtype, device=a.device)
+    _lib.check(_lib.lib().moyolo_add_cast(a.data_ptr(), _ptr(b), out.data_ptr(), _DT[dtype], a.numel(), _stream()))
+    return out
+
+
+def box_refine(h: torch.Tensor, w3: torch.Tensor, b3: torch.Tensor, ref: torch.Tensor,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _cuda(h, w3, b3, ref, out)
+    R, K = h.shape
+    if out is None:
+        out = torch.empty(R, 4, dtype=torch.float32, device=h.device)
+    elif not out.is_contiguous() or out.dtype != torch.float32 or out.numel() != R * 4:
+        raise ValueError("box_refine: out must be contiguous fp32 with R*4 elements")
+    _lib.check(_lib.lib().moyolo_box_refine(h.data_ptr(), h.stride(0), _dt(h), w3.data_ptr(), b3.data_ptr(),
+                                            ref.data_ptr(), out.data_ptr(), R, K, _stream()))
+    return out
+
+
+def score_head(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_scores: bool = True):
+    _cuda(x, w, b)
+    R, K = x.shape
+    nc = w.shape[0]
+    logits = torch.empty(R, nc, dtype=torch.float32, device=x.device)
+    scores = torch.empty(R, dtype=torch.float32, device=x.device) if want_scores else None
+    labels = torch.empty(R, dtype=torch.int32, device=x.device) if want_scores else None
+    _lib.check(_lib.lib().moyolo_score_head(x.data_ptr(), x.stride(0), _dt(x), w.data_ptr(), b.data_ptr(),
+                                            logits.data_ptr(), _ptr(scores), _ptr(labels), R, K, nc, _stream()))
+    return logits, scores, labels
+
+
+def sigmoid(x: torch.Tensor) -> torch.Tensor:
+    _cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().moyolo_sigmoid(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
+    return y
+
+
+def inverse_sigmoid(x: torch.Tensor) -> torch.Tensor:
+    _cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().moyolo_inverse_sigmoid(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
+    return y
+
+
+def pos2posemb(pos: torch.Tensor, num_pos_feats: int = 64, temperature: float = 10000.0) -> torch.Tensor:
+    _cuda(pos)
+    pos = pos.contiguous()
+    n_coord = pos.shape[-1]
+    rows = pos.numel() // n_coord
+    emb = torch.empty(*pos.shape[:-1], n_coord * num_pos_feats, dtype=torch.float32, device=pos.device)
+    _lib.check(_lib.lib().moyolo_pos2posemb(pos.data_ptr(), emb.data_ptr(), rows, n_coord, num_pos_feats,
+                                            float(temperature), _stream()))
+    return emb
+
+
+def linear_k4_relu(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    _cuda(x, w, b)
+    R = x.shape[0]
+    N = w.shape[0]
+    y = torch.empty(R, N, dtype=out_dtype, device=x.device)
+    _lib.check(_lib.lib().moyolo_linear_k4_relu(x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), _DT[out_dtype],
+                                                R, N, _stream()))
+    return y
+
+
+def track_workspace_bytes(n: int) -> int:
+    return int(_lib.lib().moyolo_track_workspace_bytes(int(n)))
+
+
+def track_assign(scores: torch.Tensor, boxes: torch.Tensor, obj_idxes: torch.Tensor, disappear_time: torch.Tensor,
+                 counters: torch.Tensor, workspace: torch.Tensor, score_thresh: float = 0.4,
+                 filter_thresh: float = 0.5, miss_tolerance: int = 5, iou_thresh: float = 0.8) -> None:
+    """In-place RuntimeTrackerBase.update (head.py:1201-1283) on device."""
+    _cuda(scores, boxes, obj_idxes, disappear_time, counters, workspace)
+    n = scores.shape[0]
+    assert obj_idxes.dtype == torch.int64 and disappear_time.dtype == torch.int64 and counters.dtype == torch.int64
+    assert workspace.numel() * workspace.element_size() >= track_workspace_bytes(n)
+    _lib.check(_lib.lib().moyolo_track_assign(
+        scores.data_ptr(), boxes.data_ptr(), obj_idxes.data_ptr(), disappear_time.data_ptr(), counters.data_ptr(), n,
+        float(score_thresh), float(filter_thresh), int(miss_tolerance), float(iou_thresh), workspace.data_ptr(),
+        _stream()))
+
+
+def track_compact(obj_idxes: torch.Tensor, fields: Sequence[torch.Tensor], outs: Sequence[torch.Tensor],
+                  n_active: torch.Tensor, active_index: torch.Tensor) -> None:
+    """Select rows with obj_idxes >= 0 (order preserved) from every field into `outs`."""
+    _cuda(obj_idxes, n_active, active_index, *fields, *outs)
+    n = obj_idxes.shape[0]
+    nf = len(fields)
+    src = (C.c_void_p * nf)(*[f.data_ptr() for f in fields])
+    dst = (C.c_void_p * nf)(*[o.data_ptr() for o in outs])
+    rb = (C.c_int64 * nf)(*[f.stride(0) * f.element_size() if f.dim() > 1 else f.element_size() for f in fields])
+    _lib.check(_lib.lib().moyolo_track_compact(obj_idxes.data_ptr(), n, n_active.data_ptr(), active_index.data_ptr(),
+                                               src, dst, rb, nf, _stream()))

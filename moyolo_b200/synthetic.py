@@ -1,0 +1,223 @@
+"""Deterministic synthetic weights, pyramids and sequences (SURVEY.md §8(d) "synthetic inputs").
+
+Everything is generated on the CPU from `torch.Generator` seeds so that the golden-vector script
+(run where the reference exists), the CPU tests and the GPU box regenerate bit-identical inputs;
+golden files store a checksum of the regenerated inputs to detect RNG drift.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+
+# feature-pyramid shapes [(H, W)] of the named configs
+PYRAMIDS: Dict[str, List[Tuple[int, int]]] = {
+    "C1": [(80, 80), (40, 40), (20, 20)],          # 640x640
+    "MOT17": [(76, 136), (38, 68), (19, 34)],      # 1088x608
+    "DanceTrack": [(100, 168), (50, 84), (25, 42)],  # 1344x800
+    "KITTI": [(48, 156), (24, 78), (12, 39)],      # 1248x384
+    "tiny": [(12, 16), (6, 8), (3, 4)],
+}
+
+
+@dataclass
+class DecoderSpec:
+    d_model: int = 256
+    n_heads: int = 8
+    d_ffn: int = 1024
+    n_levels: int = 3
+    n_points: int = 4
+    n_layers: int = 6
+    nc: int = 1
+    pos_hidden: int = 512  # query_pos_head = MLP(4, 2*hd, hd, 2)
+    qim_hidden: int = 256  # head.py:117-118
+
+    def key(self) -> str:
+        return f"d{self.d_model}h{self.n_heads}f{self.d_ffn}L{self.n_levels}P{self.n_points}n{self.n_layers}c{self.nc}"
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    return g
+
+
+def _lin(g, out_f, in_f, w_std=None, b_std=0.02):
+    w_std = w_std if w_std is not None else 1.0 / math.sqrt(in_f)
+    return torch.randn(out_f, in_f, generator=g) * w_std, torch.randn(out_f, generator=g) * b_std
+
+
+def _ln(g, d):
+    return 1.0 + 0.1 * torch.randn(d, generator=g), 0.05 * torch.randn(d, generator=g)
+
+
+def make_decoder_state(spec: DecoderSpec, seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Random-init weights with the reference's state_dict key names.
+
+    Keys: `layers.{i}.*` (decoder layers), `dec_bbox_head.{i}.layers.{j}.*`, `dec_score_head.{i}.*`,
+    `query_pos_head.layers.{j}.*`, `denoising_class_embed.weight`, `track_embed.*` (QIM).
+    sampling_offsets ~ N(0, 0.02) on top of the directional bias and attention_weights ~ N(0, 0.05)
+    so the sampling pattern and softmax are non-degenerate (the module default zeros them).
+    """
+    g = _gen(seed)
+    d, H, L, P = spec.d_model, spec.n_heads, spec.n_levels, spec.n_points
+    sd: Dict[str, torch.Tensor] = {}
+
+    def put(prefix, wb):
+        sd[prefix + ".weight"], sd[prefix + ".bias"] = wb
+
+    ang = torch.arange(H, dtype=torch.float32) * (2.0 * math.pi / H)
+    ring = torch.stack([ang.cos(), ang.sin()], -1)
+    ring = (ring / ring.abs().max(-1, keepdim=True)[0]).view(H, 1, 1, 2).repeat(1, L, P, 1)
+    ring = ring * torch.arange(1, P + 1, dtype=torch.float32).view(1, 1, -1, 1)
+    for i in range(spec.n_layers):
+        p = f"layers.{i}."
+        w, b = _lin(g, 3 * d, d)
+        sd[p + "self_attn.in_proj_weight"], sd[p + "self_attn.in_proj_bias"] = w, b
+        put(p + "self_attn.out_proj", _lin(g, d, d))
+        sd[p + "norm1.weight"], sd[p + "norm1.bias"] = _ln(g, d)
+        w, b = _lin(g, H * L * P * 2, d, w_std=0.02, b_std=0.0)
+        sd[p + "cross_attn.sampling_offsets.weight"] = w
+        sd[p + "cross_attn.sampling_offsets.bias"] = ring.reshape(-1).clone() + 0.1 * torch.randn(H * L * P * 2, generator=g)
+        put(p + "cross_attn.attention_weights", _lin(g, H * L * P, d, w_std=0.05, b_std=0.1))
+        put(p + "cross_attn.value_proj", _lin(g, d, d))
+        put(p + "cross_attn.output_proj", _lin(g, d, d))
+        sd[p + "norm2.weight"], sd[p + "norm2.bias"] = _ln(g, d)
+        put(p + "linear1", _lin(g, spec.d_ffn, d))
+        put(p + "linear2", _lin(g, d, spec.d_ffn))
+        sd[p + "norm3.weight"], sd[p + "norm3.bias"] = _ln(g, d)
+    for i in range(spec.n_layers):
+        put(f"dec_bbox_head.{i}.layers.0", _lin(g, d, d))
+        put(f"dec_bbox_head.{i}.layers.1", _lin(g, d, d))
+        put(f"dec_bbox_head.{i}.layers.2", _lin(g, 4, d, w_std=0.2 / math.sqrt(d)))
+        w, _ = _lin(g, spec.nc, d, w_std=0.1)
+        sd[f"dec_score_head.{i}.weight"] = w
+        sd[f"dec_score_head.{i}.bias"] = torch.full((spec.nc,), -3.3) + 0.05 * torch.randn(spec.nc, generator=g)
+    put("query_pos_head.layers.0", _lin(g, spec.pos_hidden, 4, w_std=0.5))
+    put("query_pos_head.layers.1", _lin(g, d, spec.pos_hidden))
+    sd["denoising_class_embed.weight"] = torch.randn(spec.nc, d, generator=g)
+    # QIM (MOTR/models/qim.py:85-105): dim_in = d, hidden = qim_hidden
+    q = "track_embed."
+    w, b = _lin(g, 3 * d, d)
+    sd[q + "self_attn.in_proj_weight"], sd[q + "self_attn.in_proj_bias"] = w, b
+    put(q + "self_attn.out_proj", _lin(g, d, d))
+    put(q + "linear1", _lin(g, spec.qim_hidden, d))
+    put(q + "linear2", _lin(g, d, spec.qim_hidden))
+    put(q + "linear_feat1", _lin(g, spec.qim_hidden, d))
+    put(q + "linear_feat2", _lin(g, d, spec.qim_hidden))
+    for n in ("norm_feat", "norm1", "norm2"):
+        sd[q + n + ".weight"], sd[q + n + ".bias"] = _ln(g, d)
+    return sd
+
+
+def sub_state(sd: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def level_sizes(shapes: Sequence[Sequence[int]]) -> int:
+    return sum(int(h) * int(w) for h, w in shapes)
+
+
+def make_core_inputs(seed: int, B: int, Q: int, n_heads: int, head_dim: int, shapes, n_points: int,
+                     outside_frac: float = 0.1):
+    """Inputs of the core op a1 (value, loc, weights); ~10% of points fall outside [0,1] (zero padding)
+    and a few hit exact borders / pixel centres."""
+    g = _gen(seed)
+    Lv, L = level_sizes(shapes), len(shapes)
+    value = torch.randn(B, Lv, n_heads, head_dim, generator=g)
+    loc = torch.rand(B, Q, n_heads, L, n_points, 2, generator=g)
+    far = torch.rand(B, Q, n_heads, L, n_points, 1, generator=g) < outside_frac
+    loc = torch.where(far, loc * 1.6 - 0.3, loc)
+    flat = loc.view(-1)
+    specials = torch.tensor([0.0, 1.0, -0.2, 1.25, 0.5, 0.5 / shapes[0][1], 1.0 - 1e-7, 1e-7])
+    n = min(len(specials), flat.numel())
+    flat[:n] = specials[:n]
+    w = torch.rand(B, Q, n_heads, L, n_points, generator=g) + 1e-5
+    w = w / w.sum((-1, -2), keepdim=True)
+    return value, loc, w
+
+
+def make_module_inputs(seed: int, B: int, Q: int, d_model: int, shapes, ref_dim: int = 4, ref_levels: int = 1):
+    """Inputs of MSDeformAttn.forward / a decoder layer: query, refer_bbox (sigmoid space), feats, query_pos."""
+    g = _gen(seed)
+    Lv = level_sizes(shapes)
+    query = torch.randn(B, Q, d_model, generator=g)
+    cxcy = torch.rand(B, Q, ref_levels, 2, generator=g)
+    if ref_dim == 4:
+        wh = torch.rand(B, Q, ref_levels, 2, generator=g) * 0.48 + 0.02
+        refer = torch.cat([cxcy, wh], -1)
+    else:
+        refer = cxcy
+    feats = torch.randn(B, Lv, d_model, generator=g)
+    query_pos = torch.randn(B, Q, d_model, generator=g) * 0.5
+    return query, refer, feats, query_pos
+
+
+def make_decoder_inputs(seed: int, B: int, Q: int, d_model: int, shapes):
+    """Inputs of the 6-layer decoders: embed, refer_bbox in LOGIT space, feats, fixed query_pos."""
+    g = _gen(seed)
+    Lv = level_sizes(shapes)
+    embed = torch.randn(B, Q, d_model, generator=g)
+    cxcy = torch.rand(B, Q, 2, generator=g) * 0.9 + 0.05
+    wh = torch.rand(B, Q, 2, generator=g) * 0.28 + 0.02
+    boxes = torch.cat([cxcy, wh], -1)
+    refer_logit = torch.log(boxes / (1 - boxes))
+    feats = torch.randn(B, Lv, d_model, generator=g)
+    query_pos = torch.randn(B, Q, d_model, generator=g) * 0.5
+    return embed, refer_logit, feats, query_pos
+
+
+def checksum(*tensors: torch.Tensor) -> float:
+    """Order-sensitive float64 checksum used to verify regenerated inputs against a golden file."""
+    acc = 0.0
+    for i, t in enumerate(tensors):
+        t64 = t.detach().double().reshape(-1)
+        idx = torch.arange(1, t64.numel() + 1, dtype=torch.float64)
+        acc += float((t64 * torch.cos(idx * 0.001 + i)).sum())
+    return acc
+
+
+@dataclass
+class SequenceSpec:
+    """A synthetic video: temporally coherent pyramid features and detect queries."""
+    name: str = "MOT17"
+    n_frames: int = 300
+    n_detect: int = 300
+    seed: int = 0
+    drift: float = 0.05
+    shapes: List[Tuple[int, int]] = field(default_factory=lambda: list(PYRAMIDS["MOT17"]))
+
+
+class SequenceGenerator:
+    """feats_0 ~ N(0,1), feats_t = feats_{t-1} + drift*N(0,1); detect embeddings/boxes drift likewise.
+
+    Generated on `device` with a device generator (bench) or on the CPU (parity tests): frames of a
+    CPU-generated sequence are bit-reproducible anywhere.
+    """
+
+    def __init__(self, spec: SequenceSpec, d_model: int = 256, device="cpu", dtype=torch.float32):
+        self.spec, self.d, self.device, self.dtype = spec, d_model, torch.device(device), dtype
+        self.g = torch.Generator(device=self.device)
+        self.g.manual_seed(1000 * spec.seed + 17)
+        Lv = level_sizes(spec.shapes)
+        self.feats = torch.randn(Lv, d_model, generator=self.g, device=self.device)
+        self.det_embed = torch.randn(spec.n_detect, d_model, generator=self.g, device=self.device)
+        cxcy = torch.rand(spec.n_detect, 2, generator=self.g, device=self.device) * 0.9 + 0.05
+        wh = torch.rand(spec.n_detect, 2, generator=self.g, device=self.device) * 0.28 + 0.02
+        self.det_box = torch.cat([cxcy, wh], -1)
+        self.t = 0
+
+    def next_frame(self):
+        """Returns (feats [Lv, C], detect_embed [nd, C], detect_refer_logit [nd, 4])."""
+        if self.t > 0:
+            s = self.spec.drift
+            self.feats = self.feats + s * torch.randn(self.feats.shape, generator=self.g, device=self.device)
+            self.det_embed = self.det_embed + s * torch.randn(self.det_embed.shape, generator=self.g,
+                                                              device=self.device)
+            jitter = 0.01 * torch.randn(self.det_box.shape, generator=self.g, device=self.device)
+            self.det_box = (self.det_box + jitter).clamp(0.02, 0.98)
+        self.t += 1
+        b = self.det_box
+        return self.feats.to(self.dtype), self.det_embed, torch.log(b / (1 - b))

@@ -1,0 +1,255 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. Mints tests/golden/*.npz by running the UNMODIFIED reference.
+
+Run in the build container (needs /root/reference):  python -m oracle.make_golden
+Inputs and weights are regenerated from seeds by moyolo_b200.synthetic (plain data generators, no
+compute); each file stores the reference outputs, the seeds/config and a checksum of the inputs so
+a consumer can detect RNG drift. Reference entry points executed:
+  kat0      MOTR/models/ops/functions/ms_deform_attn_func.py:44-64 on the case of MOTR/models/ops/test.py:21-60
+  core_*    ultralytics/nn/modules/utils.py:41-78   multi_scale_deformable_attn_pytorch
+  msda_*    ultralytics/nn/modules/transformer.py:193-287  MSDeformAttn
+  layer_*   transformer.py:394-450 DeformableTransformerDecoderLayer, :515-652 MOTRDecoderLayer
+  decoder_* transformer.py:453-510 DeformableTransformerDecoder, :663-728 MOTRTransformerDecoder
+  posemb    transformer.py:183-190 pos2posemb; utils.py:34-38 inverse_sigmoid
+  tracker_* ultralytics/nn/modules/head.py:1143-1283 RuntimeTrackerBase on MOTR Instances
+  qim_*     MOTR/models/qim.py:251-301 QueryInteractionModule._update_track_embedding
+"""
+from __future__ import annotations
+
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+
+from moyolo_b200 import synthetic as syn  # noqa: E402
+from oracle import ref_loader  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+
+
+def save(name, meta, **arrays):
+    GOLD.mkdir(parents=True, exist_ok=True)
+    arrays = {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in arrays.items()}
+    np.savez_compressed(GOLD / f"{name}.npz", meta=json.dumps(meta), **arrays)
+    print(f"  wrote {name}.npz  ({(GOLD / (name + '.npz')).stat().st_size / 1024:.1f} KiB)")
+
+
+CORE_CASES = [
+    dict(name="core_a", seed=11, B=2, Q=50, H=8, D=32, shapes=syn.PYRAMIDS["tiny"], P=4),
+    dict(name="core_b", seed=12, B=1, Q=37, H=4, D=64, shapes=[(5, 7), (3, 2)], P=8),
+    dict(name="core_c", seed=13, B=3, Q=9, H=2, D=2, shapes=[(6, 4), (3, 2), (5, 7), (1, 1)], P=2),
+]
+MSDA_CASES = [
+    dict(name="msda_ref4", seed=21, B=2, Q=33, shapes=syn.PYRAMIDS["tiny"], ref_dim=4, ref_levels=1, mask=False),
+    dict(name="msda_ref2", seed=22, B=1, Q=20, shapes=syn.PYRAMIDS["tiny"], ref_dim=2, ref_levels=3, mask=False),
+    dict(name="msda_mask", seed=23, B=2, Q=17, shapes=syn.PYRAMIDS["tiny"], ref_dim=4, ref_levels=1, mask=True),
+]
+LAYER_CASES = [
+    dict(name="layer_deformable", seed=31, cls="DeformableTransformerDecoderLayer", B=2, Q=40, shapes=syn.PYRAMIDS["tiny"]),
+    dict(name="layer_motr", seed=32, cls="MOTRDecoderLayer", B=1, Q=77, shapes=syn.PYRAMIDS["tiny"]),
+]
+DECODER_CASES = [
+    dict(name="decoder_motr_tiny", seed=41, mode="motr", B=2, Q=40, shapes=syn.PYRAMIDS["tiny"], nc=1),
+    dict(name="decoder_deformable_tiny", seed=42, mode="deformable", B=1, Q=33, shapes=syn.PYRAMIDS["tiny"], nc=1),
+    dict(name="decoder_motr_kitti_nc5", seed=43, mode="motr", B=1, Q=64, shapes=[(12, 39), (6, 20), (3, 10)], nc=5),
+    dict(name="decoder_motr_c1", seed=44, mode="motr", B=1, Q=300, shapes=syn.PYRAMIDS["C1"], nc=1),
+    dict(name="decoder_deformable_c1", seed=45, mode="deformable", B=1, Q=300, shapes=syn.PYRAMIDS["C1"], nc=1),
+]
+WEIGHT_SEED = 7
+
+
+def gen_kat0():
+    """MOTR/models/ops/test.py:21-60 with the CUDA op replaced by nothing: we keep the PyTorch side."""
+    import importlib
+    f = importlib.import_module("MOTR.models.ops.functions.ms_deform_attn_func")
+    N, M, D, Lq, L, P = 1, 2, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long)
+    S = int(shapes.prod(1).sum())
+    torch.manual_seed(3)
+    out = {}
+    for tag in ("double", "float"):
+        value = torch.rand(N, S, M, D) * 0.01
+        loc = torch.rand(N, Lq, M, L, P, 2)
+        aw = torch.rand(N, Lq, M, L, P) + 1e-5
+        aw /= aw.sum(-1, keepdim=True).sum(-2, keepdim=True)
+        if tag == "double":
+            o = f.ms_deform_attn_core_pytorch(value.double(), shapes, loc.double(), aw.double())
+        else:
+            o = f.ms_deform_attn_core_pytorch(value, shapes, loc, aw)
+        out.update({f"value_{tag}": value, f"loc_{tag}": loc, f"aw_{tag}": aw, f"out_{tag}": o})
+    save("kat0", dict(shapes=[[6, 4], [3, 2]], N=N, M=M, D=D, Lq=Lq, L=L, P=P, seed=3,
+                      source="MOTR/models/ops/test.py:21-60"), **out)
+
+
+def gen_core(U):
+    for c in CORE_CASES:
+        value, loc, w = syn.make_core_inputs(c["seed"], c["B"], c["Q"], c["H"], c["D"], c["shapes"], c["P"])
+        o32 = U.multi_scale_deformable_attn_pytorch(value, c["shapes"], loc, w)
+        o64 = U.multi_scale_deformable_attn_pytorch(value.double(), c["shapes"], loc.double(), w.double())
+        save(c["name"], dict(c, shapes=[list(s) for s in c["shapes"]], checksum=syn.checksum(value, loc, w)),
+             out_f32=o32, out_f64=o64)
+
+
+def gen_posemb(T, U):
+    g = torch.Generator().manual_seed(5)
+    pos = torch.randn(64, 4, generator=g) * 3.0
+    x = torch.cat([torch.rand(60, 4, generator=g), torch.tensor([[0.0, 1.0, 1e-7, 1 - 1e-7], [-0.5, 1.5, 0.5, 2e-5]])])
+    save("posemb", dict(seed=5), pos=pos, emb=T.pos2posemb(pos), x=x, inv=U.inverse_sigmoid(x))
+
+
+def gen_msda(T):
+    spec = syn.DecoderSpec()
+    sd = syn.make_decoder_state(spec, WEIGHT_SEED)
+    for c in MSDA_CASES:
+        m = T.MSDeformAttn(spec.d_model, spec.n_levels, spec.n_heads, spec.n_points).eval()
+        m.load_state_dict(syn.sub_state(sd, "layers.0.cross_attn."))
+        q, refer, feats, _ = syn.make_module_inputs(c["seed"], c["B"], c["Q"], spec.d_model, c["shapes"], c["ref_dim"],
+                                                    c["ref_levels"])
+        mask = None
+        if c["mask"]:
+            mask = torch.rand(c["B"], feats.shape[1], generator=torch.Generator().manual_seed(c["seed"])) < 0.2
+        with torch.no_grad():
+            o = m(q, refer, feats, [list(s) for s in c["shapes"]], mask)
+        save(c["name"], dict(c, shapes=[list(s) for s in c["shapes"]], weight_seed=WEIGHT_SEED,
+                             checksum=syn.checksum(q, refer, feats)), out=o)
+
+
+def gen_layers(T):
+    spec = syn.DecoderSpec()
+    sd = syn.make_decoder_state(spec, WEIGHT_SEED)
+    for c in LAYER_CASES:
+        cls = getattr(T, c["cls"])
+        m = cls(spec.d_model, spec.n_heads, spec.d_ffn, 0.0, torch.nn.ReLU(), spec.n_levels, spec.n_points).eval()
+        m.load_state_dict(syn.sub_state(sd, "layers.1."))
+        q, refer, feats, qpos = syn.make_module_inputs(c["seed"], c["B"], c["Q"], spec.d_model, c["shapes"], 4, 1)
+        refer = refer[:, :, 0]
+        with torch.no_grad():
+            o = m(q, refer, feats, [list(s) for s in c["shapes"]], None, None, qpos)
+        save(c["name"], dict(c, shapes=[list(s) for s in c["shapes"]], weight_seed=WEIGHT_SEED,
+                             checksum=syn.checksum(q, refer, feats, qpos)), out=o)
+
+
+def build_ref_decoder(T, spec, sd, mode):
+    layer_cls = T.MOTRDecoderLayer if mode == "motr" else T.DeformableTransformerDecoderLayer
+    layer = layer_cls(spec.d_model, spec.n_heads, spec.d_ffn, 0.0, torch.nn.ReLU(), spec.n_levels, spec.n_points)
+    dec_cls = T.MOTRTransformerDecoder if mode == "motr" else T.DeformableTransformerDecoder
+    dec = dec_cls(spec.d_model, layer, spec.n_layers).eval()
+    dec.load_state_dict(syn.sub_state(sd, "layers.") and {k: v for k, v in sd.items() if k.startswith("layers.")})
+    bbox = torch.nn.ModuleList([T.MLP(spec.d_model, spec.d_model, 4, 3) for _ in range(spec.n_layers)]).eval()
+    bbox.load_state_dict(syn.sub_state(sd, "dec_bbox_head."))
+    score = torch.nn.ModuleList([torch.nn.Linear(spec.d_model, spec.nc) for _ in range(spec.n_layers)]).eval()
+    score.load_state_dict(syn.sub_state(sd, "dec_score_head."))
+    pos = T.MLP(4, spec.pos_hidden, spec.d_model, 2).eval()
+    pos.load_state_dict(syn.sub_state(sd, "query_pos_head."))
+    return dec, bbox, score, pos
+
+
+def gen_decoders(T):
+    for c in DECODER_CASES:
+        spec = syn.DecoderSpec(nc=c["nc"])
+        sd = syn.make_decoder_state(spec, WEIGHT_SEED)
+        dec, bbox, score, pos = build_ref_decoder(T, spec, sd, c["mode"])
+        embed, refer, feats, qpos = syn.make_decoder_inputs(c["seed"], c["B"], c["Q"], spec.d_model, c["shapes"])
+        shapes = [list(s) for s in c["shapes"]]
+        with torch.no_grad():
+            if c["mode"] == "motr":
+                b, s, o = dec(embed, refer, feats, shapes, bbox, score, pos, track_query_embed=qpos)
+            else:
+                b, s = dec(embed, refer, feats, shapes, bbox, score, pos)
+                o = torch.zeros(0)
+        save(c["name"], dict(c, shapes=shapes, weight_seed=WEIGHT_SEED,
+                             checksum=syn.checksum(embed, refer, feats, qpos)), boxes=b, scores=s, hs=o)
+
+
+def gen_tracker(head, structures):
+    """Drive the reference RuntimeTrackerBase over synthetic multi-frame inputs (repair R2 applied by
+    this driver: Instances rebuilt with N = T + n_detect rows each frame)."""
+    Instances = structures.Instances
+    for name, seed, nd, n_frames, dup in (("tracker_a", 51, 40, 12, 0.3), ("tracker_b", 52, 120, 8, 0.5),
+                                          ("tracker_empty", 53, 10, 4, 0.0)):
+        g = torch.Generator().manual_seed(seed)
+        trk = head.RuntimeTrackerBase()
+        ids = torch.zeros(0, dtype=torch.long)
+        dis = torch.zeros(0, dtype=torch.long)
+        tboxes = torch.zeros(0, 4)
+        rec = {}
+        for t in range(n_frames):
+            T_ = ids.shape[0]
+            nb = torch.cat([torch.rand(nd, 2, generator=g) * 0.8 + 0.1, torch.rand(nd, 2, generator=g) * 0.2 + 0.03], 1)
+            n_dup = int(dup * nd)
+            if n_dup and T_ + nd > 1:  # near-duplicates of other boxes so the IoU>0.8 filter fires
+                allb = torch.cat([tboxes, nb], 0)
+                src = torch.randint(0, allb.shape[0], (n_dup,), generator=g)
+                nb[:n_dup] = allb[src] * (1 + 0.02 * torch.randn(n_dup, 4, generator=g))
+            boxes = torch.cat([tboxes * (1 + 0.01 * torch.randn(T_, 4, generator=g)), nb], 0).float()
+            if name == "tracker_empty":
+                scores = torch.rand(T_ + nd, generator=g) * 0.3  # nothing ever reaches 0.4
+            else:
+                scores = torch.rand(T_ + nd, generator=g)
+                scores[:4] = torch.tensor([0.4, 0.5, 0.39999998, 0.49999997])[: min(4, T_ + nd)]
+            ids_in = torch.cat([ids, torch.full((nd,), -1, dtype=torch.long)])
+            dis_in = torch.cat([dis, torch.zeros(nd, dtype=torch.long)])
+            inst = Instances((1, 1))
+            inst.scores = scores.clone()
+            inst.obj_idxes = ids_in.clone()[:, None]
+            inst.disappear_time = dis_in.clone()[:, None]
+            inst.pred_boxes = boxes.clone()
+            pre = (int(trk.max_obj_id), int(trk.max_obj_id_pre))  # ints: the reference mutates these tensors in place
+            trk.update(inst)
+            ids_out, dis_out = inst.obj_idxes[:, 0].clone(), inst.disappear_time[:, 0].clone()
+            rec[f"scores_{t}"], rec[f"boxes_{t}"] = scores, boxes
+            rec[f"ids_in_{t}"], rec[f"dis_in_{t}"] = ids_in, dis_in
+            rec[f"ids_out_{t}"], rec[f"dis_out_{t}"] = ids_out, dis_out
+            rec[f"counters_in_{t}"] = torch.tensor(pre)
+            rec[f"counters_out_{t}"] = torch.tensor([int(trk.max_obj_id), int(trk.max_obj_id_pre)])
+            act = ids_out >= 0
+            ids, dis, tboxes = ids_out[act], dis_out[act], boxes[act]
+        save(name, dict(seed=seed, n_detect=nd, n_frames=n_frames, source="head.py:1143-1283"), **rec)
+
+
+def gen_qim(qim, structures):
+    import argparse
+    spec = syn.DecoderSpec()
+    sd = syn.make_decoder_state(spec, WEIGHT_SEED)
+    args = argparse.Namespace(merger_dropout=0.1, update_query_pos=False, random_drop=0.1, fp_ratio=0.3)
+    m = qim.QueryInteractionModule(args, spec.d_model, spec.qim_hidden, spec.d_model * 2).eval()
+    missing, unexpected = m.load_state_dict(syn.sub_state(sd, "track_embed."), strict=False)
+    assert not unexpected and all(k.startswith("fsqm") for k in missing), (missing, unexpected)
+    for name, seed, T_ in (("qim_a", 61, 23), ("qim_one", 62, 1)):
+        g = torch.Generator().manual_seed(seed)
+        inst = structures.Instances((1, 1))
+        ref_pts = torch.randn(T_, 4, generator=g) * 1.5
+        qpos = torch.randn(T_, spec.d_model, generator=g) * 0.5
+        emb = torch.randn(T_, spec.d_model, generator=g)
+        boxes = torch.rand(T_, 4, generator=g)
+        boxes[0] = torch.tensor([0.0, 1.0, 1e-6, 0.5])[:4]
+        inst.ref_pts, inst.query_pos, inst.output_embedding, inst.pred_boxes = ref_pts.clone(), qpos.clone(), emb, boxes
+        with torch.no_grad():
+            o = m._update_track_embedding(inst)
+        save(name, dict(seed=seed, T=T_, weight_seed=WEIGHT_SEED), ref_pts=ref_pts, query_pos=qpos, out_embed=emb,
+             pred_boxes=boxes, new_query_pos=o.query_pos, new_ref_pts=o.ref_pts)
+
+
+def main():
+    assert ref_loader.available(), "needs /root/reference"
+    torch.set_num_threads(8)
+    T, U = ref_loader.load_decoder_modules()
+    print("decoder-side goldens (light loader)")
+    gen_core(U)
+    gen_posemb(T, U)
+    gen_msda(T)
+    gen_layers(T)
+    gen_decoders(T)
+    print("head-side goldens (full reference import with stubs)")
+    head, qim, structures = ref_loader.load_full_reference()
+    gen_kat0()
+    gen_tracker(head, structures)
+    gen_qim(qim, structures)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,125 @@
+"""CPU: pin the oracle (oracle/torch_port.py, oracle/msda_core.c, oracle/tracker_port.py) against the
+golden vectors minted from the unmodified reference (oracle/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_rms
+from moyolo_b200 import synthetic as syn
+from oracle import c_core, make_golden as mg
+from oracle import torch_port as tp
+from oracle.tracker_port import TrackerPort
+
+FP32_TOL = 1e-4  # max|a-b| <= 1e-4 * rms(ref), SURVEY.md §8(c)
+
+
+def test_kat0_reference_known_answer():
+    """MOTR/models/ops/test.py:21-60: fp64 allclose (default tol), fp32 rtol=1e-2 atol=1e-3."""
+    meta, g = load_golden("kat0")
+    shapes = meta["shapes"]
+    for tag, dt in (("double", np.float64), ("float", np.float32)):
+        v, loc, aw = (g[f"{k}_{tag}"].astype(dt) for k in ("value", "loc", "aw"))
+        ref = g[f"out_{tag}"]
+        out_c = c_core.msda_core(v, shapes, loc, aw)
+        tv, tl, ta = map(torch.from_numpy, (v, loc, aw))
+        out_gs = tp.msda_core_gridsample(tv, shapes, tl, ta).numpy()
+        out_ga = tp.msda_core_gather(tv, shapes, tl, ta).numpy()
+        for o in (out_c, out_gs, out_ga):
+            if tag == "double":
+                assert np.allclose(o, ref)
+            else:
+                assert np.allclose(o, ref, rtol=1e-2, atol=1e-3)
+            assert rel_rms(o, ref) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", mg.CORE_CASES, ids=lambda c: c["name"])
+def test_core_restatements(case):
+    meta, g = load_golden(case["name"])
+    value, loc, w = syn.make_core_inputs(case["seed"], case["B"], case["Q"], case["H"], case["D"], case["shapes"],
+                                         case["P"])
+    assert abs(syn.checksum(value, loc, w) - meta["checksum"]) < 1e-6 * max(1.0, abs(meta["checksum"]))
+    shapes = meta["shapes"]
+    assert rel_rms(tp.msda_core_gridsample(value, shapes, loc, w).numpy(), g["out_f32"]) < 1e-6
+    assert rel_rms(tp.msda_core_gather(value, shapes, loc, w).numpy(), g["out_f32"]) < FP32_TOL
+    assert rel_rms(c_core.msda_core(value.numpy(), shapes, loc.numpy(), w.numpy()), g["out_f32"]) < FP32_TOL
+    o64 = c_core.msda_core(value.double().numpy(), shapes, loc.double().numpy(), w.double().numpy())
+    assert rel_rms(o64, g["out_f64"]) < 1e-12
+    o64 = tp.msda_core_gather(value.double(), shapes, loc.double(), w.double()).numpy()
+    assert rel_rms(o64, g["out_f64"]) < 1e-12
+
+
+def test_posemb_and_inverse_sigmoid():
+    _, g = load_golden("posemb")
+    assert rel_rms(tp.pos2posemb(torch.from_numpy(g["pos"])).numpy(), g["emb"]) < 1e-6
+    assert np.array_equal(tp.inverse_sigmoid(torch.from_numpy(g["x"])).numpy(), g["inv"])
+
+
+@pytest.mark.parametrize("case", mg.MSDA_CASES, ids=lambda c: c["name"])
+def test_msdeform_attn_port(case):
+    meta, g = load_golden(case["name"])
+    spec = syn.DecoderSpec()
+    sd = syn.make_decoder_state(spec, meta["weight_seed"])
+    q, refer, feats, _ = syn.make_module_inputs(case["seed"], case["B"], case["Q"], spec.d_model, case["shapes"],
+                                                case["ref_dim"], case["ref_levels"])
+    assert abs(syn.checksum(q, refer, feats) - meta["checksum"]) < 1e-6 * max(1.0, abs(meta["checksum"]))
+    mask = None
+    if case["mask"]:
+        mask = torch.rand(case["B"], feats.shape[1], generator=torch.Generator().manual_seed(case["seed"])) < 0.2
+    p = syn.sub_state(sd, "layers.0.cross_attn.")
+    for core in (tp.msda_core_gridsample, tp.msda_core_gather):
+        o = tp.msdeform_attn_forward(p, q, refer, feats, meta["shapes"], spec.n_heads, spec.n_levels, spec.n_points,
+                                     mask, core)
+        assert rel_rms(o.numpy(), g["out"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", mg.LAYER_CASES, ids=lambda c: c["name"])
+def test_decoder_layer_port(case):
+    meta, g = load_golden(case["name"])
+    spec = syn.DecoderSpec()
+    sd = syn.make_decoder_state(spec, meta["weight_seed"])
+    q, refer, feats, qpos = syn.make_module_inputs(case["seed"], case["B"], case["Q"], spec.d_model, case["shapes"], 4, 1)
+    o = tp.decoder_layer_forward(syn.sub_state(sd, "layers.1."), q, refer[:, :, 0], feats, meta["shapes"],
+                                 spec.n_heads, spec.n_levels, spec.n_points, None, None, qpos)
+    assert rel_rms(o.numpy(), g["out"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("case", [c for c in mg.DECODER_CASES if "c1" not in c["name"]], ids=lambda c: c["name"])
+def test_decoder_port(case):
+    meta, g = load_golden(case["name"])
+    spec = syn.DecoderSpec(nc=case["nc"])
+    sd = syn.make_decoder_state(spec, meta["weight_seed"])
+    embed, refer, feats, qpos = syn.make_decoder_inputs(case["seed"], case["B"], case["Q"], spec.d_model, case["shapes"])
+    assert abs(syn.checksum(embed, refer, feats, qpos) - meta["checksum"]) < 1e-6 * max(1.0, abs(meta["checksum"]))
+    with torch.no_grad():
+        b, s, hs = tp.decoder_forward(sd, embed, refer, feats, meta["shapes"], spec.n_heads, spec.n_levels,
+                                      spec.n_points, spec.n_layers, case["mode"], qpos)
+    assert b.shape == g["boxes"].shape and s.shape == g["scores"].shape
+    assert rel_rms(b.numpy(), g["boxes"]) < FP32_TOL
+    assert rel_rms(s.numpy(), g["scores"]) < FP32_TOL
+    if case["mode"] == "motr":
+        assert rel_rms(hs.numpy(), g["hs"]) < FP32_TOL
+
+
+@pytest.mark.parametrize("name", ["tracker_a", "tracker_b", "tracker_empty"])
+def test_tracker_port_matches_reference_class(name):
+    """Bit-exact IDs / disappear counters / max_obj_id against the reference RuntimeTrackerBase."""
+    meta, g = load_golden(name)
+    trk = TrackerPort()
+    for t in range(meta["n_frames"]):
+        assert (trk.max_obj_id, trk.max_obj_id_pre) == tuple(int(x) for x in g[f"counters_in_{t}"])
+        ids, dis = g[f"ids_in_{t}"].copy(), g[f"dis_in_{t}"].copy()
+        trk.update(g[f"scores_{t}"], g[f"boxes_{t}"], ids, dis)
+        assert np.array_equal(ids, g[f"ids_out_{t}"]), f"frame {t}"
+        assert np.array_equal(dis, g[f"dis_out_{t}"]), f"frame {t}"
+        assert (trk.max_obj_id, trk.max_obj_id_pre) == tuple(int(x) for x in g[f"counters_out_{t}"]), f"frame {t}"
+
+
+@pytest.mark.parametrize("name", ["qim_a", "qim_one"])
+def test_qim_port(name):
+    meta, g = load_golden(name)
+    sd = syn.make_decoder_state(syn.DecoderSpec(), meta["weight_seed"])
+    t = {k: torch.from_numpy(v) for k, v in g.items()}
+    with torch.no_grad():
+        qp, rp = tp.qim_update(sd, t["ref_pts"], t["query_pos"], t["out_embed"], t["pred_boxes"])
+    assert rel_rms(qp.numpy(), g["new_query_pos"]) < FP32_TOL
+    assert np.array_equal(rp.numpy(), g["new_ref_pts"])
