@@ -221,3 +221,17 @@ class SequenceGenerator:
         self.t += 1
         b = self.det_box
         return self.feats.to(self.dtype), self.det_embed, torch.log(b / (1 - b))
+
+
+def calibrate_score_bias(sd: Dict[str, torch.Tensor], frame0_logits: torch.Tensor, spec: DecoderSpec,
+                         birth_frac: float = 0.05, thresh: float = 0.4) -> Dict[str, torch.Tensor]:
+    """Shift the last decoder score-head bias so that `birth_frac` of frame-0 queries score >= thresh
+    ("score_head ... so scores straddle 0.4/0.5"). `frame0_logits` are the raw
+    logits [N, nc] of frame 0 computed with the un-shifted weights; returns a new state dict."""
+    best = frame0_logits.detach().float().cpu().max(-1).values
+    q = torch.quantile(best, 1.0 - birth_frac).item()
+    target = math.log(thresh / (1.0 - thresh))
+    out = dict(sd)
+    key = f"dec_score_head.{spec.n_layers - 1}.bias"
+    out[key] = sd[key] + (target - q) + 1e-3
+    return out
