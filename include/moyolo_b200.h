@@ -119,7 +119,7 @@ int moyolo_msda_fused_forward(const void* value, int value_dtype, int64_t value_
  * in_dtype applies to x and w (F32 or BF16); bias is fp32 (may be NULL); out_dtype F32 or BF16.
  * Optional row mask: if `zero_rows` (device uint8 [M]) is non-NULL, rows with a non-zero entry
  * are written as zeros (value_mask semantics of transformer.py:265-266).
- * The tcgen05 engine needs K % 64 == 0, N % 16 == 0, 16-byte aligned x, w and ldx*2 % 16 == 0.
+ * The tcgen05 engine needs K % 64 == 0, N % 32 == 0, 16-byte aligned x, w and ldx*2 % 16 == 0.
  * -------------------------------------------------------------------------------------------*/
 int moyolo_linear(const void* x, int64_t ldx, const void* w, const float* bias, void* y,
                   int64_t ldy, int64_t M, int N, int K, int in_dtype, int out_dtype, int epilogue,

@@ -125,7 +125,7 @@ extern "C" int moyolo_linear(const void* x, int64_t ldx, const void* w, const fl
     MOYOLO_REQUIRE(in_dtype == MOYOLO_BF16, MOYOLO_ERR_UNSUPPORTED,
                    "moyolo_linear: the tcgen05 engine takes bf16 operands");
     MOYOLO_REQUIRE(linear_tcgen05_supported(x, ldx, w, M, N, K), MOYOLO_ERR_ALIGNMENT,
-                   "moyolo_linear: tcgen05 engine needs K%%64==0, N%%16==0, 16B-aligned x/w/ldx");
+                   "moyolo_linear: tcgen05 engine needs K%%64==0, N%%32==0, 16B-aligned x/w/ldx");
     return linear_tcgen05(x, ldx, w, bias, y, ldy, M, N, K, out_dtype, relu, zero_rows, st);
   }
   MOYOLO_REQUIRE(engine == MOYOLO_GEMM_SIMT, MOYOLO_ERR_BAD_ARG, "moyolo_linear: bad engine %d", engine);

@@ -60,6 +60,8 @@ def msda_sampled(value: torch.Tensor, shapes, loc: torch.Tensor, weights: torch.
     if n_levels != L:
         raise ValueError(f"value_shapes has {n_levels} levels but sampling locations have {L}")
     out = torch.empty(B, Q, H * Dh, dtype=value.dtype, device=value.device)
+    if B * Q == 0:
+        return out
     _lib.check(_lib.lib().moyolo_msda_sampled_forward(
         value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, H, Dh, P,
         loc.data_ptr(), weights.data_ptr(), _dt(loc), B * Q, _ptr(row_offsets), out.data_ptr(), H * Dh,
@@ -92,6 +94,8 @@ def msda_fused(value: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch
         raise ValueError("refer must be fp32")
     if out is None:
         out = torch.empty(R, Cc, dtype=value.dtype, device=value.device)
+    if R == 0:
+        return out
     _lib.check(_lib.lib().moyolo_msda_fused_forward(
         value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, n_heads, Dh, n_points,
         offsets.data_ptr(), offsets.stride(0), logits.data_ptr(), logits.stride(0), refer.data_ptr(),

@@ -228,10 +228,15 @@ def calibrate_score_bias(sd: Dict[str, torch.Tensor], frame0_logits: torch.Tenso
     """Shift the last decoder score-head bias so that `birth_frac` of frame-0 queries score >= thresh
     ("score_head ... so scores straddle 0.4/0.5"). `frame0_logits` are the raw
     logits [N, nc] of frame 0 computed with the un-shifted weights; returns a new state dict."""
-    best = frame0_logits.detach().float().cpu().max(-1).values
-    q = torch.quantile(best, 1.0 - birth_frac).item()
+    best = torch.sort(frame0_logits.detach().float().cpu().max(-1).values).values
+    n = best.numel()
+    k = min(max(int(round((1.0 - birth_frac) * n)), 1), n - 1)
+    lo, hi = max(k - 3, 1), min(k + 3, n - 1)
+    gaps = best[lo:hi + 1] - best[lo - 1:hi]
+    j = lo + int(torch.argmax(gaps))
+    q = 0.5 * (best[j] + best[j - 1]).item()  # threshold lands mid-gap: no score sits on the threshold
     target = math.log(thresh / (1.0 - thresh))
     out = dict(sd)
     key = f"dec_score_head.{spec.n_layers - 1}.bias"
-    out[key] = sd[key] + (target - q) + 1e-3
+    out[key] = sd[key] + (target - q)
     return out
