@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — decoder frames/sec of the DecoderTracker hot path on B200 (contract: see DESIGN.md §Measurement).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # reference CPU path (oracle port)
+
+A "step" is one frame of the hot path for every lock-step sequence on the GPU: query assembly ->
+6-layer deformable decoder -> box/score heads -> track-query update. The N=1 workload is
+BASELINE.json configs[1]: a MOT17-shaped synthetic sequence (1088x608 -> pyramid (76,136),(38,68),
+(19,34)), 300 detect queries + carried track queries, bf16. At N>1 every rank tracks its own
+sequence(s) (weak scaling, no collective in the frame loop; one NCCL all_gather of the track rows at
+the end, inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "decoder_frames_per_sec"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="moyolo", choices=["moyolo", "reference"])
+    ap.add_argument("--workload", default="MOT17", choices=["MOT17", "DanceTrack", "KITTI", "C1", "tiny"])
+    ap.add_argument("--seqs-per-gpu", type=int, default=1, help="lock-step sequences per GPU")
+    ap.add_argument("--n-detect", type=int, default=300)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-frames", type=int, default=12, help="frames of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed regions."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0]))
+                mx = max(mx, float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ workload
+def build_state(args, spec, syn, shapes, device):
+    """Weights (seed 0) with the score head calibrated on frame 0 of sequence 0 using the GPU path."""
+    from moyolo_b200.tracker import TrackEngine
+    sd = syn.make_decoder_state(spec, 0)
+    eng = TrackEngine(sd, spec, shapes, device, args.precision, args.n_detect, 1)
+    g = syn.SequenceGenerator(syn.SequenceSpec(args.workload, 1, args.n_detect, 0, shapes=shapes), spec.d_model, device)
+    f, de, dr = g.next_frame()
+    out = eng.step(f[None], de[None], dr[None])[0]
+    return syn.calibrate_score_bias(sd, out["logits"], spec, 0.035)
+
+
+def make_frames(args, syn, spec, shapes, device, seq_seed, n_frames, lp):
+    g = syn.SequenceGenerator(syn.SequenceSpec(args.workload, n_frames, args.n_detect, seq_seed, shapes=shapes),
+                              spec.d_model, device)
+    frames = []
+    for _ in range(n_frames):
+        f, de, dr = g.next_frame()
+        frames.append((f.to(lp).contiguous(), de.contiguous(), dr.contiguous()))
+    return frames
+
+
+def gather_bytes(B, Lv, C, R, H, L, P, s_v):
+    """Compulsory bytes of one deformable-gather launch: value once + raw offsets and
+    logits + reference boxes + output."""
+    return B * Lv * C * s_v + R * H * L * P * 3 * 4 + R * 4 * 4 + R * C * s_v
+
+
+def run_moyolo(args):
+    from moyolo_b200 import _lib, ops, synthetic as syn
+    from moyolo_b200 import sharding
+    from moyolo_b200.tracker import DecoderWeights, TrackEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert _lib.lib().moyolo_device_supported() == 1, "libmoyolo_b200 targets sm_100a (B200) only"
+
+    spec = syn.DecoderSpec()
+    shapes = [list(s) for s in syn.PYRAMIDS[args.workload]]
+    lp = torch.bfloat16 if args.precision == "bf16" else torch.float32
+    S, K, Wm = args.seqs_per_gpu, args.steps, args.warmup
+    sd = build_state(args, spec, syn, shapes, device)
+    weights = DecoderWeights(sd, spec, device, args.precision)
+    eng = TrackEngine(sd, spec, shapes, device, args.precision, args.n_detect, S, weights=weights)
+
+    # frames resident in HBM before the timed region: K distinct frames per sequence slot
+    seqs = [make_frames(args, syn, spec, shapes, device, 1 + rank * S + s, K, lp) for s in range(S)]
+    warm = make_frames(args, syn, spec, shapes, device, 9999, max(Wm, 1), lp)
+
+    def batch(t, src):
+        return (torch.stack([src[s][t][0] for s in range(S)]), torch.stack([src[s][t][1] for s in range(S)]),
+                torch.stack([src[s][t][2] for s in range(S)]))
+
+    dev_batches = [batch(t, seqs) for t in range(K)]
+    del seqs
+    feat_bytes = dev_batches[0][0].numel() * dev_batches[0][0].element_size()
+    in_bytes = sum(x.numel() * x.element_size() for x in dev_batches[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def final_gather(rows):
+        local = sharding.finalize_rows(rows, device)
+        return sharding.gather_track_rows(local)
+
+    def warmup():
+        """W untimed frames through the identical code path (incl. row packing and the final gather,
+        so lazily loaded kernels and allocator pools are warm), then drop all tracks."""
+        eng.reset()
+        wrows = []
+        for t in range(Wm):
+            w = warm[t % len(warm)]
+            outs = eng.step(torch.stack([w[0]] * S), torch.stack([w[1]] * S), torch.stack([w[2]] * S))
+            for s in range(S):
+                o = outs[s]
+                wrows.append(sharding.pack_track_rows(s, t, o["ids"], o["boxes"], o["scores"], o["labels"]))
+                tuple(o[k].to("cpu", non_blocking=True) for k in ("ids", "boxes", "scores", "labels"))
+        final_gather(wrows)
+        eng.reset()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+
+    # ---------------- leg 1: `value` — inputs resident in HBM ----------------
+    warmup()
+    ops.LAUNCHES = 0
+    tracks_seen = []
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rows = []
+    for t in range(K):
+        outs = eng.step(*dev_batches[t])
+        for s in range(S):
+            o = outs[s]
+            rows.append(sharding.pack_track_rows(rank * S + s, t, o["ids"], o["boxes"], o["scores"], o["labels"]))
+        tracks_seen.append(sum(eng.n_tracks()))
+    table = final_gather(rows)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = ops.LAUNCHES
+    n_rows_table = int(table.shape[0])
+
+    # ---------------- leg 2: roofline of the deformable gather (rank 0, instrumented re-run) ---------
+    roof = None
+    if rank == 0:
+        warmup()
+        pairs, nbytes = [], []
+
+        def pre(B, Lv, C, R, H, L, P, s_v):
+            nbytes.append(gather_bytes(B, Lv, C, R, H, L, P, s_v))
+            a = torch.cuda.Event(enable_timing=True)
+            a.record()
+            pairs.append([a, None])
+
+        def post():
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            pairs[-1][1] = b
+
+        ops.GATHER_HOOK = (pre, post)
+        n_inst = min(K, 60)
+        for t in range(n_inst):
+            eng.step(*dev_batches[t])
+        ops.GATHER_HOOK = None
+        torch.cuda.synchronize()
+        g_ms = sum(a.elapsed_time(b) for a, b in pairs)
+        peaks = {}
+        pk = ROOT / "MEASURED_PEAKS.json"
+        if pk.exists():
+            peaks = json.loads(pk.read_text())
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach = sum(nbytes) / (g_ms * 1e-3) / 1e9 if g_ms > 0 else 0.0
+        roof = {"bound": "hbm", "kernel": "msda_gather_kernel<bf16,32,fused>", "achieved": round(ach, 1),
+                "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                "launches_timed": len(pairs), "avg_launch_us": round(g_ms * 1e3 / max(len(pairs), 1), 3),
+                "algorithmic_bytes_per_launch": int(sum(nbytes) / max(len(nbytes), 1)),
+                "note": "compulsory bytes (value once + offsets/logits + refs + out) / CUDA-event time around each "
+                        "gather launch inside the frame loop; value is L2-resident right after the value_proj GEMM"}
+
+    # ---------------- leg 3: `e2e` — host buffers, H2D + D2H inside the timed region ----------------
+    host_batches = [tuple(x.cpu().pin_memory() for x in b) for b in dev_batches]
+    warmup()
+    barrier()
+    d2h_bytes = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host_out = []
+    e0.record()
+    for t in range(K):
+        hb = host_batches[t]
+        f, de, dr = (x.to(device, non_blocking=True) for x in hb)
+        outs = eng.step(f, de, dr)
+        for s in range(S):
+            o = outs[s]
+            res = tuple(o[k].to("cpu", non_blocking=True) for k in ("ids", "boxes", "scores", "labels"))
+            host_out.append(res)
+            if t == K - 1:
+                d2h_bytes += sum(x.numel() * x.element_size() for x in res)
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    ms_e2e = float(ms2.item())
+
+    clocks = sampler.stop() if rank == 0 else None
+    frames_total = K * S * world
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(frames_total / (ms_total * 1e-3), 2), "unit": UNIT, "n_gpus": world,
+            "steps": K, "warmup": Wm, "ms_per_step": round(ms_total / K, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}-shaped synthetic sequence, pyramid {shapes}, {args.n_detect} detect "
+                                   f"queries + carried track queries, 6-layer decoder d=256 h=8 L=3 P=4, track update",
+                       "baseline_config": "BASELINE.json configs[1]", "sequences_per_gpu": S, "frames_per_sequence": K,
+                       "queries_per_frame_mean": round(args.n_detect + sum(tracks_seen) / max(len(tracks_seen), 1) / S, 1),
+                       "tracks_carried_max": max(tracks_seen) if tracks_seen else 0, "track_rows_gathered": n_rows_table,
+                       "parallelism": f"sequence-sharded x{world}",
+                       "l2": f"inputs larger than L2: {K} distinct frame buffers of {feat_bytes / 1e6:.1f} MB cycled "
+                             f"({K * in_bytes / 1e9:.2f} GB per rank)"},
+            "e2e": {"value": round(frames_total / (ms_e2e * 1e-3), 2), "unit": UNIT,
+                    "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                    "ms_per_step": round(ms_e2e / K, 4)},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(args, sd, spec, shapes, [tuple(x[0] for x in b) for b in dev_batches])
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ CPU arms
+def cpu_baseline(args, sd, spec, shapes, frames_dev, n_frames=None):
+    """The oracle port (reference algorithm restated in PyTorch CPU ops, oracle/torch_port.py +
+    oracle/tracker_port.py) timed on this box's host cores over the first frames of the same sequence."""
+    from oracle import torch_port as tp
+    from oracle.tracker_port import track_sequence_port
+    n = min(n_frames or args.cpu_frames, len(frames_dev))
+    torch.set_num_threads(os.cpu_count() or 1)
+    frames = [tuple(x.float().cpu() for x in frames_dev[t]) for t in range(n)]
+    sd_cpu = {k: v.float().cpu() for k, v in sd.items()}
+    track_sequence_port(sd_cpu, frames[:1], shapes, spec.n_heads, spec.n_levels, spec.n_points, spec.n_layers, spec.nc)
+    t0 = time.perf_counter()
+    track_sequence_port(sd_cpu, frames, shapes, spec.n_heads, spec.n_levels, spec.n_points, spec.n_layers, spec.nc)
+    dt = time.perf_counter() - t0
+    return {"value": round(n / dt, 3), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"first {n} frames of sequence 0 (same weights/inputs, fp32, {torch.get_num_threads()} threads)"}
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path. The reference is Python and does
+    not exist on the GPU box, so this times the oracle port (pinned to the reference by tests/golden)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from moyolo_b200 import synthetic as syn
+    from oracle import torch_port as tp
+    from oracle.tracker_port import track_sequence_port
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = syn.DecoderSpec()
+    shapes = [list(s) for s in syn.PYRAMIDS[args.workload]]
+    sd = syn.make_decoder_state(spec, 0)
+    K, Wm = args.steps, args.warmup
+    g = syn.SequenceGenerator(syn.SequenceSpec(args.workload, K, args.n_detect, 1, shapes=shapes), spec.d_model, "cpu")
+    first = g.next_frame()
+    first = tuple(t.clone() for t in first)
+    with torch.no_grad():
+        _, s0, _ = tp.decoder_forward(sd, first[1][None], first[2][None], first[0][None], shapes, spec.n_heads,
+                                      spec.n_levels, spec.n_points, spec.n_layers, "motr", tp.pos2posemb(first[2])[None])
+    sd = syn.calibrate_score_bias(sd, s0[0, 0], spec, 0.035)
+    warm = [first] * max(Wm, 1)
+    track_sequence_port(sd, warm[:Wm], shapes, spec.n_heads, spec.n_levels, spec.n_points, spec.n_layers, spec.nc)
+    # bounded sample: at most ~3 minutes of CPU work; a step is one frame of the same workload
+    budget_s, done, t_total = 170.0, 0, 0.0
+    frames = [first]
+    chunk = 10
+    while done < K and t_total < budget_s:
+        n = min(chunk, K - done)
+        while len(frames) < done + n:
+            frames.append(tuple(t.clone() for t in g.next_frame()))
+        # note: each chunk restarts from an empty track set (bounded sample), tracks ramp up inside it
+        t0 = time.perf_counter()
+        track_sequence_port(sd, frames[done:done + n], shapes, spec.n_heads, spec.n_levels, spec.n_points,
+                            spec.n_layers, spec.nc)
+        t_total += time.perf_counter() - t0
+        done += n
+    fps = done / t_total
+    cores = torch.get_num_threads()
+    sample = f"{done} of {K} frames (chunks of {chunk}, fp32, {cores} threads)"
+    line = {"impl": "reference", "metric": METRIC, "value": round(fps, 3), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": K, "warmup": Wm, "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}-shaped synthetic sequence, pyramid {shapes}, {args.n_detect} detect "
+                                   f"queries + carried track queries, 6-layer decoder d=256 h=8 L=3 P=4, track update",
+                       "baseline_config": "BASELINE.json configs[1]"},
+            "cpu_baseline": {"value": round(fps, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(fps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_moyolo(a)

@@ -38,6 +38,17 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+# number of kernels launched through the C ABI since the last reset (bench.py `gpu_launches`)
+LAUNCHES = 0
+# optional (pre, post) callables invoked around every deformable-gather launch (bench.py roofline leg)
+GATHER_HOOK = None
+
+
+def _count(n: int = 1) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
+
 def _shapes_arr(shapes: Sequence[Sequence[int]]):
     flat = [int(v) for hw in shapes for v in hw]
     return (C.c_int32 * len(flat))(*flat), len(flat) // 2
@@ -62,6 +73,7 @@ def msda_sampled(value: torch.Tensor, shapes, loc: torch.Tensor, weights: torch.
     out = torch.empty(B, Q, H * Dh, dtype=value.dtype, device=value.device)
     if B * Q == 0:
         return out
+    _count(1)
     _lib.check(_lib.lib().moyolo_msda_sampled_forward(
         value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, H, Dh, P,
         loc.data_ptr(), weights.data_ptr(), _dt(loc), B * Q, _ptr(row_offsets), out.data_ptr(), H * Dh,
@@ -96,11 +108,17 @@ def msda_fused(value: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch
         out = torch.empty(R, Cc, dtype=value.dtype, device=value.device)
     if R == 0:
         return out
+    _count(1)
+    hook = GATHER_HOOK
+    if hook is not None:
+        hook[0](B, Lv, Cc, R, n_heads, L, n_points, value.element_size())
     _lib.check(_lib.lib().moyolo_msda_fused_forward(
         value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, n_heads, Dh, n_points,
         offsets.data_ptr(), offsets.stride(0), logits.data_ptr(), logits.stride(0), refer.data_ptr(),
         refer.shape[1], refer.shape[2], softmax_mode, R, _ptr(row_offsets), out.data_ptr(), out.stride(0),
         _stream()))
+    if hook is not None:
+        hook[1]()
     return out
 
 
@@ -120,6 +138,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out_dtyp
     out_dtype = out_dtype or x.dtype
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=x.device)
+    _count(1)
     _lib.check(_lib.lib().moyolo_linear(
         x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), out.data_ptr(), out.stride(0), M, N, K, _dt(x),
         _dt(out), _lib.EPI_RELU if relu else _lib.EPI_NONE, _ptr(zero_rows), engine, _stream()))
@@ -135,6 +154,7 @@ def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, row_offset
     if out is None:
         out = torch.empty(R, Cc, dtype=q.dtype, device=q.device)
     host = (C.c_int32 * len(row_offsets_host))(*[int(x) for x in row_offsets_host])
+    _count(1)
     _lib.check(_lib.lib().moyolo_self_attention(
         q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
         out.stride(0), _dt(q), len(row_offsets_host) - 1, row_offsets.data_ptr(), host, n_heads, Cc // n_heads,
@@ -152,6 +172,7 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], gamma: torc
     out_f32 = torch.empty(R, Cc, dtype=torch.float32, device=x.device) if want_f32 else None
     out_lp = torch.empty(R, Cc, dtype=lp_dtype, device=x.device) if want_lp else None
     out_pos = torch.empty(R, Cc, dtype=lp_dtype, device=x.device) if pos is not None else None
+    _count(1)
     _lib.check(_lib.lib().moyolo_add_layernorm(
         x.data_ptr(), _ptr(residual), gamma.data_ptr(), beta.data_ptr(), float(eps), R, Cc, _ptr(out_f32),
         _ptr(out_lp), _ptr(pos), _ptr(out_pos), _DT[lp_dtype], _stream()))
@@ -161,6 +182,7 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], gamma: torc
 def add_cast(a: torch.Tensor, b: Optional[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
     _cuda(a, b)
     out = torch.empty(a.shape, dtype=dtype, device=a.device)
+    _count(1)
     _lib.check(_lib.lib().moyolo_add_cast(a.data_ptr(), _ptr(b), out.data_ptr(), _DT[dtype], a.numel(), _stream()))
     return out
 
@@ -173,6 +195,7 @@ def box_refine(h: torch.Tensor, w3: torch.Tensor, b3: torch.Tensor, ref: torch.T
         out = torch.empty(R, 4, dtype=torch.float32, device=h.device)
     elif not out.is_contiguous() or out.dtype != torch.float32 or out.numel() != R * 4:
         raise ValueError("box_refine: out must be contiguous fp32 with R*4 elements")
+    _count(1)
     _lib.check(_lib.lib().moyolo_box_refine(h.data_ptr(), h.stride(0), _dt(h), w3.data_ptr(), b3.data_ptr(),
                                             ref.data_ptr(), out.data_ptr(), R, K, _stream()))
     return out
@@ -185,6 +208,7 @@ def score_head(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_scores: b
     logits = torch.empty(R, nc, dtype=torch.float32, device=x.device)
     scores = torch.empty(R, dtype=torch.float32, device=x.device) if want_scores else None
     labels = torch.empty(R, dtype=torch.int32, device=x.device) if want_scores else None
+    _count(1)
     _lib.check(_lib.lib().moyolo_score_head(x.data_ptr(), x.stride(0), _dt(x), w.data_ptr(), b.data_ptr(),
                                             logits.data_ptr(), _ptr(scores), _ptr(labels), R, K, nc, _stream()))
     return logits, scores, labels
@@ -194,6 +218,7 @@ def sigmoid(x: torch.Tensor) -> torch.Tensor:
     _cuda(x)
     x = x.contiguous()
     y = torch.empty_like(x)
+    _count(1)
     _lib.check(_lib.lib().moyolo_sigmoid(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
     return y
 
@@ -202,6 +227,7 @@ def inverse_sigmoid(x: torch.Tensor) -> torch.Tensor:
     _cuda(x)
     x = x.contiguous()
     y = torch.empty_like(x)
+    _count(1)
     _lib.check(_lib.lib().moyolo_inverse_sigmoid(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
     return y
 
@@ -212,6 +238,7 @@ def pos2posemb(pos: torch.Tensor, num_pos_feats: int = 64, temperature: float = 
     n_coord = pos.shape[-1]
     rows = pos.numel() // n_coord
     emb = torch.empty(*pos.shape[:-1], n_coord * num_pos_feats, dtype=torch.float32, device=pos.device)
+    _count(1)
     _lib.check(_lib.lib().moyolo_pos2posemb(pos.data_ptr(), emb.data_ptr(), rows, n_coord, num_pos_feats,
                                             float(temperature), _stream()))
     return emb
@@ -222,6 +249,7 @@ def linear_k4_relu(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_dtype:
     R = x.shape[0]
     N = w.shape[0]
     y = torch.empty(R, N, dtype=out_dtype, device=x.device)
+    _count(1)
     _lib.check(_lib.lib().moyolo_linear_k4_relu(x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), _DT[out_dtype],
                                                 R, N, _stream()))
     return y
@@ -239,6 +267,7 @@ def track_assign(scores: torch.Tensor, boxes: torch.Tensor, obj_idxes: torch.Ten
     n = scores.shape[0]
     assert obj_idxes.dtype == torch.int64 and disappear_time.dtype == torch.int64 and counters.dtype == torch.int64
     assert workspace.numel() * workspace.element_size() >= track_workspace_bytes(n)
+    _count(1)
     _lib.check(_lib.lib().moyolo_track_assign(
         scores.data_ptr(), boxes.data_ptr(), obj_idxes.data_ptr(), disappear_time.data_ptr(), counters.data_ptr(), n,
         float(score_thresh), float(filter_thresh), int(miss_tolerance), float(iou_thresh), workspace.data_ptr(),
@@ -254,5 +283,6 @@ def track_compact(obj_idxes: torch.Tensor, fields: Sequence[torch.Tensor], outs:
     src = (C.c_void_p * nf)(*[f.data_ptr() for f in fields])
     dst = (C.c_void_p * nf)(*[o.data_ptr() for o in outs])
     rb = (C.c_int64 * nf)(*[f.stride(0) * f.element_size() if f.dim() > 1 else f.element_size() for f in fields])
+    _count(1 + nf)
     _lib.check(_lib.lib().moyolo_track_compact(obj_idxes.data_ptr(), n, n_active.data_ptr(), active_index.data_ptr(),
                                                src, dst, rb, nf, _stream()))
