@@ -130,11 +130,14 @@ int moyolo_linear(const void* x, int64_t ldx, const void* w, const float* bias, 
  * q, k, v: [R, n_heads*head_dim] slices with row strides ldq/ldk/ldv (elements) of dtype `dtype`;
  * attn_mask: optional additive fp32 [Rq, Rk] mask for the dense single-batch case (NULL in eval).
  * out: [R, n_heads*head_dim], row stride ldo, dtype `dtype`. row_offsets as above (host-side
- * `row_offsets_host` [B+1] mirrors it for grid sizing). head_dim must be 32 or 64. */
+ * `row_offsets_host` [B+1] mirrors it for grid sizing; it may over-estimate the device values, extra
+ * CTAs exit). If `seg_len` (device int32 [B]) is non-NULL sequence b attends over rows
+ * [row_offsets[b], row_offsets[b] + seg_len[b]) only. head_dim must be 32 or 64. */
 int moyolo_self_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                           int64_t ldv, void* out, int64_t ldo, int dtype, int batch,
-                          const int32_t* row_offsets, const int32_t* row_offsets_host, int n_heads,
-                          int head_dim, const float* attn_mask, moyolo_stream_t stream);
+                          const int32_t* row_offsets, const int32_t* row_offsets_host,
+                          const int32_t* seg_len, int n_heads, int head_dim, const float* attn_mask,
+                          moyolo_stream_t stream);
 
 /* out = LayerNorm(x + residual) * gamma + beta over the last dim C (eps as given), fp32 math.
  * x: [R, C] fp32 (GEMM output), residual: [R, C] fp32 (may be NULL).
@@ -197,9 +200,44 @@ int moyolo_track_assign(const float* scores, const float* boxes, int64_t* obj_id
                         int64_t* disappear_time, int64_t* counters, int64_t n, float score_thresh,
                         float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace,
                         moyolo_stream_t stream);
+/* Batched form: one CTA per sequence over rows [row_offsets[s], row_offsets[s+1]) of the frame arrays;
+ * counters int64 [n_seq, 2]; workspace n_seq * moyolo_track_workspace_bytes(max_rows_per_seq) bytes. */
+int moyolo_track_assign_batched(const float* scores, const float* boxes, int64_t* obj_idxes,
+                                int64_t* disappear_time, int64_t* counters, const int32_t* row_offsets,
+                                int n_seq, int64_t max_rows_per_seq, float score_thresh, float filter_thresh,
+                                int miss_tolerance, float iou_thresh, void* workspace, moyolo_stream_t stream);
 int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,
                          int32_t* active_index, const void* const* src_host, void* const* dst_host,
                          const int64_t* row_bytes_host, int n_fields, moyolo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Device-resident frame state for lock-step sequences (fixed capacity `cap` tracks per sequence; all
+ * counts in device memory so a frame replays as one CUDA graph for a padded row count `rows_pad`).
+ *
+ * moyolo_frame_assemble: builds the frame's query rows, tracks first then detect queries per sequence
+ *   (head.py:1056-1064,1108-1109): x [rows_pad,C] (class_embed[t_label] | det_embed), refer_logit
+ *   [rows_pad,4], pos [rows_pad,C] (t_qpos | pos2posemb(det_refer)), ids/dis [rows_pad] (prev | -1/0),
+ *   row_offsets [n_seq+1]. State arrays are [n_seq, cap, ...]; n_tracks int32 [n_seq].
+ * moyolo_frame_compact: per sequence, rows with ids >= 0 in order: n_active [n_seq], active_index,
+ *   QIM inputs gathered to frame-layout compact buffers c_* (sequence s at row_offsets[s]) and
+ *   t_label/t_ids/t_dis written straight to the state arrays.
+ * moyolo_frame_writeback: t_qpos <- new_qpos rows, t_ref <- inverse_sigmoid(c_box), n_tracks <- n_active
+ *   (MOTR/models/qim.py:298-300).
+ * -------------------------------------------------------------------------------------------*/
+int moyolo_frame_assemble(int n_seq, int n_detect, int C, int cap, const int32_t* n_tracks,
+                          const float* t_ref, const float* t_qpos, const int32_t* t_label,
+                          const int64_t* t_ids, const int64_t* t_dis, const float* class_embed,
+                          const float* det_embed, const float* det_refer, float* x, float* refer_logit,
+                          float* pos, int64_t* ids, int64_t* dis, int32_t* row_offsets, int64_t rows_pad,
+                          int num_pos_feats, float temperature, moyolo_stream_t stream);
+int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* row_offsets, const int64_t* ids,
+                         const int64_t* dis, const int32_t* labels, const float* refer_logit,
+                         const float* pos, const float* hs, const float* boxes, int32_t* n_active,
+                         int32_t* active_index, float* c_ref, float* c_pos, float* c_hs, float* c_box,
+                         int32_t* t_label, int64_t* t_ids, int64_t* t_dis, moyolo_stream_t stream);
+int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,
+                           const float* new_qpos, const float* c_box, float* t_qpos, float* t_ref,
+                           int32_t* n_tracks, moyolo_stream_t stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -29,7 +29,7 @@ SIGNATURES = {
     "moyolo_msda_fused_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _l, _p, _i, _i, _i,
                                        _l, _p, _p, _l, _p]),
     "moyolo_linear": (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _i, _p]),
-    "moyolo_self_attention": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _i, _i, _p, _p, _i, _i, _p, _p]),
+    "moyolo_self_attention": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
     "moyolo_add_layernorm": (_i, [_p, _p, _p, _p, _f, _l, _i, _p, _p, _p, _p, _i, _p]),
     "moyolo_add_cast": (_i, [_p, _p, _p, _i, _l, _p]),
     "moyolo_box_refine": (_i, [_p, _l, _i, _p, _p, _p, _p, _l, _i, _p]),
@@ -41,6 +41,11 @@ SIGNATURES = {
     "moyolo_track_workspace_bytes": (_l, [_l]),
     "moyolo_track_assign": (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _i, _f, _p, _p]),
     "moyolo_track_compact": (_i, [_p, _l, _p, _p, _p, _p, _p, _i, _p]),
+    "moyolo_track_assign_batched": (_i, [_p, _p, _p, _p, _p, _p, _i, _l, _f, _f, _i, _f, _p, _p]),
+    "moyolo_frame_assemble": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l,
+                                   _i, _f, _p]),
+    "moyolo_frame_compact": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "moyolo_frame_writeback": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 
 

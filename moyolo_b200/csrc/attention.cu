@@ -16,7 +16,7 @@ template <typename T, int DH>
 __global__ void __launch_bounds__(kAttThreads) self_attention_kernel(
     const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk, const T* __restrict__ v,
     int64_t ldv, T* __restrict__ out, int64_t ldo, int batch, const int32_t* __restrict__ row_offsets,
-    const float* __restrict__ attn_mask) {
+    const int32_t* __restrict__ seg_len, const float* __restrict__ attn_mask) {
   constexpr int DPL = DH / 32;  // output dims per lane
   __shared__ float s_k[kKT][DH + 1];
   __shared__ float s_v[kKT][DH];
@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(kAttThreads) self_attention_kernel(
   int b = 0, tile = blockIdx.x, seq_start = 0, seq_len = 0;
   for (; b < batch; ++b) {
     seq_start = row_offsets[b];
-    seq_len = row_offsets[b + 1] - seq_start;
+    seq_len = seg_len ? seg_len[b] : row_offsets[b + 1] - seq_start;
     const int nt = (seq_len + kQT - 1) / kQT;
     if (tile < nt) break;
     tile -= nt;
@@ -135,8 +135,9 @@ using namespace moyolo;
 
 extern "C" int moyolo_self_attention(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
                                      int64_t ldv, void* out, int64_t ldo, int dtype, int batch,
-                                     const int32_t* row_offsets, const int32_t* row_offsets_host, int n_heads,
-                                     int head_dim, const float* attn_mask, moyolo_stream_t stream) {
+                                     const int32_t* row_offsets, const int32_t* row_offsets_host,
+                                     const int32_t* seg_len, int n_heads, int head_dim, const float* attn_mask,
+                                     moyolo_stream_t stream) {
   MOYOLO_REQUIRE(q && k && v && out && row_offsets && row_offsets_host, MOYOLO_ERR_BAD_ARG,
                  "self_attention: null pointer");
   MOYOLO_REQUIRE(batch > 0 && n_heads > 0, MOYOLO_ERR_BAD_ARG, "self_attention: bad batch/n_heads");
@@ -154,7 +155,7 @@ extern "C" int moyolo_self_attention(const void* q, int64_t ldq, const void* k, 
 #define LAUNCH(T, DH)                                                                              \
   self_attention_kernel<T, DH><<<grid, kAttThreads, 0, st>>>(                                       \
       static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv, \
-      static_cast<T*>(out), ldo, batch, row_offsets, attn_mask)
+      static_cast<T*>(out), ldo, batch, row_offsets, seg_len, attn_mask)
   if (dtype == MOYOLO_F32) {
     if (head_dim == 32) LAUNCH(float, 32); else LAUNCH(float, 64);
   } else if (dtype == MOYOLO_BF16) {

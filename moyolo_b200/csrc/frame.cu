@@ -1,0 +1,219 @@
+// Device-resident frame state for lock-step sequences: query assembly, active-track compaction and
+// state write-back as single launches over all sequences, so a whole frame (assembly -> decoder ->
+// ID assignment -> QIM update -> write-back) has static launch shapes for a padded row count and can
+// be replayed as one CUDA graph with the per-sequence track counts living in device memory.
+//
+// Reference semantics:
+//   assemble : head.py:1056-1064,1108-1109 (tracks first, then detect queries), head.py:888-900
+//              (track content = class embedding of argmax previous logits), transformer.py:183-190
+//              (pos2posemb of the detect boxes) and repair R2 (ids = cat(prev, -1), disappear = cat(prev, 0)).
+//   compact  : MOTR/models/qim.py:184-187 (ids >= 0) + instances.py:152-178 (row selection).
+//   writeback: qim.py:298-300 (query_pos <- QIM output, ref_pts <- inverse_sigmoid(pred_boxes)).
+#include "common.cuh"
+
+namespace moyolo {
+
+__device__ __forceinline__ float inv_sigmoid_(float x) {
+  x = fminf(fmaxf(x, 0.0f), 1.0f);
+  return logf(fmaxf(x, 1e-5f) / fmaxf(1.0f - x, 1e-5f));
+}
+
+// grid = rows_pad blocks (one row per block), C threads cover the embedding row.
+__global__ void frame_assemble_kernel(int n_seq, int n_detect, int C, int cap, const int32_t* __restrict__ n_tracks,
+                                      const float* __restrict__ t_ref, const float* __restrict__ t_qpos,
+                                      const int32_t* __restrict__ t_label, const int64_t* __restrict__ t_ids,
+                                      const int64_t* __restrict__ t_dis, const float* __restrict__ class_embed,
+                                      const float* __restrict__ det_embed, const float* __restrict__ det_refer,
+                                      float* __restrict__ x, float* __restrict__ refer_logit, float* __restrict__ pos,
+                                      int64_t* __restrict__ ids, int64_t* __restrict__ dis,
+                                      int32_t* __restrict__ row_offsets, int num_pos_feats, float temperature) {
+  const int row = blockIdx.x;
+  // locate the sequence of this row: offsets are the running sum of (T_s + n_detect)
+  int s = 0, off = 0, T = 0;
+  for (; s < n_seq; ++s) {
+    T = n_tracks[s];
+    if (row < off + T + n_detect) break;
+    off += T + n_detect;
+  }
+  if (row == 0 && threadIdx.x == 0) {
+    int acc = 0;
+    row_offsets[0] = 0;
+    for (int i = 0; i < n_seq; ++i) {
+      acc += n_tracks[i] + n_detect;
+      row_offsets[i + 1] = acc;
+    }
+  }
+  float* xr = x + static_cast<int64_t>(row) * C;
+  float* pr = pos + static_cast<int64_t>(row) * C;
+  if (s == n_seq) {  // padding row: finite zeros, never an object
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { xr[c] = 0.0f; pr[c] = 0.0f; }
+    if (threadIdx.x < 4) refer_logit[row * 4 + threadIdx.x] = 0.0f;
+    if (threadIdx.x == 0) { ids[row] = -1; dis[row] = 0; }
+    return;
+  }
+  const int j = row - off;
+  if (j < T) {  // carried track
+    const int64_t src = static_cast<int64_t>(s) * cap + j;
+    const float* ce = class_embed + static_cast<int64_t>(t_label[src]) * C;
+    const float* qp = t_qpos + src * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { xr[c] = ce[c]; pr[c] = qp[c]; }
+    if (threadIdx.x < 4) refer_logit[row * 4 + threadIdx.x] = t_ref[src * 4 + threadIdx.x];
+    if (threadIdx.x == 0) { ids[row] = t_ids[src]; dis[row] = t_dis[src]; }
+  } else {      // detect query
+    const int64_t src = static_cast<int64_t>(s) * n_detect + (j - T);
+    const float* de = det_embed + src * C;
+    const float* dr = det_refer + src * 4;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      xr[c] = de[c];
+      const int coord = c / num_pos_feats, i = c % num_pos_feats;
+      const float p = dr[coord] * 6.283185307179586f;
+      const float e = p / powf(temperature, static_cast<float>(2 * (i / 2)) / static_cast<float>(num_pos_feats));
+      pr[c] = (i & 1) ? cosf(e) : sinf(e);
+    }
+    if (threadIdx.x < 4) refer_logit[row * 4 + threadIdx.x] = dr[threadIdx.x];
+    if (threadIdx.x == 0) { ids[row] = -1; dis[row] = 0; }
+  }
+}
+
+__device__ int block_exclusive_scan_f(int v, int* total, int* s_warp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = (lane < (blockDim.x >> 5)) ? s_warp[lane] : 0;
+    int winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    s_warp[lane] = winc - w;
+    if (lane == 31) s_warp[32] = winc;
+  }
+  __syncthreads();
+  *total = s_warp[32];
+  return s_warp[warp] + inc - v;
+}
+
+// grid = n_seq, 1024 threads: select ids >= 0 in order, then copy every field the next frame needs.
+__global__ void __launch_bounds__(1024) frame_compact_kernel(
+    int C, int cap, const int32_t* __restrict__ row_offsets, const int64_t* __restrict__ ids,
+    const int64_t* __restrict__ dis, const int32_t* __restrict__ labels, const float* __restrict__ refer_logit,
+    const float* __restrict__ pos, const float* __restrict__ hs, const float* __restrict__ boxes,
+    int32_t* __restrict__ n_active, int32_t* __restrict__ active_index, float* __restrict__ c_ref,
+    float* __restrict__ c_pos, float* __restrict__ c_hs, float* __restrict__ c_box, int32_t* __restrict__ t_label,
+    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis) {
+  __shared__ int s_warp[33];
+  const int s = blockIdx.x;
+  const int off = row_offsets[s];
+  const int n = row_offsets[s + 1] - off;
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int begin = min(static_cast<int>(threadIdx.x) * per, n);
+  const int end = min(begin + per, n);
+  int local = 0;
+  for (int i = begin; i < end; ++i) local += ids[off + i] >= 0 ? 1 : 0;
+  int total;
+  int rank = block_exclusive_scan_f(local, &total, s_warp);
+  total = min(total, cap);
+  for (int i = begin; i < end; ++i)
+    if (ids[off + i] >= 0) {
+      if (rank < cap) active_index[off + rank] = i;
+      ++rank;
+    }
+  if (threadIdx.x == 0) n_active[s] = total;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < total; j += nwarps) {
+    const int64_t src = off + active_index[off + j];
+    const int64_t dst = off + j;  // compact rows keep the frame layout: sequence s starts at row_offsets[s]
+    for (int c = lane; c < C; c += 32) {
+      c_pos[dst * C + c] = pos[src * C + c];
+      c_hs[dst * C + c] = hs[src * C + c];
+    }
+    if (lane < 4) {
+      c_ref[dst * 4 + lane] = refer_logit[src * 4 + lane];
+      c_box[dst * 4 + lane] = boxes[src * 4 + lane];
+    }
+    if (lane == 0) {
+      const int64_t st = static_cast<int64_t>(s) * cap + j;
+      t_label[st] = labels[src];
+      t_ids[st] = ids[src];
+      t_dis[st] = dis[src];
+    }
+  }
+}
+
+// grid = (n_seq, chunks): t_qpos[s, j] = new_qpos[off_s + j]; t_ref[s, j] = inverse_sigmoid(c_box[off_s + j]).
+__global__ void frame_writeback_kernel(int C, int cap, const int32_t* __restrict__ row_offsets,
+                                       const int32_t* __restrict__ n_active, const float* __restrict__ new_qpos,
+                                       const float* __restrict__ c_box, float* __restrict__ t_qpos,
+                                       float* __restrict__ t_ref, int32_t* __restrict__ n_tracks) {
+  const int s = blockIdx.x;
+  const int off = row_offsets[s];
+  const int k = n_active[s];
+  const int warp = (blockIdx.y * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.y * blockDim.x) >> 5;
+  for (int j = warp; j < k; j += nwarps) {
+    const int64_t src = off + j, dst = static_cast<int64_t>(s) * cap + j;
+    for (int c = lane; c < C; c += 32) t_qpos[dst * C + c] = new_qpos[src * C + c];
+    if (lane < 4) t_ref[dst * 4 + lane] = inv_sigmoid_(c_box[src * 4 + lane]);
+  }
+  if (blockIdx.y == 0 && threadIdx.x == 0) n_tracks[s] = k;
+}
+
+}  // namespace moyolo
+
+using namespace moyolo;
+
+extern "C" int moyolo_frame_assemble(int n_seq, int n_detect, int C, int cap, const int32_t* n_tracks,
+                                     const float* t_ref, const float* t_qpos, const int32_t* t_label,
+                                     const int64_t* t_ids, const int64_t* t_dis, const float* class_embed,
+                                     const float* det_embed, const float* det_refer, float* x, float* refer_logit,
+                                     float* pos, int64_t* ids, int64_t* dis, int32_t* row_offsets, int64_t rows_pad,
+                                     int num_pos_feats, float temperature, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(n_tracks && t_ref && t_qpos && t_label && t_ids && t_dis && class_embed && det_embed && det_refer &&
+                     x && refer_logit && pos && ids && dis && row_offsets,
+                 MOYOLO_ERR_BAD_ARG, "frame_assemble: null pointer");
+  MOYOLO_REQUIRE(n_seq > 0 && n_detect >= 0 && C > 0 && cap > 0 && rows_pad > 0, MOYOLO_ERR_BAD_SHAPE,
+                 "frame_assemble: bad sizes");
+  MOYOLO_REQUIRE(C == 4 * num_pos_feats, MOYOLO_ERR_BAD_SHAPE, "frame_assemble: C must equal 4*num_pos_feats");
+  const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
+  frame_assemble_kernel<<<static_cast<unsigned>(rows_pad), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      n_seq, n_detect, C, cap, n_tracks, t_ref, t_qpos, t_label, t_ids, t_dis, class_embed, det_embed, det_refer, x,
+      refer_logit, pos, ids, dis, row_offsets, num_pos_feats, temperature);
+  return check_launch("frame_assemble_kernel");
+}
+
+extern "C" int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* row_offsets, const int64_t* ids,
+                                    const int64_t* dis, const int32_t* labels, const float* refer_logit,
+                                    const float* pos, const float* hs, const float* boxes, int32_t* n_active,
+                                    int32_t* active_index, float* c_ref, float* c_pos, float* c_hs, float* c_box,
+                                    int32_t* t_label, int64_t* t_ids, int64_t* t_dis, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(row_offsets && ids && dis && labels && refer_logit && pos && hs && boxes && n_active &&
+                     active_index && c_ref && c_pos && c_hs && c_box && t_label && t_ids && t_dis,
+                 MOYOLO_ERR_BAD_ARG, "frame_compact: null pointer");
+  MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_compact: bad sizes");
+  frame_compact_kernel<<<n_seq, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+      C, cap, row_offsets, ids, dis, labels, refer_logit, pos, hs, boxes, n_active, active_index, c_ref, c_pos, c_hs,
+      c_box, t_label, t_ids, t_dis);
+  return check_launch("frame_compact_kernel");
+}
+
+extern "C" int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,
+                                      const float* new_qpos, const float* c_box, float* t_qpos, float* t_ref,
+                                      int32_t* n_tracks, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(row_offsets && n_active && new_qpos && c_box && t_qpos && t_ref && n_tracks, MOYOLO_ERR_BAD_ARG,
+                 "frame_writeback: null pointer");
+  MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_writeback: bad sizes");
+  dim3 grid(n_seq, 8);
+  frame_writeback_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, cap, row_offsets, n_active, new_qpos,
+                                                                             c_box, t_qpos, t_ref, n_tracks);
+  return check_launch("frame_writeback_kernel");
+}

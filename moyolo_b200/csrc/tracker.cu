@@ -75,8 +75,21 @@ __host__ __device__ inline TrackWs carve_ws(void* ws, int64_t n) {
 __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
     const float* __restrict__ scores, const float* __restrict__ boxes, int64_t* __restrict__ obj_idxes,
     int64_t* __restrict__ disappear_time, int64_t* __restrict__ counters, int n, float score_thresh,
-    float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace) {
+    float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace,
+    const int32_t* __restrict__ row_offsets, int64_t ws_stride) {
   __shared__ int s_warp[33];
+  if (row_offsets != nullptr) {  // batched: one CTA per sequence, rows [row_offsets[s], row_offsets[s+1])
+    const int seq = blockIdx.x;
+    const int off = row_offsets[seq];
+    n = row_offsets[seq + 1] - off;
+    scores += off;
+    boxes += static_cast<int64_t>(off) * 4;
+    obj_idxes += off;
+    disappear_time += off;
+    counters += 2 * seq;
+    workspace = static_cast<char*>(workspace) + static_cast<int64_t>(seq) * ws_stride;
+    if (n <= 0) return;
+  }
   const TrackWs ws = carve_ws(workspace, n);
   const int per = (n + kTrkThreads - 1) / kTrkThreads;
   const int begin = min(static_cast<int>(threadIdx.x) * per, n);
@@ -236,8 +249,23 @@ extern "C" int moyolo_track_assign(const float* scores, const float* boxes, int6
   if (n == 0) return MOYOLO_OK;
   track_assign_kernel<<<1, kTrkThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       scores, boxes, obj_idxes, disappear_time, counters, static_cast<int>(n), score_thresh, filter_thresh,
-      miss_tolerance, iou_thresh, workspace);
+      miss_tolerance, iou_thresh, workspace, nullptr, 0);
   return check_launch("track_assign_kernel");
+}
+
+extern "C" int moyolo_track_assign_batched(const float* scores, const float* boxes, int64_t* obj_idxes,
+                                           int64_t* disappear_time, int64_t* counters, const int32_t* row_offsets,
+                                           int n_seq, int64_t max_rows_per_seq, float score_thresh,
+                                           float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace,
+                                           moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(scores && boxes && obj_idxes && disappear_time && counters && row_offsets && workspace,
+                 MOYOLO_ERR_BAD_ARG, "track_assign_batched: null pointer");
+  MOYOLO_REQUIRE(n_seq > 0 && max_rows_per_seq > 0 && max_rows_per_seq <= kTrkMaxN, MOYOLO_ERR_BAD_SHAPE,
+                 "track_assign_batched: max_rows_per_seq must be in (0, %d]", kTrkMaxN);
+  track_assign_kernel<<<n_seq, kTrkThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      scores, boxes, obj_idxes, disappear_time, counters, 0, score_thresh, filter_thresh, miss_tolerance, iou_thresh,
+      workspace, row_offsets, moyolo_track_workspace_bytes(max_rows_per_seq));
+  return check_launch("track_assign_kernel(batched)");
 }
 
 extern "C" int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,

@@ -147,7 +147,7 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out_dtyp
 
 def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, row_offsets: torch.Tensor,
                    row_offsets_host: Sequence[int], n_heads: int, attn_mask: Optional[torch.Tensor] = None,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   out: Optional[torch.Tensor] = None, seg_len: Optional[torch.Tensor] = None) -> torch.Tensor:
     """softmax(q k^T / sqrt(Dh)) v per (sequence, head); q/k/v are [R, C] column slices."""
     _cuda(q, k, v, row_offsets, attn_mask)
     R, Cc = q.shape
@@ -157,8 +157,8 @@ def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, row_offset
     _count(1)
     _lib.check(_lib.lib().moyolo_self_attention(
         q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
-        out.stride(0), _dt(q), len(row_offsets_host) - 1, row_offsets.data_ptr(), host, n_heads, Cc // n_heads,
-        _ptr(attn_mask), _stream()))
+        out.stride(0), _dt(q), len(row_offsets_host) - 1, row_offsets.data_ptr(), host, _ptr(seg_len), n_heads,
+        Cc // n_heads, _ptr(attn_mask), _stream()))
     return out
 
 
@@ -286,3 +286,43 @@ def track_compact(obj_idxes: torch.Tensor, fields: Sequence[torch.Tensor], outs:
     _count(1 + nf)
     _lib.check(_lib.lib().moyolo_track_compact(obj_idxes.data_ptr(), n, n_active.data_ptr(), active_index.data_ptr(),
                                                src, dst, rb, nf, _stream()))
+
+
+def track_assign_batched(scores, boxes, ids, dis, counters, row_offsets, n_seq: int, max_rows_per_seq: int,
+                         workspace, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, iou_thresh=0.8) -> None:
+    """RuntimeTrackerBase.update for every lock-step sequence in one launch (one CTA per sequence)."""
+    _cuda(scores, boxes, ids, dis, counters, row_offsets, workspace)
+    assert workspace.numel() * workspace.element_size() >= n_seq * track_workspace_bytes(max_rows_per_seq)
+    _count(1)
+    _lib.check(_lib.lib().moyolo_track_assign_batched(
+        scores.data_ptr(), boxes.data_ptr(), ids.data_ptr(), dis.data_ptr(), counters.data_ptr(),
+        row_offsets.data_ptr(), n_seq, max_rows_per_seq, float(score_thresh), float(filter_thresh),
+        int(miss_tolerance), float(iou_thresh), workspace.data_ptr(), _stream()))
+
+
+def frame_assemble(n_seq, n_detect, C, cap, n_tracks, t_ref, t_qpos, t_label, t_ids, t_dis, class_embed, det_embed,
+                   det_refer, x, refer_logit, pos, ids, dis, row_offsets, rows_pad, num_pos_feats=64,
+                   temperature=10000.0) -> None:
+    _count(1)
+    _lib.check(_lib.lib().moyolo_frame_assemble(
+        n_seq, n_detect, C, cap, n_tracks.data_ptr(), t_ref.data_ptr(), t_qpos.data_ptr(), t_label.data_ptr(),
+        t_ids.data_ptr(), t_dis.data_ptr(), class_embed.data_ptr(), det_embed.data_ptr(), det_refer.data_ptr(),
+        x.data_ptr(), refer_logit.data_ptr(), pos.data_ptr(), ids.data_ptr(), dis.data_ptr(), row_offsets.data_ptr(),
+        rows_pad, num_pos_feats, float(temperature), _stream()))
+
+
+def frame_compact(n_seq, C, cap, row_offsets, ids, dis, labels, refer_logit, pos, hs, boxes, n_active, active_index,
+                  c_ref, c_pos, c_hs, c_box, t_label, t_ids, t_dis) -> None:
+    _count(1)
+    _lib.check(_lib.lib().moyolo_frame_compact(
+        n_seq, C, cap, row_offsets.data_ptr(), ids.data_ptr(), dis.data_ptr(), labels.data_ptr(),
+        refer_logit.data_ptr(), pos.data_ptr(), hs.data_ptr(), boxes.data_ptr(), n_active.data_ptr(),
+        active_index.data_ptr(), c_ref.data_ptr(), c_pos.data_ptr(), c_hs.data_ptr(), c_box.data_ptr(),
+        t_label.data_ptr(), t_ids.data_ptr(), t_dis.data_ptr(), _stream()))
+
+
+def frame_writeback(n_seq, C, cap, row_offsets, n_active, new_qpos, c_box, t_qpos, t_ref, n_tracks) -> None:
+    _count(1)
+    _lib.check(_lib.lib().moyolo_frame_writeback(
+        n_seq, C, cap, row_offsets.data_ptr(), n_active.data_ptr(), new_qpos.data_ptr(), c_box.data_ptr(),
+        t_qpos.data_ptr(), t_ref.data_ptr(), n_tracks.data_ptr(), _stream()))

@@ -325,8 +325,9 @@ def _calibrated_state(syn, tp, spec, sd, frame0, shapes):
     return syn.calibrate_score_bias(sd, s[0, 0], spec, 0.08)
 
 
-@pytest.mark.parametrize("precision,margin,box_tol", [("fp32", 2e-5, 1e-4), ("bf16", 2e-2, 5e-3)])
-def test_track_sequence_vs_oracle(dev, precision, margin, box_tol):
+@pytest.mark.parametrize("precision,margin,box_tol,graphs", [("fp32", 2e-5, 1e-4, True), ("bf16", 2e-2, 5e-3, True),
+                                                             ("fp32", 2e-5, 1e-4, False)])
+def test_track_sequence_vs_oracle(dev, precision, margin, box_tol, graphs):
     """Track-ID assignment on synthetic sequences: two lock-step sequences on the GPU vs two
     independent CPU oracle (O3) runs.
     (1) free-running: IDs must be identical and boxes within tolerance on every frame until an oracle
@@ -349,7 +350,7 @@ def test_track_sequence_vs_oracle(dev, precision, margin, box_tol):
     sd = _calibrated_state(syn, tp, spec, sd, frames[0][0], shapes)
     refs = [track_sequence_port(sd, frames[s], shapes, spec.n_heads, spec.n_levels, spec.n_points, spec.n_layers,
                                 spec.nc) for s in range(S)]
-    eng = TrackEngine(sd, spec, shapes, dev, precision, nd, S)
+    eng = TrackEngine(sd, spec, shapes, dev, precision, nd, S, use_graphs=graphs)
     alive = [True] * S
     compared = 0
     forced = [TrackerPort() for _ in range(S)]
@@ -369,8 +370,8 @@ def test_track_sequence_vs_oracle(dev, precision, margin, box_tol):
             assert eng.counters[s].tolist() == [forced[s].max_obj_id, forced[s].max_obj_id_pre], (s, t)
             act = ids >= 0
             prev[s] = (ids[act], dis[act])
-            assert np.array_equal(eng.t_ids[s].cpu().numpy(), ids[act]) and \
-                np.array_equal(eng.t_dis[s].cpu().numpy(), dis[act]), (s, t, "carried state")
+            assert np.array_equal(eng.track_ids(s).cpu().numpy(), ids[act]) and \
+                np.array_equal(eng.track_disappear(s).cpu().numpy(), dis[act]), (s, t, "carried state")
             # (1) free-running vs O3
             if not alive[s]:
                 continue
