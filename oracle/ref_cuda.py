@@ -1,0 +1,34 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. ctypes front-end of oracle/_ref/libmsda_ref_cuda.so: the
+reference's own CUDA forward kernel (MOTR/models/ops/src/cuda/ms_deform_im2col_cuda.cuh:237-299,923-954)
+compiled for sm_100a by oracle/Makefile. Never imported by the product package."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import torch
+
+_SO = Path(__file__).resolve().parent / "_ref" / "libmsda_ref_cuda.so"
+_lib = None
+
+
+def available() -> bool:
+    return _SO.exists()
+
+
+def msda_im2col(value: torch.Tensor, shapes, loc: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+    """value [B,S,H,D] fp32 cuda, loc [B,Q,H,L,P,2], weights [B,Q,H,L,P] -> [B,Q,H*D] (legacy op layout)."""
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(str(_SO))
+    B, S, H, D = value.shape
+    Q, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+    sh = torch.as_tensor(shapes, dtype=torch.int64, device=value.device)
+    lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    out = torch.zeros(B, Q, H * D, dtype=torch.float32, device=value.device)
+    rc = _lib.ref_msda_im2col_f32(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(value.data_ptr()),
+                                  C.c_void_p(sh.data_ptr()), C.c_void_p(lsi.data_ptr()), C.c_void_p(loc.data_ptr()),
+                                  C.c_void_p(weights.data_ptr()), B, S, H, D, L, Q, P, C.c_void_p(out.data_ptr()))
+    if rc != 0:
+        raise RuntimeError(f"reference kernel launch failed: cudaError {rc}")
+    return out

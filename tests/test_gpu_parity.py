@@ -388,3 +388,19 @@ def test_track_sequence_vs_oracle(dev, precision, margin, box_tol, graphs):
     if precision == "fp32":
         assert compared >= 10, f"margin rule excluded too many frames ({compared} compared)"
     assert max(rr["n_tracks_in"] for rr in refs[0]) > 0, "sequence never carried a track"
+
+
+def test_core_vs_reference_cuda_kernel(dev):
+    """Our gather against the REFERENCE's own CUDA kernel (MOTR/models/ops/src/cuda/
+    ms_deform_im2col_cuda.cuh) compiled for sm_100a into oracle/_ref by oracle/Makefile."""
+    from oracle import ref_cuda
+    if not ref_cuda.available():
+        pytest.skip("oracle/_ref/libmsda_ref_cuda.so not built (needs the reference tree at build time)")
+    m, ops, syn, mg, tp = _mods()
+    for name, B, Q in (("tiny", 2, 50), ("C1", 1, 300), ("MOT17", 2, 357)):
+        shapes = [list(s) for s in syn.PYRAMIDS[name]]
+        value, loc, w = syn.make_core_inputs(3 + Q, B, Q, 8, 32, shapes, 4)
+        v, l, ww = value.to(dev), loc.to(dev), w.to(dev)
+        ref = ref_cuda.msda_im2col(v, shapes, l, ww)
+        out = ops.msda_sampled(v, shapes, l, ww)
+        assert rel_rms(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5, name
