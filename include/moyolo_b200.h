@@ -201,11 +201,13 @@ int moyolo_track_assign(const float* scores, const float* boxes, int64_t* obj_id
                         float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace,
                         moyolo_stream_t stream);
 /* Batched form: one CTA per sequence over rows [row_offsets[s], row_offsets[s+1]) of the frame arrays;
- * counters int64 [n_seq, 2]; workspace n_seq * moyolo_track_workspace_bytes(max_rows_per_seq) bytes. */
+ * counters int64 [n_seq, 2]; workspace n_seq * moyolo_track_workspace_bytes(max_rows_per_seq) bytes.
+ * ctrl (may be NULL): frame control block, see moyolo_frame_assemble; a set abort flag makes the call a no-op. */
 int moyolo_track_assign_batched(const float* scores, const float* boxes, int64_t* obj_idxes,
                                 int64_t* disappear_time, int64_t* counters, const int32_t* row_offsets,
                                 int n_seq, int64_t max_rows_per_seq, float score_thresh, float filter_thresh,
-                                int miss_tolerance, float iou_thresh, void* workspace, moyolo_stream_t stream);
+                                int miss_tolerance, float iou_thresh, void* workspace, const int32_t* ctrl,
+                                moyolo_stream_t stream);
 int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,
                          int32_t* active_index, const void* const* src_host, void* const* dst_host,
                          const int64_t* row_bytes_host, int n_fields, moyolo_stream_t stream);
@@ -223,21 +225,39 @@ int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,
  *   t_label/t_ids/t_dis written straight to the state arrays.
  * moyolo_frame_writeback: t_qpos <- new_qpos rows, t_ref <- inverse_sigmoid(c_box), n_tracks <- n_active
  *   (MOTR/models/qim.py:298-300).
+ * moyolo_frame_emit: the frame's results. frame_rows [rows_pad, 8] fp32 = (id, cx, cy, w, h, score, label,
+ *   seq) for every row (padding rows id = -1) -- what a host reads back with one copy -- and the tracked
+ *   objects (ids >= 0) appended to the device-resident track table [table_cap, 9] fp32 =
+ *   (seq, frame, id, cx, cy, w, h, score, cls), the row format of the sharding gather (the MOTChallenge /
+ *   TrackResults.save_txt fields, ultralytics/engine/results.py:475-512). seq_ids int32 [n_seq] maps the
+ *   lock-step slot to the global sequence index.
+ *
+ * ctrl: device int32 [8] control block = {abort, frame counter, table cursor, table overflow, rows wanted
+ *   by the aborting frame, ...}. The host may launch a frame speculatively with a rows_pad derived from an
+ *   OLDER frame's track counts: if the real row count does not fit, frame_assemble sets the sticky abort
+ *   flag, builds an in-bounds detect-only frame, and every state-writing call (track_assign_batched,
+ *   frame_compact, frame_writeback, frame_emit) of this and later frames is a no-op until the host clears
+ *   the flag and re-launches. ctrl may be NULL for assemble/compact/writeback (no speculation).
  * -------------------------------------------------------------------------------------------*/
 int moyolo_frame_assemble(int n_seq, int n_detect, int C, int cap, const int32_t* n_tracks,
                           const float* t_ref, const float* t_qpos, const int32_t* t_label,
                           const int64_t* t_ids, const int64_t* t_dis, const float* class_embed,
                           const float* det_embed, const float* det_refer, float* x, float* refer_logit,
                           float* pos, int64_t* ids, int64_t* dis, int32_t* row_offsets, int64_t rows_pad,
-                          int num_pos_feats, float temperature, moyolo_stream_t stream);
+                          int num_pos_feats, float temperature, int32_t* ctrl, moyolo_stream_t stream);
 int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* row_offsets, const int64_t* ids,
                          const int64_t* dis, const int32_t* labels, const float* refer_logit,
                          const float* pos, const float* hs, const float* boxes, int32_t* n_active,
                          int32_t* active_index, float* c_ref, float* c_pos, float* c_hs, float* c_box,
-                         int32_t* t_label, int64_t* t_ids, int64_t* t_dis, moyolo_stream_t stream);
+                         int32_t* t_label, int64_t* t_ids, int64_t* t_dis, const int32_t* ctrl,
+                         moyolo_stream_t stream);
 int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,
                            const float* new_qpos, const float* c_box, float* t_qpos, float* t_ref,
-                           int32_t* n_tracks, moyolo_stream_t stream);
+                           int32_t* n_tracks, const int32_t* ctrl, moyolo_stream_t stream);
+int moyolo_frame_emit(int n_seq, int64_t rows_pad, const int32_t* row_offsets, const int64_t* ids,
+                      const float* boxes, const float* scores, const int32_t* labels, const int32_t* n_active,
+                      const int32_t* active_index, const int32_t* seq_ids, float* frame_rows, float* table,
+                      int64_t table_cap, int32_t* ctrl, moyolo_stream_t stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -41,11 +41,13 @@ SIGNATURES = {
     "moyolo_track_workspace_bytes": (_l, [_l]),
     "moyolo_track_assign": (_i, [_p, _p, _p, _p, _p, _l, _f, _f, _i, _f, _p, _p]),
     "moyolo_track_compact": (_i, [_p, _l, _p, _p, _p, _p, _p, _i, _p]),
-    "moyolo_track_assign_batched": (_i, [_p, _p, _p, _p, _p, _p, _i, _l, _f, _f, _i, _f, _p, _p]),
+    "moyolo_track_assign_batched": (_i, [_p, _p, _p, _p, _p, _p, _i, _l, _f, _f, _i, _f, _p, _p, _p]),
     "moyolo_frame_assemble": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l,
-                                   _i, _f, _p]),
-    "moyolo_frame_compact": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
-    "moyolo_frame_writeback": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
+                                   _i, _f, _p, _p]),
+    "moyolo_frame_compact": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                                  _p]),
+    "moyolo_frame_writeback": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "moyolo_frame_emit": (_i, [_i, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _p, _p]),
 }
 
 

@@ -12,6 +12,10 @@ constexpr int kQT = 16;   // queries per CTA (4 per warp)
 constexpr int kKT = 64;   // keys per tile
 constexpr int kQPW = 4;   // queries per warp
 
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
 template <typename T, int DH>
 __global__ void __launch_bounds__(kAttThreads) self_attention_kernel(
     const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk, const T* __restrict__ v,
@@ -129,6 +133,189 @@ __global__ void __launch_bounds__(kAttThreads) self_attention_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// bf16 tensor-core variant (eval path: no attn_mask). One CTA = (sequence, head, 64 queries), four
+// warps of 16 queries; K/V stream through a double-buffered cp.async ring in 64-key tiles; S = Q K^T
+// and O += P V run on mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with the online softmax held in
+// registers (the S accumulator fragment is re-used as the A fragment of P V). The problem is
+// 300..1200 queries x head_dim 32: ~0.1 GFLOP per launch, so the design goal is latency (few dependent
+// steps, no shared-memory round trip for P), not tensor throughput.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMQT = 64;  // queries per CTA
+constexpr int kMKT = 64;  // keys per tile
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 -> 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128, 3) self_attention_mma_kernel(
+    const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
+    const __nv_bfloat16* __restrict__ v, int64_t ldv, __nv_bfloat16* __restrict__ out, int64_t ldo, int batch,
+    const int32_t* __restrict__ row_offsets, const int32_t* __restrict__ seg_len) {
+  constexpr int PITCH = DH + 8;      // bf16 elements; (DH+8)*2 bytes keeps ldmatrix rows on distinct banks
+  constexpr int KS = DH / 16;        // k-steps of S = Q K^T
+  constexpr int NT = DH / 8;         // n-tiles of O
+  constexpr int CPR = DH / 8;        // 16-byte chunks per row
+  __shared__ __align__(16) __nv_bfloat16 s_q[kMQT][PITCH];
+  __shared__ __align__(16) __nv_bfloat16 s_k[2][kMKT][PITCH];
+  __shared__ __align__(16) __nv_bfloat16 s_v[2][kMKT][PITCH];
+
+  int b = 0, tile = blockIdx.x, seq_start = 0, seq_len = 0;
+  for (; b < batch; ++b) {
+    seq_start = row_offsets[b];
+    seq_len = seg_len ? seg_len[b] : row_offsets[b + 1] - seq_start;
+    const int nt = (seq_len + kMQT - 1) / kMQT;
+    if (tile < nt) break;
+    tile -= nt;
+  }
+  if (b == batch) return;
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = tile * kMQT;
+  const int n_kt = (seq_len + kMKT - 1) / kMKT;
+
+  auto load_kv = [&](int kt, int buf) {
+    for (int i = threadIdx.x; i < kMKT * CPR; i += 128) {
+      const int r = i / CPR, c = i % CPR;
+      const int kl = kt * kMKT + r;
+      const bool ok = kl < seq_len;
+      const int64_t row = seq_start + (ok ? kl : 0);
+      cp_async16(smem_addr(&s_k[buf][r][c * 8]), k + row * ldk + head * DH + c * 8, ok);
+      cp_async16(smem_addr(&s_v[buf][r][c * 8]), v + row * ldv + head * DH + c * 8, ok);
+    }
+  };
+  for (int i = threadIdx.x; i < kMQT * CPR; i += 128) {
+    const int r = i / CPR, c = i % CPR;
+    const bool ok = q0 + r < seq_len;
+    const int64_t row = seq_start + (ok ? q0 + r : 0);
+    cp_async16(smem_addr(&s_q[r][c * 8]), q + row * ldq + head * DH + c * 8, ok);
+  }
+  load_kv(0, 0);
+  cp_async_commit();
+
+  uint32_t qa[KS][4];
+  float o[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+  // softmax in base 2: exp(x*scale - m*scale) = exp2((x - m) * scale*log2(e))
+  const float sl2 = rsqrtf(static_cast<float>(DH)) * 1.4426950408889634f;
+
+  for (int kt = 0; kt < n_kt; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < n_kt) {
+      load_kv(kt + 1, buf ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (kt == 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        ldmatrix_x4(smem_addr(&s_q[warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][ks * 16 + (lane >> 4) * 8]), qa[ks]);
+    }
+    // ---- S = Q K^T for 64 keys: 8 n-tiles of 8 keys ----
+    float s[kMKT / 8][4];
+#pragma unroll
+    for (int j = 0; j < kMKT / 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+#pragma unroll
+      for (int kp = 0; kp < KS / 2; ++kp) {  // one ldmatrix.x4 covers 32 head dims = 2 k-steps
+        uint32_t kb[4];
+        ldmatrix_x4(smem_addr(&s_k[buf][j * 8 + (lane & 7)][kp * 32 + (lane >> 3) * 8]), kb);
+        mma_bf16_16816(s[j], qa[2 * kp], kb[0], kb[1]);
+        mma_bf16_16816(s[j], qa[2 * kp + 1], kb[2], kb[3]);
+      }
+    }
+    // ---- online softmax (rows g and g+8 of the warp's 16 queries) ----
+    const int kbase = kt * kMKT;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kMKT / 8; ++j) {
+      const int key = kbase + j * 8 + 2 * t;
+      if (key >= seq_len) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+      if (key + 1 >= seq_len) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every tile holds >= 1 valid key
+    const float c0 = exp2f((m0 - mn0) * sl2), c1 = exp2f((m1 - mn1) * sl2);
+    m0 = mn0;
+    m1 = mn1;
+    float rs0 = 0.0f, rs1 = 0.0f;
+    uint32_t pa[kMKT / 16][4];
+#pragma unroll
+    for (int j = 0; j < kMKT / 8; ++j) {
+      const float p0 = exp2f((s[j][0] - mn0) * sl2), p1 = exp2f((s[j][1] - mn0) * sl2);
+      const float p2 = exp2f((s[j][2] - mn1) * sl2), p3 = exp2f((s[j][3] - mn1) * sl2);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      pa[j >> 1][(j & 1) * 2 + 0] = float2_to_bf16x2(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = float2_to_bf16x2(p2, p3);
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+    // ---- O += P V ----
+#pragma unroll
+    for (int kk = 0; kk < kMKT / 16; ++kk) {
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t vb[4];
+        ldmatrix_x4_trans(smem_addr(&s_v[buf][kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]), vb);
+        mma_bf16_16816(o[2 * np], pa[kk], vb[0], vb[1]);
+        mma_bf16_16816(o[2 * np + 1], pa[kk], vb[2], vb[3]);
+      }
+    }
+    __syncthreads();  // all warps done with `buf` before the next iteration's prefetch overwrites it
+  }
+
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    if (r0 < seq_len)
+      *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(seq_start + r0) * ldo + head * DH + n * 8 + 2 * t) =
+          float2_to_bf16x2(o[n][0] * i0, o[n][1] * i0);
+    if (r1 < seq_len)
+      *reinterpret_cast<uint32_t*>(out + static_cast<int64_t>(seq_start + r1) * ldo + head * DH + n * 8 + 2 * t) =
+          float2_to_bf16x2(o[n][2] * i1, o[n][3] * i1);
+  }
+}
+
 }  // namespace moyolo
 
 using namespace moyolo;
@@ -143,14 +330,31 @@ extern "C" int moyolo_self_attention(const void* q, int64_t ldq, const void* k, 
   MOYOLO_REQUIRE(batch > 0 && n_heads > 0, MOYOLO_ERR_BAD_ARG, "self_attention: bad batch/n_heads");
   MOYOLO_REQUIRE(head_dim == 32 || head_dim == 64, MOYOLO_ERR_UNSUPPORTED,
                  "self_attention: head_dim must be 32 or 64, got %d", head_dim);
+  // tensor-core path: bf16, no additive mask, 4-byte aligned rows (eval mode of the decoder and QIM)
+  const bool mma = dtype == MOYOLO_BF16 && attn_mask == nullptr && aligned16(q) && aligned16(k) && aligned16(v) &&
+                   (ldq % 8 == 0) && (ldk % 8 == 0) && (ldv % 8 == 0) && (ldo % 2 == 0) &&
+                   (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
+  const int qt = mma ? kMQT : kQT;
   int64_t tiles = 0;
   for (int b = 0; b < batch; ++b) {
     const int n = row_offsets_host[b + 1] - row_offsets_host[b];
     MOYOLO_REQUIRE(n >= 0, MOYOLO_ERR_BAD_SHAPE, "self_attention: row_offsets must be non-decreasing");
-    tiles += (n + kQT - 1) / kQT;
+    tiles += (n + qt - 1) / qt;
   }
   if (tiles == 0) return MOYOLO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (mma) {
+    dim3 mgrid(static_cast<unsigned>(tiles), n_heads);
+    const __nv_bfloat16 *qq = static_cast<const __nv_bfloat16*>(q), *kk = static_cast<const __nv_bfloat16*>(k),
+                        *vv = static_cast<const __nv_bfloat16*>(v);
+    if (head_dim == 32)
+      self_attention_mma_kernel<32><<<mgrid, 128, 0, st>>>(qq, ldq, kk, ldk, vv, ldv, static_cast<__nv_bfloat16*>(out),
+                                                          ldo, batch, row_offsets, seg_len);
+    else
+      self_attention_mma_kernel<64><<<mgrid, 128, 0, st>>>(qq, ldq, kk, ldk, vv, ldv, static_cast<__nv_bfloat16*>(out),
+                                                          ldo, batch, row_offsets, seg_len);
+    return check_launch("self_attention_mma_kernel");
+  }
   dim3 grid(static_cast<unsigned>(tiles), n_heads);
 #define LAUNCH(T, DH)                                                                              \
   self_attention_kernel<T, DH><<<grid, kAttThreads, 0, st>>>(                                       \

@@ -76,6 +76,65 @@ __global__ void __launch_bounds__(kRowWarps * 32) add_layernorm_kernel(
   }
 }
 
+// d_model = 256 fast path: one warp per row, every lane owns two float4 column groups
+// (cols 4*lane..+3 and 128+4*lane..+3) so all global accesses are full 512-byte warp transactions.
+template <typename LP_T>
+__device__ __forceinline__ void store_lp4(LP_T* dst, float a, float b, float c, float d);
+template <>
+__device__ __forceinline__ void store_lp4<float>(float* dst, float a, float b, float c, float d) {
+  *reinterpret_cast<float4*>(dst) = make_float4(a, b, c, d);
+}
+template <>
+__device__ __forceinline__ void store_lp4<__nv_bfloat16>(__nv_bfloat16* dst, float a, float b, float c, float d) {
+  uint2 u;
+  u.x = float2_to_bf16x2(a, b);
+  u.y = float2_to_bf16x2(c, d);
+  *reinterpret_cast<uint2*>(dst) = u;
+}
+
+constexpr int kLn256Warps = 8;
+
+template <typename LP_T>
+__global__ void __launch_bounds__(kLn256Warps * 32) add_layernorm256_kernel(
+    const float* __restrict__ x, const float* __restrict__ residual, const float* __restrict__ gamma,
+    const float* __restrict__ beta, float eps, int64_t rows, float* __restrict__ out_f32,
+    LP_T* __restrict__ out_lp, const float* __restrict__ pos, LP_T* __restrict__ out_pos_lp) {
+  constexpr int C = 256;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kLn256Warps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int64_t o0 = row * C + lane * 4, o1 = o0 + 128;
+  float4 a = *reinterpret_cast<const float4*>(x + o0), b = *reinterpret_cast<const float4*>(x + o1);
+  if (residual) {
+    const float4 ra = *reinterpret_cast<const float4*>(residual + o0), rb = *reinterpret_cast<const float4*>(residual + o1);
+    a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
+    b.x += rb.x; b.y += rb.y; b.z += rb.z; b.w += rb.w;
+  }
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + lane * 4), gb = *reinterpret_cast<const float4*>(gamma + 128 + lane * 4);
+  const float4 ba = *reinterpret_cast<const float4*>(beta + lane * 4), bb = *reinterpret_cast<const float4*>(beta + 128 + lane * 4);
+  const float mean = warp_sum(((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * (1.0f / C);
+  a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
+  b.x -= mean; b.y -= mean; b.z -= mean; b.w -= mean;
+  const float sq = warp_sum(((a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w)) +
+                            ((b.x * b.x + b.y * b.y) + (b.z * b.z + b.w * b.w)));
+  const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+  a.x = a.x * rstd * ga.x + ba.x; a.y = a.y * rstd * ga.y + ba.y; a.z = a.z * rstd * ga.z + ba.z; a.w = a.w * rstd * ga.w + ba.w;
+  b.x = b.x * rstd * gb.x + bb.x; b.y = b.y * rstd * gb.y + bb.y; b.z = b.z * rstd * gb.z + bb.z; b.w = b.w * rstd * gb.w + bb.w;
+  if (out_f32) {
+    *reinterpret_cast<float4*>(out_f32 + o0) = a;
+    *reinterpret_cast<float4*>(out_f32 + o1) = b;
+  }
+  if (out_lp) {
+    store_lp4<LP_T>(out_lp + o0, a.x, a.y, a.z, a.w);
+    store_lp4<LP_T>(out_lp + o1, b.x, b.y, b.z, b.w);
+  }
+  if (out_pos_lp) {
+    const float4 pa = *reinterpret_cast<const float4*>(pos + o0), pb = *reinterpret_cast<const float4*>(pos + o1);
+    store_lp4<LP_T>(out_pos_lp + o0, a.x + pa.x, a.y + pa.y, a.z + pa.z, a.w + pa.w);
+    store_lp4<LP_T>(out_pos_lp + o1, b.x + pb.x, b.y + pb.y, b.z + pb.z, b.w + pb.w);
+  }
+}
+
 template <typename LP_T>
 __global__ void add_cast_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                 LP_T* __restrict__ out, int64_t n) {
@@ -183,6 +242,22 @@ extern "C" int moyolo_add_layernorm(const float* x, const float* residual, const
                  "add_layernorm: out_pos_lp requested without pos");
   if (rows == 0) return MOYOLO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool fast = C == 256 && aligned16(x) && aligned16(gamma) && aligned16(beta) &&
+                    (residual == nullptr || aligned16(residual)) && (out_f32 == nullptr || aligned16(out_f32)) &&
+                    (out_lp == nullptr || aligned16(out_lp)) && (pos == nullptr || aligned16(pos)) &&
+                    (out_pos_lp == nullptr || aligned16(out_pos_lp));
+  if (fast && (lp_dtype == MOYOLO_BF16 || lp_dtype == MOYOLO_F32)) {
+    const unsigned blocks = static_cast<unsigned>((rows + kLn256Warps - 1) / kLn256Warps);
+    if (lp_dtype == MOYOLO_BF16)
+      add_layernorm256_kernel<__nv_bfloat16><<<blocks, kLn256Warps * 32, 0, st>>>(
+          x, residual, gamma, beta, eps, rows, out_f32, static_cast<__nv_bfloat16*>(out_lp), pos,
+          static_cast<__nv_bfloat16*>(out_pos_lp));
+    else
+      add_layernorm256_kernel<float><<<blocks, kLn256Warps * 32, 0, st>>>(
+          x, residual, gamma, beta, eps, rows, out_f32, static_cast<float*>(out_lp), pos,
+          static_cast<float*>(out_pos_lp));
+    return check_launch("add_layernorm256_kernel");
+  }
   if (lp_dtype == MOYOLO_BF16) {
     add_layernorm_kernel<__nv_bfloat16><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
         x, residual, gamma, beta, eps, rows, C, out_f32, static_cast<__nv_bfloat16*>(out_lp), pos,

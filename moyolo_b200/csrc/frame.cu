@@ -13,6 +13,9 @@
 
 namespace moyolo {
 
+// control block shared by the frame kernels (device int32[8])
+enum { kCtrlAbort = 0, kCtrlFrame = 1, kCtrlCursor = 2, kCtrlTableOverflow = 3, kCtrlAbortRows = 4 };
+
 __device__ __forceinline__ float inv_sigmoid_(float x) {
   x = fminf(fmaxf(x, 0.0f), 1.0f);
   return logf(fmaxf(x, 1e-5f) / fmaxf(1.0f - x, 1e-5f));
@@ -26,12 +29,20 @@ __global__ void frame_assemble_kernel(int n_seq, int n_detect, int C, int cap, c
                                       const float* __restrict__ det_embed, const float* __restrict__ det_refer,
                                       float* __restrict__ x, float* __restrict__ refer_logit, float* __restrict__ pos,
                                       int64_t* __restrict__ ids, int64_t* __restrict__ dis,
-                                      int32_t* __restrict__ row_offsets, int num_pos_feats, float temperature) {
+                                      int32_t* __restrict__ row_offsets, int num_pos_feats, float temperature,
+                                      int rows_pad, int32_t* __restrict__ ctrl) {
   const int row = blockIdx.x;
+  // Speculative launch guard: the host picks rows_pad from the track counts of an EARLIER frame. If the
+  // real row count does not fit (or an earlier frame already aborted), every block consistently
+  // builds a detect-only frame (in bounds, results discarded) and the sticky abort flag tells the
+  // state-writing kernels of this and later frames to do nothing until the host re-launches.
+  int total_rows = 0;
+  for (int i = 0; i < n_seq; ++i) total_rows += n_tracks[i] + n_detect;
+  const bool aborted = ctrl != nullptr && (ctrl[kCtrlAbort] != 0 || total_rows > rows_pad);
   // locate the sequence of this row: offsets are the running sum of (T_s + n_detect)
   int s = 0, off = 0, T = 0;
   for (; s < n_seq; ++s) {
-    T = n_tracks[s];
+    T = aborted ? 0 : n_tracks[s];
     if (row < off + T + n_detect) break;
     off += T + n_detect;
   }
@@ -39,8 +50,12 @@ __global__ void frame_assemble_kernel(int n_seq, int n_detect, int C, int cap, c
     int acc = 0;
     row_offsets[0] = 0;
     for (int i = 0; i < n_seq; ++i) {
-      acc += n_tracks[i] + n_detect;
+      acc += (aborted ? 0 : n_tracks[i]) + n_detect;
       row_offsets[i + 1] = acc;
+    }
+    if (aborted && ctrl[kCtrlAbort] == 0) {
+      ctrl[kCtrlAbortRows] = total_rows;
+      ctrl[kCtrlAbort] = 1;
     }
   }
   float* xr = x + static_cast<int64_t>(row) * C;
@@ -109,8 +124,9 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
     const float* __restrict__ pos, const float* __restrict__ hs, const float* __restrict__ boxes,
     int32_t* __restrict__ n_active, int32_t* __restrict__ active_index, float* __restrict__ c_ref,
     float* __restrict__ c_pos, float* __restrict__ c_hs, float* __restrict__ c_box, int32_t* __restrict__ t_label,
-    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis) {
+    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis, const int32_t* __restrict__ ctrl) {
   __shared__ int s_warp[33];
+  if (ctrl != nullptr && ctrl[kCtrlAbort] != 0) return;  // aborted frame: leave the track state untouched
   const int s = blockIdx.x;
   const int off = row_offsets[s];
   const int n = row_offsets[s + 1] - off;
@@ -154,7 +170,9 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
 __global__ void frame_writeback_kernel(int C, int cap, const int32_t* __restrict__ row_offsets,
                                        const int32_t* __restrict__ n_active, const float* __restrict__ new_qpos,
                                        const float* __restrict__ c_box, float* __restrict__ t_qpos,
-                                       float* __restrict__ t_ref, int32_t* __restrict__ n_tracks) {
+                                       float* __restrict__ t_ref, int32_t* __restrict__ n_tracks,
+                                       const int32_t* __restrict__ ctrl) {
+  if (ctrl != nullptr && ctrl[kCtrlAbort] != 0) return;
   const int s = blockIdx.x;
   const int off = row_offsets[s];
   const int k = n_active[s];
@@ -168,6 +186,65 @@ __global__ void frame_writeback_kernel(int C, int cap, const int32_t* __restrict
   if (blockIdx.y == 0 && threadIdx.x == 0) n_tracks[s] = k;
 }
 
+// One CTA: (a) packs every row of the frame as [id, cx, cy, w, h, score, label, seq] fp32 into `frame_rows`
+// (the per-frame result a host reads back with ONE copy), (b) appends the tracked objects (ids >= 0,
+// the compacted order of frame_compact) to the device-resident track table
+// [seq, frame, id, cx, cy, w, h, score, cls] at the cursor held in ctrl, (c) advances the frame counter.
+__global__ void __launch_bounds__(256) frame_emit_kernel(
+    int n_seq, int rows_pad, const int32_t* __restrict__ row_offsets, const int64_t* __restrict__ ids,
+    const float* __restrict__ boxes, const float* __restrict__ scores, const int32_t* __restrict__ labels,
+    const int32_t* __restrict__ n_active, const int32_t* __restrict__ active_index,
+    const int32_t* __restrict__ seq_ids, float* __restrict__ frame_rows, float* __restrict__ table, int table_cap,
+    int32_t* __restrict__ ctrl) {
+  if (ctrl[kCtrlAbort] != 0) return;
+  const int total = row_offsets[n_seq];
+  for (int r = threadIdx.x; r < rows_pad; r += blockDim.x) {
+    float* o = frame_rows + static_cast<int64_t>(r) * 8;
+    if (r < total) {
+      int s = 0;
+      while (s + 1 < n_seq && r >= row_offsets[s + 1]) ++s;
+      const float4 b = *reinterpret_cast<const float4*>(boxes + static_cast<int64_t>(r) * 4);
+      *reinterpret_cast<float4*>(o) = make_float4(static_cast<float>(ids[r]), b.x, b.y, b.z);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(b.w, scores[r], static_cast<float>(labels[r]),
+                                                      static_cast<float>(seq_ids[s]));
+    } else {
+      *reinterpret_cast<float4*>(o) = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+      *reinterpret_cast<float4*>(o + 4) = make_float4(0.0f, 0.0f, 0.0f, -1.0f);
+    }
+  }
+  const int frame = ctrl[kCtrlFrame];
+  int base = ctrl[kCtrlCursor];
+  bool overflow = false;
+  for (int s = 0; s < n_seq; ++s) {
+    const int off = row_offsets[s], k = n_active[s];
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+      const int64_t src = off + active_index[off + j];
+      const int dst = base + j;
+      if (dst < table_cap) {
+        float* t = table + static_cast<int64_t>(dst) * 9;
+        t[0] = static_cast<float>(seq_ids[s]);
+        t[1] = static_cast<float>(frame);
+        t[2] = static_cast<float>(ids[src]);
+        t[3] = boxes[src * 4 + 0];
+        t[4] = boxes[src * 4 + 1];
+        t[5] = boxes[src * 4 + 2];
+        t[6] = boxes[src * 4 + 3];
+        t[7] = scores[src];
+        t[8] = static_cast<float>(labels[src]);
+      } else {
+        overflow = true;
+      }
+    }
+    base += k;
+  }
+  const int any_overflow = __syncthreads_or(overflow ? 1 : 0);  // also orders the reads of ctrl above
+  if (threadIdx.x == 0) {
+    ctrl[kCtrlCursor] = base < table_cap ? base : table_cap;
+    if (any_overflow) ctrl[kCtrlTableOverflow] = 1;
+    ctrl[kCtrlFrame] = frame + 1;
+  }
+}
+
 }  // namespace moyolo
 
 using namespace moyolo;
@@ -177,7 +254,7 @@ extern "C" int moyolo_frame_assemble(int n_seq, int n_detect, int C, int cap, co
                                      const int64_t* t_ids, const int64_t* t_dis, const float* class_embed,
                                      const float* det_embed, const float* det_refer, float* x, float* refer_logit,
                                      float* pos, int64_t* ids, int64_t* dis, int32_t* row_offsets, int64_t rows_pad,
-                                     int num_pos_feats, float temperature, moyolo_stream_t stream) {
+                                     int num_pos_feats, float temperature, int32_t* ctrl, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(n_tracks && t_ref && t_qpos && t_label && t_ids && t_dis && class_embed && det_embed && det_refer &&
                      x && refer_logit && pos && ids && dis && row_offsets,
                  MOYOLO_ERR_BAD_ARG, "frame_assemble: null pointer");
@@ -187,7 +264,7 @@ extern "C" int moyolo_frame_assemble(int n_seq, int n_detect, int C, int cap, co
   const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
   frame_assemble_kernel<<<static_cast<unsigned>(rows_pad), threads, 0, static_cast<cudaStream_t>(stream)>>>(
       n_seq, n_detect, C, cap, n_tracks, t_ref, t_qpos, t_label, t_ids, t_dis, class_embed, det_embed, det_refer, x,
-      refer_logit, pos, ids, dis, row_offsets, num_pos_feats, temperature);
+      refer_logit, pos, ids, dis, row_offsets, num_pos_feats, temperature, static_cast<int>(rows_pad), ctrl);
   return check_launch("frame_assemble_kernel");
 }
 
@@ -195,25 +272,44 @@ extern "C" int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* ro
                                     const int64_t* dis, const int32_t* labels, const float* refer_logit,
                                     const float* pos, const float* hs, const float* boxes, int32_t* n_active,
                                     int32_t* active_index, float* c_ref, float* c_pos, float* c_hs, float* c_box,
-                                    int32_t* t_label, int64_t* t_ids, int64_t* t_dis, moyolo_stream_t stream) {
+                                    int32_t* t_label, int64_t* t_ids, int64_t* t_dis, const int32_t* ctrl,
+                                    moyolo_stream_t stream) {
   MOYOLO_REQUIRE(row_offsets && ids && dis && labels && refer_logit && pos && hs && boxes && n_active &&
                      active_index && c_ref && c_pos && c_hs && c_box && t_label && t_ids && t_dis,
                  MOYOLO_ERR_BAD_ARG, "frame_compact: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_compact: bad sizes");
   frame_compact_kernel<<<n_seq, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
       C, cap, row_offsets, ids, dis, labels, refer_logit, pos, hs, boxes, n_active, active_index, c_ref, c_pos, c_hs,
-      c_box, t_label, t_ids, t_dis);
+      c_box, t_label, t_ids, t_dis, ctrl);
   return check_launch("frame_compact_kernel");
 }
 
 extern "C" int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,
                                       const float* new_qpos, const float* c_box, float* t_qpos, float* t_ref,
-                                      int32_t* n_tracks, moyolo_stream_t stream) {
+                                      int32_t* n_tracks, const int32_t* ctrl, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(row_offsets && n_active && new_qpos && c_box && t_qpos && t_ref && n_tracks, MOYOLO_ERR_BAD_ARG,
                  "frame_writeback: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_writeback: bad sizes");
   dim3 grid(n_seq, 8);
   frame_writeback_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, cap, row_offsets, n_active, new_qpos,
-                                                                             c_box, t_qpos, t_ref, n_tracks);
+                                                                             c_box, t_qpos, t_ref, n_tracks, ctrl);
   return check_launch("frame_writeback_kernel");
+}
+
+extern "C" int moyolo_frame_emit(int n_seq, int64_t rows_pad, const int32_t* row_offsets, const int64_t* ids,
+                                 const float* boxes, const float* scores, const int32_t* labels,
+                                 const int32_t* n_active, const int32_t* active_index, const int32_t* seq_ids,
+                                 float* frame_rows, float* table, int64_t table_cap, int32_t* ctrl,
+                                 moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(row_offsets && ids && boxes && scores && labels && n_active && active_index && seq_ids &&
+                     frame_rows && table && ctrl,
+                 MOYOLO_ERR_BAD_ARG, "frame_emit: null pointer");
+  MOYOLO_REQUIRE(n_seq > 0 && rows_pad > 0 && table_cap >= 0 && table_cap < (1ll << 31), MOYOLO_ERR_BAD_SHAPE,
+                 "frame_emit: bad sizes");
+  MOYOLO_REQUIRE(aligned16(boxes) && aligned16(frame_rows), MOYOLO_ERR_ALIGNMENT,
+                 "frame_emit: boxes / frame_rows must be 16-byte aligned");
+  frame_emit_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      n_seq, static_cast<int>(rows_pad), row_offsets, ids, boxes, scores, labels, n_active, active_index, seq_ids,
+      frame_rows, table, static_cast<int>(table_cap), ctrl);
+  return check_launch("frame_emit_kernel");
 }

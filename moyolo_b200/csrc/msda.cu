@@ -5,14 +5,18 @@
 // transformer.py:268-285) and the legacy im2col kernel (MOTR/models/ops/src/cuda/
 // ms_deform_im2col_cuda.cuh:237-299). Written from the arithmetic, not from that kernel:
 //
-//  * work item = one (query row, head). An item is owned by G = head_dim*sizeof(T)/16 adjacent
-//    lanes, each lane holding one 128-bit slice of the head's channels, so a whole value row of
-//    one head is fetched by ONE coalesced 16*G-byte request and there is no cross-lane reduction.
-//  * phase 1 (setup): the G lanes split the L*P sampling points, compute softmax (group shuffles),
-//    location, floor/fractions and stage, per corner, {spatial index | -1, bilinear*attention
-//    weight} in shared memory.
-//  * phase 2 (gather): every lane walks the staged 4*L*P corners, 8 independent 128-bit loads in
-//    flight per step, FMA into fp32 accumulators, one 128-bit (bf16) / 2x128-bit (fp32) store.
+//  * work item = one (query row, head), owned by ONE WARP. The head's value row (head_dim channels,
+//    64..256 bytes) is covered by G = head_dim*sizeof(T)/16 adjacent lanes holding one 128-bit slice
+//    each, so the warp splits into 32/G sub-groups that gather different bilinear corners at the same
+//    time: all 4*L*P corner rows of the item (48 at L=3, P=4) are in flight after ONE round of
+//    128-bit loads (6 per lane), which is what bounds the latency of the small per-frame launches.
+//  * phase 1 (setup): lane p owns sampling point p: softmax over the L*P logits with warp shuffles,
+//    sampling location, floor/fractions; per corner {spatial index | -1, bilinear*attention weight}
+//    is staged in shared memory (8 bytes per corner).
+//  * phase 2 (gather): sub-group s walks corners s, s+32/G, ...; fp32 FMAs into per-lane partial sums.
+//  * phase 3: recursive-halving shuffle reduction across the sub-groups (7 shuffles for bf16/32
+//    instead of 24 for a plain butterfly); afterwards the 32 lanes hold the head's output channels
+//    and issue one coalesced 64..256-byte store.
 //
 // The value tensor is read channel-last ([B, Lv, heads, head_dim], arbitrary position stride), i.e.
 // straight out of the value_proj GEMM — no NCHW transposes, no [B*H, Dh, Q, L*P] temporaries.
@@ -50,8 +54,9 @@ struct MsdaParams {
   int64_t out_row_stride;
 };
 
-constexpr int kGatherThreads = 64;
-constexpr int kMaxPointsPerLane = 8;  // L*P <= 8*G
+constexpr int kGatherWarps = 8;  // items (warps) per CTA
+constexpr int kGatherThreads = kGatherWarps * 32;
+constexpr int kMaxPointsPerLane = 2;  // L*P <= 64
 
 // Bilinear corner staging shared by both kernels: pixel = loc*size - 0.5, zero padding
 // (grid_sample align_corners=False / ms_deform_im2col_cuda.cuh:285-291 give the same numbers).
@@ -102,51 +107,49 @@ __device__ __forceinline__ void fused_location(const MsdaParams& p, int64_t row,
   }
 }
 
-template <typename VT, int DH, bool FUSED>
+// U = corner rounds kept in flight per loop trip (all of them when 4*L*P == U*32/G).
+template <typename VT, int DH, bool FUSED, int U>
 __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaParams p) {
-  constexpr int G = DH * static_cast<int>(sizeof(VT)) / 16;  // lanes per item
+  constexpr int G = DH * static_cast<int>(sizeof(VT)) / 16;  // lanes per value row
   constexpr int CH = 16 / static_cast<int>(sizeof(VT));      // channels per lane
-  constexpr int ITEMS = kGatherThreads / G;
-  static_assert(G >= 4 && G <= 32 && (G & (G - 1)) == 0, "head row must be 64..512 bytes");
+  constexpr int NSG = 32 / G;                                // sub-groups per warp
+  static_assert(G >= 4 && G <= 16 && CH >= NSG, "head row must be 64..256 bytes");
 
   extern __shared__ __align__(16) int smem_i[];
   const int LP = p.lv.n * p.n_points;
   const int NU = LP * 4;
-  const int NUp = (NU + 7) & ~7;
+  const int NUp = (NU + NSG * U - 1) / (NSG * U) * (NSG * U);
 
-  const int item_local = threadIdx.x / G;
-  const int sub = threadIdx.x % G;
-  const int64_t item = static_cast<int64_t>(blockIdx.x) * ITEMS + item_local;
-  const bool valid = item < p.rows * p.n_heads;
-  const int64_t row = valid ? item / p.n_heads : 0;
-  const int head = valid ? static_cast<int>(item % p.n_heads) : 0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t item = static_cast<int64_t>(blockIdx.x) * kGatherWarps + warp;
+  if (item >= p.rows * p.n_heads) return;  // warp-uniform
+  const int64_t row = item / p.n_heads;
+  const int head = static_cast<int>(item % p.n_heads);
 
-  int* s_pos = smem_i + item_local * NUp * 2;
+  int* s_pos = smem_i + warp * NUp * 2;
   float* s_w = reinterpret_cast<float*>(s_pos + NUp);
 
-  // ---------------- phase 1: per-point setup, points split across the G lanes ----------------
+  // ---------------- phase 1: lane `l` owns sampling points l and l + 32 ----------------
   float aw[kMaxPointsPerLane];
   if (FUSED) {
     float lg[kMaxPointsPerLane];
     float m = -INFINITY;
 #pragma unroll
     for (int i = 0; i < kMaxPointsPerLane; ++i) {
-      const int pt = sub + i * G;
-      lg[i] = (valid && pt < LP) ? p.logits[row * p.logits_row_stride + head * LP + pt] : -INFINITY;
+      const int pt = lane + i * 32;
+      lg[i] = pt < LP ? __ldg(p.logits + row * p.logits_row_stride + head * LP + pt) : -INFINITY;
       m = fmaxf(m, lg[i]);
     }
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    m = warp_max(m);
     if (p.softmax_mode == MOYOLO_SOFTMAX_PLUS1) m = 0.0f;  // exp(x)/(1+sum exp(x)), no shift
     float s = 0.0f;
 #pragma unroll
     for (int i = 0; i < kMaxPointsPerLane; ++i) {
-      const int pt = sub + i * G;
-      aw[i] = (valid && pt < LP) ? expf(lg[i] - m) : 0.0f;
+      const int pt = lane + i * 32;
+      aw[i] = pt < LP ? expf(lg[i] - m) : 0.0f;
       s += aw[i];
     }
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    s = warp_sum(s);
     if (p.softmax_mode == MOYOLO_SOFTMAX_PLUS1) s += 1.0f;
     const float inv = 1.0f / s;
 #pragma unroll
@@ -154,55 +157,50 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaP
   }
 #pragma unroll
   for (int i = 0; i < kMaxPointsPerLane; ++i) {
-    const int pt = sub + i * G;
+    const int pt = lane + i * 32;
     if (pt < LP) {
-      Corners c;
-      if (valid) {
-        const int level = pt / p.n_points;
-        float lx, ly, a;
-        if (FUSED) {
-          fused_location(p, row, head, pt, level, &lx, &ly);
-          a = aw[i];
-        } else {
-          const int64_t idx = (row * p.n_heads + head) * LP + pt;
-          const float* loc = static_cast<const float*>(p.loc);
-          lx = loc[idx * 2];
-          ly = loc[idx * 2 + 1];
-          a = static_cast<const float*>(p.weights)[idx];
-        }
-        c = make_corners(lx, ly, p.lv.h[level], p.lv.w[level], p.lv.start[level], a);
+      const int level = pt / p.n_points;
+      float lx, ly, a;
+      if (FUSED) {
+        fused_location(p, row, head, pt, level, &lx, &ly);
+        a = aw[i];
       } else {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { c.pos[k] = -1; c.w[k] = 0.0f; }
+        const int64_t idx = (row * p.n_heads + head) * LP + pt;
+        const float2 l2 = __ldg(reinterpret_cast<const float2*>(p.loc) + idx);
+        lx = l2.x;
+        ly = l2.y;
+        a = __ldg(static_cast<const float*>(p.weights) + idx);
       }
+      const Corners c = make_corners(lx, ly, p.lv.h[level], p.lv.w[level], p.lv.start[level], a);
       *reinterpret_cast<int4*>(s_pos + pt * 4) = make_int4(c.pos[0], c.pos[1], c.pos[2], c.pos[3]);
       *reinterpret_cast<float4*>(s_w + pt * 4) = make_float4(c.w[0], c.w[1], c.w[2], c.w[3]);
     }
   }
-  for (int u = NU + sub; u < NUp; u += G) { s_pos[u] = -1; s_w[u] = 0.0f; }
+  for (int u = NU + lane; u < NUp; u += 32) { s_pos[u] = -1; s_w[u] = 0.0f; }
   __syncwarp();
 
-  // ---------------- phase 2: gather ----------------
+  // ---------------- phase 2: gather, sub-group sg takes corners sg, sg + NSG, ... ----------------
   float acc[CH];
 #pragma unroll
   for (int k = 0; k < CH; ++k) acc[k] = 0.0f;
 
+  const int sg = lane / G, sub = lane % G;
   const int b = batch_of_row(row, p.row_offsets, p.batch, p.rows_per_batch);
   const VT* base = static_cast<const VT*>(p.value) + static_cast<int64_t>(b) * p.value_batch_stride +
                    head * DH + sub * CH;
   const int64_t ps = p.value_pos_stride;
 
-  for (int u0 = 0; u0 < NUp; u0 += 8) {
-    uint4 v[8];
-    float w[8];
+  for (int u0 = sg; u0 < NUp; u0 += NSG * U) {
+    uint4 v[U];
+    float w[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int pos = s_pos[u0 + i];
-      w[i] = s_w[u0 + i];
+    for (int i = 0; i < U; ++i) {
+      const int pos = s_pos[u0 + i * NSG];
+      w[i] = s_w[u0 + i * NSG];
       v[i] = (pos >= 0) ? ldg128(base + pos * ps) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < U; ++i) {
       if constexpr (sizeof(VT) == 2) {
         const float2 a0 = bf16x2_to_float2(v[i].x), a1 = bf16x2_to_float2(v[i].y);
         const float2 a2 = bf16x2_to_float2(v[i].z), a3 = bf16x2_to_float2(v[i].w);
@@ -223,17 +221,41 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaP
     }
   }
 
-  if (valid) {
-    VT* o = static_cast<VT*>(p.out) + row * p.out_row_stride + head * DH + sub * CH;
-    if constexpr (sizeof(VT) == 2) {
-      uint4 r;
-      r.x = float2_to_bf16x2(acc[0], acc[1]);
-      r.y = float2_to_bf16x2(acc[2], acc[3]);
-      r.z = float2_to_bf16x2(acc[4], acc[5]);
-      r.w = float2_to_bf16x2(acc[6], acc[7]);
-      *reinterpret_cast<uint4*>(o) = r;
+  // ---------------- phase 3: recursive-halving reduction across the sub-groups ----------------
+  // Each round the lane keeps one half of its channels and receives the partner's partial sums for
+  // that half, so after log2(NSG) rounds every lane holds CH/NSG finished channels.
+  int ch = 0;
+  {
+    int n = CH;
+#pragma unroll
+    for (int off = 16; off >= G; off >>= 1) {
+      n >>= 1;
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < CH / 2; ++i) {
+        if (i < n) {
+          const float send = up ? acc[i] : acc[i + n];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+          acc[i] = (up ? acc[i + n] : acc[i]) + recv;
+        }
+      }
+      ch += up ? n : 0;
+    }
+  }
+  constexpr int NF = CH / NSG;  // finished channels per lane: 1 or 2
+  VT* o = static_cast<VT*>(p.out) + row * p.out_row_stride + head * DH + sub * CH + ch;
+  if constexpr (sizeof(VT) == 2) {
+    if constexpr (NF == 1) {
+      const float hi = __shfl_xor_sync(0xffffffffu, acc[0], G);  // odd-channel partner (last round's bit)
+      if ((lane & G) == 0) *reinterpret_cast<uint32_t*>(o) = float2_to_bf16x2(acc[0], hi);
     } else {
-      *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<uint32_t*>(o) = float2_to_bf16x2(acc[0], acc[1]);
+    }
+  } else {
+    if constexpr (NF == 1) {
+      *o = acc[0];
+    } else {
+      *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
     }
   }
 }
@@ -307,18 +329,27 @@ __global__ void msda_generic_kernel(const MsdaParams p, int head_dim) {
 }
 
 
+template <typename VT, int DH, bool FUSED, int U>
+static int launch_fast_u(const MsdaParams& p, cudaStream_t st) {
+  constexpr int G = DH * static_cast<int>(sizeof(VT)) / 16;
+  constexpr int NSG = 32 / G;
+  const int NU = p.lv.n * p.n_points * 4;
+  const int NUp = (NU + NSG * U - 1) / (NSG * U) * (NSG * U);
+  const size_t smem = static_cast<size_t>(kGatherWarps) * NUp * 8;
+  const int64_t items = p.rows * p.n_heads;
+  const int64_t blocks = (items + kGatherWarps - 1) / kGatherWarps;
+  if (blocks == 0) return MOYOLO_OK;
+  msda_gather_kernel<VT, DH, FUSED, U><<<static_cast<unsigned>(blocks), kGatherThreads, smem, st>>>(p);
+  return check_launch("msda_gather_kernel");
+}
+
 template <typename VT, int DH, bool FUSED>
 static int launch_fast(const MsdaParams& p, cudaStream_t st) {
-  constexpr int G = DH * static_cast<int>(sizeof(VT)) / 16;
-  constexpr int ITEMS = kGatherThreads / G;
-  const int LP = p.lv.n * p.n_points;
-  const int NUp = (LP * 4 + 7) & ~7;
-  const size_t smem = static_cast<size_t>(ITEMS) * NUp * 8;
-  const int64_t items = p.rows * p.n_heads;
-  const int64_t blocks = (items + ITEMS - 1) / ITEMS;
-  if (blocks == 0) return MOYOLO_OK;
-  msda_gather_kernel<VT, DH, FUSED><<<static_cast<unsigned>(blocks), kGatherThreads, smem, st>>>(p);
-  return check_launch("msda_gather_kernel");
+  constexpr int NSG = 32 / (DH * static_cast<int>(sizeof(VT)) / 16);
+  const int rounds = (p.lv.n * p.n_points * 4 + NSG - 1) / NSG;  // corner rounds per sub-group
+  // keep every round in flight when there are few (6 at L=3,P=4 bf16); otherwise trips of 8
+  if (rounds % 6 == 0 && rounds <= 12) return launch_fast_u<VT, DH, FUSED, 6>(p, st);
+  return launch_fast_u<VT, DH, FUSED, 8>(p, st);
 }
 
 template <bool FUSED>
@@ -328,8 +359,8 @@ static int dispatch(const MsdaParams& p, int value_dtype, int aux_dtype, int hea
   const bool fast_ok = (value_dtype != MOYOLO_F64) && (aux_dtype == MOYOLO_F32) &&
                        (head_dim == 32 || head_dim == 64) && aligned16(p.value) && aligned16(p.out) &&
                        (p.value_pos_stride * esz) % 16 == 0 && (p.value_batch_stride * esz) % 16 == 0 &&
-                       (p.out_row_stride * esz) % 16 == 0 &&
-                       LP <= kMaxPointsPerLane * (head_dim * esz / 16) && LP * 4 * 8 * 16 <= 48 * 1024;
+                       (p.out_row_stride * esz) % 16 == 0 && LP <= 32 * kMaxPointsPerLane &&
+                       (FUSED || (reinterpret_cast<uintptr_t>(p.loc) & 7u) == 0);
   if (fast_ok) {
     if (value_dtype == MOYOLO_BF16) {
       return head_dim == 32 ? launch_fast<__nv_bfloat16, 32, FUSED>(p, st)

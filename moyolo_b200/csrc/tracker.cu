@@ -76,8 +76,9 @@ __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
     const float* __restrict__ scores, const float* __restrict__ boxes, int64_t* __restrict__ obj_idxes,
     int64_t* __restrict__ disappear_time, int64_t* __restrict__ counters, int n, float score_thresh,
     float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace,
-    const int32_t* __restrict__ row_offsets, int64_t ws_stride) {
+    const int32_t* __restrict__ row_offsets, int64_t ws_stride, const int32_t* __restrict__ ctrl) {
   __shared__ int s_warp[33];
+  if (ctrl != nullptr && ctrl[0] != 0) return;  // aborted speculative frame (see frame.cu): ID counters untouched
   if (row_offsets != nullptr) {  // batched: one CTA per sequence, rows [row_offsets[s], row_offsets[s+1])
     const int seq = blockIdx.x;
     const int off = row_offsets[seq];
@@ -249,7 +250,7 @@ extern "C" int moyolo_track_assign(const float* scores, const float* boxes, int6
   if (n == 0) return MOYOLO_OK;
   track_assign_kernel<<<1, kTrkThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       scores, boxes, obj_idxes, disappear_time, counters, static_cast<int>(n), score_thresh, filter_thresh,
-      miss_tolerance, iou_thresh, workspace, nullptr, 0);
+      miss_tolerance, iou_thresh, workspace, nullptr, 0, nullptr);
   return check_launch("track_assign_kernel");
 }
 
@@ -257,14 +258,14 @@ extern "C" int moyolo_track_assign_batched(const float* scores, const float* box
                                            int64_t* disappear_time, int64_t* counters, const int32_t* row_offsets,
                                            int n_seq, int64_t max_rows_per_seq, float score_thresh,
                                            float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace,
-                                           moyolo_stream_t stream) {
+                                           const int32_t* ctrl, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(scores && boxes && obj_idxes && disappear_time && counters && row_offsets && workspace,
                  MOYOLO_ERR_BAD_ARG, "track_assign_batched: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && max_rows_per_seq > 0 && max_rows_per_seq <= kTrkMaxN, MOYOLO_ERR_BAD_SHAPE,
                  "track_assign_batched: max_rows_per_seq must be in (0, %d]", kTrkMaxN);
   track_assign_kernel<<<n_seq, kTrkThreads, 0, static_cast<cudaStream_t>(stream)>>>(
       scores, boxes, obj_idxes, disappear_time, counters, 0, score_thresh, filter_thresh, miss_tolerance, iou_thresh,
-      workspace, row_offsets, moyolo_track_workspace_bytes(max_rows_per_seq));
+      workspace, row_offsets, moyolo_track_workspace_bytes(max_rows_per_seq), ctrl);
   return check_launch("track_assign_kernel(batched)");
 }
 

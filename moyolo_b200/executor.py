@@ -204,3 +204,57 @@ def pos_mlp_forward(mp: MlpPack, refer, dt):
     first = mp.hidden[0]
     h = ops.linear_k4_relu(refer, mp.first_w_f32, first.b, dt)
     return ops.linear(h, mp.last_lp.w, mp.last_lp.b, out_dtype=torch.float32, engine=_GEMM_ENGINE)
+
+
+# ------------------------------------------------------------------------------------------------
+# Workspace variants used by the frame engine (moyolo_b200.tracker): identical kernel chain, but every
+# output goes to a pre-allocated FrameWorkspace buffer so a frame is allocation-free and its box head /
+# value projection can run on side branches of the frame graph.
+# ------------------------------------------------------------------------------------------------
+def offlog_width(spec) -> int:
+    """Columns of the fused sampling_offsets|attention_weights GEMM: H*L*P*2 + H*L*P."""
+    return spec.n_heads * spec.n_levels * spec.n_points * 3
+
+
+def qkv_proj(xq_lp, x_lp, w, b, out, C: int, eng) -> None:
+    """nn.MultiheadAttention in-projection with q = k = x + pos, v = x (transformer.py:637-638):
+    out[:, :2C] = xq . [Wq;Wk]^T, out[:, 2C:] = x . Wv^T."""
+    ops.linear(xq_lp, w[:2 * C], b[:2 * C], out=out[:, :2 * C], engine=eng)
+    ops.linear(x_lp, w[2 * C:], b[2 * C:], out=out[:, 2 * C:], engine=eng)
+
+
+def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offsets, row_offsets_host, pos_cur,
+                 pos_next, dt, before_gather=None) -> None:
+    """One post-norm decoder layer on workspace buffers. In: ws.x (fp32 residual), ws.x_lp, ws.xq_lp
+    (= x + pos operand). Out: the same three for the next layer (xq only when pos_next is given)."""
+    C = pk.C
+    eng = _GEMM_ENGINE
+    f32 = dt == torch.float32
+    ops.linear(ws.xq_lp, pk.qk.w, pk.qk.b, out=ws.qkv[:, :2 * C], engine=eng)
+    ops.linear(ws.x_lp, pk.v.w, pk.v.b, out=ws.qkv[:, 2 * C:], engine=eng)
+    ops.self_attention(ws.qkv[:, :C], ws.qkv[:, C:2 * C], ws.qkv[:, 2 * C:], row_offsets, row_offsets_host,
+                       pk.n_heads, None, out=ws.att)
+    ops.linear(ws.att, pk.o.w, pk.o.b, out=ws.t, engine=eng)
+    g, b_, e = pk.norms[0]
+    ops.add_layernorm(ws.t, ws.x, g, b_, e, out_f32=ws.x1, pos=pos_cur, out_pos=ws.x1q_lp)
+    pkm = pk.msda
+    ops.linear(ws.x1q_lp, pkm.offlog.w, pkm.offlog.b, out=ws.ol, engine=eng)
+    if before_gather is not None:
+        before_gather()
+    ops.msda_fused(value_view, shapes, ws.ol[:, :pkm.n_off], ws.ol[:, pkm.n_off:], refer, pkm.n_heads, pkm.n_points,
+                   batch, pkm.softmax_mode, row_offsets, out=ws.g)
+    ops.linear(ws.g, pkm.out.w, pkm.out.b, out=ws.t, engine=eng)
+    g, b_, e = pk.norms[1]
+    ops.add_layernorm(ws.t, ws.x1, g, b_, e, out_f32=ws.x2, out_lp=None if f32 else ws.x2_lp)
+    ops.linear(ws.x2_lp, pk.ffn1.w, pk.ffn1.b, relu=True, out=ws.h, engine=eng)
+    ops.linear(ws.h, pk.ffn2.w, pk.ffn2.b, out=ws.t, engine=eng)
+    g, b_, e = pk.norms[2]
+    ops.add_layernorm(ws.t, ws.x2, g, b_, e, out_f32=ws.x, out_lp=None if f32 else ws.x_lp, pos=pos_next,
+                      out_pos=ws.xq_lp if pos_next is not None else None)
+
+
+def bbox_head_ws(mp: MlpPack, ws, refer_in, refer_out) -> None:
+    """sigmoid(MLP3(x) + inverse_sigmoid(refer)) (transformer.py:709) from ws.x_lp into refer_out."""
+    ops.linear(ws.x_lp, mp.hidden[0].w, mp.hidden[0].b, relu=True, out=ws.bh1, engine=_GEMM_ENGINE)
+    ops.linear(ws.bh1, mp.hidden[1].w, mp.hidden[1].b, relu=True, out=ws.bh2, engine=_GEMM_ENGINE)
+    ops.box_refine(ws.bh2, mp.last_w, mp.last_b, refer_in, out=refer_out)

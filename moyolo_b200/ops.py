@@ -164,14 +164,21 @@ def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, row_offset
 
 def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor,
                   eps: float, want_f32: bool = True, want_lp: bool = False,
-                  lp_dtype: Optional[torch.dtype] = None, pos: Optional[torch.Tensor] = None):
-    """LayerNorm(x + residual); returns (out_f32 | None, out_lp | None, out_plus_pos_lp | None)."""
+                  lp_dtype: Optional[torch.dtype] = None, pos: Optional[torch.Tensor] = None,
+                  out_f32: Optional[torch.Tensor] = None, out_lp: Optional[torch.Tensor] = None,
+                  out_pos: Optional[torch.Tensor] = None):
+    """LayerNorm(x + residual); returns (out_f32 | None, out_lp | None, out_plus_pos_lp | None).
+    Pre-allocated outputs may be passed (out_f32 may alias `residual`: every row is read before written)."""
     _cuda(x, residual, gamma, beta, pos)
     R, Cc = x.shape
-    lp_dtype = lp_dtype or torch.float32
-    out_f32 = torch.empty(R, Cc, dtype=torch.float32, device=x.device) if want_f32 else None
-    out_lp = torch.empty(R, Cc, dtype=lp_dtype, device=x.device) if want_lp else None
-    out_pos = torch.empty(R, Cc, dtype=lp_dtype, device=x.device) if pos is not None else None
+    lp_dtype = lp_dtype or (out_lp.dtype if out_lp is not None else (out_pos.dtype if out_pos is not None
+                                                                      else torch.float32))
+    if out_f32 is None and want_f32:
+        out_f32 = torch.empty(R, Cc, dtype=torch.float32, device=x.device)
+    if out_lp is None and want_lp:
+        out_lp = torch.empty(R, Cc, dtype=lp_dtype, device=x.device)
+    if out_pos is None and pos is not None:
+        out_pos = torch.empty(R, Cc, dtype=lp_dtype, device=x.device)
     _count(1)
     _lib.check(_lib.lib().moyolo_add_layernorm(
         x.data_ptr(), _ptr(residual), gamma.data_ptr(), beta.data_ptr(), float(eps), R, Cc, _ptr(out_f32),
@@ -179,9 +186,11 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], gamma: torc
     return out_f32, out_lp, out_pos
 
 
-def add_cast(a: torch.Tensor, b: Optional[torch.Tensor], dtype: torch.dtype) -> torch.Tensor:
+def add_cast(a: torch.Tensor, b: Optional[torch.Tensor], dtype: torch.dtype,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(a, b)
-    out = torch.empty(a.shape, dtype=dtype, device=a.device)
+    if out is None:
+        out = torch.empty(a.shape, dtype=dtype, device=a.device)
     _count(1)
     _lib.check(_lib.lib().moyolo_add_cast(a.data_ptr(), _ptr(b), out.data_ptr(), _DT[dtype], a.numel(), _stream()))
     return out
@@ -201,23 +210,27 @@ def box_refine(h: torch.Tensor, w3: torch.Tensor, b3: torch.Tensor, ref: torch.T
     return out
 
 
-def score_head(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_scores: bool = True):
+def score_head(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_scores: bool = True, out=None):
+    """out: optional (logits [R,nc] f32, scores [R] f32, labels [R] i32) pre-allocated."""
     _cuda(x, w, b)
     R, K = x.shape
     nc = w.shape[0]
-    logits = torch.empty(R, nc, dtype=torch.float32, device=x.device)
-    scores = torch.empty(R, dtype=torch.float32, device=x.device) if want_scores else None
-    labels = torch.empty(R, dtype=torch.int32, device=x.device) if want_scores else None
+    if out is not None:
+        logits, scores, labels = out
+    else:
+        logits = torch.empty(R, nc, dtype=torch.float32, device=x.device)
+        scores = torch.empty(R, dtype=torch.float32, device=x.device) if want_scores else None
+        labels = torch.empty(R, dtype=torch.int32, device=x.device) if want_scores else None
     _count(1)
     _lib.check(_lib.lib().moyolo_score_head(x.data_ptr(), x.stride(0), _dt(x), w.data_ptr(), b.data_ptr(),
                                             logits.data_ptr(), _ptr(scores), _ptr(labels), R, K, nc, _stream()))
     return logits, scores, labels
 
 
-def sigmoid(x: torch.Tensor) -> torch.Tensor:
+def sigmoid(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(x)
     x = x.contiguous()
-    y = torch.empty_like(x)
+    y = torch.empty_like(x) if out is None else out
     _count(1)
     _lib.check(_lib.lib().moyolo_sigmoid(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
     return y
@@ -232,12 +245,14 @@ def inverse_sigmoid(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def pos2posemb(pos: torch.Tensor, num_pos_feats: int = 64, temperature: float = 10000.0) -> torch.Tensor:
+def pos2posemb(pos: torch.Tensor, num_pos_feats: int = 64, temperature: float = 10000.0,
+               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     _cuda(pos)
     pos = pos.contiguous()
     n_coord = pos.shape[-1]
     rows = pos.numel() // n_coord
-    emb = torch.empty(*pos.shape[:-1], n_coord * num_pos_feats, dtype=torch.float32, device=pos.device)
+    emb = out if out is not None else torch.empty(*pos.shape[:-1], n_coord * num_pos_feats, dtype=torch.float32,
+                                                  device=pos.device)
     _count(1)
     _lib.check(_lib.lib().moyolo_pos2posemb(pos.data_ptr(), emb.data_ptr(), rows, n_coord, num_pos_feats,
                                             float(temperature), _stream()))
@@ -289,7 +304,8 @@ def track_compact(obj_idxes: torch.Tensor, fields: Sequence[torch.Tensor], outs:
 
 
 def track_assign_batched(scores, boxes, ids, dis, counters, row_offsets, n_seq: int, max_rows_per_seq: int,
-                         workspace, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, iou_thresh=0.8) -> None:
+                         workspace, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, iou_thresh=0.8,
+                         ctrl=None) -> None:
     """RuntimeTrackerBase.update for every lock-step sequence in one launch (one CTA per sequence)."""
     _cuda(scores, boxes, ids, dis, counters, row_offsets, workspace)
     assert workspace.numel() * workspace.element_size() >= n_seq * track_workspace_bytes(max_rows_per_seq)
@@ -297,32 +313,42 @@ def track_assign_batched(scores, boxes, ids, dis, counters, row_offsets, n_seq: 
     _lib.check(_lib.lib().moyolo_track_assign_batched(
         scores.data_ptr(), boxes.data_ptr(), ids.data_ptr(), dis.data_ptr(), counters.data_ptr(),
         row_offsets.data_ptr(), n_seq, max_rows_per_seq, float(score_thresh), float(filter_thresh),
-        int(miss_tolerance), float(iou_thresh), workspace.data_ptr(), _stream()))
+        int(miss_tolerance), float(iou_thresh), workspace.data_ptr(), _ptr(ctrl), _stream()))
 
 
 def frame_assemble(n_seq, n_detect, C, cap, n_tracks, t_ref, t_qpos, t_label, t_ids, t_dis, class_embed, det_embed,
                    det_refer, x, refer_logit, pos, ids, dis, row_offsets, rows_pad, num_pos_feats=64,
-                   temperature=10000.0) -> None:
+                   temperature=10000.0, ctrl=None) -> None:
     _count(1)
     _lib.check(_lib.lib().moyolo_frame_assemble(
         n_seq, n_detect, C, cap, n_tracks.data_ptr(), t_ref.data_ptr(), t_qpos.data_ptr(), t_label.data_ptr(),
         t_ids.data_ptr(), t_dis.data_ptr(), class_embed.data_ptr(), det_embed.data_ptr(), det_refer.data_ptr(),
         x.data_ptr(), refer_logit.data_ptr(), pos.data_ptr(), ids.data_ptr(), dis.data_ptr(), row_offsets.data_ptr(),
-        rows_pad, num_pos_feats, float(temperature), _stream()))
+        rows_pad, num_pos_feats, float(temperature), _ptr(ctrl), _stream()))
 
 
 def frame_compact(n_seq, C, cap, row_offsets, ids, dis, labels, refer_logit, pos, hs, boxes, n_active, active_index,
-                  c_ref, c_pos, c_hs, c_box, t_label, t_ids, t_dis) -> None:
+                  c_ref, c_pos, c_hs, c_box, t_label, t_ids, t_dis, ctrl=None) -> None:
     _count(1)
     _lib.check(_lib.lib().moyolo_frame_compact(
         n_seq, C, cap, row_offsets.data_ptr(), ids.data_ptr(), dis.data_ptr(), labels.data_ptr(),
         refer_logit.data_ptr(), pos.data_ptr(), hs.data_ptr(), boxes.data_ptr(), n_active.data_ptr(),
         active_index.data_ptr(), c_ref.data_ptr(), c_pos.data_ptr(), c_hs.data_ptr(), c_box.data_ptr(),
-        t_label.data_ptr(), t_ids.data_ptr(), t_dis.data_ptr(), _stream()))
+        t_label.data_ptr(), t_ids.data_ptr(), t_dis.data_ptr(), _ptr(ctrl), _stream()))
 
 
-def frame_writeback(n_seq, C, cap, row_offsets, n_active, new_qpos, c_box, t_qpos, t_ref, n_tracks) -> None:
+def frame_writeback(n_seq, C, cap, row_offsets, n_active, new_qpos, c_box, t_qpos, t_ref, n_tracks, ctrl=None) -> None:
     _count(1)
     _lib.check(_lib.lib().moyolo_frame_writeback(
         n_seq, C, cap, row_offsets.data_ptr(), n_active.data_ptr(), new_qpos.data_ptr(), c_box.data_ptr(),
-        t_qpos.data_ptr(), t_ref.data_ptr(), n_tracks.data_ptr(), _stream()))
+        t_qpos.data_ptr(), t_ref.data_ptr(), n_tracks.data_ptr(), _ptr(ctrl), _stream()))
+
+
+def frame_emit(n_seq, rows_pad, row_offsets, ids, boxes, scores, labels, n_active, active_index, seq_ids, frame_rows,
+               table, ctrl) -> None:
+    """Per-frame packed result rows + append of the tracked objects to the device track table."""
+    _count(1)
+    _lib.check(_lib.lib().moyolo_frame_emit(
+        n_seq, rows_pad, row_offsets.data_ptr(), ids.data_ptr(), boxes.data_ptr(), scores.data_ptr(),
+        labels.data_ptr(), n_active.data_ptr(), active_index.data_ptr(), seq_ids.data_ptr(), frame_rows.data_ptr(),
+        table.data_ptr(), table.shape[0], ctrl.data_ptr(), _stream()))

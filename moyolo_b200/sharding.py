@@ -93,27 +93,32 @@ def run_sharded(make_engine, sequences: Sequence[Dict], rank: int, world_size: i
     """Track every sequence; return the gathered table on all ranks.
 
     sequences[i] = {"n_frames": int, "frames": callable t -> (feats, det_embed, det_refer)}.
-    make_engine(n_seq) -> object with .reset() and .step(feats [S,..], det_embed, det_refer) returning a
-    list of per-sequence dicts (moyolo_b200.tracker.TrackEngine).
-    Sequences that end early keep stepping on their last frame but stop recording (lock-step batch).
+    make_engine(n_seq) -> moyolo_b200.tracker.TrackEngine (or an object with the same reset /
+    set_seq_ids / submit / track_table interface). The engine appends the tracked objects of every
+    frame to a device-resident table itself, so the frame loop below only enqueues work.
+    Sequences that end early keep stepping on their last frame (lock-step batch); their surplus rows
+    are dropped when the table is read.
     """
     counts = [s["n_frames"] for s in sequences]
     mine = lpt_assign(counts, world_size)[rank]
-    rows: List[torch.Tensor] = []
+    tables: List[torch.Tensor] = []
     device = None
     for grp in lockstep_groups(mine, counts, max_in_flight):
         eng = make_engine(len(grp))
         eng.reset()
+        eng.set_seq_ids(grp)
         for t in range(max(counts[i] for i in grp)):
             batch = [sequences[i]["frames"](min(t, counts[i] - 1)) for i in grp]
             feats = torch.stack([b[0] for b in batch])
             de = torch.stack([b[1] for b in batch])
             dr = torch.stack([b[2] for b in batch])
             device = feats.device
-            outs = eng.step(feats, de, dr)
-            for slot, i in enumerate(grp):
-                if t < counts[i]:
-                    o = outs[slot]
-                    rows.append(pack_track_rows(i, t, o["ids"], o["boxes"], o["scores"], o["labels"]))
-    local = finalize_rows(rows, device or torch.device("cpu"))
+            eng.submit(feats, de, dr, want_rows=False, sync_inputs=True)
+        tab = eng.track_table()
+        n_frames = torch.as_tensor(counts, dtype=torch.float32, device=tab.device)
+        if tab.shape[0]:
+            tab = tab[tab[:, 1] < n_frames[tab[:, 0].long()]]
+        tables.append(tab.clone())
+    local = torch.cat(tables, 0) if tables else torch.zeros(0, ROW_WIDTH, dtype=torch.float32,
+                                                            device=device or torch.device("cpu"))
     return gather_track_rows(local, group)

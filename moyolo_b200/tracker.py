@@ -11,11 +11,21 @@ Mirrors the frame semantics of MOTRTrack.forward / _post_process_single_image
     MOTR/models/qim.py:184-187) and QIM._update_track_embedding (qim.py:251-301) produce the next
     frame's track queries.
 
-Several independent sequences run in lock-step as one ragged batch; frames of one
-sequence are strictly ordered. ALL state lives on the device in fixed-capacity arrays with the
-per-sequence track counts in device memory, so the launch shapes of a frame depend only on the
-padded row count: each padded size is captured once as a CUDA graph and replayed. The host reads
-back one int32 per sequence and frame (the active-track count that selects the next graph).
+Execution model (DESIGN.md "Frame pipeline"):
+  * Several independent sequences run in lock-step as one ragged batch; frames of
+    one sequence are strictly ordered.
+  * ALL state lives on the device in fixed-capacity arrays with the per-sequence track counts in
+    device memory, and every intermediate of a frame lives in a pre-allocated per-plan workspace, so
+    the launches of a frame depend only on the padded row count: each (padded size, input slot) is
+    captured once as a CUDA graph and replayed. Inside the graph the all-layers value projection and
+    every layer's box head run on side branches next to the main chain.
+  * The host runs AHEAD of the device: `submit()` enqueues frame t while frame t-1 is still running,
+    picking the padded size from the newest track counts it already knows plus a margin. If the real
+    row count does not fit, the device aborts that frame (and any later one) without touching the
+    track state and the host re-launches it with the exact size (moyolo_frame_assemble, `ctrl`).
+    Inputs go through a 2-deep device ring filled on a copy stream, so the host->device copy of frame
+    t+1 overlaps the compute of frame t; results leave as ONE packed [rows, 8] copy per frame and as
+    rows appended on the device to a resident track table.
 """
 from __future__ import annotations
 
@@ -26,6 +36,8 @@ import torch
 from . import executor as ex
 from . import ops
 from .synthetic import DecoderSpec, level_sizes
+
+CTRL_ABORT, CTRL_FRAME, CTRL_CURSOR, CTRL_TABLE_OVERFLOW, CTRL_ABORT_ROWS = 0, 1, 2, 3, 4
 
 
 class DecoderWeights:
@@ -59,8 +71,7 @@ class DecoderWeights:
         f = lambda t: t.to(device).float().contiguous()  # noqa: E731
         w = lambda t: t.to(device).to(dt).contiguous()  # noqa: E731
         self.qim = {
-            "qk_w": w(sd[q + "self_attn.in_proj_weight"][:2 * C]), "qk_b": f(sd[q + "self_attn.in_proj_bias"][:2 * C]),
-            "v_w": w(sd[q + "self_attn.in_proj_weight"][2 * C:]), "v_b": f(sd[q + "self_attn.in_proj_bias"][2 * C:]),
+            "qkv_w": w(sd[q + "self_attn.in_proj_weight"]), "qkv_b": f(sd[q + "self_attn.in_proj_bias"]),
             "o_w": w(sd[q + "self_attn.out_proj.weight"]), "o_b": f(sd[q + "self_attn.out_proj.bias"]),
             "l1_w": w(sd[q + "linear1.weight"]), "l1_b": f(sd[q + "linear1.bias"]),
             "l2_w": w(sd[q + "linear2.weight"]), "l2_b": f(sd[q + "linear2.bias"]),
@@ -71,77 +82,85 @@ class DecoderWeights:
             self.qim[n] = (f(sd[q + n + ".weight"]), f(sd[q + n + ".bias"]))
 
 
-def decode_frame(W: DecoderWeights, x_f32, refer_logit, pos, feats_lp, shapes, n_seq: int, ro, ro_host):
-    """MOTRTransformerDecoder.forward in eval mode (transformer.py:676-728) over a ragged batch.
+class FrameWorkspace:
+    """Every intermediate tensor of one frame for a padded row count R (allocated once, outside any
+    graph capture; kernels write through `out=` so a frame performs no allocation)."""
 
-    x_f32 [R, C], refer_logit [R, 4], pos [R, C] fp32; feats_lp [n_seq*Lv, C] in the GEMM dtype; ro
-    device row offsets [n_seq+1]; ro_host a host list that bounds them (grid sizing only).
-    Returns boxes [R,4], logits [R,nc], scores [R], labels [R] (int32), hs [R,C] fp32.
-    """
-    dt, spec = W.dt, W.spec
-    C, n_l = spec.d_model, spec.n_layers
-    Lv = feats_lp.shape[0] // n_seq
-    values = ops.linear(feats_lp, W.value_proj.w, W.value_proj.b, out_dtype=dt, engine=ex._GEMM_ENGINE)
-    values = values.view(n_seq, Lv, n_l * C)
-    refer = ops.sigmoid(refer_logit)
-    x_lp = x_f32 if dt == torch.float32 else ops.add_cast(x_f32, None, dt)
-    xq_lp = ops.add_cast(x_f32, pos, dt)
-    R = x_f32.shape[0]
-    for i, pk in enumerate(W.layers):
-        pos_next = pos if i + 1 < n_l else None
-        x_f32, x_lp, xq_lp = ex.run_layer(pk, x_f32, x_lp, xq_lp, refer.view(R, 1, 4),
-                                          values[:, :, i * C:(i + 1) * C], shapes, n_seq, ro, ro_host, False, None,
-                                          pos, pos_next, dt)
-        refer = ex.bbox_head(W.bbox[i], x_lp, refer)
-    logits, scores, labels = ops.score_head(x_lp, W.score_w, W.score_b)
-    return refer, logits, scores, labels, x_f32
-
-
-def qim_update(W: DecoderWeights, ref_pts, query_pos, out_embed, ro, ro_host, seg_len=None):
-    """QueryInteractionModule._update_track_embedding (MOTR/models/qim.py:251-301) for the active tracks
-    of every sequence at once: rows of sequence s are [ro[s], ro[s] + seg_len[s]) (the rest of the
-    [R, .] buffers is padding). ref_pts [R,4] logits, query_pos / out_embed [R,C] fp32.
-    Returns new_query_pos [R,C] fp32 (ref_pts <- inverse_sigmoid(pred_boxes) is fused in the write-back)."""
-    R, C = out_embed.shape
-    dt, q, H = W.dt, W.qim, 8  # nn.MultiheadAttention(dim_in, 8, ...) qim.py:88
-    eng = ex._GEMM_ENGINE
-    dev = out_embed.device
-    qpos = ops.pos2posemb(ref_pts)                                   # qim.py:255
-    qk_lp = ops.add_cast(qpos, out_embed, dt)                        # :271
-    tgt_lp = out_embed if dt == torch.float32 else ops.add_cast(out_embed, None, dt)
-    qkv = torch.empty(R, 3 * C, dtype=dt, device=dev)
-    ops.linear(qk_lp, q["qk_w"], q["qk_b"], out=qkv[:, :2 * C], engine=eng)
-    ops.linear(tgt_lp, q["v_w"], q["v_b"], out=qkv[:, 2 * C:], engine=eng)
-    att = ops.self_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], ro, ro_host, H, seg_len=seg_len)
-    t2 = ops.linear(att, q["o_w"], q["o_b"], out_dtype=torch.float32, engine=eng)
-    tgt_f32, tgt_lp, _ = ops.add_layernorm(t2, out_embed, *q["norm1"], 1e-5, True, True, dt)     # :277-278
-    h = ops.linear(tgt_lp, q["l1_w"], q["l1_b"], relu=True, engine=eng)
-    t3 = ops.linear(h, q["l2_w"], q["l2_b"], out_dtype=torch.float32, engine=eng)                 # :280
-    _, tgt_lp, _ = ops.add_layernorm(t3, tgt_f32, *q["norm2"], 1e-5, False, True, dt)             # :281-282
-    h = ops.linear(tgt_lp, q["f1_w"], q["f1_b"], relu=True, engine=eng)
-    f2 = ops.linear(h, q["f2_w"], q["f2_b"], out_dtype=torch.float32, engine=eng)                 # :290
-    new_qpos, _, _ = ops.add_layernorm(f2, query_pos, *q["norm_feat"], 1e-5, True, False, dt)     # :294-298
-    return new_qpos
+    def __init__(self, R: int, S: int, spec: DecoderSpec, dt: torch.dtype, dev, d_qim: int):
+        C, F, nl = spec.d_model, spec.d_ffn, spec.n_layers
+        f32 = dict(dtype=torch.float32, device=dev)
+        lp = dict(dtype=dt, device=dev)
+        z = torch.zeros
+        self.R = R
+        # frame inputs built by frame_assemble
+        self.x = z(R, C, **f32)              # residual stream
+        self.refer_logit = z(R, 4, **f32)
+        self.pos = z(R, C, **f32)
+        self.ids = z(R, dtype=torch.int64, device=dev)
+        self.dis = z(R, dtype=torch.int64, device=dev)
+        self.ro = z(S + 1, dtype=torch.int32, device=dev)
+        self.refer = [z(R, 4, **f32) for _ in range(nl + 1)]   # sigmoid(refer) and the refined boxes per layer
+        # decoder layer
+        self.x_lp = self.x if dt == torch.float32 else z(R, C, **lp)
+        self.xq_lp = z(R, C, **lp)
+        self.qkv = z(R, 3 * C, **lp)
+        self.att = z(R, C, **lp)
+        self.t = z(R, C, **f32)              # GEMM output feeding an add+LayerNorm
+        self.x1 = z(R, C, **f32)
+        self.x1q_lp = z(R, C, **lp)
+        self.ol = z(R, ex.offlog_width(spec), **f32)
+        self.g = z(R, C, **lp)
+        self.x2 = z(R, C, **f32)
+        self.x2_lp = self.x2 if dt == torch.float32 else z(R, C, **lp)
+        self.h = z(R, F, **lp)
+        # box head (side branch)
+        self.bh1 = z(R, C, **lp)
+        self.bh2 = z(R, C, **lp)
+        # heads + track update
+        self.logits = z(R, spec.nc, **f32)
+        self.scores = z(R, **f32)
+        self.labels = z(R, dtype=torch.int32, device=dev)
+        self.assign_ws = z(S * ops.track_workspace_bytes(R), dtype=torch.uint8, device=dev)
+        self.n_active = z(S, dtype=torch.int32, device=dev)
+        self.active_index = z(R, dtype=torch.int32, device=dev)
+        self.c_ref = z(R, 4, **f32)
+        self.c_pos = z(R, C, **f32)
+        self.c_hs = z(R, C, **f32)
+        self.c_box = z(R, 4, **f32)
+        self.frame_rows = z(R, 8, **f32)
+        self.info = z(S + 8, dtype=torch.int32, device=dev)
+        # QIM
+        self.q_pos = z(R, C, **f32)
+        self.q_qk_lp = z(R, C, **lp)
+        self.q_tgt_lp = self.c_hs if dt == torch.float32 else z(R, C, **lp)
+        self.q_tgt = z(R, C, **f32)
+        self.q_tgt_lp2 = self.q_tgt if dt == torch.float32 else z(R, C, **lp)
+        self.q_tgt_lp3 = z(R, C, **lp)
+        self.q_h = z(R, d_qim, **lp)
+        self.q_new = z(R, C, **f32)
 
 
 class _FramePlan:
-    """Static buffers (and optionally the captured CUDA graph) of one padded frame size."""
-    __slots__ = ("rows_pad", "graph", "ids", "boxes", "scores", "labels", "logits", "n_active", "ro", "n_launch")
+    """Workspace (and optionally the captured CUDA graph) of one (padded frame size, input slot)."""
+    __slots__ = ("rows_pad", "slot", "graph", "ws", "n_launch")
 
 
 class TrackEngine:
     """Lock-step tracker for `n_seq` independent sequences on one GPU."""
 
+    DEPTH = 4  # host result ring (frames in flight <= 2)
+
     def __init__(self, sd, spec: DecoderSpec, shapes, device, precision: str = "bf16", n_detect: int = 300,
                  n_seq: int = 1, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, iou_thresh=0.8,
-                 weights: Optional[DecoderWeights] = None, cap: int = 512, bucket: int = 32,
-                 use_graphs: bool = True):
+                 weights: Optional[DecoderWeights] = None, cap: int = 512, bucket: int = 64, margin: int = 32,
+                 use_graphs: bool = True, table_rows: int = 1 << 18, branches: bool = True):
         self.dev = torch.device(device)
         self.spec, self.shapes, self.n_detect, self.n_seq = spec, [list(s) for s in shapes], n_detect, n_seq
         self.Lv = level_sizes(shapes)
         self.W = weights or DecoderWeights(sd, spec, self.dev, precision)
         self.thr = (score_thresh, filter_thresh, miss_tolerance, iou_thresh)
-        self.cap, self.bucket, self.use_graphs = cap, bucket, use_graphs
+        self.cap, self.bucket, self.margin, self.use_graphs = cap, bucket, margin, use_graphs
+        self.branches = branches
         S, C, dev = n_seq, spec.d_model, self.dev
         # device-resident track state (fixed capacity)
         self.n_tracks = torch.zeros(S, dtype=torch.int32, device=dev)
@@ -151,106 +170,213 @@ class TrackEngine:
         self.t_ids = torch.zeros(S, cap, dtype=torch.int64, device=dev)
         self.t_dis = torch.zeros(S, cap, dtype=torch.int64, device=dev)
         self.counters = torch.zeros(S, 2, dtype=torch.int64, device=dev)
-        # static frame inputs (graphs read these)
-        self.feats_in = torch.zeros(S, self.Lv, C, dtype=self.W.dt, device=dev)
-        self.det_embed_in = torch.zeros(S, n_detect, C, device=dev)
-        self.det_refer_in = torch.zeros(S, n_detect, 4, device=dev)
-        self._count_host = torch.zeros(S, dtype=torch.int32).pin_memory()
-        self._T = [0] * S
-        self._plans: Dict[int, _FramePlan] = {}
-        self.frame_idx = 0
+        self.ctrl = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.seq_ids = torch.arange(S, dtype=torch.int32, device=dev)
+        self.table = torch.zeros(table_rows, 9, device=dev)
+        # 2-deep input ring (graphs read these) and the all-layers value tensor shared by every plan
+        self.feats_in = [torch.zeros(S, self.Lv, C, dtype=self.W.dt, device=dev) for _ in range(2)]
+        self.det_embed_in = [torch.zeros(S, n_detect, C, device=dev) for _ in range(2)]
+        self.det_refer_in = [torch.zeros(S, n_detect, 4, device=dev) for _ in range(2)]
+        self.values = torch.zeros(S, self.Lv, spec.n_layers * C, dtype=self.W.dt, device=dev)
+        # streams / events
+        self._main = torch.cuda.current_stream(dev)
+        self._copy = torch.cuda.Stream(dev)
+        self._s_val = torch.cuda.Stream(dev)
+        self._s_box = torch.cuda.Stream(dev)
+        self._ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
+        self._ev_copy = [torch.cuda.Event() for _ in range(2)]
+        # pinned host rings: [n_active (S) | ctrl (8)] and the packed frame rows
+        self._max_rows = self._round(S * (n_detect + cap))
+        self._h_info = torch.zeros(self.DEPTH, S + 8, dtype=torch.int32).pin_memory()
+        self._h_rows = torch.zeros(self.DEPTH, self._max_rows, 8).pin_memory()
+        self._plans: Dict[tuple, _FramePlan] = {}
+        self._host_reset()
 
-    # ---- state -------------------------------------------------------------------------------
+    # ---- host-side bookkeeping ---------------------------------------------------------------
+    def _host_reset(self):
+        self._T = [0] * self.n_seq          # exact track counts after frame `_known`
+        self._known = -1                    # newest frame whose counts the host has read
+        self._next = 0                      # next frame index to submit
+        self._inflight: List[dict] = []     # submitted, not yet harvested (oldest first)
+        self._T_before: Dict[int, List[int]] = {0: [0] * self.n_seq}  # frame -> track counts it started with
+        self._last_plan: Optional[_FramePlan] = None
+        self.frame_idx = 0
+        self.aborts = 0
+
     def reset(self, seq: Optional[int] = None):
-        """is_first semantics (head.py:199-205): drop all tracks, fresh ID counters."""
+        """is_first semantics (head.py:199-205): drop all tracks, fresh ID counters (and, for a full
+        reset, an empty track table and frame counter)."""
+        self.drain()
         if seq is None:
             self.n_tracks.zero_()
             self.counters.zero_()
-            self._T = [0] * self.n_seq
-            self.frame_idx = 0
+            self.ctrl.zero_()
+            self._host_reset()
         else:
             self.n_tracks[seq] = 0
             self.counters[seq].zero_()
             self._T[seq] = 0
 
+    def set_seq_ids(self, ids) -> None:
+        """Global sequence index of every lock-step slot (the `seq` column of the emitted rows)."""
+        self.drain()
+        self.seq_ids.copy_(torch.as_tensor(list(ids), dtype=torch.int32))
+
     def n_tracks_host(self) -> List[int]:
+        self.drain()
         return list(self._T)
 
     n_tracks_list = n_tracks_host
 
     def track_ids(self, s: int) -> torch.Tensor:
+        self.drain()
         return self.t_ids[s, :self._T[s]]
 
     def track_disappear(self, s: int) -> torch.Tensor:
+        self.drain()
         return self.t_dis[s, :self._T[s]]
 
-    # ---- one frame ----------------------------------------------------------------------------
-    def _body(self, rows_pad: int) -> _FramePlan:
-        """Every launch of one frame for a padded row count (graph-capturable: no host sync, shapes
-        depend on rows_pad only, counts are read from device memory by the kernels)."""
-        W, dev, S, nd, C = self.W, self.dev, self.n_seq, self.n_detect, self.spec.d_model
-        R = rows_pad
-        x = torch.empty(R, C, device=dev)
-        refer_logit = torch.empty(R, 4, device=dev)
-        pos = torch.empty(R, C, device=dev)
-        ids = torch.empty(R, dtype=torch.int64, device=dev)
-        dis = torch.empty(R, dtype=torch.int64, device=dev)
-        ro = torch.empty(S + 1, dtype=torch.int32, device=dev)
+    def track_table(self) -> torch.Tensor:
+        """Rows [seq, frame, id, cx, cy, w, h, score, cls] of every tracked object emitted so far
+        (device tensor, ordered by frame, then slot, then query order)."""
+        self.drain()
+        info = self.ctrl.cpu()
+        if int(info[CTRL_TABLE_OVERFLOW]):
+            raise RuntimeError(f"moyolo_b200: track table capacity ({self.table.shape[0]} rows) exceeded; "
+                               "construct TrackEngine with a larger table_rows")
+        return self.table[:int(info[CTRL_CURSOR])]
+
+    # ---- one frame: every launch ----------------------------------------------------------------
+    def _body(self, p: _FramePlan) -> None:
+        """All launches of one frame for plan `p` (graph-capturable: no host sync, no allocation, shapes
+        depend on rows_pad only; counts are read from device memory by the kernels)."""
+        W, S, nd, C, ws, R = self.W, self.n_seq, self.n_detect, self.spec.d_model, p.ws, p.rows_pad
+        dt, spec, n_l = W.dt, self.spec, self.spec.n_layers
+        cur = torch.cuda.current_stream(self.dev)
+        feats = self.feats_in[p.slot].view(S * self.Lv, C)
+        fork = self.branches
+        # side branch: value projection of ALL layers in one GEMM (transformer.py:264; feats is the same
+        # tensor in every layer, transformer.py:705)
+        if fork:
+            self._s_val.wait_stream(cur)
+            with torch.cuda.stream(self._s_val):
+                ops.linear(feats, W.value_proj.w, W.value_proj.b, out=self.values.view(S * self.Lv, n_l * C),
+                           engine=ex._GEMM_ENGINE)
+        else:
+            ops.linear(feats, W.value_proj.w, W.value_proj.b, out=self.values.view(S * self.Lv, n_l * C),
+                       engine=ex._GEMM_ENGINE)
         ops.frame_assemble(S, nd, C, self.cap, self.n_tracks, self.t_ref, self.t_qpos, self.t_label, self.t_ids,
-                           self.t_dis, W.class_embed, self.det_embed_in, self.det_refer_in, x, refer_logit, pos, ids,
-                           dis, ro, R)
+                           self.t_dis, W.class_embed, self.det_embed_in[p.slot], self.det_refer_in[p.slot], ws.x,
+                           ws.refer_logit, ws.pos, ws.ids, ws.dis, ws.ro, R, ctrl=self.ctrl)
         # host-side bound of the device offsets, used for grid sizing only: sum_s ceil(N_s/16) <= R/16 + S
         ro_host = [16 * i for i in range(S)] + [16 * S + R]
-        feats_lp = self.feats_in.view(S * self.Lv, C)
-        boxes, logits, scores, labels, hs = decode_frame(W, x, refer_logit, pos, feats_lp, self.shapes, S, ro, ro_host)
-        st, ft, mt, it = self.thr
-        ws = torch.empty(S * ops.track_workspace_bytes(R), dtype=torch.uint8, device=dev)
-        ops.track_assign_batched(scores, boxes, ids, dis, self.counters, ro, S, R, ws, st, ft, mt, it)
-        n_active = torch.empty(S, dtype=torch.int32, device=dev)
-        active_index = torch.empty(R, dtype=torch.int32, device=dev)
-        c_ref = torch.zeros(R, 4, device=dev)
-        c_pos = torch.zeros(R, C, device=dev)
-        c_hs = torch.zeros(R, C, device=dev)
-        c_box = torch.zeros(R, 4, device=dev)
-        ops.frame_compact(S, C, self.cap, ro, ids, dis, labels, refer_logit, pos, hs, boxes, n_active, active_index,
-                          c_ref, c_pos, c_hs, c_box, self.t_label, self.t_ids, self.t_dis)
-        new_qpos = qim_update(W, c_ref, c_pos, c_hs, ro, ro_host, seg_len=n_active)
-        ops.frame_writeback(S, C, self.cap, ro, n_active, new_qpos, c_box, self.t_qpos, self.t_ref, self.n_tracks)
-        p = _FramePlan()
-        p.rows_pad, p.graph = R, None
-        p.ids, p.boxes, p.scores, p.labels, p.logits, p.n_active, p.ro = ids, boxes, scores, labels, logits, n_active, ro
-        return p
+        ops.sigmoid(ws.refer_logit, out=ws.refer[0])                      # transformer.py:690
+        if dt != torch.float32:
+            ops.add_cast(ws.x, None, dt, out=ws.x_lp)
+        ops.add_cast(ws.x, ws.pos, dt, out=ws.xq_lp)
+        for i, pk in enumerate(W.layers):
+            last = i + 1 == n_l
+            value_view = self.values[:, :, i * C:(i + 1) * C]
 
+            def before_gather(i=i):
+                if not fork:
+                    return
+                if i == 0:
+                    cur.wait_stream(self._s_val)
+                else:
+                    cur.wait_stream(self._s_box)   # refer[i] comes from the box head of layer i-1
+
+            ex.run_layer_ws(pk, ws, ws.refer[i].view(R, 1, 4), value_view, self.shapes, S, ws.ro, ro_host,
+                            ws.pos, None if last else ws.pos, dt, before_gather)
+            # box refinement of this layer (transformer.py:709): only the NEXT layer's gather needs it
+            if fork and not last:
+                self._s_box.wait_stream(cur)
+                with torch.cuda.stream(self._s_box):
+                    ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
+            else:
+                ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
+        boxes = ws.refer[n_l]
+        ops.score_head(ws.x_lp, W.score_w, W.score_b, out=(ws.logits, ws.scores, ws.labels))
+        st, ft, mt, it = self.thr
+        ops.track_assign_batched(ws.scores, boxes, ws.ids, ws.dis, self.counters, ws.ro, S, R, ws.assign_ws, st, ft,
+                                 mt, it, ctrl=self.ctrl)
+        ops.frame_compact(S, C, self.cap, ws.ro, ws.ids, ws.dis, ws.labels, ws.refer_logit, ws.pos, ws.x, boxes,
+                          ws.n_active, ws.active_index, ws.c_ref, ws.c_pos, ws.c_hs, ws.c_box, self.t_label,
+                          self.t_ids, self.t_dis, ctrl=self.ctrl)
+        ops.frame_emit(S, R, ws.ro, ws.ids, boxes, ws.scores, ws.labels, ws.n_active, ws.active_index, self.seq_ids,
+                       ws.frame_rows, self.table, self.ctrl)
+        self._qim_update(ws, ro_host)
+        ops.frame_writeback(S, C, self.cap, ws.ro, ws.n_active, ws.q_new, ws.c_box, self.t_qpos, self.t_ref,
+                            self.n_tracks, ctrl=self.ctrl)
+        ws.info[:S].copy_(ws.n_active, non_blocking=True)   # what the host reads back after the frame
+        ws.info[S:].copy_(self.ctrl, non_blocking=True)
+
+    def _qim_update(self, ws: FrameWorkspace, ro_host) -> None:
+        """QueryInteractionModule._update_track_embedding (MOTR/models/qim.py:251-301) for the active
+        tracks of every sequence at once: rows of sequence s are [ro[s], ro[s] + n_active[s]) of the
+        compact buffers (the rest is padding). ref_pts <- inverse_sigmoid(pred_boxes) (qim.py:299) is
+        fused into frame_writeback."""
+        W = self.W
+        C = self.spec.d_model
+        dt, q, H = W.dt, W.qim, 8  # nn.MultiheadAttention(dim_in, 8, ...) qim.py:88
+        eng = ex._GEMM_ENGINE
+        ops.pos2posemb(ws.c_ref, out=ws.q_pos)                                       # qim.py:255
+        ops.add_cast(ws.q_pos, ws.c_hs, dt, out=ws.q_qk_lp)                          # :271 q = k = tgt + query_pos
+        if dt != torch.float32:
+            ops.add_cast(ws.c_hs, None, dt, out=ws.q_tgt_lp)
+        ex.qkv_proj(ws.q_qk_lp, ws.q_tgt_lp, q["qkv_w"], q["qkv_b"], ws.qkv, C, eng)
+        ops.self_attention(ws.qkv[:, :C], ws.qkv[:, C:2 * C], ws.qkv[:, 2 * C:], ws.ro, ro_host, H, out=ws.att,
+                           seg_len=ws.n_active)
+        ops.linear(ws.att, q["o_w"], q["o_b"], out=ws.t, engine=eng)
+        ops.add_layernorm(ws.t, ws.c_hs, *q["norm1"], 1e-5, out_f32=ws.q_tgt,                       # :277-278
+                          out_lp=None if dt == torch.float32 else ws.q_tgt_lp2)
+        ops.linear(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], relu=True, out=ws.q_h, engine=eng)
+        ops.linear(ws.q_h, q["l2_w"], q["l2_b"], out=ws.t, engine=eng)                               # :280
+        ops.add_layernorm(ws.t, ws.q_tgt, *q["norm2"], 1e-5, want_f32=False, out_lp=ws.q_tgt_lp3)   # :281-282
+        ops.linear(ws.q_tgt_lp3, q["f1_w"], q["f1_b"], relu=True, out=ws.q_h, engine=eng)
+        ops.linear(ws.q_h, q["f2_w"], q["f2_b"], out=ws.t, engine=eng)                               # :290
+        ops.add_layernorm(ws.t, ws.c_pos, *q["norm_feat"], 1e-5, out_f32=ws.q_new)                  # :294-298
+
+    # ---- plans ------------------------------------------------------------------------------------
     def _state_snapshot(self):
         return [t.clone() for t in (self.n_tracks, self.t_ref, self.t_qpos, self.t_label, self.t_ids, self.t_dis,
-                                    self.counters)]
+                                    self.counters, self.ctrl)]
 
     def _state_restore(self, snap):
         for dst, src in zip((self.n_tracks, self.t_ref, self.t_qpos, self.t_label, self.t_ids, self.t_dis,
-                             self.counters), snap):
+                             self.counters, self.ctrl), snap):
             dst.copy_(src)
 
-    def _plan(self, rows_pad: int) -> _FramePlan:
-        p = self._plans.get(rows_pad)
-        if p is None:
-            snap = self._state_snapshot()
+    def _plan(self, rows_pad: int, slot: int) -> _FramePlan:
+        p = self._plans.get((rows_pad, slot))
+        if p is not None:
+            return p
+        p = _FramePlan()
+        p.rows_pad, p.slot, p.graph, p.n_launch = rows_pad, slot, None, 0
+        other = self._plans.get((rows_pad, slot ^ 1))
+        # both input slots of one size share a workspace: frames are serialised on the main stream
+        p.ws = other.ws if other is not None else FrameWorkspace(rows_pad, self.n_seq, self.spec, self.W.dt, self.dev,
+                                                                 self.W.qim["l1_w"].shape[0])
+        if self.use_graphs:
             torch.cuda.synchronize(self.dev)
+            snap = self._state_snapshot()
             side = torch.cuda.Stream(self.dev)
             side.wait_stream(torch.cuda.current_stream(self.dev))
             with torch.cuda.stream(side):  # one eager pass: loads modules, sets kernel attributes
-                self._body(rows_pad)
+                self._body(p)
             torch.cuda.current_stream(self.dev).wait_stream(side)
             torch.cuda.synchronize(self.dev)
             self._state_restore(snap)
             g = torch.cuda.CUDAGraph()
             before = ops.LAUNCHES
             with torch.cuda.graph(g):
-                p = self._body(rows_pad)
+                self._body(p)
             p.graph = g
             p.n_launch = ops.LAUNCHES - before  # kernels replayed by every graph launch
             ops.LAUNCHES = before
             self._state_restore(snap)  # capture does not execute, but keep the invariant explicit
-            self._plans[rows_pad] = p
+            torch.cuda.synchronize(self.dev)
+        self._plans[(rows_pad, slot)] = p
         return p
 
     def prepare(self, max_tracks_per_seq: int) -> int:
@@ -258,11 +384,13 @@ class TrackEngine:
         sequence (done at start-up so no capture happens in the frame loop). Returns #graphs."""
         if not self.use_graphs:
             return 0
+        self.drain()
         lo = self.n_seq * self.n_detect
-        hi = self.n_seq * (self.n_detect + max_tracks_per_seq)
+        hi = self.n_seq * (self.n_detect + max_tracks_per_seq) + self.margin
         r = self._round(lo)
         while r <= self._round(hi):
-            self._plan(r)
+            self._plan(r, 0)
+            self._plan(r, 1)
             r += self.bucket
         return len(self._plans)
 
@@ -270,46 +398,142 @@ class TrackEngine:
         b = self.bucket
         return (rows + b - 1) // b * b
 
-    def load_inputs(self, feats: torch.Tensor, det_embed: torch.Tensor, det_refer: torch.Tensor) -> None:
-        """Copy (device or pinned-host) frame inputs into the static input buffers."""
-        if feats.data_ptr() != self.feats_in.data_ptr():
-            if feats.dtype == self.feats_in.dtype or not feats.is_cuda:
-                self.feats_in.copy_(feats.reshape(self.feats_in.shape), non_blocking=True)
+    # ---- pipelined frame loop ---------------------------------------------------------------------
+    def _load_inputs(self, slot: int, feats, det_embed, det_refer, frame: int, sync_inputs: bool) -> None:
+        """Copy (device or pinned-host) frame inputs into ring slot `slot` on the copy stream, after the
+        frame that last read this slot (frame - 2) has finished."""
+        cs = self._copy
+        if frame >= 2:
+            cs.wait_event(self._ev_done[(frame - 2) % self.DEPTH])
+        if sync_inputs:  # inputs still being produced on the caller's stream
+            cs.wait_stream(self._main)
+        for t in (feats, det_embed, det_refer):
+            if t.is_cuda:
+                t.record_stream(cs)  # the caller may drop its reference before the async copy has run
+        with torch.cuda.stream(cs):
+            dst = self.feats_in[slot]
+            if feats.dtype == dst.dtype or not feats.is_cuda:
+                dst.copy_(feats.reshape(dst.shape), non_blocking=True)
             else:  # dtype conversion on device through the library's own cast kernel
-                src = feats.reshape(-1).float().contiguous()
-                self.feats_in.view(-1).copy_(ops.add_cast(src, None, self.feats_in.dtype))
-        if det_embed.data_ptr() != self.det_embed_in.data_ptr():
-            self.det_embed_in.copy_(det_embed.reshape(self.det_embed_in.shape), non_blocking=True)
-        if det_refer.data_ptr() != self.det_refer_in.data_ptr():
-            self.det_refer_in.copy_(det_refer.reshape(self.det_refer_in.shape), non_blocking=True)
+                ops.add_cast(feats.reshape(-1).float().contiguous(), None, dst.dtype, out=dst.view(-1))
+            self.det_embed_in[slot].copy_(det_embed.reshape(self.det_embed_in[slot].shape), non_blocking=True)
+            self.det_refer_in[slot].copy_(det_refer.reshape(self.det_refer_in[slot].shape), non_blocking=True)
+            self._ev_copy[slot].record(cs)
+
+    def _launch(self, frame: int, rows_pad: int, want_rows: bool) -> dict:
+        slot = frame % 2
+        p = self._plan(rows_pad, slot)
+        main = self._main
+        h = frame % self.DEPTH
+        with torch.cuda.stream(main):
+            main.wait_event(self._ev_copy[slot])
+            if self.use_graphs:
+                p.graph.replay()
+                ops.LAUNCHES += p.n_launch
+            else:
+                self._body(p)
+            # the frame's host-visible results: [active-track counts | control block] and, optionally, the
+            # packed rows -- one small device->host copy each
+            self._h_info[h].copy_(p.ws.info, non_blocking=True)
+            if want_rows:
+                self._h_rows[h, :rows_pad].copy_(p.ws.frame_rows, non_blocking=True)
+            self._ev_done[h].record(main)
+        self._last_plan = p
+        return {"frame": frame, "plan": p, "rows_pad": rows_pad, "want_rows": want_rows}
+
+    def _harvest(self, upto: int, block: bool) -> None:
+        """Read the results of in-flight frames <= upto (oldest first). A frame whose speculative size
+        did not fit is re-run (with every later in-flight frame) using the exact counts."""
+        while self._inflight and self._inflight[0]["frame"] <= upto:
+            rec = self._inflight[0]
+            ev = self._ev_done[rec["frame"] % self.DEPTH]
+            if not block and not ev.query():
+                return
+            ev.synchronize()
+            info = self._h_info[rec["frame"] % self.DEPTH]
+            if int(info[self.n_seq + CTRL_ABORT]) != 0:
+                self._recover()
+                continue
+            self._inflight.pop(0)
+            self._T = [int(v) for v in info[:self.n_seq].tolist()]
+            self._known = rec["frame"]
+            self._T_before[rec["frame"] + 1] = list(self._T)
+            self._T_before.pop(rec["frame"] - self.DEPTH, None)
+
+    def _recover(self) -> None:
+        """The oldest in-flight frame aborted on the device (its padded size was too small): nothing it or
+        any later frame did touched the track state. Re-launch them in order with exact sizes."""
+        torch.cuda.synchronize(self.dev)
+        redo = self._inflight
+        self._inflight = []
+        self.ctrl[CTRL_ABORT:CTRL_ABORT + 1].zero_()
+        self.aborts += 1
+        for rec in redo:
+            rows = sum(self._T) + self.n_seq * self.n_detect
+            new = self._launch(rec["frame"], self._round(rows), rec["want_rows"])
+            self._inflight.append(new)
+            self._harvest(rec["frame"], block=True)
+
+    def submit(self, feats: torch.Tensor, det_embed: torch.Tensor, det_refer: torch.Tensor,
+               want_rows: bool = True, sync_inputs: bool = False) -> int:
+        """Enqueue the next frame without waiting for it. feats [n_seq, Lv, C] (GEMM dtype or fp32;
+        device or pinned host), det_embed [n_seq, nd, C] fp32, det_refer [n_seq, nd, 4] fp32 logit-space
+        boxes. Unless sync_inputs is set the tensors must be complete when submit() is called (their copy
+        runs on the engine's copy stream, which is then not ordered after the caller's stream), and they
+        must not be modified until the frame after next has been submitted. Returns the frame index for
+        `collect`."""
+        t = self._next
+        self._harvest(t - 2, block=True)    # at most two frames in flight
+        self._harvest(t - 1, block=False)   # use the newest counts if they are already here
+        self._load_inputs(t % 2, feats, det_embed, det_refer, t, sync_inputs)
+        rows = sum(self._T) + self.n_seq * self.n_detect
+        exact = self._known == t - 1
+        rows_pad = self._round(rows if exact else rows + self.margin)
+        rows_pad = min(rows_pad, self._max_rows)
+        self._inflight.append(self._launch(t, rows_pad, want_rows))
+        self._next = t + 1
+        self.frame_idx = self._next
+        return t
+
+    def drain(self) -> None:
+        """Wait for every submitted frame (host counts become exact)."""
+        self._harvest(self._next - 1, block=True)
+
+    def collect(self, frame: int) -> List[Dict[str, torch.Tensor]]:
+        """Host-side results of a submitted frame (submitted with want_rows=True; at most DEPTH-2 frames
+        back): per sequence a dict of CPU tensors ids (int64, -1 = no object), boxes (cx,cy,w,h normalised),
+        scores, labels for its N = T + n_detect rows, in query order. Views of a pinned ring: copy
+        them if they must outlive the next two submits."""
+        self._harvest(frame, block=True)
+        rows = self._h_rows[frame % self.DEPTH]
+        Tb = self._T_before.get(frame)   # exact once the previous frame has been harvested
+        if Tb is None or frame < self._next - (self.DEPTH - 2):
+            raise RuntimeError("collect(): frame results are no longer available")
+        outs, off = [], 0
+        for s in range(self.n_seq):
+            n = Tb[s] + self.n_detect
+            r = rows[off:off + n]
+            outs.append({"ids": r[:, 0].long(), "boxes": r[:, 1:5], "scores": r[:, 5], "labels": r[:, 6].int()})
+            off += n
+        return outs
 
     def step(self, feats: torch.Tensor, det_embed: torch.Tensor, det_refer: torch.Tensor) -> List[Dict[str, torch.Tensor]]:
-        """feats [n_seq, Lv, C] (GEMM dtype or fp32), det_embed [n_seq, nd, C] fp32, det_refer
-        [n_seq, nd, 4] fp32 logit-space boxes. Returns one dict per sequence with the N = T + nd rows
-        of this frame: ids (int64, -1 = no object), boxes (cx,cy,w,h normalised), scores, labels, logits.
-        The returned tensors are views of per-size static buffers: consume or copy them before the next
-        frame of the same padded size."""
+        """Synchronous frame: submit + wait. Returns one dict per sequence with the N = T + nd rows of this
+        frame as DEVICE tensors: ids (int64, -1 = no object), boxes (cx,cy,w,h normalised), scores, labels,
+        logits. They are views of the plan's workspace: consume or copy them before the next frame."""
         S, nd = self.n_seq, self.n_detect
-        self.load_inputs(feats, det_embed, det_refer)
-        rows = sum(self._T) + S * nd
-        rows_pad = self._round(rows)
-        if self.use_graphs:
-            p = self._plan(rows_pad)
-            p.graph.replay()
-            ops.LAUNCHES += p.n_launch
-        else:
-            p = self._body(rows_pad)
-        # the one host read-back of the frame: active-track counts (they size the next frame)
-        self._count_host.copy_(p.n_active, non_blocking=True)
-        torch.cuda.current_stream(self.dev).synchronize()
+        self.drain()
+        T_in = list(self._T)
+        t = self.submit(feats, det_embed, det_refer, want_rows=False, sync_inputs=True)
+        self._harvest(t, block=True)
+        ws = self._last_plan.ws
         outs, off = [], 0
+        boxes = ws.refer[self.spec.n_layers]
         for s in range(S):
-            n = self._T[s] + nd
-            outs.append({"ids": p.ids[off:off + n], "boxes": p.boxes[off:off + n], "scores": p.scores[off:off + n],
-                         "labels": p.labels[off:off + n], "logits": p.logits[off:off + n]})
+            n = T_in[s] + nd
+            outs.append({"ids": ws.ids[off:off + n], "boxes": boxes[off:off + n], "scores": ws.scores[off:off + n],
+                         "labels": ws.labels[off:off + n], "logits": ws.logits[off:off + n]})
             off += n
-        self._T = [int(v) for v in self._count_host.tolist()]
-        self.frame_idx += 1
         return outs
 
 

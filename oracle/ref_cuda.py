@@ -10,6 +10,7 @@ import torch
 
 _SO = Path(__file__).resolve().parent / "_ref" / "libmsda_ref_cuda.so"
 _lib = None
+_shape_cache = {}
 
 
 def available() -> bool:
@@ -23,8 +24,11 @@ def msda_im2col(value: torch.Tensor, shapes, loc: torch.Tensor, weights: torch.T
         _lib = C.CDLL(str(_SO))
     B, S, H, D = value.shape
     Q, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
-    sh = torch.as_tensor(shapes, dtype=torch.int64, device=value.device)
-    lsi = torch.cat((sh.new_zeros((1,)), sh.prod(1).cumsum(0)[:-1]))
+    key = (tuple(tuple(int(x) for x in hw) for hw in shapes), str(value.device))
+    if key not in _shape_cache:  # built once per pyramid so the call is CUDA-graph capturable
+        sh_ = torch.as_tensor(shapes, dtype=torch.int64, device=value.device)
+        _shape_cache[key] = (sh_, torch.cat((sh_.new_zeros((1,)), sh_.prod(1).cumsum(0)[:-1])))
+    sh, lsi = _shape_cache[key]
     out = torch.zeros(B, Q, H * D, dtype=torch.float32, device=value.device)
     rc = _lib.ref_msda_im2col_f32(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(value.data_ptr()),
                                   C.c_void_p(sh.data_ptr()), C.c_void_p(lsi.data_ptr()), C.c_void_p(loc.data_ptr()),

@@ -404,3 +404,54 @@ def test_core_vs_reference_cuda_kernel(dev):
         ref = ref_cuda.msda_im2col(v, shapes, l, ww)
         out = ops.msda_sampled(v, shapes, l, ww)
         assert rel_rms(out.cpu().numpy(), ref.cpu().numpy()) < 1e-5, name
+
+
+def test_pipelined_submit_equals_synchronous_steps(dev):
+    """The host-ahead pipeline (submit/collect, speculative padded sizes, device-side abort + re-launch)
+    must produce exactly the rows of the synchronous step() loop: bit-identical IDs AND boxes/scores
+    (same kernels, same inputs; padding rows never influence real rows). margin=0 with an 8-row bucket
+    forces mis-speculation whenever the track count crosses a bucket boundary, so the abort path runs."""
+    m, ops, syn, mg, tp = _mods()
+    from moyolo_b200.tracker import DecoderWeights, TrackEngine
+    spec = syn.DecoderSpec()
+    sd = syn.make_decoder_state(spec, 7)
+    shapes = [list(s) for s in syn.PYRAMIDS["tiny"]]
+    n_frames, nd, S = 10, 64, 2
+    gens = [syn.SequenceGenerator(syn.SequenceSpec(name="tiny", n_frames=n_frames, n_detect=nd, seed=s, shapes=shapes),
+                                  spec.d_model) for s in range(S)]
+    frames = [[tuple(t.clone() for t in g.next_frame()) for _ in range(n_frames)] for g in gens]
+    sd = _calibrated_state(syn, tp, spec, sd, frames[0][0], shapes)
+    W = DecoderWeights(sd, spec, dev, "bf16")
+    batches = [tuple(torch.stack([frames[s][t][k] for s in range(S)]).to(dev) for k in range(3)) for t in range(n_frames)]
+    torch.cuda.synchronize()
+
+    ref = TrackEngine(sd, spec, shapes, dev, "bf16", nd, S, weights=W)
+    ref_rows = []
+    for t in range(n_frames):
+        outs = ref.step(*batches[t])
+        ref_rows.append([{k: v.clone().cpu() for k, v in o.items()} for o in outs])
+    ref_table = ref.track_table().clone().cpu()
+    assert ref_table.shape[0] > 0 and max(ref.n_tracks_host()) > 0
+
+    for margin, bucket in ((0, 8), (32, 64)):
+        eng = TrackEngine(sd, spec, shapes, dev, "bf16", nd, S, weights=W, margin=margin, bucket=bucket)
+        eng.set_seq_ids([5, 9])
+        got = {}
+        for t in range(n_frames):
+            eng.submit(*batches[t], want_rows=True)
+            if t > 0:
+                got[t - 1] = [{k: v.clone() for k, v in o.items()} for o in eng.collect(t - 1)]
+        got[n_frames - 1] = [{k: v.clone() for k, v in o.items()} for o in eng.collect(n_frames - 1)]
+        table = eng.track_table().clone().cpu()
+        if margin == 0:
+            assert eng.aborts > 0, "the abort / re-launch path was not exercised"
+        for t in range(n_frames):
+            for s in range(S):
+                for k in ("ids", "boxes", "scores"):
+                    assert torch.equal(got[t][s][k], ref_rows[t][s][k].to(got[t][s][k].dtype)), (margin, t, s, k)
+                assert torch.equal(got[t][s]["labels"], ref_rows[t][s]["labels"]), (margin, t, s)
+        # the device-resident table: same rows, slot ids remapped to the global sequence ids
+        want = ref_table.clone()
+        want[:, 0] = torch.where(ref_table[:, 0] == 0, torch.tensor(5.0), torch.tensor(9.0))
+        assert torch.equal(table, want), margin
+        assert ref.n_tracks_host() == eng.n_tracks_host()
