@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=12, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-tracks", type=int, default=160, help="pre-capture frame graphs up to this many tracks/seq")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed `value` leg (ncu --profile-from-start off)")
     return ap.parse_args()
 
 
@@ -185,12 +187,17 @@ def run_moyolo(args):
     ops.LAUNCHES = 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:
+        torch.cuda.cudart().cudaProfilerStart()
     e0.record()
     for t in range(K):
         eng.submit(*dev_batches[t], want_rows=False)
     local_table = eng.track_table()
     table = sharding.gather_track_rows(local_table)
     e1.record()
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.cudart().cudaProfilerStop()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=device)
     if world > 1:
