@@ -125,6 +125,23 @@ int moyolo_linear(const void* x, int64_t ldx, const void* w, const float* bias, 
                   int64_t ldy, int64_t M, int N, int K, int in_dtype, int out_dtype, int epilogue,
                   const uint8_t* zero_rows, int engine, moyolo_stream_t stream);
 
+/* Two A operands in ONE launch: y[:, :n_split] = x1 . w[:n_split]^T, y[:, n_split:] = x2 . w[n_split:]^T (+ bias).
+ * The packed in-projection of nn.MultiheadAttention with q = k = x + pos, v = x (transformer.py:637-638):
+ * x1 = x + pos, x2 = x, n_split = 2C. bf16 operands, tcgen05 engine only; n_split % 64 == 0. */
+int moyolo_linear_dual(const void* x1, int64_t ldx1, const void* x2, int64_t ldx2, int n_split,
+                       const void* w, const float* bias, void* y, int64_t ldy, int64_t M, int N, int K,
+                       int out_dtype, moyolo_stream_t stream);
+
+/* Post-norm residual block in one launch (transformer.py:640-641, 646-647, 578-579; qim.py:277-298):
+ *   t = x[M,K] . w[N,K]^T + bias;  out = LayerNorm(t + residual) * gamma + beta   (N == 256, eps as given)
+ * written as out_f32 [M,N] fp32, out_lp [M,N] bf16 and out_pos_lp [M,N] bf16 = out + pos (any may be NULL).
+ * x, w bf16 (tcgen05 engine); residual/pos/out_* contiguous [M, N]. The LayerNorm row is spread over the
+ * 8 CTAs of a thread-block cluster; statistics are exchanged through distributed shared memory. */
+int moyolo_linear_add_layernorm(const void* x, int64_t ldx, const void* w, const float* bias,
+                                const float* residual, const float* gamma, const float* beta, float eps,
+                                int64_t M, int N, int K, float* out_f32, void* out_lp, const float* pos,
+                                void* out_pos_lp, moyolo_stream_t stream);
+
 /* Query self-attention over ragged sequences (transformer.py:637-641 with nn.MultiheadAttention
  * semantics: scores = (q/sqrt(head_dim)) . k^T, softmax over all keys of the same sequence, . v).
  * q, k, v: [R, n_heads*head_dim] slices with row strides ldq/ldk/ldv (elements) of dtype `dtype`;

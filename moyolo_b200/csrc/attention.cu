@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(kAttThreads) self_attention_kernel(
     const T* __restrict__ q, int64_t ldq, const T* __restrict__ k, int64_t ldk, const T* __restrict__ v,
     int64_t ldv, T* __restrict__ out, int64_t ldo, int batch, const int32_t* __restrict__ row_offsets,
     const int32_t* __restrict__ seg_len, const float* __restrict__ attn_mask) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int DPL = DH / 32;  // output dims per lane
   __shared__ float s_k[kKT][DH + 1];
   __shared__ float s_v[kKT][DH];
@@ -173,6 +175,8 @@ __global__ void __launch_bounds__(128, 3) self_attention_mma_kernel(
     const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
     const __nv_bfloat16* __restrict__ v, int64_t ldv, __nv_bfloat16* __restrict__ out, int64_t ldo, int batch,
     const int32_t* __restrict__ row_offsets, const int32_t* __restrict__ seg_len) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int PITCH = DH + 8;      // bf16 elements; (DH+8)*2 bytes keeps ldmatrix rows on distinct banks
   constexpr int KS = DH / 16;        // k-steps of S = Q K^T
   constexpr int NT = DH / 8;         // n-tiles of O
@@ -348,16 +352,16 @@ extern "C" int moyolo_self_attention(const void* q, int64_t ldq, const void* k, 
     const __nv_bfloat16 *qq = static_cast<const __nv_bfloat16*>(q), *kk = static_cast<const __nv_bfloat16*>(k),
                         *vv = static_cast<const __nv_bfloat16*>(v);
     if (head_dim == 32)
-      self_attention_mma_kernel<32><<<mgrid, 128, 0, st>>>(qq, ldq, kk, ldk, vv, ldv, static_cast<__nv_bfloat16*>(out),
+      launch_k(self_attention_mma_kernel<32>, dim3(mgrid), dim3(128), 0, st, qq, ldq, kk, ldk, vv, ldv, static_cast<__nv_bfloat16*>(out),
                                                           ldo, batch, row_offsets, seg_len);
     else
-      self_attention_mma_kernel<64><<<mgrid, 128, 0, st>>>(qq, ldq, kk, ldk, vv, ldv, static_cast<__nv_bfloat16*>(out),
+      launch_k(self_attention_mma_kernel<64>, dim3(mgrid), dim3(128), 0, st, qq, ldq, kk, ldk, vv, ldv, static_cast<__nv_bfloat16*>(out),
                                                           ldo, batch, row_offsets, seg_len);
     return check_launch("self_attention_mma_kernel");
   }
   dim3 grid(static_cast<unsigned>(tiles), n_heads);
 #define LAUNCH(T, DH)                                                                              \
-  self_attention_kernel<T, DH><<<grid, kAttThreads, 0, st>>>(                                       \
+  launch_k(self_attention_kernel<T, DH>, dim3(grid), dim3(kAttThreads), 0, st,                                        \
       static_cast<const T*>(q), ldq, static_cast<const T*>(k), ldk, static_cast<const T*>(v), ldv, \
       static_cast<T*>(out), ldo, batch, row_offsets, seg_len, attn_mask)
   if (dtype == MOYOLO_F32) {

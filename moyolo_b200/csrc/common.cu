@@ -1,5 +1,6 @@
 // Status / error plumbing and small host helpers shared by every entry point.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -16,6 +17,14 @@ int fail(int code, const char* fmt, ...) {
   vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
   va_end(ap);
   return code;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MOYOLO_PDL");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
 }
 
 int check_launch(const char* what) {

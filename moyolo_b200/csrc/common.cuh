@@ -21,6 +21,36 @@ int check_launch(const char* what);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization so
+// that, inside a stream or a captured graph, the next kernel's CTAs are scheduled while the previous
+// kernel drains (the frame is a chain of ~100 short dependent launches). Contract for kernels:
+//   * pdl_trigger() once every resource the CTA needs has been acquired (TMEM columns in particular:
+//     a dependent that grabbed TMEM first could otherwise starve the kernel it waits for);
+//   * pdl_wait() before the first access to any global memory that is not immutable during a frame
+//     (weights, biases and LayerNorm parameters are immutable; activations, masks and state are not).
+// MOYOLO_PDL=0 in the environment disables the attribute (the device instructions are then no-ops).
+bool pdl_enabled();
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 struct LevelTable {
   int n;
   int h[MOYOLO_MAX_LEVELS];

@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) add_layernorm_kernel(
     const float* __restrict__ x, const float* __restrict__ residual, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, int64_t rows, int C, float* __restrict__ out_f32,
     LP_T* __restrict__ out_lp, const float* __restrict__ pos, LP_T* __restrict__ out_pos_lp) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(kLn256Warps * 32) add_layernorm256_kernel(
     const float* __restrict__ x, const float* __restrict__ residual, const float* __restrict__ gamma,
     const float* __restrict__ beta, float eps, int64_t rows, float* __restrict__ out_f32,
     LP_T* __restrict__ out_lp, const float* __restrict__ pos, LP_T* __restrict__ out_pos_lp) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int C = 256;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kLn256Warps + (threadIdx.x >> 5);
@@ -138,6 +142,8 @@ __global__ void __launch_bounds__(kLn256Warps * 32) add_layernorm256_kernel(
 template <typename LP_T>
 __global__ void add_cast_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                 LP_T* __restrict__ out, int64_t n) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     out[i] = from_float<LP_T>(a[i] + (b ? b[i] : 0.0f));
@@ -147,6 +153,8 @@ template <typename HT>
 __global__ void __launch_bounds__(kRowWarps * 32) box_refine_kernel(
     const HT* __restrict__ h, int64_t ldh, const float* __restrict__ w3, const float* __restrict__ b3,
     const float* __restrict__ ref, float* __restrict__ new_ref, int64_t rows, int K) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -170,6 +178,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) score_head_kernel(
     const XT* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
     float* __restrict__ logits, float* __restrict__ scores, int32_t* __restrict__ labels, int64_t rows,
     int K, int nc) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -189,6 +199,8 @@ __global__ void __launch_bounds__(kRowWarps * 32) score_head_kernel(
 }
 
 __global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, int inverse) {
+  pdl_trigger();
+  pdl_wait();
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     y[i] = inverse ? inverse_sigmoidf_(x[i]) : sigmoidf_(x[i]);
@@ -196,6 +208,8 @@ __global__ void sigmoid_kernel(const float* __restrict__ x, float* __restrict__ 
 
 __global__ void pos2posemb_kernel(const float* __restrict__ pos, float* __restrict__ emb, int64_t rows,
                                   int n_coord, int F, float temperature) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = rows * n_coord * F;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -211,6 +225,8 @@ __global__ void pos2posemb_kernel(const float* __restrict__ pos, float* __restri
 template <typename TO>
 __global__ void linear_k4_relu_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                       const float* __restrict__ b, TO* __restrict__ y, int64_t rows, int N) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = rows * N;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -249,21 +265,21 @@ extern "C" int moyolo_add_layernorm(const float* x, const float* residual, const
   if (fast && (lp_dtype == MOYOLO_BF16 || lp_dtype == MOYOLO_F32)) {
     const unsigned blocks = static_cast<unsigned>((rows + kLn256Warps - 1) / kLn256Warps);
     if (lp_dtype == MOYOLO_BF16)
-      add_layernorm256_kernel<__nv_bfloat16><<<blocks, kLn256Warps * 32, 0, st>>>(
+      launch_k(add_layernorm256_kernel<__nv_bfloat16>, dim3(blocks), dim3(kLn256Warps * 32), 0, st, 
           x, residual, gamma, beta, eps, rows, out_f32, static_cast<__nv_bfloat16*>(out_lp), pos,
           static_cast<__nv_bfloat16*>(out_pos_lp));
     else
-      add_layernorm256_kernel<float><<<blocks, kLn256Warps * 32, 0, st>>>(
+      launch_k(add_layernorm256_kernel<float>, dim3(blocks), dim3(kLn256Warps * 32), 0, st, 
           x, residual, gamma, beta, eps, rows, out_f32, static_cast<float*>(out_lp), pos,
           static_cast<float*>(out_pos_lp));
     return check_launch("add_layernorm256_kernel");
   }
   if (lp_dtype == MOYOLO_BF16) {
-    add_layernorm_kernel<__nv_bfloat16><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+    launch_k(add_layernorm_kernel<__nv_bfloat16>, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st, 
         x, residual, gamma, beta, eps, rows, C, out_f32, static_cast<__nv_bfloat16*>(out_lp), pos,
         static_cast<__nv_bfloat16*>(out_pos_lp));
   } else if (lp_dtype == MOYOLO_F32) {
-    add_layernorm_kernel<float><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+    launch_k(add_layernorm_kernel<float>, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st, 
         x, residual, gamma, beta, eps, rows, C, out_f32, static_cast<float*>(out_lp), pos,
         static_cast<float*>(out_pos_lp));
   } else {
@@ -278,9 +294,9 @@ extern "C" int moyolo_add_cast(const float* a, const float* b, void* out_lp, int
   if (n == 0) return MOYOLO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (lp_dtype == MOYOLO_BF16)
-    add_cast_kernel<__nv_bfloat16><<<ew_blocks(n), 256, 0, st>>>(a, b, static_cast<__nv_bfloat16*>(out_lp), n);
+    launch_k(add_cast_kernel<__nv_bfloat16>, dim3(ew_blocks(n)), dim3(256), 0, st, a, b, static_cast<__nv_bfloat16*>(out_lp), n);
   else if (lp_dtype == MOYOLO_F32)
-    add_cast_kernel<float><<<ew_blocks(n), 256, 0, st>>>(a, b, static_cast<float*>(out_lp), n);
+    launch_k(add_cast_kernel<float>, dim3(ew_blocks(n)), dim3(256), 0, st, a, b, static_cast<float*>(out_lp), n);
   else
     return fail(MOYOLO_ERR_UNSUPPORTED, "add_cast: unsupported lp_dtype %d", lp_dtype);
   return check_launch("add_cast_kernel");
@@ -294,10 +310,10 @@ extern "C" int moyolo_box_refine(const void* h, int64_t ldh, int h_dtype, const 
   if (rows == 0) return MOYOLO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (h_dtype == MOYOLO_BF16)
-    box_refine_kernel<__nv_bfloat16><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+    launch_k(box_refine_kernel<__nv_bfloat16>, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st, 
         static_cast<const __nv_bfloat16*>(h), ldh, w3, b3, ref, new_ref, rows, K);
   else if (h_dtype == MOYOLO_F32)
-    box_refine_kernel<float><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(static_cast<const float*>(h), ldh,
+    launch_k(box_refine_kernel<float>, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st, static_cast<const float*>(h), ldh,
                                                                         w3, b3, ref, new_ref, rows, K);
   else
     return fail(MOYOLO_ERR_UNSUPPORTED, "box_refine: unsupported h_dtype %d", h_dtype);
@@ -312,10 +328,10 @@ extern "C" int moyolo_score_head(const void* x, int64_t ldx, int x_dtype, const 
   if (rows == 0) return MOYOLO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_dtype == MOYOLO_BF16)
-    score_head_kernel<__nv_bfloat16><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+    launch_k(score_head_kernel<__nv_bfloat16>, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st, 
         static_cast<const __nv_bfloat16*>(x), ldx, w, b, logits, scores, labels, rows, K, nc);
   else if (x_dtype == MOYOLO_F32)
-    score_head_kernel<float><<<row_blocks(rows), kRowWarps * 32, 0, st>>>(
+    launch_k(score_head_kernel<float>, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st, 
         static_cast<const float*>(x), ldx, w, b, logits, scores, labels, rows, K, nc);
   else
     return fail(MOYOLO_ERR_UNSUPPORTED, "score_head: unsupported x_dtype %d", x_dtype);
@@ -325,14 +341,14 @@ extern "C" int moyolo_score_head(const void* x, int64_t ldx, int x_dtype, const 
 extern "C" int moyolo_sigmoid(const float* x, float* y, int64_t n, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(x && y && n >= 0, MOYOLO_ERR_BAD_ARG, "sigmoid: bad arguments");
   if (n == 0) return MOYOLO_OK;
-  sigmoid_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, 0);
+  launch_k(sigmoid_kernel, dim3(ew_blocks(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, y, n, 0);
   return check_launch("sigmoid_kernel");
 }
 
 extern "C" int moyolo_inverse_sigmoid(const float* x, float* y, int64_t n, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(x && y && n >= 0, MOYOLO_ERR_BAD_ARG, "inverse_sigmoid: bad arguments");
   if (n == 0) return MOYOLO_OK;
-  sigmoid_kernel<<<ew_blocks(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, 1);
+  launch_k(sigmoid_kernel, dim3(ew_blocks(n)), dim3(256), 0, static_cast<cudaStream_t>(stream), x, y, n, 1);
   return check_launch("inverse_sigmoid_kernel");
 }
 
@@ -341,7 +357,7 @@ extern "C" int moyolo_pos2posemb(const float* pos, float* emb, int64_t rows, int
   MOYOLO_REQUIRE(pos && emb, MOYOLO_ERR_BAD_ARG, "pos2posemb: null pointer");
   MOYOLO_REQUIRE(rows >= 0 && n_coord > 0 && num_pos_feats > 0, MOYOLO_ERR_BAD_SHAPE, "pos2posemb: bad sizes");
   if (rows == 0) return MOYOLO_OK;
-  pos2posemb_kernel<<<ew_blocks(rows * n_coord * num_pos_feats), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(pos2posemb_kernel, dim3(ew_blocks(rows * n_coord * num_pos_feats)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       pos, emb, rows, n_coord, num_pos_feats, temperature);
   return check_launch("pos2posemb_kernel");
 }
@@ -353,10 +369,10 @@ extern "C" int moyolo_linear_k4_relu(const float* x, const float* w, const float
   if (rows == 0) return MOYOLO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (out_dtype == MOYOLO_BF16)
-    linear_k4_relu_kernel<__nv_bfloat16><<<ew_blocks(rows * N), 256, 0, st>>>(
+    launch_k(linear_k4_relu_kernel<__nv_bfloat16>, dim3(ew_blocks(rows * N)), dim3(256), 0, st, 
         x, w, b, static_cast<__nv_bfloat16*>(y), rows, N);
   else if (out_dtype == MOYOLO_F32)
-    linear_k4_relu_kernel<float><<<ew_blocks(rows * N), 256, 0, st>>>(x, w, b, static_cast<float*>(y), rows, N);
+    launch_k(linear_k4_relu_kernel<float>, dim3(ew_blocks(rows * N)), dim3(256), 0, st, x, w, b, static_cast<float*>(y), rows, N);
   else
     return fail(MOYOLO_ERR_UNSUPPORTED, "linear_k4_relu: unsupported out_dtype %d", out_dtype);
   return check_launch("linear_k4_relu_kernel");

@@ -31,6 +31,8 @@ __global__ void frame_assemble_kernel(int n_seq, int n_detect, int C, int cap, c
                                       int64_t* __restrict__ ids, int64_t* __restrict__ dis,
                                       int32_t* __restrict__ row_offsets, int num_pos_feats, float temperature,
                                       int rows_pad, int32_t* __restrict__ ctrl) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x;
   // Speculative launch guard: the host picks rows_pad from the track counts of an EARLIER frame. If the
   // real row count does not fit (or an earlier frame already aborted), every block consistently
@@ -125,6 +127,8 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
     int32_t* __restrict__ n_active, int32_t* __restrict__ active_index, float* __restrict__ c_ref,
     float* __restrict__ c_pos, float* __restrict__ c_hs, float* __restrict__ c_box, int32_t* __restrict__ t_label,
     int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis, const int32_t* __restrict__ ctrl) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int s_warp[33];
   if (ctrl != nullptr && ctrl[kCtrlAbort] != 0) return;  // aborted frame: leave the track state untouched
   const int s = blockIdx.x;
@@ -172,6 +176,8 @@ __global__ void frame_writeback_kernel(int C, int cap, const int32_t* __restrict
                                        const float* __restrict__ c_box, float* __restrict__ t_qpos,
                                        float* __restrict__ t_ref, int32_t* __restrict__ n_tracks,
                                        const int32_t* __restrict__ ctrl) {
+  pdl_trigger();
+  pdl_wait();
   if (ctrl != nullptr && ctrl[kCtrlAbort] != 0) return;
   const int s = blockIdx.x;
   const int off = row_offsets[s];
@@ -196,6 +202,8 @@ __global__ void __launch_bounds__(256) frame_emit_kernel(
     const int32_t* __restrict__ n_active, const int32_t* __restrict__ active_index,
     const int32_t* __restrict__ seq_ids, float* __restrict__ frame_rows, float* __restrict__ table, int table_cap,
     int32_t* __restrict__ ctrl) {
+  pdl_trigger();
+  pdl_wait();
   if (ctrl[kCtrlAbort] != 0) return;
   const int total = row_offsets[n_seq];
   for (int r = threadIdx.x; r < rows_pad; r += blockDim.x) {
@@ -262,7 +270,7 @@ extern "C" int moyolo_frame_assemble(int n_seq, int n_detect, int C, int cap, co
                  "frame_assemble: bad sizes");
   MOYOLO_REQUIRE(C == 4 * num_pos_feats, MOYOLO_ERR_BAD_SHAPE, "frame_assemble: C must equal 4*num_pos_feats");
   const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
-  frame_assemble_kernel<<<static_cast<unsigned>(rows_pad), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(frame_assemble_kernel, dim3(static_cast<unsigned>(rows_pad)), dim3(threads), 0, static_cast<cudaStream_t>(stream), 
       n_seq, n_detect, C, cap, n_tracks, t_ref, t_qpos, t_label, t_ids, t_dis, class_embed, det_embed, det_refer, x,
       refer_logit, pos, ids, dis, row_offsets, num_pos_feats, temperature, static_cast<int>(rows_pad), ctrl);
   return check_launch("frame_assemble_kernel");
@@ -278,7 +286,7 @@ extern "C" int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* ro
                      active_index && c_ref && c_pos && c_hs && c_box && t_label && t_ids && t_dis,
                  MOYOLO_ERR_BAD_ARG, "frame_compact: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_compact: bad sizes");
-  frame_compact_kernel<<<n_seq, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(frame_compact_kernel, dim3(n_seq), dim3(1024), 0, static_cast<cudaStream_t>(stream), 
       C, cap, row_offsets, ids, dis, labels, refer_logit, pos, hs, boxes, n_active, active_index, c_ref, c_pos, c_hs,
       c_box, t_label, t_ids, t_dis, ctrl);
   return check_launch("frame_compact_kernel");
@@ -291,7 +299,7 @@ extern "C" int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* 
                  "frame_writeback: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_writeback: bad sizes");
   dim3 grid(n_seq, 8);
-  frame_writeback_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, cap, row_offsets, n_active, new_qpos,
+  launch_k(frame_writeback_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), C, cap, row_offsets, n_active, new_qpos,
                                                                              c_box, t_qpos, t_ref, n_tracks, ctrl);
   return check_launch("frame_writeback_kernel");
 }
@@ -308,7 +316,7 @@ extern "C" int moyolo_frame_emit(int n_seq, int64_t rows_pad, const int32_t* row
                  "frame_emit: bad sizes");
   MOYOLO_REQUIRE(aligned16(boxes) && aligned16(frame_rows), MOYOLO_ERR_ALIGNMENT,
                  "frame_emit: boxes / frame_rows must be 16-byte aligned");
-  frame_emit_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(frame_emit_kernel, dim3(1), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       n_seq, static_cast<int>(rows_pad), row_offsets, ids, boxes, scores, labels, n_active, active_index, seq_ids,
       frame_rows, table, static_cast<int>(table_cap), ctrl);
   return check_launch("frame_emit_kernel");

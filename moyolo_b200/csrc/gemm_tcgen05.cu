@@ -1,4 +1,4 @@
-// tcgen05 / TMA / TMEM GEMM for sm_100a:  y[M,N] = act(x[M,K] . w[N,K]^T + bias), bf16 operands,
+// tcgen05 / TMA / TMEM GEMMs for sm_100a:  y[M,N] = act(x[M,K] . w[N,K]^T + bias), bf16 operands,
 // fp32 accumulation in tensor memory. Serves every dense contraction of the decoder hot path
 // (value_proj for all layers at once, sampling_offsets|attention_weights, output_proj, MHA in/out
 // projections, FFN, bbox-MLP hidden layers; nn.Linear call sites of
@@ -6,14 +6,25 @@
 //
 // Both operands are K-major (x rows and nn.Linear's [out,in] weight rows are contiguous in K), so no
 // transposes are needed: TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages [128 x 64] x-tiles and
-// [BN x 64] w-tiles into a 4-deep shared-memory ring; one elected thread issues
-// tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16) four times per stage; accumulators live in
-// BN TMEM columns; four epilogue warps read them back with tcgen05.ld (one output row per thread),
-// add bias / ReLU / row mask and store fp32 or bf16.
+// [BN x 64] w-tiles in shared memory; one elected thread issues tcgen05.mma.cta_group::1.kind::f16
+// (M=128, N=BN, K=16); accumulators live in TMEM; epilogue warps read them back with tcgen05.ld
+// (one output row per thread).
 //
-// Warp roles (192 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2..5
-// epilogue (TMEM lane quadrant = warp_id % 4). One output tile per CTA; BN is chosen small (32) when
-// M is small so that the few hundred query rows still spread over many SMs.
+// Two kernels:
+//  * gemm_tcgen05_kernel<BN, TO, LN> — one output tile per CTA, tuned for LATENCY (the few-hundred-row
+//    query GEMMs of a frame are a chain of short dependent launches): weight tiles are requested
+//    before the programmatic-dependency wait, activation tiles right after it, bias/gamma/beta and the
+//    residual rows are prefetched while the MMAs run. Options: two A operands split at a column
+//    (q,k from x+pos and v from x in ONE launch, transformer.py:637-638), and LN=true: the
+//    residual-add + LayerNorm (+ "+pos" operand of the next GEMM) of the post-norm blocks
+//    (transformer.py:640-641, 646-647, 578-579) fused into the epilogue. A LayerNorm row spans the
+//    256/BN CTAs of a thread-block cluster; row statistics are exchanged through distributed shared
+//    memory (two-pass mean / centred variance, two cluster barriers).
+//  * gemm_stream_kernel — persistent, weight-resident kernel for the tall value projection
+//    (M = S*Lv ~ 10^4..10^5 rows, K = 256): every CTA keeps its [128 x 256] weight slab in shared
+//    memory, streams x-tiles through a 6-deep TMA ring, double-buffers the accumulator in TMEM so the
+//    epilogue of tile i overlaps the MMAs of tile i+1, and writes bf16 through swizzled shared-memory
+//    slabs with TMA stores (full-line writes instead of one row per thread).
 #include <cuda.h>
 
 #include <mutex>
@@ -26,6 +37,7 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;  // 64 bf16 = 128 bytes = one SWIZZLE_128B row
 constexpr int kStages = 4;
 constexpr int kGemmThreads = 192;
+constexpr int kLnCols = 256;  // LayerNorm width of the fused epilogue (d_model)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -35,6 +47,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(
@@ -54,6 +69,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -98,45 +119,115 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-struct GemmSmem {
-  // data ring first: every stage base must be 1024-byte aligned for SWIZZLE_128B
-  // (sizes are multiples of 1024: A 16 KiB, B BN*128 B with BN % 8 == 0 ... BN >= 32 -> 4 KiB)
+// ---- thread-block cluster helpers (fused LayerNorm epilogue) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, uint32_t rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
+// Everything the epilogues need besides the tensor maps.
+struct GemmEpi {
+  const float* bias;
+  void* y;
+  int64_t ldy;
+  int64_t M;
+  int N;
+  int K;
+  int relu;
+  const uint8_t* zero_rows;
+  int n_split;  // output columns >= n_split take their A operand from the second tensor map
+  // LN epilogue (N == 256): out = LayerNorm(acc + bias + residual) * gamma + beta
+  const float* residual;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* out_f32;
+  void* out_lp;
+  const float* pos;
+  void* out_pos_lp;
+};
+
+template <int BN, bool LN>
+struct GemmCtl {
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t tmem_full;
   uint32_t tmem_base;
+  float bias[BN];
+  float gamma[LN ? BN : 1];
+  float beta[LN ? BN : 1];
+  float red[LN ? 2 : 1][LN ? kLnCols / BN : 1][LN ? kBM : 1];  // [pass][peer CTA][row]
 };
 
-template <int BN, typename TO>
+template <typename TO>
+__device__ __forceinline__ void store16(TO* dst, const float (&v)[16], bool vec_ok) {
+  if (vec_ok) {
+    if constexpr (sizeof(TO) == 2) {
+      uint4 a, b;
+      a.x = float2_to_bf16x2(v[0], v[1]);   a.y = float2_to_bf16x2(v[2], v[3]);
+      a.z = float2_to_bf16x2(v[4], v[5]);   a.w = float2_to_bf16x2(v[6], v[7]);
+      b.x = float2_to_bf16x2(v[8], v[9]);   b.y = float2_to_bf16x2(v[10], v[11]);
+      b.z = float2_to_bf16x2(v[12], v[13]); b.w = float2_to_bf16x2(v[14], v[15]);
+      reinterpret_cast<uint4*>(dst)[0] = a;
+      reinterpret_cast<uint4*>(dst)[1] = b;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[j] = from_float<TO>(v[j]);
+  }
+}
+
+template <int BN, typename TO, bool LN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                    const float* __restrict__ bias, TO* __restrict__ y, int64_t ldy, int64_t M, int N, int K,
-                    int relu, const uint8_t* __restrict__ zero_rows) {
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_x2,
+                    const __grid_constant__ CUtensorMap tmap_w, const GemmEpi e) {
   constexpr uint32_t kABytes = kBM * kBK * 2;
   constexpr uint32_t kBBytes = BN * kBK * 2;
   constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;  // power of two >= 32 (BN in {32,64,128,256})
+  constexpr int NC = kLnCols / BN;                   // CTAs per LayerNorm row (cluster size) when LN
   extern __shared__ uint8_t smem_raw[];
-  // 1024-byte align the dynamic shared memory window
+  // 1024-byte align the dynamic shared memory window (SWIZZLE_128B atoms)
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = base;
   uint8_t* smem_b = base + kStages * kABytes;
-  GemmSmem* ctl = reinterpret_cast<GemmSmem*>(smem_b + kStages * kBBytes);
+  using Ctl = GemmCtl<BN, LN>;
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem_b + kStages * kBBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * kBM;
   const int n0 = blockIdx.x * BN;
-  const int num_kb = K / kBK;
+  const int num_kb = e.K / kBK;
+  const int pre = num_kb < kStages ? num_kb : kStages;  // k-blocks whose stage is free at start
 
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(smem_u32(&ctl->full[s]), 1);
+      mbar_init(smem_u32(&ctl->full[s]), 2);  // one arrive.expect_tx per operand
       mbar_init(smem_u32(&ctl->empty[s]), 1);
     }
     mbar_init(smem_u32(&ctl->tmem_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // weights are immutable during a frame: request them before waiting on the previous kernel
+    for (int kb = 0; kb < pre; ++kb) {
+      const uint32_t full = smem_u32(&ctl->full[kb]);
+      mbar_expect_tx(full, kBBytes);
+      tma_load_2d(smem_u32(smem_b + kb * kBBytes), &tmap_w, full, kb * kBK, n0);
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
@@ -144,32 +235,48 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp >= 2) {  // per-column epilogue constants (immutable)
+    for (int i = threadIdx.x - 64; i < BN; i += kGemmThreads - 64) {
+      const bool in = n0 + i < e.N;
+      ctl->bias[i] = (e.bias != nullptr && in) ? __ldg(e.bias + n0 + i) : 0.0f;
+      if constexpr (LN) {
+        ctl->gamma[i] = __ldg(e.gamma + n0 + i);
+        ctl->beta[i] = __ldg(e.beta + n0 + i);
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();  // TMEM is allocated: the next kernel may start its own prologue
+  if constexpr (LN) cluster_arrive();  // #0: peers are running (required before any DSMEM access)
   const uint32_t tmem_acc = ctl->tmem_base;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
+      const CUtensorMap* ta = (n0 >= e.n_split) ? &tmap_x2 : &tmap_x;
+      pdl_wait();  // activations come from the previous kernel
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(smem_u32(&ctl->empty[s]), ph ^ 1);
         const uint32_t full = smem_u32(&ctl->full[s]);
-        mbar_expect_tx(full, kABytes + kBBytes);
-        tma_load_2d(smem_u32(smem_a + s * kABytes), &tmap_x, full, kb * kBK, m0);
-        tma_load_2d(smem_u32(smem_b + s * kBBytes), &tmap_w, full, kb * kBK, n0);
+        if (kb >= pre) {
+          mbar_wait(smem_u32(&ctl->empty[s]), ((kb / kStages) & 1) ^ 1);
+          mbar_expect_tx(full, kBBytes);
+          tma_load_2d(smem_u32(smem_b + s * kBBytes), &tmap_w, full, kb * kBK, n0);
+        }
+        mbar_expect_tx(full, kABytes);
+        tma_load_2d(smem_u32(smem_a + s * kABytes), ta, full, kb * kBK, m0);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(kBM, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(smem_u32(&ctl->full[s]), ph);
+        mbar_wait(smem_u32(&ctl->full[s]), (kb / kStages) & 1);
         tc_fence_after();
         const uint64_t adesc = make_smem_desc(smem_u32(smem_a + s * kABytes));
         const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + s * kBBytes));
@@ -182,47 +289,139 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       }
       umma_commit(smem_u32(&ctl->tmem_full));   // accumulator complete
     }
+    __syncwarp();
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quadrant = warp % 4, one output row per thread =====
     const int quad = warp & 3;
-    const int64_t row = static_cast<int64_t>(m0) + quad * 32 + lane;
-    mbar_wait(smem_u32(&ctl->tmem_full), 0);
-    tc_fence_after();
-    const bool row_ok = row < M;
-    const bool zero = row_ok && zero_rows != nullptr && zero_rows[row] != 0;
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(y) & 15u) == 0 && (ldy * sizeof(TO)) % 16 == 0;
+    const int rl = quad * 32 + lane;  // row inside the tile
+    const int64_t row = static_cast<int64_t>(m0) + rl;
+    const bool row_ok = row < e.M;
+    const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
+    pdl_wait();
+    if constexpr (!LN) {
+      const bool zero = row_ok && e.zero_rows != nullptr && e.zero_rows[row] != 0;
+      TO* yrow = static_cast<TO*>(e.y) + row * e.ldy + n0;
+      const bool vec_ok = (reinterpret_cast<uintptr_t>(e.y) & 15u) == 0 && (e.ldy * sizeof(TO)) % 16 == 0;
+      mbar_wait(smem_u32(&ctl->tmem_full), 0);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + c0, r);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!row_ok || n0 + c0 >= N) continue;
-      float v[16];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tbase + c0, r0);
+        tmem_ld16(tbase + c0 + 16, r1);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[16];
+        if (n0 + c0 < e.N) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float t = __uint_as_float(r[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.0f);
-        if (relu) t = fmaxf(t, 0.0f);
-        v[j] = zero ? 0.0f : t;
-      }
-      TO* dst = y + row * ldy + n0 + c0;
-      if (vec_ok) {
-        if constexpr (sizeof(TO) == 2) {
-          uint4 a, b;
-          a.x = float2_to_bf16x2(v[0], v[1]);   a.y = float2_to_bf16x2(v[2], v[3]);
-          a.z = float2_to_bf16x2(v[4], v[5]);   a.w = float2_to_bf16x2(v[6], v[7]);
-          b.x = float2_to_bf16x2(v[8], v[9]);   b.y = float2_to_bf16x2(v[10], v[11]);
-          b.z = float2_to_bf16x2(v[12], v[13]); b.w = float2_to_bf16x2(v[14], v[15]);
-          reinterpret_cast<uint4*>(dst)[0] = a;
-          reinterpret_cast<uint4*>(dst)[1] = b;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j = 0; j < 16; ++j) {
+            float t = __uint_as_float(r0[j]) + ctl->bias[c0 + j];
+            if (e.relu) t = fmaxf(t, 0.0f);
+            v[j] = zero ? 0.0f : t;
+          }
+          store16<TO>(yrow + c0, v, vec_ok);
         }
-      } else {
+        if (n0 + c0 + 16 < e.N) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) dst[j] = from_float<TO>(v[j]);
+          for (int j = 0; j < 16; ++j) {
+            float t = __uint_as_float(r1[j]) + ctl->bias[c0 + 16 + j];
+            if (e.relu) t = fmaxf(t, 0.0f);
+            v[j] = zero ? 0.0f : t;
+          }
+          store16<TO>(yrow + c0 + 16, v, vec_ok);
+        }
       }
+    } else {
+      static_assert(!LN || BN == 32, "the fused LayerNorm epilogue holds one 32-column slab per thread");
+      const uint32_t my_rank = cluster_ctarank();
+      // residual row slab (and the +pos operand) prefetched while the MMAs run
+      float v[32], pv[32];
+      const int64_t goff = row * kLnCols + n0;
+      const bool want_pos = e.out_pos_lp != nullptr;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), p4 = r4;
+        if (row_ok && e.residual != nullptr) r4 = *reinterpret_cast<const float4*>(e.residual + goff + 4 * j);
+        if (row_ok && want_pos) p4 = *reinterpret_cast<const float4*>(e.pos + goff + 4 * j);
+        v[4 * j] = r4.x; v[4 * j + 1] = r4.y; v[4 * j + 2] = r4.z; v[4 * j + 3] = r4.w;
+        pv[4 * j] = p4.x; pv[4 * j + 1] = p4.y; pv[4 * j + 2] = p4.z; pv[4 * j + 3] = p4.w;
+      }
+      mbar_wait(smem_u32(&ctl->tmem_full), 0);
+      tc_fence_after();
+      {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tbase, r0);
+        tmem_ld16(tbase + 16, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] += __uint_as_float(r0[j]) + ctl->bias[j];
+          v[16 + j] += __uint_as_float(r1[j]) + ctl->bias[16 + j];
+        }
+      }
+      // pass 1: row mean over the 256 columns held by the NC CTAs of the cluster
+      float ps = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ps += v[j];
+      cluster_wait();  // #0
+      const uint32_t slot0 = smem_u32(&ctl->red[0][my_rank][rl]);
+#pragma unroll
+      for (int p = 0; p < NC; ++p) st_cluster_f32(slot0, p, ps);
+      cluster_arrive();
+      cluster_wait();  // #1
+      float tot = 0.0f;
+#pragma unroll
+      for (int p = 0; p < NC; ++p) tot += ctl->red[0][p][rl];
+      const float mean = tot * (1.0f / kLnCols);
+      float pq = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        v[j] -= mean;
+        pq = fmaf(v[j], v[j], pq);
+      }
+      const uint32_t slot1 = smem_u32(&ctl->red[1][my_rank][rl]);
+#pragma unroll
+      for (int p = 0; p < NC; ++p) st_cluster_f32(slot1, p, pq);
+      cluster_arrive();
+      cluster_wait();  // #2
+      float sq = 0.0f;
+#pragma unroll
+      for (int p = 0; p < NC; ++p) sq += ctl->red[1][p][rl];
+      const float rstd = rsqrtf(sq * (1.0f / kLnCols) + e.eps);
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] * rstd * ctl->gamma[j] + ctl->beta[j];
+        if (e.out_f32 != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(e.out_f32 + goff + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (e.out_lp != nullptr) {
+          TO* d = static_cast<TO*>(e.out_lp) + goff;
+          float h0[16], h1[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { h0[j] = v[j]; h1[j] = v[16 + j]; }
+          store16<TO>(d, h0, true);
+          store16<TO>(d + 16, h1, true);
+        }
+        if (want_pos) {
+          TO* d = static_cast<TO*>(e.out_pos_lp) + goff;
+          float h0[16], h1[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { h0[j] = v[j] + pv[j]; h1[j] = v[16 + j] + pv[16 + j]; }
+          store16<TO>(d, h0, true);
+          store16<TO>(d + 16, h1, true);
+        }
+      }
+    }
+  }
+  if constexpr (LN) {
+    if (warp < 2) {  // producer / MMA warps take part in the three cluster barriers
+      cluster_wait();
+      cluster_arrive();
+      cluster_wait();
+      cluster_arrive();
+      cluster_wait();
     }
   }
 
@@ -231,6 +430,183 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent weight-resident kernel for tall x (value projection). K == 256, N % 128 == 0.
+// CTA c owns output-column tile (c % n_tiles) and walks the row tiles group, group + n_groups, ...
+// ------------------------------------------------------------------------------------------------
+constexpr int kSBN = 128;
+constexpr int kSK = 256;
+constexpr int kSKB = kSK / kBK;   // 4 k-blocks
+constexpr int kSStages = 6;       // x-tile ring: 6 x 16 KiB
+constexpr int kSlabBytes = 32 * 128;  // one epilogue slab: 32 rows x 64 bf16
+
+struct StreamCtl {
+  uint64_t full[kSStages];
+  uint64_t empty[kSStages];
+  uint64_t b_full;
+  uint64_t acc_full[2];
+  uint64_t acc_empty[2];
+  uint32_t tmem_base;
+  float bias[kSBN];
+};
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                   const __grid_constant__ CUtensorMap tmap_y, const float* __restrict__ bias,
+                   const uint8_t* __restrict__ zero_rows, int64_t M, int n_tiles, int n_groups) {
+  constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KiB
+  constexpr uint32_t kBBytes = kSBN * kBK * 2;  // 16 KiB per k-block
+  constexpr uint32_t kTmemCols = 2 * kSBN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_b = base;                                  // 4 x 16 KiB, resident
+  uint8_t* smem_a = smem_b + kSKB * kBBytes;               // 6 x 16 KiB ring
+  uint8_t* smem_o = smem_a + kSStages * kABytes;           // 4 warps x 2 slabs x 4 KiB
+  StreamCtl* ctl = reinterpret_cast<StreamCtl*>(smem_o + 8 * kSlabBytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x % n_tiles;
+  const int group = blockIdx.x / n_tiles;
+  const int n0 = n_tile * kSBN;
+  const int m_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  const int my_tiles = group < m_tiles ? (m_tiles - group + n_groups - 1) / n_groups : 0;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_y)) : "memory");
+    for (int s = 0; s < kSStages; ++s) {
+      mbar_init(smem_u32(&ctl->full[s]), 1);
+      mbar_init(smem_u32(&ctl->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ctl->b_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&ctl->acc_full[s]), 1);
+      mbar_init(smem_u32(&ctl->acc_empty[s]), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t bf = smem_u32(&ctl->b_full);
+    mbar_expect_tx(bf, kSKB * kBBytes);
+    for (int kb = 0; kb < kSKB; ++kb) tma_load_2d(smem_u32(smem_b + kb * kBBytes), &tmap_w, bf, kb * kBK, n0);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < kSBN; i += kGemmThreads - 64) ctl->bias[i] = bias ? __ldg(bias + n0 + i) : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_trigger();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      int it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int m0 = (group + t * n_groups) * kBM;
+        for (int kb = 0; kb < kSKB; ++kb, ++it) {
+          const int s = it % kSStages;
+          mbar_wait(smem_u32(&ctl->empty[s]), ((it / kSStages) & 1) ^ 1);
+          const uint32_t full = smem_u32(&ctl->full[s]);
+          mbar_expect_tx(full, kABytes);
+          tma_load_2d(smem_u32(smem_a + s * kABytes), &tmap_x, full, kb * kBK, m0);
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, kSBN);
+      mbar_wait(smem_u32(&ctl->b_full), 0);
+      int it = 0;
+      for (int t = 0; t < my_tiles; ++t) {
+        const int as = t & 1;
+        mbar_wait(smem_u32(&ctl->acc_empty[as]), ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * kSBN;
+        for (int kb = 0; kb < kSKB; ++kb, ++it) {
+          const int s = it % kSStages;
+          mbar_wait(smem_u32(&ctl->full[s]), (it / kSStages) & 1);
+          tc_fence_after();
+          const uint64_t adesc = make_smem_desc(smem_u32(smem_a + s * kABytes));
+          const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + kb * kBBytes));
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) umma_bf16(tacc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&ctl->empty[s]));
+        }
+        umma_commit(smem_u32(&ctl->acc_full[as]));
+      }
+    }
+    __syncwarp();
+  } else {
+    // epilogue warp `quad` owns rows [quad*32, quad*32+32) of every tile and two private 4 KiB slabs
+    const int quad = warp & 3;
+    uint8_t* slab = smem_o + quad * 2 * kSlabBytes;
+    pdl_wait();
+    int n_store = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int as = t & 1;
+      const int m0 = (group + t * n_groups) * kBM;
+      const int64_t row = static_cast<int64_t>(m0) + quad * 32 + lane;
+      const bool zero = zero_rows != nullptr && row < M && zero_rows[row] != 0;
+      mbar_wait(smem_u32(&ctl->acc_full[as]), (t >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + as * kSBN + (static_cast<uint32_t>(quad * 32) << 16);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint8_t* sl = slab + (n_store & 1) * kSlabBytes;
+        // the TMA store issued two slabs ago must have finished READING this slab
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 64; c += 16) {
+          uint32_t r[16];
+          tmem_ld16(tacc + half * 64 + c, r);
+          tmem_ld_wait();
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = zero ? 0.0f : __uint_as_float(r[j]) + ctl->bias[half * 64 + c + j];
+          uint4 a, b;
+          a.x = float2_to_bf16x2(v[0], v[1]);   a.y = float2_to_bf16x2(v[2], v[3]);
+          a.z = float2_to_bf16x2(v[4], v[5]);   a.w = float2_to_bf16x2(v[6], v[7]);
+          b.x = float2_to_bf16x2(v[8], v[9]);   b.y = float2_to_bf16x2(v[10], v[11]);
+          b.z = float2_to_bf16x2(v[12], v[13]); b.w = float2_to_bf16x2(v[14], v[15]);
+          // SWIZZLE_128B: 16-byte chunk j of row r lives at chunk (j ^ (r & 7))
+          const int j0 = c / 8;
+          *reinterpret_cast<uint4*>(sl + lane * 128 + (((j0) ^ (lane & 7)) << 4)) = a;
+          *reinterpret_cast<uint4*>(sl + lane * 128 + (((j0 + 1) ^ (lane & 7)) << 4)) = b;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_y, smem_u32(sl), n0 + half * 64, m0 + quad * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++n_store;
+      }
+      // all TMEM reads of this accumulator stage are complete (wait::ld above): hand it back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctl->acc_empty[as]));
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
   }
 }
 
@@ -276,27 +652,89 @@ bool linear_tcgen05_supported(const void* x, int64_t ldx, const void* w, int64_t
          M < (1ll << 31);
 }
 
-template <int BN, typename TO>
-static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tw, const float* bias, void* y, int64_t ldy,
-                       int64_t M, int N, int K, int relu, const uint8_t* zero_rows, cudaStream_t st) {
-  constexpr size_t smem = kStages * (kBM * kBK * 2 + BN * kBK * 2) + sizeof(GemmSmem) + 1024;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  unsigned cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster_x;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <int BN, typename TO, bool LN>
+static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tx2, const CUtensorMap& tw, const GemmEpi& e,
+                       cudaStream_t st) {
+  constexpr size_t smem = kStages * (kBM * kBK * 2 + BN * kBK * 2) + sizeof(GemmCtl<BN, LN>) + 1024;
   static bool configured = false;  // per template instantiation
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
-    if (e != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(e));
+    cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, TO, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+    if (err != cudaSuccess)
+      return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(err));
     configured = true;
   }
-  dim3 grid((N + BN - 1) / BN, static_cast<unsigned>((M + kBM - 1) / kBM));
-  gemm_tcgen05_kernel<BN, TO><<<grid, kGemmThreads, smem, st>>>(tx, tw, bias, static_cast<TO*>(y), ldy, M, N, K, relu,
-                                                               zero_rows);
+  dim3 grid((e.N + BN - 1) / BN, static_cast<unsigned>((e.M + kBM - 1) / kBM));
+  if constexpr (LN)
+    launch_cluster(gemm_tcgen05_kernel<BN, TO, LN>, grid, dim3(kGemmThreads), smem, st, kLnCols / BN, tx, tx2, tw, e);
+  else
+    launch_k(gemm_tcgen05_kernel<BN, TO, LN>, grid, dim3(kGemmThreads), smem, st, tx, tx2, tw, e);
   return check_launch("gemm_tcgen05_kernel");
 }
 
-int linear_tcgen05(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy, int64_t M, int N,
-                   int K, int out_dtype, int relu, const uint8_t* zero_rows, cudaStream_t st) {
-  // Tile width: wide tiles amortise the x-tile for the big value_proj GEMM; narrow tiles spread the
-  // few-hundred-row query GEMMs over more SMs (they are latency- not throughput-bound).
+static int launch_stream(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy, int64_t M,
+                         int N, const uint8_t* zero_rows, cudaStream_t st) {
+  constexpr size_t smem = kSKB * kSBN * kBK * 2 + kSStages * kBM * kBK * 2 + 8 * kSlabBytes + sizeof(StreamCtl) + 1024;
+  static bool configured = false;
+  static int n_sm = 0;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+    if (err != cudaSuccess)
+      return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(stream smem=%zu): %s", smem, cudaGetErrorString(err));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    configured = true;
+  }
+  CUtensorMap tx, tw, ty;
+  int rc = make_tmap(&tx, x, M, kSK, ldx, kBM);
+  if (rc != MOYOLO_OK) return rc;
+  rc = make_tmap(&tw, w, N, kSK, kSK, kSBN);
+  if (rc != MOYOLO_OK) return rc;
+  rc = make_tmap(&ty, y, M, N, ldy, 32);
+  if (rc != MOYOLO_OK) return rc;
+  const int n_tiles = N / kSBN;
+  const int m_tiles = static_cast<int>((M + kBM - 1) / kBM);
+  int n_groups = n_sm / n_tiles;
+  if (n_groups < 1) n_groups = 1;
+  if (n_groups > m_tiles) n_groups = m_tiles;
+  launch_k(gemm_stream_kernel, dim3(n_tiles * n_groups), dim3(kGemmThreads), smem, st, tx, tw, ty, bias, zero_rows, M,
+           n_tiles, n_groups);
+  return check_launch("gemm_stream_kernel");
+}
+
+// x2 / n_split: optional second A operand for output columns >= n_split (n_split % 64 == 0).
+int linear_tcgen05(const void* x, int64_t ldx, const void* x2, int64_t ldx2, int n_split, const void* w,
+                   const float* bias, void* y, int64_t ldy, int64_t M, int N, int K, int out_dtype, int relu,
+                   const uint8_t* zero_rows, cudaStream_t st) {
+  MOYOLO_REQUIRE(out_dtype == MOYOLO_F32 || out_dtype == MOYOLO_BF16, MOYOLO_ERR_UNSUPPORTED,
+                 "tcgen05 engine writes fp32 or bf16");
+  // tall x, K == 256: persistent weight-resident kernel (value projection)
+  if (x2 == nullptr && M >= 4096 && K == kSK && N % kSBN == 0 && out_dtype == MOYOLO_BF16 && !relu && aligned16(y) &&
+      (ldy * 2) % 16 == 0)
+    return launch_stream(x, ldx, w, bias, y, ldy, M, N, zero_rows, st);
+  // Tile width: narrow tiles spread the few-hundred-row query GEMMs over more SMs (latency-bound).
   int bn;
   if (M > 2048 && N % 256 == 0) bn = 256;
   else if (M > 2048 && N % 128 == 0) bn = 128;
@@ -304,16 +742,28 @@ int linear_tcgen05(const void* x, int64_t ldx, const void* w, const float* bias,
   else if (N % 32 == 0) bn = 32;
   else bn = 16;
   MOYOLO_REQUIRE(bn != 16, MOYOLO_ERR_UNSUPPORTED, "tcgen05 engine needs N %% 32 == 0 (N=%d)", N);
-  CUtensorMap tx, tw;
+  if (x2 != nullptr) {
+    MOYOLO_REQUIRE(n_split > 0 && n_split < N && n_split % 64 == 0, MOYOLO_ERR_BAD_SHAPE,
+                   "dual-operand GEMM: n_split (%d) must be a multiple of 64 inside (0, N)", n_split);
+    if (bn > 64) bn = 64;
+  }
+  CUtensorMap tx, tx2, tw;
   int rc = make_tmap(&tx, x, M, K, ldx, kBM);
   if (rc != MOYOLO_OK) return rc;
+  if (x2 != nullptr) {
+    rc = make_tmap(&tx2, x2, M, K, ldx2, kBM);
+    if (rc != MOYOLO_OK) return rc;
+  } else {
+    tx2 = tx;
+  }
   rc = make_tmap(&tw, w, N, K, K, bn);
   if (rc != MOYOLO_OK) return rc;
-#define GO(BN)                                                                                              \
-  (out_dtype == MOYOLO_F32 ? launch_gemm<BN, float>(tx, tw, bias, y, ldy, M, N, K, relu, zero_rows, st)     \
-                           : launch_gemm<BN, __nv_bfloat16>(tx, tw, bias, y, ldy, M, N, K, relu, zero_rows, st))
-  MOYOLO_REQUIRE(out_dtype == MOYOLO_F32 || out_dtype == MOYOLO_BF16, MOYOLO_ERR_UNSUPPORTED,
-                 "tcgen05 engine writes fp32 or bf16");
+  GemmEpi e{};
+  e.bias = bias; e.y = y; e.ldy = ldy; e.M = M; e.N = N; e.K = K; e.relu = relu; e.zero_rows = zero_rows;
+  e.n_split = x2 != nullptr ? n_split : N;
+#define GO(BN)                                                                        \
+  (out_dtype == MOYOLO_F32 ? launch_gemm<BN, float, false>(tx, tx2, tw, e, st)        \
+                           : launch_gemm<BN, __nv_bfloat16, false>(tx, tx2, tw, e, st))
   switch (bn) {
     case 256: return GO(256);
     case 128: return GO(128);
@@ -321,6 +771,26 @@ int linear_tcgen05(const void* x, int64_t ldx, const void* w, const float* bias,
     default: return GO(32);
   }
 #undef GO
+}
+
+bool linear_ln_tcgen05_supported(const void* x, int64_t ldx, const void* w, int64_t M, int N, int K) {
+  return N == kLnCols && linear_tcgen05_supported(x, ldx, w, M, N, K);
+}
+
+// out = LayerNorm(x . w^T + bias + residual) * gamma + beta, N == 256, all row-major contiguous [M, 256].
+int linear_ln_tcgen05(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual,
+                      const float* gamma, const float* beta, float eps, int64_t M, int K, float* out_f32, void* out_lp,
+                      const float* pos, void* out_pos_lp, cudaStream_t st) {
+  CUtensorMap tx, tw;
+  int rc = make_tmap(&tx, x, M, K, ldx, kBM);
+  if (rc != MOYOLO_OK) return rc;
+  rc = make_tmap(&tw, w, kLnCols, K, K, 32);
+  if (rc != MOYOLO_OK) return rc;
+  GemmEpi e{};
+  e.bias = bias; e.M = M; e.N = kLnCols; e.K = K; e.n_split = kLnCols;
+  e.residual = residual; e.gamma = gamma; e.beta = beta; e.eps = eps;
+  e.out_f32 = out_f32; e.out_lp = out_lp; e.pos = pos; e.out_pos_lp = out_pos_lp;
+  return launch_gemm<32, __nv_bfloat16, true>(tx, tx, tw, e, st);
 }
 
 }  // namespace moyolo

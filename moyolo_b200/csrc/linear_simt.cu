@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) linear_simt_kernel(const TI* __restrict__
                                                           TO* __restrict__ y, int64_t ldy, int64_t M,
                                                           int N, int K, int relu,
                                                           const uint8_t* __restrict__ zero_rows) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
   const int tid = threadIdx.x;
@@ -78,7 +80,7 @@ template <typename TI, typename TO>
 static int launch_simt(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy,
                        int64_t M, int N, int K, int relu, const uint8_t* zero_rows, cudaStream_t st) {
   dim3 grid((N + BN - 1) / BN, static_cast<unsigned>((M + BM - 1) / BM));
-  linear_simt_kernel<TI, TO><<<grid, 256, 0, st>>>(static_cast<const TI*>(x), ldx, static_cast<const TI*>(w),
+  launch_k(linear_simt_kernel<TI, TO>, dim3(grid), dim3(256), 0, st, static_cast<const TI*>(x), ldx, static_cast<const TI*>(w),
                                                    bias, static_cast<TO*>(y), ldy, M, N, K, relu, zero_rows);
   return check_launch("linear_simt_kernel");
 }
@@ -98,10 +100,14 @@ int linear_simt(const void* x, int64_t ldx, const void* w, const float* bias, vo
 }
 
 // implemented in gemm_tcgen05.cu
-int linear_tcgen05(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy,
-                   int64_t M, int N, int K, int out_dtype, int relu, const uint8_t* zero_rows,
-                   cudaStream_t st);
+int linear_tcgen05(const void* x, int64_t ldx, const void* x2, int64_t ldx2, int n_split, const void* w,
+                   const float* bias, void* y, int64_t ldy, int64_t M, int N, int K, int out_dtype, int relu,
+                   const uint8_t* zero_rows, cudaStream_t st);
 bool linear_tcgen05_supported(const void* x, int64_t ldx, const void* w, int64_t M, int N, int K);
+bool linear_ln_tcgen05_supported(const void* x, int64_t ldx, const void* w, int64_t M, int N, int K);
+int linear_ln_tcgen05(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual,
+                      const float* gamma, const float* beta, float eps, int64_t M, int K, float* out_f32, void* out_lp,
+                      const float* pos, void* out_pos_lp, cudaStream_t st);
 
 }  // namespace moyolo
 
@@ -126,8 +132,42 @@ extern "C" int moyolo_linear(const void* x, int64_t ldx, const void* w, const fl
                    "moyolo_linear: the tcgen05 engine takes bf16 operands");
     MOYOLO_REQUIRE(linear_tcgen05_supported(x, ldx, w, M, N, K), MOYOLO_ERR_ALIGNMENT,
                    "moyolo_linear: tcgen05 engine needs K%%64==0, N%%32==0, 16B-aligned x/w/ldx");
-    return linear_tcgen05(x, ldx, w, bias, y, ldy, M, N, K, out_dtype, relu, zero_rows, st);
+    return linear_tcgen05(x, ldx, nullptr, 0, 0, w, bias, y, ldy, M, N, K, out_dtype, relu, zero_rows, st);
   }
   MOYOLO_REQUIRE(engine == MOYOLO_GEMM_SIMT, MOYOLO_ERR_BAD_ARG, "moyolo_linear: bad engine %d", engine);
   return linear_simt(x, ldx, w, bias, y, ldy, M, N, K, in_dtype, out_dtype, relu, zero_rows, st);
+}
+
+extern "C" int moyolo_linear_dual(const void* x1, int64_t ldx1, const void* x2, int64_t ldx2, int n_split,
+                                  const void* w, const float* bias, void* y, int64_t ldy, int64_t M, int N, int K,
+                                  int out_dtype, moyolo_stream_t stream) {
+  using namespace moyolo;
+  MOYOLO_REQUIRE(x1 && x2 && w && y, MOYOLO_ERR_BAD_ARG, "moyolo_linear_dual: null pointer");
+  MOYOLO_REQUIRE(M >= 0 && N > 0 && K > 0 && ldx1 >= K && ldx2 >= K && ldy >= N, MOYOLO_ERR_BAD_SHAPE,
+                 "moyolo_linear_dual: bad sizes");
+  if (M == 0) return MOYOLO_OK;
+  MOYOLO_REQUIRE(linear_tcgen05_supported(x1, ldx1, w, M, N, K) && linear_tcgen05_supported(x2, ldx2, w, M, N, K),
+                 MOYOLO_ERR_ALIGNMENT, "moyolo_linear_dual: needs K%%64==0, N%%32==0, 16B-aligned operands");
+  return linear_tcgen05(x1, ldx1, x2, ldx2, n_split, w, bias, y, ldy, M, N, K, out_dtype, 0, nullptr,
+                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int moyolo_linear_add_layernorm(const void* x, int64_t ldx, const void* w, const float* bias,
+                                           const float* residual, const float* gamma, const float* beta, float eps,
+                                           int64_t M, int N, int K, float* out_f32, void* out_lp, const float* pos,
+                                           void* out_pos_lp, moyolo_stream_t stream) {
+  using namespace moyolo;
+  MOYOLO_REQUIRE(x && w && gamma && beta, MOYOLO_ERR_BAD_ARG, "moyolo_linear_add_layernorm: null pointer");
+  MOYOLO_REQUIRE(out_pos_lp == nullptr || pos != nullptr, MOYOLO_ERR_BAD_ARG,
+                 "moyolo_linear_add_layernorm: out_pos_lp requested without pos");
+  MOYOLO_REQUIRE(M >= 0 && K > 0 && ldx >= K, MOYOLO_ERR_BAD_SHAPE, "moyolo_linear_add_layernorm: bad sizes");
+  if (M == 0) return MOYOLO_OK;
+  MOYOLO_REQUIRE(linear_ln_tcgen05_supported(x, ldx, w, M, N, K), MOYOLO_ERR_UNSUPPORTED,
+                 "moyolo_linear_add_layernorm: needs N == 256, K %% 64 == 0 and 16B-aligned bf16 operands");
+  MOYOLO_REQUIRE((residual == nullptr || aligned16(residual)) && (out_f32 == nullptr || aligned16(out_f32)) &&
+                     (out_lp == nullptr || aligned16(out_lp)) && (pos == nullptr || aligned16(pos)) &&
+                     (out_pos_lp == nullptr || aligned16(out_pos_lp)),
+                 MOYOLO_ERR_ALIGNMENT, "moyolo_linear_add_layernorm: row buffers must be 16-byte aligned");
+  return linear_ln_tcgen05(x, ldx, w, bias, residual, gamma, beta, eps, M, K, out_f32, out_lp, pos, out_pos_lp,
+                           static_cast<cudaStream_t>(stream));
 }

@@ -110,6 +110,8 @@ __device__ __forceinline__ void fused_location(const MsdaParams& p, int64_t row,
 // U = corner rounds kept in flight per loop trip (all of them when 4*L*P == U*32/G).
 template <typename VT, int DH, bool FUSED, int U>
 __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaParams p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int G = DH * static_cast<int>(sizeof(VT)) / 16;  // lanes per value row
   constexpr int CH = 16 / static_cast<int>(sizeof(VT));      // channels per lane
   constexpr int NSG = 32 / G;                                // sub-groups per warp
@@ -264,6 +266,8 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaP
 // MOTR/models/ops/test.py:21-60). One thread per output scalar; correctness path, not a fast path.
 template <typename VT, typename AT, bool FUSED>
 __global__ void msda_generic_kernel(const MsdaParams p, int head_dim) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t total = p.rows * p.n_heads * head_dim;
   const int LP = p.lv.n * p.n_points;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
@@ -339,7 +343,7 @@ static int launch_fast_u(const MsdaParams& p, cudaStream_t st) {
   const int64_t items = p.rows * p.n_heads;
   const int64_t blocks = (items + kGatherWarps - 1) / kGatherWarps;
   if (blocks == 0) return MOYOLO_OK;
-  msda_gather_kernel<VT, DH, FUSED, U><<<static_cast<unsigned>(blocks), kGatherThreads, smem, st>>>(p);
+  launch_k(msda_gather_kernel<VT, DH, FUSED, U>, dim3(static_cast<unsigned>(blocks)), dim3(kGatherThreads), smem, st, p);
   return check_launch("msda_gather_kernel");
 }
 
@@ -374,14 +378,14 @@ static int dispatch(const MsdaParams& p, int value_dtype, int aux_dtype, int hea
   if (value_dtype == MOYOLO_F64) {
     MOYOLO_REQUIRE(!FUSED && aux_dtype == MOYOLO_F64, MOYOLO_ERR_UNSUPPORTED,
                    "fp64 value needs fp64 loc/weights in pre-normalised mode");
-    msda_generic_kernel<double, double, false><<<blocks, 256, 0, st>>>(p, head_dim);
+    launch_k(msda_generic_kernel<double, double, false>, dim3(blocks), dim3(256), 0, st, p, head_dim);
   } else {
     MOYOLO_REQUIRE(aux_dtype == MOYOLO_F32, MOYOLO_ERR_UNSUPPORTED,
                    "loc/weights must be fp32 for fp32/bf16 value");
     if (value_dtype == MOYOLO_F32)
-      msda_generic_kernel<float, float, FUSED><<<blocks, 256, 0, st>>>(p, head_dim);
+      launch_k(msda_generic_kernel<float, float, FUSED>, dim3(blocks), dim3(256), 0, st, p, head_dim);
     else
-      msda_generic_kernel<__nv_bfloat16, float, FUSED><<<blocks, 256, 0, st>>>(p, head_dim);
+      launch_k(msda_generic_kernel<__nv_bfloat16, float, FUSED>, dim3(blocks), dim3(256), 0, st, p, head_dim);
   }
   return check_launch("msda_generic_kernel");
 }

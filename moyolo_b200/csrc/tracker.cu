@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
     int64_t* __restrict__ disappear_time, int64_t* __restrict__ counters, int n, float score_thresh,
     float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace,
     const int32_t* __restrict__ row_offsets, int64_t ws_stride, const int32_t* __restrict__ ctrl) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int s_warp[33];
   if (ctrl != nullptr && ctrl[0] != 0) return;  // aborted speculative frame (see frame.cu): ID counters untouched
   if (row_offsets != nullptr) {  // batched: one CTA per sequence, rows [row_offsets[s], row_offsets[s+1])
@@ -206,6 +208,8 @@ __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
 __global__ void __launch_bounds__(kTrkThreads) track_select_kernel(const int64_t* __restrict__ obj_idxes,
                                                                    int n, int32_t* __restrict__ n_active,
                                                                    int32_t* __restrict__ active_index) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ int s_warp[33];
   const int per = (n + kTrkThreads - 1) / kTrkThreads;
   const int begin = min(static_cast<int>(threadIdx.x) * per, n);
@@ -222,6 +226,8 @@ __global__ void __launch_bounds__(kTrkThreads) track_select_kernel(const int64_t
 __global__ void track_gather_rows_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
                                          const int32_t* __restrict__ n_active,
                                          const int32_t* __restrict__ active_index, int row_words) {
+  pdl_trigger();
+  pdl_wait();
   const int na = *n_active;
   for (int j = blockIdx.x; j < na; j += gridDim.x) {
     const uint32_t* s = src + static_cast<int64_t>(active_index[j]) * row_words;
@@ -248,7 +254,7 @@ extern "C" int moyolo_track_assign(const float* scores, const float* boxes, int6
   MOYOLO_REQUIRE(n >= 0 && n <= kTrkMaxN, MOYOLO_ERR_BAD_SHAPE, "track_assign: n must be in [0, %d], got %lld",
                  kTrkMaxN, (long long)n);
   if (n == 0) return MOYOLO_OK;
-  track_assign_kernel<<<1, kTrkThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(track_assign_kernel, dim3(1), dim3(kTrkThreads), 0, static_cast<cudaStream_t>(stream), 
       scores, boxes, obj_idxes, disappear_time, counters, static_cast<int>(n), score_thresh, filter_thresh,
       miss_tolerance, iou_thresh, workspace, nullptr, 0, nullptr);
   return check_launch("track_assign_kernel");
@@ -263,7 +269,7 @@ extern "C" int moyolo_track_assign_batched(const float* scores, const float* box
                  MOYOLO_ERR_BAD_ARG, "track_assign_batched: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && max_rows_per_seq > 0 && max_rows_per_seq <= kTrkMaxN, MOYOLO_ERR_BAD_SHAPE,
                  "track_assign_batched: max_rows_per_seq must be in (0, %d]", kTrkMaxN);
-  track_assign_kernel<<<n_seq, kTrkThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  launch_k(track_assign_kernel, dim3(n_seq), dim3(kTrkThreads), 0, static_cast<cudaStream_t>(stream), 
       scores, boxes, obj_idxes, disappear_time, counters, 0, score_thresh, filter_thresh, miss_tolerance, iou_thresh,
       workspace, row_offsets, moyolo_track_workspace_bytes(max_rows_per_seq), ctrl);
   return check_launch("track_assign_kernel(batched)");
@@ -277,7 +283,7 @@ extern "C" int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t
   MOYOLO_REQUIRE(n_fields == 0 || (src_host && dst_host && row_bytes_host), MOYOLO_ERR_BAD_ARG,
                  "track_compact: null field table");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  track_select_kernel<<<1, kTrkThreads, 0, st>>>(obj_idxes, static_cast<int>(n), n_active, active_index);
+  launch_k(track_select_kernel, dim3(1), dim3(kTrkThreads), 0, st, obj_idxes, static_cast<int>(n), n_active, active_index);
   int rc = check_launch("track_select_kernel");
   if (rc != MOYOLO_OK || n == 0) return rc;
   for (int f = 0; f < n_fields; ++f) {
@@ -285,7 +291,7 @@ extern "C" int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t
                    "track_compact: field %d row size must be a positive multiple of 4 bytes", f);
     const int row_words = static_cast<int>(row_bytes_host[f] / 4);
     const int threads = row_words >= 128 ? 128 : 32;
-    track_gather_rows_kernel<<<static_cast<unsigned>(n < 1184 ? n : 1184), threads, 0, st>>>(
+    launch_k(track_gather_rows_kernel, dim3(static_cast<unsigned>(n < 1184 ? n : 1184)), dim3(threads), 0, st, 
         static_cast<const uint32_t*>(src_host[f]), static_cast<uint32_t*>(dst_host[f]), n_active, active_index,
         row_words);
     rc = check_launch("track_gather_rows_kernel");

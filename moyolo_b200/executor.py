@@ -16,6 +16,7 @@ stay fp32).
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -24,6 +25,9 @@ from . import _lib, ops
 
 _DEFAULT_PRECISION = "fp32"
 _GEMM_ENGINE = _lib.GEMM_AUTO
+# bf16 frame path: merge the q,k / v in-projections into one dual-operand GEMM and fold residual-add +
+# LayerNorm into the epilogue of the GEMM that feeds it (8 launches per decoder layer instead of 12).
+FUSE_EPILOGUES = os.environ.get("MOYOLO_FUSE", "1") != "0"
 
 
 def set_default_precision(p: str) -> None:
@@ -41,6 +45,11 @@ def set_gemm_engine(engine: int) -> None:
     """Force the GEMM engine (GEMM_AUTO / GEMM_SIMT / GEMM_TCGEN05) — used by tests and profiling."""
     global _GEMM_ENGINE
     _GEMM_ENGINE = engine
+
+
+def fused_epilogues(dt: torch.dtype, C: int) -> bool:
+    """True when the dual-operand GEMM and the GEMM+LayerNorm epilogue serve this configuration."""
+    return FUSE_EPILOGUES and dt == torch.bfloat16 and C == 256 and _GEMM_ENGINE != _lib.GEMM_SIMT
 
 
 def lp_dtype(precision: str) -> torch.dtype:
@@ -86,6 +95,7 @@ class LayerPack:
         sa = layer.self_attn
         C = sa.embed_dim
         self.C, self.n_heads = C, sa.num_heads
+        self.qkv = LinearPack(sa.in_proj_weight, sa.in_proj_bias, dt)
         self.qk = LinearPack(sa.in_proj_weight[:2 * C], sa.in_proj_bias[:2 * C], dt)
         self.v = LinearPack(sa.in_proj_weight[2 * C:], sa.in_proj_bias[2 * C:], dt)
         self.o = LinearPack(sa.out_proj.weight, sa.out_proj.bias, dt)
@@ -219,6 +229,9 @@ def offlog_width(spec) -> int:
 def qkv_proj(xq_lp, x_lp, w, b, out, C: int, eng) -> None:
     """nn.MultiheadAttention in-projection with q = k = x + pos, v = x (transformer.py:637-638):
     out[:, :2C] = xq . [Wq;Wk]^T, out[:, 2C:] = x . Wv^T."""
+    if fused_epilogues(xq_lp.dtype, C):
+        ops.linear_dual(xq_lp, x_lp, 2 * C, w, b, out=out)
+        return
     ops.linear(xq_lp, w[:2 * C], b[:2 * C], out=out[:, :2 * C], engine=eng)
     ops.linear(x_lp, w[2 * C:], b[2 * C:], out=out[:, 2 * C:], engine=eng)
 
@@ -230,6 +243,30 @@ def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offset
     C = pk.C
     eng = _GEMM_ENGINE
     f32 = dt == torch.float32
+    fuse = fused_epilogues(dt, C)
+    pkm = pk.msda
+    if fuse:
+        ops.linear_dual(ws.xq_lp, ws.x_lp, 2 * C, pk.qkv.w, pk.qkv.b, out=ws.qkv)
+        ops.self_attention(ws.qkv[:, :C], ws.qkv[:, C:2 * C], ws.qkv[:, 2 * C:], row_offsets, row_offsets_host,
+                           pk.n_heads, None, out=ws.att)
+        g, b_, e = pk.norms[0]
+        if pos_cur is not None:
+            ops.linear_add_layernorm(ws.att, pk.o.w, pk.o.b, ws.x, g, b_, e, out_f32=ws.x1, pos=pos_cur,
+                                     out_pos=ws.x1q_lp)
+        else:
+            ops.linear_add_layernorm(ws.att, pk.o.w, pk.o.b, ws.x, g, b_, e, out_f32=ws.x1, out_lp=ws.x1q_lp)
+        ops.linear(ws.x1q_lp, pkm.offlog.w, pkm.offlog.b, out=ws.ol, engine=eng)
+        if before_gather is not None:
+            before_gather()
+        ops.msda_fused(value_view, shapes, ws.ol[:, :pkm.n_off], ws.ol[:, pkm.n_off:], refer, pkm.n_heads,
+                       pkm.n_points, batch, pkm.softmax_mode, row_offsets, out=ws.g)
+        g, b_, e = pk.norms[1]
+        ops.linear_add_layernorm(ws.g, pkm.out.w, pkm.out.b, ws.x1, g, b_, e, out_f32=ws.x2, out_lp=ws.x2_lp)
+        ops.linear(ws.x2_lp, pk.ffn1.w, pk.ffn1.b, relu=True, out=ws.h, engine=eng)
+        g, b_, e = pk.norms[2]
+        ops.linear_add_layernorm(ws.h, pk.ffn2.w, pk.ffn2.b, ws.x2, g, b_, e, out_f32=ws.x, out_lp=ws.x_lp,
+                                 pos=pos_next, out_pos=ws.xq_lp if pos_next is not None else None)
+        return
     ops.linear(ws.xq_lp, pk.qk.w, pk.qk.b, out=ws.qkv[:, :2 * C], engine=eng)
     ops.linear(ws.x_lp, pk.v.w, pk.v.b, out=ws.qkv[:, 2 * C:], engine=eng)
     ops.self_attention(ws.qkv[:, :C], ws.qkv[:, C:2 * C], ws.qkv[:, 2 * C:], row_offsets, row_offsets_host,
@@ -237,7 +274,6 @@ def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offset
     ops.linear(ws.att, pk.o.w, pk.o.b, out=ws.t, engine=eng)
     g, b_, e = pk.norms[0]
     ops.add_layernorm(ws.t, ws.x, g, b_, e, out_f32=ws.x1, pos=pos_cur, out_pos=ws.x1q_lp)
-    pkm = pk.msda
     ops.linear(ws.x1q_lp, pkm.offlog.w, pkm.offlog.b, out=ws.ol, engine=eng)
     if before_gather is not None:
         before_gather()

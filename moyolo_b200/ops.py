@@ -145,6 +145,42 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out_dtyp
     return out
 
 
+def linear_dual(x1: torch.Tensor, x2: torch.Tensor, n_split: int, w: torch.Tensor, b: Optional[torch.Tensor],
+                out: torch.Tensor) -> torch.Tensor:
+    """out[:, :n_split] = x1 . w[:n_split]^T, out[:, n_split:] = x2 . w[n_split:]^T (+ b) in one launch
+    (bf16 operands, tcgen05). The MHA in-projection with q = k = x + pos, v = x (transformer.py:637-638)."""
+    _cuda(x1, x2, w, b, out)
+    M, K = x1.shape
+    N = w.shape[0]
+    if x1.stride(1) != 1 or x2.stride(1) != 1 or not w.is_contiguous() or x2.shape != x1.shape:
+        raise ValueError("linear_dual: x1/x2 must be [M, K] with contiguous columns, w contiguous [N, K]")
+    _count(1)
+    _lib.check(_lib.lib().moyolo_linear_dual(
+        x1.data_ptr(), x1.stride(0), x2.data_ptr(), x2.stride(0), int(n_split), w.data_ptr(), _ptr(b), out.data_ptr(),
+        out.stride(0), M, N, K, _dt(out), _stream()))
+    return out
+
+
+def linear_add_layernorm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+                         gamma: torch.Tensor, beta: torch.Tensor, eps: float, out_f32: Optional[torch.Tensor] = None,
+                         out_lp: Optional[torch.Tensor] = None, pos: Optional[torch.Tensor] = None,
+                         out_pos: Optional[torch.Tensor] = None) -> None:
+    """LayerNorm(x . w^T + b + residual) with the GEMM, the residual add and the LayerNorm in ONE launch
+    (N == 256, bf16 operands; outputs written through the given buffers, any of which may be None)."""
+    _cuda(x, w, b, residual, gamma, beta, out_f32, out_lp, pos, out_pos)
+    M, K = x.shape
+    N = w.shape[0]
+    if x.stride(1) != 1 or not w.is_contiguous():
+        raise ValueError("linear_add_layernorm: x must have contiguous columns, w contiguous [N, K]")
+    for t in (residual, out_f32, out_lp, pos, out_pos):
+        if t is not None and (not t.is_contiguous() or t.shape != (M, N)):
+            raise ValueError("linear_add_layernorm: row buffers must be contiguous [M, N]")
+    _count(1)
+    _lib.check(_lib.lib().moyolo_linear_add_layernorm(
+        x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), _ptr(residual), gamma.data_ptr(), beta.data_ptr(),
+        float(eps), M, N, K, _ptr(out_f32), _ptr(out_lp), _ptr(pos), _ptr(out_pos), _stream()))
+
+
 def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, row_offsets: torch.Tensor,
                    row_offsets_host: Sequence[int], n_heads: int, attn_mask: Optional[torch.Tensor] = None,
                    out: Optional[torch.Tensor] = None, seg_len: Optional[torch.Tensor] = None) -> torch.Tensor:

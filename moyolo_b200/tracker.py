@@ -327,6 +327,16 @@ class TrackEngine:
         ex.qkv_proj(ws.q_qk_lp, ws.q_tgt_lp, q["qkv_w"], q["qkv_b"], ws.qkv, C, eng)
         ops.self_attention(ws.qkv[:, :C], ws.qkv[:, C:2 * C], ws.qkv[:, 2 * C:], ws.ro, ro_host, H, out=ws.att,
                            seg_len=ws.n_active)
+        if ex.fused_epilogues(dt, C) and q["l1_w"].shape[0] % 64 == 0:
+            ops.linear_add_layernorm(ws.att, q["o_w"], q["o_b"], ws.c_hs, *q["norm1"], 1e-5, out_f32=ws.q_tgt,   # :277-278
+                                     out_lp=ws.q_tgt_lp2)
+            ops.linear(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], relu=True, out=ws.q_h, engine=eng)
+            ops.linear_add_layernorm(ws.q_h, q["l2_w"], q["l2_b"], ws.q_tgt, *q["norm2"], 1e-5,                  # :280-282
+                                     out_lp=ws.q_tgt_lp3)
+            ops.linear(ws.q_tgt_lp3, q["f1_w"], q["f1_b"], relu=True, out=ws.q_h, engine=eng)
+            ops.linear_add_layernorm(ws.q_h, q["f2_w"], q["f2_b"], ws.c_pos, *q["norm_feat"], 1e-5,              # :290-298
+                                     out_f32=ws.q_new)
+            return
         ops.linear(ws.att, q["o_w"], q["o_b"], out=ws.t, engine=eng)
         ops.add_layernorm(ws.t, ws.c_hs, *q["norm1"], 1e-5, out_f32=ws.q_tgt,                       # :277-278
                           out_lp=None if dt == torch.float32 else ws.q_tgt_lp2)

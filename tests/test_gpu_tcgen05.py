@@ -73,3 +73,83 @@ def test_tcgen05_rejects_bad_shapes(dev):
         ops.linear(x, w, None, engine=_lib.GEMM_TCGEN05)  # K % 64 != 0
     y = ops.linear(x, w, None)  # AUTO falls back to the CUDA-core engine
     assert y.shape == (8, 32)
+
+
+@pytest.mark.parametrize("M,N", [(4096, 256), (8400, 1536), (13566, 1536), (54264, 1536), (4097, 128)])
+def test_stream_gemm_value_proj(dev, M, N):
+    """Persistent weight-resident kernel (tall x, K = 256, bf16 out through TMA stores), incl. the value_mask
+    row zeroing (transformer.py:265-266) and writing into a column slice of a wider tensor."""
+    from moyolo_b200 import _lib, ops
+    K = 256
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    b = torch.randn(N, generator=g)
+    ref = torch.nn.functional.linear(x.double(), w.double(), b.double())
+    xd, wd, bd = x.to(dev), w.to(dev), b.to(dev)
+    tol = float(ref.abs().max()) * 2 ** -8 + 1e-6
+    y = ops.linear(xd, wd, bd, out_dtype=torch.bfloat16, engine=_lib.GEMM_TCGEN05)
+    torch.cuda.synchronize()
+    assert float((y.float().cpu().double() - ref).abs().max()) <= tol
+    zr = torch.rand(M, generator=g) < 0.25
+    wide = torch.full((M, N + 128), 7.0, dtype=torch.bfloat16, device=dev)
+    ops.linear(xd, wd, bd, zero_rows=zr.to(dev, torch.uint8), out=wide[:, 64:64 + N], engine=_lib.GEMM_TCGEN05)
+    got = wide[:, 64:64 + N].float().cpu()
+    assert torch.equal(got[zr], torch.zeros(int(zr.sum()), N)) and torch.equal(got[~zr], y.float().cpu()[~zr])
+    assert bool((wide[:, :64] == 7).all()) and bool((wide[:, 64 + N:] == 7).all())
+
+
+@pytest.mark.parametrize("M", [1, 300, 382, 1408])
+def test_linear_dual(dev, M):
+    """q,k from x+pos and v from x in one launch == two separate GEMMs (bitwise: same tiles, same order)."""
+    from moyolo_b200 import _lib, ops
+    C = 256
+    g = torch.Generator().manual_seed(M)
+    x1 = torch.randn(M, C, generator=g).bfloat16().to(dev)
+    x2 = torch.randn(M, C, generator=g).bfloat16().to(dev)
+    w = (torch.randn(3 * C, C, generator=g) / 16).bfloat16().to(dev)
+    b = torch.randn(3 * C, generator=g).to(dev)
+    out = torch.empty(M, 3 * C, dtype=torch.bfloat16, device=dev)
+    ops.linear_dual(x1, x2, 2 * C, w, b, out=out)
+    ref = torch.cat([torch.nn.functional.linear(x1.double(), w[:2 * C].double(), b[:2 * C].double()),
+                     torch.nn.functional.linear(x2.double(), w[2 * C:].double(), b[2 * C:].double())], 1).cpu()
+    assert float((out.float().cpu().double() - ref).abs().max()) <= float(ref.abs().max()) * 2 ** -8 + 1e-6
+    a = ops.linear(x1, w[:2 * C], b[:2 * C], out_dtype=torch.bfloat16, engine=_lib.GEMM_TCGEN05)
+    c = ops.linear(x2, w[2 * C:], b[2 * C:], out_dtype=torch.bfloat16, engine=_lib.GEMM_TCGEN05)
+    assert torch.equal(out[:, :2 * C], a) and torch.equal(out[:, 2 * C:], c)
+
+
+@pytest.mark.parametrize("M,K", [(1, 256), (300, 256), (382, 1024), (1408, 256), (1000, 1024)])
+def test_linear_add_layernorm(dev, M, K):
+    """GEMM + residual + LayerNorm (+pos operand) in one launch (cluster/DSMEM row statistics) against an fp64
+    reference on the same bf16 operands: fp32 output within 2e-5*rms (accumulation order), bf16 outputs within
+    bf16 rounding; and against the unfused kernel pair within 2e-5*rms."""
+    from moyolo_b200 import _lib, ops
+    C = 256
+    g = torch.Generator().manual_seed(M + K)
+    x = torch.randn(M, K, generator=g).bfloat16()
+    w = (torch.randn(C, K, generator=g) / K ** 0.5).bfloat16()
+    b, res, pos = torch.randn(C, generator=g), torch.randn(M, C, generator=g) * 2 + 0.5, torch.randn(M, C, generator=g)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+    t = torch.nn.functional.linear(x.double(), w.double(), b.double()) + res.double()
+    ref = torch.nn.functional.layer_norm(t, (C,), gamma.double(), beta.double(), 1e-5)
+    d = lambda z: z.to(dev)  # noqa: E731
+    o32 = torch.empty(M, C, device=dev)
+    olp = torch.empty(M, C, dtype=torch.bfloat16, device=dev)
+    opos = torch.empty(M, C, dtype=torch.bfloat16, device=dev)
+    ops.linear_add_layernorm(d(x), d(w), d(b), d(res), d(gamma), d(beta), 1e-5, out_f32=o32, out_lp=olp, pos=d(pos),
+                             out_pos=opos)
+    torch.cuda.synchronize()
+    assert rel_rms(o32.cpu().numpy(), ref.numpy()) < 2e-5
+    assert float((olp.float().cpu().double() - ref).abs().max()) <= float(ref.abs().max()) * 2 ** -8 + 1e-5
+    rp = ref + pos.double()
+    assert float((opos.float().cpu().double() - rp).abs().max()) <= float(rp.abs().max()) * 2 ** -8 + 1e-5
+    tt = ops.linear(d(x), d(w), d(b), out_dtype=torch.float32, engine=_lib.GEMM_TCGEN05)
+    u32, _, _ = ops.add_layernorm(tt, d(res), d(gamma), d(beta), 1e-5)
+    assert rel_rms(o32.cpu().numpy(), u32.cpu().numpy()) < 2e-5
+    # optional outputs / no residual
+    o2 = torch.empty(M, C, device=dev)
+    ops.linear_add_layernorm(d(x), d(w), None, None, d(gamma), d(beta), 1e-5, out_f32=o2)
+    ref2 = torch.nn.functional.layer_norm(torch.nn.functional.linear(x.double(), w.double()), (C,), gamma.double(),
+                                          beta.double(), 1e-5)
+    assert rel_rms(o2.cpu().numpy(), ref2.numpy()) < 2e-5
