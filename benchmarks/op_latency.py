@@ -60,6 +60,18 @@ def main():
     bv = rn(6 * C)
     vout = torch.empty(S * Lv, 6 * C, dtype=bf, device=dev)
     res[f"gemm_value_proj_{S * Lv}x1536x256"] = timed(lambda: ops.linear(feats, wv, bv, out=vout), n=10)
+    # fused variants
+    wq = (rn(768, 256) / 16).to(bf); bq = rn(768)
+    xa, xb2 = rn(R, 256).to(bf), rn(R, 256).to(bf)
+    oq = torch.empty(R, 768, dtype=bf, device=dev)
+    res["gemm_qkv_dual"] = timed(lambda: ops.linear_dual(xa, xb2, 512, wq, bq, out=oq))
+    for K in (256, 1024):
+        wl = (rn(256, K) / K ** 0.5).to(bf); bl = rn(256)
+        xin = rn(R, K).to(bf)
+        rs, ps = rn(R, 256), rn(R, 256)
+        gam, bet = rn(256), rn(256)
+        o32 = torch.empty(R, 256, device=dev); olp = torch.empty(R, 256, dtype=bf, device=dev); opl = torch.empty(R, 256, dtype=bf, device=dev)
+        res[f"gemm_ln_K{K}"] = timed(lambda: ops.linear_add_layernorm(xin, wl, bl, rs, gam, bet, 1e-5, out_f32=o32, out_lp=olp, pos=ps, out_pos=opl))
     # attention
     qkv = rn(R, 3 * C).to(bf)
     per = R // S

@@ -236,12 +236,15 @@ int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,
  * moyolo_frame_assemble: builds the frame's query rows, tracks first then detect queries per sequence
  *   (head.py:1056-1064,1108-1109): x [rows_pad,C] (class_embed[t_label] | det_embed), refer_logit
  *   [rows_pad,4], pos [rows_pad,C] (t_qpos | pos2posemb(det_refer)), ids/dis [rows_pad] (prev | -1/0),
- *   row_offsets [n_seq+1]. State arrays are [n_seq, cap, ...]; n_tracks int32 [n_seq].
+ *   row_offsets [n_seq+1]. State arrays are [n_seq, cap, ...]; n_tracks int32 [n_seq]. Optional fused outputs
+ *   (NULL = skip): refer_sig [rows_pad,4] = sigmoid(refer_logit) (transformer.py:690) and the first layer's GEMM
+ *   operands x_lp = x, xq_lp = x + pos as `lp_dtype`.
  * moyolo_frame_compact: per sequence, rows with ids >= 0 in order: n_active [n_seq], active_index,
  *   QIM inputs gathered to frame-layout compact buffers c_* (sequence s at row_offsets[s]) and
- *   t_label/t_ids/t_dis written straight to the state arrays.
+ *   t_label/t_ids/t_dis written straight to the state arrays. Optional (NULL = skip) QIM operands as `lp_dtype`:
+ *   q_qk_lp = c_hs + pos2posemb(c_ref) (qim.py:255,271), q_tgt_lp = c_hs.
  * moyolo_frame_writeback: t_qpos <- new_qpos rows, t_ref <- inverse_sigmoid(c_box), n_tracks <- n_active
- *   (MOTR/models/qim.py:298-300).
+ *   (MOTR/models/qim.py:298-300); optional info int32 [n_seq+8] = (n_active | ctrl), the frame summary a host reads.
  * moyolo_frame_emit: the frame's results. frame_rows [rows_pad, 8] fp32 = (id, cx, cy, w, h, score, label,
  *   seq) for every row (padding rows id = -1) -- what a host reads back with one copy -- and the tracked
  *   objects (ids >= 0) appended to the device-resident track table [table_cap, 9] fp32 =
@@ -261,20 +264,53 @@ int moyolo_frame_assemble(int n_seq, int n_detect, int C, int cap, const int32_t
                           const int64_t* t_ids, const int64_t* t_dis, const float* class_embed,
                           const float* det_embed, const float* det_refer, float* x, float* refer_logit,
                           float* pos, int64_t* ids, int64_t* dis, int32_t* row_offsets, int64_t rows_pad,
-                          int num_pos_feats, float temperature, int32_t* ctrl, moyolo_stream_t stream);
+                          int num_pos_feats, float temperature, int32_t* ctrl, float* refer_sig, void* x_lp,
+                          void* xq_lp, int lp_dtype, moyolo_stream_t stream);
 int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* row_offsets, const int64_t* ids,
                          const int64_t* dis, const int32_t* labels, const float* refer_logit,
                          const float* pos, const float* hs, const float* boxes, int32_t* n_active,
                          int32_t* active_index, float* c_ref, float* c_pos, float* c_hs, float* c_box,
                          int32_t* t_label, int64_t* t_ids, int64_t* t_dis, const int32_t* ctrl,
+                         void* q_qk_lp, void* q_tgt_lp, int lp_dtype, int num_pos_feats, float temperature,
                          moyolo_stream_t stream);
 int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,
                            const float* new_qpos, const float* c_box, float* t_qpos, float* t_ref,
-                           int32_t* n_tracks, const int32_t* ctrl, moyolo_stream_t stream);
+                           int32_t* n_tracks, const int32_t* ctrl, int32_t* info, moyolo_stream_t stream);
 int moyolo_frame_emit(int n_seq, int64_t rows_pad, const int32_t* row_offsets, const int64_t* ids,
                       const float* boxes, const float* scores, const int32_t* labels, const int32_t* n_active,
                       const int32_t* active_index, const int32_t* seq_ids, float* frame_rows, float* table,
                       int64_t table_cap, int32_t* ctrl, moyolo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side frame submission: the stream operations around one captured frame graph as ONE call
+ * (the frame itself takes ~0.35 ms on the device; issuing these from an interpreter costs more).
+ *   on copy_stream: [wait ev_slot_free] [wait for main_stream if sync_inputs] n_inputs x memcpyAsync
+ *                   (host-pinned or device sources, UVA) -> record ev_copy
+ *   on main_stream: wait ev_copy -> launch graph_exec -> n_outputs x memcpyAsync -> record ev_done
+ * All handles are plain CUDA runtime handles (cudaStream_t, cudaEvent_t, cudaGraphExec_t) owned by the
+ * caller. With n_inputs == 0 only the main-stream part runs.
+ * -------------------------------------------------------------------------------------------*/
+#define MOYOLO_SUBMIT_MAX_COPIES 4
+typedef struct {
+  void* copy_stream;
+  void* main_stream;
+  int main_stream_valid; /* must be 1 (guards against a zeroed descriptor; stream 0 is a valid handle) */
+  int sync_inputs;
+  void* ev_slot_free;
+  void* ev_scratch;
+  void* ev_copy;
+  void* ev_done;
+  void* graph_exec;
+  int n_inputs;
+  int n_outputs;
+  const void* in_src[MOYOLO_SUBMIT_MAX_COPIES];
+  void* in_dst[MOYOLO_SUBMIT_MAX_COPIES];
+  int64_t in_bytes[MOYOLO_SUBMIT_MAX_COPIES];
+  const void* out_src[MOYOLO_SUBMIT_MAX_COPIES];
+  void* out_dst[MOYOLO_SUBMIT_MAX_COPIES];
+  int64_t out_bytes[MOYOLO_SUBMIT_MAX_COPIES];
+} moyolo_frame_submit_t;
+int moyolo_frame_submit(const moyolo_frame_submit_t* d);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -20,6 +20,15 @@ GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
 
 _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
+class FrameSubmit(C.Structure):
+    """moyolo_frame_submit_t (include/moyolo_b200.h)."""
+    _fields_ = [("copy_stream", _p), ("main_stream", _p), ("main_stream_valid", _i), ("sync_inputs", _i),
+                ("ev_slot_free", _p), ("ev_scratch", _p), ("ev_copy", _p), ("ev_done", _p), ("graph_exec", _p),
+                ("n_inputs", _i), ("n_outputs", _i),
+                ("in_src", _p * 4), ("in_dst", _p * 4), ("in_bytes", _l * 4),
+                ("out_src", _p * 4), ("out_dst", _p * 4), ("out_bytes", _l * 4)]
+
+
 # name -> (restype, argtypes); must list every symbol include/moyolo_b200.h declares
 SIGNATURES = {
     "moyolo_version": (_i, []),
@@ -45,10 +54,11 @@ SIGNATURES = {
     "moyolo_track_compact": (_i, [_p, _l, _p, _p, _p, _p, _p, _i, _p]),
     "moyolo_track_assign_batched": (_i, [_p, _p, _p, _p, _p, _p, _i, _l, _f, _f, _i, _f, _p, _p, _p]),
     "moyolo_frame_assemble": (_i, [_i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l,
-                                   _i, _f, _p, _p]),
+                                   _i, _f, _p, _p, _p, _p, _i, _p]),
     "moyolo_frame_compact": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p,
-                                  _p]),
-    "moyolo_frame_writeback": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+                                  _p, _p, _i, _i, _f, _p]),
+    "moyolo_frame_writeback": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "moyolo_frame_submit": (_i, [C.POINTER(FrameSubmit)]),
     "moyolo_frame_emit": (_i, [_i, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _p, _p]),
 }
 

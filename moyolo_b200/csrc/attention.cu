@@ -3,6 +3,8 @@
 // Sequences are ragged (carried tracks + detect queries differ per lock-step sequence), keys never
 // cross a sequence boundary. Flash-style: one CTA = (sequence, head, 16 queries); K/V are streamed
 // through shared memory in 64-key tiles with an online softmax; fp32 math, exp via expf.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace moyolo {
@@ -320,6 +322,193 @@ __global__ void __launch_bounds__(128, 3) self_attention_mma_kernel(
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Split-key variant for head_dim 32 (the decoder's configuration): one CTA = (sequence, head, 16
+// queries); its four warps hold the SAME 16 queries and take every fourth 32-key tile each, with a
+// private double-buffered cp.async ring (no block-wide barrier inside the loop). The four partial
+// (max, sum, O) triples are merged through shared memory at the end. At 300-400 queries this gives
+// 4x more CTAs (all SMs busy) and a 3x shorter dependent chain than the 64-query kernel above.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSQT = 16;  // queries per CTA
+constexpr int kSKT = 32;  // keys per tile
+constexpr int kSNB = 4;   // K/V ring depth per warp
+constexpr size_t kSplitkSmem = sizeof(__nv_bfloat16) * (8 * kSNB * kSKT * (32 + 8) + 4 * kSQT * (32 + 8));
+
+__global__ void __launch_bounds__(128) self_attention_splitk32_kernel(
+    const __nv_bfloat16* __restrict__ q, int64_t ldq, const __nv_bfloat16* __restrict__ k, int64_t ldk,
+    const __nv_bfloat16* __restrict__ v, int64_t ldv, __nv_bfloat16* __restrict__ out, int64_t ldo, int batch,
+    const int32_t* __restrict__ row_offsets, const int32_t* __restrict__ seg_len) {
+  pdl_trigger();
+  pdl_wait();
+  constexpr int DH = 32;
+  constexpr int PITCH = DH + 8;
+  constexpr int KS = DH / 16;
+  constexpr int NT = DH / 8;
+  constexpr int CPR = DH / 8;
+  // dynamic shared memory: per warp a kSNB-deep K/V ring (all of a warp's tiles are in flight at once
+  // for sequences up to 4*kSNB*32 = 512 keys) and a private copy of the Q tile
+  extern __shared__ __align__(16) uint8_t att_smem[];
+  typedef __nv_bfloat16 (*KvRing)[kSNB][kSKT][PITCH];
+  typedef __nv_bfloat16 (*QTile)[kSQT][PITCH];
+  KvRing s_k = reinterpret_cast<KvRing>(att_smem);  // [4][kSNB][kSKT][PITCH]; re-used as the fp32 partial-O buffer
+  KvRing s_v = reinterpret_cast<KvRing>(att_smem + sizeof(__nv_bfloat16) * 4 * kSNB * kSKT * PITCH);
+  QTile s_q = reinterpret_cast<QTile>(att_smem + sizeof(__nv_bfloat16) * 8 * kSNB * kSKT * PITCH);
+  __shared__ float s_m[4][kSQT], s_l[4][kSQT];
+
+  int b = 0, tile = blockIdx.x, seq_start = 0, seq_len = 0;
+  for (; b < batch; ++b) {
+    seq_start = row_offsets[b];
+    seq_len = seg_len ? seg_len[b] : row_offsets[b + 1] - seq_start;
+    const int nt = (seq_len + kSQT - 1) / kSQT;
+    if (tile < nt) break;
+    tile -= nt;
+  }
+  if (b == batch) return;
+  const int head = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = tile * kSQT;
+  const int n_kt = (seq_len + kSKT - 1) / kSKT;
+
+  auto load_kv = [&](int kt, int buf) {
+    for (int i = lane; i < kSKT * CPR; i += 32) {
+      const int r = i / CPR, c = i % CPR;
+      const int kl = kt * kSKT + r;
+      const bool ok = kl < seq_len;
+      const int64_t row = seq_start + (ok ? kl : 0);
+      cp_async16(smem_addr(&s_k[warp][buf][r][c * 8]), k + row * ldk + head * DH + c * 8, ok);
+      cp_async16(smem_addr(&s_v[warp][buf][r][c * 8]), v + row * ldv + head * DH + c * 8, ok);
+    }
+  };
+  for (int i = lane; i < kSQT * CPR; i += 32) {
+    const int r = i / CPR, c = i % CPR;
+    const bool ok = q0 + r < seq_len;
+    const int64_t row = seq_start + (ok ? q0 + r : 0);
+    cp_async16(smem_addr(&s_q[warp][r][c * 8]), q + row * ldq + head * DH + c * 8, ok);
+  }
+  // prologue: Q + the first kSNB-1 tiles of this warp, one commit group per tile
+#pragma unroll
+  for (int p = 0; p < kSNB - 1; ++p) {
+    if (warp + 4 * p < n_kt) load_kv(warp + 4 * p, p);
+    cp_async_commit();
+  }
+
+  uint32_t qa[KS][4];
+  float o[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) { o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.0f; }
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+  const float sl2 = rsqrtf(static_cast<float>(DH)) * 1.4426950408889634f;
+
+  int it = 0;
+  for (int kt = warp; kt < n_kt; kt += 4, ++it) {
+    const int buf = it % kSNB;
+    if (kt + 4 * (kSNB - 1) < n_kt) load_kv(kt + 4 * (kSNB - 1), (it + kSNB - 1) % kSNB);
+    cp_async_commit();            // uniform group count: group `it` holds tile `it` of this warp
+    cp_async_wait<kSNB - 1>();
+    __syncwarp();
+    if (it == 0) {
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks)
+        ldmatrix_x4(smem_addr(&s_q[warp][(lane & 7) + ((lane >> 3) & 1) * 8][ks * 16 + (lane >> 4) * 8]), qa[ks]);
+    }
+    float s[kSKT / 8][4];
+#pragma unroll
+    for (int j = 0; j < kSKT / 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+      uint32_t kb[4];
+      ldmatrix_x4(smem_addr(&s_k[warp][buf][j * 8 + (lane & 7)][(lane >> 3) * 8]), kb);
+      mma_bf16_16816(s[j], qa[0], kb[0], kb[1]);
+      mma_bf16_16816(s[j], qa[1], kb[2], kb[3]);
+    }
+    const int kbase = kt * kSKT;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kSKT / 8; ++j) {
+      const int key = kbase + j * 8 + 2 * t;
+      if (key >= seq_len) { s[j][0] = -INFINITY; s[j][2] = -INFINITY; }
+      if (key + 1 >= seq_len) { s[j][1] = -INFINITY; s[j][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every tile holds >= 1 valid key
+    const float c0 = exp2f((m0 - mn0) * sl2), c1 = exp2f((m1 - mn1) * sl2);
+    m0 = mn0;
+    m1 = mn1;
+    float rs0 = 0.0f, rs1 = 0.0f;
+    uint32_t pa[kSKT / 16][4];
+#pragma unroll
+    for (int j = 0; j < kSKT / 8; ++j) {
+      const float p0 = exp2f((s[j][0] - mn0) * sl2), p1 = exp2f((s[j][1] - mn0) * sl2);
+      const float p2 = exp2f((s[j][2] - mn1) * sl2), p3 = exp2f((s[j][3] - mn1) * sl2);
+      rs0 += p0 + p1;
+      rs1 += p2 + p3;
+      pa[j >> 1][(j & 1) * 2 + 0] = float2_to_bf16x2(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = float2_to_bf16x2(p2, p3);
+    }
+    l0 = l0 * c0 + rs0;
+    l1 = l1 * c1 + rs1;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { o[n][0] *= c0; o[n][1] *= c0; o[n][2] *= c1; o[n][3] *= c1; }
+#pragma unroll
+    for (int kk = 0; kk < kSKT / 16; ++kk) {
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {
+        uint32_t vb[4];
+        ldmatrix_x4_trans(smem_addr(&s_v[warp][buf][kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][np * 16 + (lane >> 4) * 8]), vb);
+        mma_bf16_16816(o[2 * np], pa[kk], vb[0], vb[1]);
+        mma_bf16_16816(o[2 * np + 1], pa[kk], vb[2], vb[3]);
+      }
+    }
+    __syncwarp();  // every lane is done with `buf` before the next prefetch overwrites it
+  }
+  cp_async_wait<0>();  // warps without a tile still own the Q copy group
+  __syncwarp();
+
+  // ---- merge the four key-range partials ----
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  float* po = reinterpret_cast<float*>(&s_k[warp][0][0][0]);  // [16][DH] fp32 = 2 KiB of this warp's own ring
+  if (t == 0) {
+    s_m[warp][g] = m0; s_m[warp][g + 8] = m1;
+    s_l[warp][g] = l0; s_l[warp][g + 8] = l1;
+  }
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+    *reinterpret_cast<float2*>(po + g * DH + n * 8 + 2 * t) = make_float2(o[n][0], o[n][1]);
+    *reinterpret_cast<float2*>(po + (g + 8) * DH + n * 8 + 2 * t) = make_float2(o[n][2], o[n][3]);
+  }
+  __syncthreads();
+  const int r = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
+  if (q0 + r < seq_len) {
+    float M = fmaxf(fmaxf(s_m[0][r], s_m[1][r]), fmaxf(s_m[2][r], s_m[3][r]));
+    float L = 0.0f, acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float mw = s_m[w][r];
+      const float a = mw == -INFINITY ? 0.0f : exp2f((mw - M) * sl2);
+      L = fmaf(a, s_l[w][r], L);
+      const float4 ov = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(&s_k[w][0][0][0]) + r * DH + c4);
+      acc[0] = fmaf(a, ov.x, acc[0]);
+      acc[1] = fmaf(a, ov.y, acc[1]);
+      acc[2] = fmaf(a, ov.z, acc[2]);
+      acc[3] = fmaf(a, ov.w, acc[3]);
+    }
+    const float inv = 1.0f / L;
+    uint2 pk;
+    pk.x = float2_to_bf16x2(acc[0] * inv, acc[1] * inv);
+    pk.y = float2_to_bf16x2(acc[2] * inv, acc[3] * inv);
+    *reinterpret_cast<uint2*>(out + static_cast<int64_t>(seq_start + q0 + r) * ldo + head * DH + c4) = pk;
+  }
+}
+
 }  // namespace moyolo
 
 using namespace moyolo;
@@ -338,7 +527,9 @@ extern "C" int moyolo_self_attention(const void* q, int64_t ldq, const void* k, 
   const bool mma = dtype == MOYOLO_BF16 && attn_mask == nullptr && aligned16(q) && aligned16(k) && aligned16(v) &&
                    (ldq % 8 == 0) && (ldk % 8 == 0) && (ldv % 8 == 0) && (ldo % 2 == 0) &&
                    (reinterpret_cast<uintptr_t>(out) & 3u) == 0;
-  const int qt = mma ? kMQT : kQT;
+  static const bool allow_splitk = [] { const char* e = getenv("MOYOLO_ATT_SPLITK"); return !(e && e[0] == '0'); }();
+  const bool splitk = allow_splitk && mma && head_dim == 32 && (ldo % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
+  const int qt = splitk ? kSQT : (mma ? kMQT : kQT);
   int64_t tiles = 0;
   for (int b = 0; b < batch; ++b) {
     const int n = row_offsets_host[b + 1] - row_offsets_host[b];
@@ -351,7 +542,17 @@ extern "C" int moyolo_self_attention(const void* q, int64_t ldq, const void* k, 
     dim3 mgrid(static_cast<unsigned>(tiles), n_heads);
     const __nv_bfloat16 *qq = static_cast<const __nv_bfloat16*>(q), *kk = static_cast<const __nv_bfloat16*>(k),
                         *vv = static_cast<const __nv_bfloat16*>(v);
-    if (head_dim == 32)
+    if (splitk) {
+      static bool configured = false;
+      if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(self_attention_splitk32_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSplitkSmem));
+        if (e != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
+        configured = true;
+      }
+      launch_k(self_attention_splitk32_kernel, dim3(mgrid), dim3(128), kSplitkSmem, st, qq, ldq, kk, ldk, vv, ldv,
+               static_cast<__nv_bfloat16*>(out), ldo, batch, row_offsets, seg_len);
+    } else if (head_dim == 32)
       launch_k(self_attention_mma_kernel<32>, dim3(mgrid), dim3(128), 0, st, qq, ldq, kk, ldk, vv, ldv, static_cast<__nv_bfloat16*>(out),
                                                           ldo, batch, row_offsets, seg_len);
     else

@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(kLn256Warps * 32) add_layernorm256_kernel(
     const float* __restrict__ beta, float eps, int64_t rows, float* __restrict__ out_f32,
     LP_T* __restrict__ out_lp, const float* __restrict__ pos, LP_T* __restrict__ out_pos_lp) {
   pdl_trigger();
-  pdl_wait();
   constexpr int C = 256;
   const int lane = threadIdx.x & 31;
+  const float4 ga = *reinterpret_cast<const float4*>(gamma + lane * 4), gb = *reinterpret_cast<const float4*>(gamma + 128 + lane * 4);
+  const float4 ba = *reinterpret_cast<const float4*>(beta + lane * 4), bb = *reinterpret_cast<const float4*>(beta + 128 + lane * 4);
+  pdl_wait();
   const int64_t row = static_cast<int64_t>(blockIdx.x) * kLn256Warps + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int64_t o0 = row * C + lane * 4, o1 = o0 + 128;
@@ -114,8 +116,6 @@ __global__ void __launch_bounds__(kLn256Warps * 32) add_layernorm256_kernel(
     a.x += ra.x; a.y += ra.y; a.z += ra.z; a.w += ra.w;
     b.x += rb.x; b.y += rb.y; b.z += rb.z; b.w += rb.w;
   }
-  const float4 ga = *reinterpret_cast<const float4*>(gamma + lane * 4), gb = *reinterpret_cast<const float4*>(gamma + 128 + lane * 4);
-  const float4 ba = *reinterpret_cast<const float4*>(beta + lane * 4), bb = *reinterpret_cast<const float4*>(beta + 128 + lane * 4);
   const float mean = warp_sum(((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) * (1.0f / C);
   a.x -= mean; a.y -= mean; a.z -= mean; a.w -= mean;
   b.x -= mean; b.y -= mean; b.z -= mean; b.w -= mean;
@@ -169,6 +169,44 @@ __global__ void __launch_bounds__(kRowWarps * 32) box_refine_kernel(
   if (lane < 4) {
     float t = lane == 0 ? d[0] : (lane == 1 ? d[1] : (lane == 2 ? d[2] : d[3]));
     t += b3[lane] + inverse_sigmoidf_(ref[row * 4 + lane]);
+    new_ref[row * 4 + lane] = sigmoidf_(t);
+  }
+}
+
+// K == 256, bf16 hidden: every lane owns 8 consecutive k (one 128-bit load of h); its w3 slices are
+// immutable and are fetched before the programmatic-dependency wait.
+__global__ void __launch_bounds__(kRowWarps * 32) box_refine256_kernel(
+    const __nv_bfloat16* __restrict__ h, int64_t ldh, const float* __restrict__ w3, const float* __restrict__ b3,
+    const float* __restrict__ ref, float* __restrict__ new_ref, int64_t rows) {
+  pdl_trigger();
+  const int lane = threadIdx.x & 31;
+  float w[4][8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(w3 + j * 256 + lane * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w3 + j * 256 + lane * 8 + 4));
+    w[j][0] = a.x; w[j][1] = a.y; w[j][2] = a.z; w[j][3] = a.w;
+    w[j][4] = b.x; w[j][5] = b.y; w[j][6] = b.z; w[j][7] = b.w;
+  }
+  const float bias = lane < 4 ? __ldg(b3 + lane) : 0.0f;
+  pdl_wait();
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kRowWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const uint4 hv = *reinterpret_cast<const uint4*>(h + row * ldh + lane * 8);
+  const float rf = lane < 4 ? ref[row * 4 + lane] : 0.5f;
+  const float2 h0 = bf16x2_to_float2(hv.x), h1 = bf16x2_to_float2(hv.y), h2 = bf16x2_to_float2(hv.z),
+               h3 = bf16x2_to_float2(hv.w);
+  const float hf[8] = {h0.x, h0.y, h1.x, h1.y, h2.x, h2.y, h3.x, h3.y};
+  float d[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc = fmaf(hf[k], w[j][k], acc);
+    d[j] = warp_sum(acc);
+  }
+  if (lane < 4) {
+    const float t = (lane == 0 ? d[0] : (lane == 1 ? d[1] : (lane == 2 ? d[2] : d[3]))) + bias + inverse_sigmoidf_(rf);
     new_ref[row * 4 + lane] = sigmoidf_(t);
   }
 }
@@ -309,7 +347,10 @@ extern "C" int moyolo_box_refine(const void* h, int64_t ldh, int h_dtype, const 
   MOYOLO_REQUIRE(rows >= 0 && K > 0 && ldh >= K, MOYOLO_ERR_BAD_SHAPE, "box_refine: bad sizes");
   if (rows == 0) return MOYOLO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (h_dtype == MOYOLO_BF16)
+  if (h_dtype == MOYOLO_BF16 && K == 256 && aligned16(h) && (ldh * 2) % 16 == 0 && aligned16(w3))
+    launch_k(box_refine256_kernel, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st,
+             static_cast<const __nv_bfloat16*>(h), ldh, w3, b3, ref, new_ref, rows);
+  else if (h_dtype == MOYOLO_BF16)
     launch_k(box_refine_kernel<__nv_bfloat16>, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st, 
         static_cast<const __nv_bfloat16*>(h), ldh, w3, b3, ref, new_ref, rows, K);
   else if (h_dtype == MOYOLO_F32)

@@ -30,10 +30,26 @@ __global__ void frame_assemble_kernel(int n_seq, int n_detect, int C, int cap, c
                                       float* __restrict__ x, float* __restrict__ refer_logit, float* __restrict__ pos,
                                       int64_t* __restrict__ ids, int64_t* __restrict__ dis,
                                       int32_t* __restrict__ row_offsets, int num_pos_feats, float temperature,
-                                      int rows_pad, int32_t* __restrict__ ctrl) {
+                                      int rows_pad, int32_t* __restrict__ ctrl, float* __restrict__ refer_sig,
+                                      void* __restrict__ x_lp, void* __restrict__ xq_lp, int lp_bf16) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x;
+  // optional fused outputs: sigmoid(refer) (transformer.py:690) and the GEMM operand copies x, x + pos
+  auto emit_lp = [&](int c, float xv, float pv) {
+    const int64_t o = static_cast<int64_t>(row) * C + c;
+    if (lp_bf16) {
+      if (x_lp) static_cast<__nv_bfloat16*>(x_lp)[o] = __float2bfloat16_rn(xv);
+      if (xq_lp) static_cast<__nv_bfloat16*>(xq_lp)[o] = __float2bfloat16_rn(xv + pv);
+    } else {
+      if (x_lp) static_cast<float*>(x_lp)[o] = xv;
+      if (xq_lp) static_cast<float*>(xq_lp)[o] = xv + pv;
+    }
+  };
+  auto emit_ref = [&](int k, float logit) {
+    refer_logit[row * 4 + k] = logit;
+    if (refer_sig) refer_sig[row * 4 + k] = 1.0f / (1.0f + expf(-logit));
+  };
   // Speculative launch guard: the host picks rows_pad from the track counts of an EARLIER frame. If the
   // real row count does not fit (or an earlier frame already aborted), every block consistently
   // builds a detect-only frame (in bounds, results discarded) and the sticky abort flag tells the
@@ -63,8 +79,8 @@ __global__ void frame_assemble_kernel(int n_seq, int n_detect, int C, int cap, c
   float* xr = x + static_cast<int64_t>(row) * C;
   float* pr = pos + static_cast<int64_t>(row) * C;
   if (s == n_seq) {  // padding row: finite zeros, never an object
-    for (int c = threadIdx.x; c < C; c += blockDim.x) { xr[c] = 0.0f; pr[c] = 0.0f; }
-    if (threadIdx.x < 4) refer_logit[row * 4 + threadIdx.x] = 0.0f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { xr[c] = 0.0f; pr[c] = 0.0f; emit_lp(c, 0.0f, 0.0f); }
+    if (threadIdx.x < 4) emit_ref(threadIdx.x, 0.0f);
     if (threadIdx.x == 0) { ids[row] = -1; dis[row] = 0; }
     return;
   }
@@ -73,21 +89,29 @@ __global__ void frame_assemble_kernel(int n_seq, int n_detect, int C, int cap, c
     const int64_t src = static_cast<int64_t>(s) * cap + j;
     const float* ce = class_embed + static_cast<int64_t>(t_label[src]) * C;
     const float* qp = t_qpos + src * C;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) { xr[c] = ce[c]; pr[c] = qp[c]; }
-    if (threadIdx.x < 4) refer_logit[row * 4 + threadIdx.x] = t_ref[src * 4 + threadIdx.x];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float xv = ce[c], pv = qp[c];
+      xr[c] = xv;
+      pr[c] = pv;
+      emit_lp(c, xv, pv);
+    }
+    if (threadIdx.x < 4) emit_ref(threadIdx.x, t_ref[src * 4 + threadIdx.x]);
     if (threadIdx.x == 0) { ids[row] = t_ids[src]; dis[row] = t_dis[src]; }
   } else {      // detect query
     const int64_t src = static_cast<int64_t>(s) * n_detect + (j - T);
     const float* de = det_embed + src * C;
     const float* dr = det_refer + src * 4;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      xr[c] = de[c];
+      const float xv = de[c];
+      xr[c] = xv;
       const int coord = c / num_pos_feats, i = c % num_pos_feats;
       const float p = dr[coord] * 6.283185307179586f;
       const float e = p / powf(temperature, static_cast<float>(2 * (i / 2)) / static_cast<float>(num_pos_feats));
-      pr[c] = (i & 1) ? cosf(e) : sinf(e);
+      const float pv = (i & 1) ? cosf(e) : sinf(e);
+      pr[c] = pv;
+      emit_lp(c, xv, pv);
     }
-    if (threadIdx.x < 4) refer_logit[row * 4 + threadIdx.x] = dr[threadIdx.x];
+    if (threadIdx.x < 4) emit_ref(threadIdx.x, dr[threadIdx.x]);
     if (threadIdx.x == 0) { ids[row] = -1; dis[row] = 0; }
   }
 }
@@ -126,7 +150,8 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
     const float* __restrict__ pos, const float* __restrict__ hs, const float* __restrict__ boxes,
     int32_t* __restrict__ n_active, int32_t* __restrict__ active_index, float* __restrict__ c_ref,
     float* __restrict__ c_pos, float* __restrict__ c_hs, float* __restrict__ c_box, int32_t* __restrict__ t_label,
-    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis, const int32_t* __restrict__ ctrl) {
+    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis, const int32_t* __restrict__ ctrl,
+    void* __restrict__ q_qk_lp, void* __restrict__ q_tgt_lp, int lp_bf16, int num_pos_feats, float temperature) {
   pdl_trigger();
   pdl_wait();
   __shared__ int s_warp[33];
@@ -155,7 +180,22 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
     const int64_t dst = off + j;  // compact rows keep the frame layout: sequence s starts at row_offsets[s]
     for (int c = lane; c < C; c += 32) {
       c_pos[dst * C + c] = pos[src * C + c];
-      c_hs[dst * C + c] = hs[src * C + c];
+      const float h = hs[src * C + c];
+      c_hs[dst * C + c] = h;
+      // QIM operands (qim.py:255, 271): q = k = tgt + pos2posemb(ref_pts), v = tgt
+      if (q_qk_lp != nullptr || q_tgt_lp != nullptr) {
+        const int coord = c / num_pos_feats, i = c % num_pos_feats;
+        const float p = refer_logit[src * 4 + coord] * 6.283185307179586f;
+        const float e = p / powf(temperature, static_cast<float>(2 * (i / 2)) / static_cast<float>(num_pos_feats));
+        const float qp = (i & 1) ? cosf(e) : sinf(e);
+        if (lp_bf16) {
+          if (q_qk_lp) static_cast<__nv_bfloat16*>(q_qk_lp)[dst * C + c] = __float2bfloat16_rn(qp + h);
+          if (q_tgt_lp) static_cast<__nv_bfloat16*>(q_tgt_lp)[dst * C + c] = __float2bfloat16_rn(h);
+        } else {
+          if (q_qk_lp) static_cast<float*>(q_qk_lp)[dst * C + c] = qp + h;
+          if (q_tgt_lp) static_cast<float*>(q_tgt_lp)[dst * C + c] = h;
+        }
+      }
     }
     if (lane < 4) {
       c_ref[dst * 4 + lane] = refer_logit[src * 4 + lane];
@@ -175,9 +215,14 @@ __global__ void frame_writeback_kernel(int C, int cap, const int32_t* __restrict
                                        const int32_t* __restrict__ n_active, const float* __restrict__ new_qpos,
                                        const float* __restrict__ c_box, float* __restrict__ t_qpos,
                                        float* __restrict__ t_ref, int32_t* __restrict__ n_tracks,
-                                       const int32_t* __restrict__ ctrl) {
+                                       const int32_t* __restrict__ ctrl, int32_t* __restrict__ info) {
   pdl_trigger();
   pdl_wait();
+  // host-visible frame summary: [n_active (n_seq) | ctrl (8)], written even for an aborted frame
+  if (info != nullptr && blockIdx.y == 0 && threadIdx.x < 32) {
+    if (threadIdx.x == 0) info[blockIdx.x] = n_active[blockIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x < 8 && ctrl != nullptr) info[gridDim.x + threadIdx.x] = ctrl[threadIdx.x];
+  }
   if (ctrl != nullptr && ctrl[kCtrlAbort] != 0) return;
   const int s = blockIdx.x;
   const int off = row_offsets[s];
@@ -262,17 +307,21 @@ extern "C" int moyolo_frame_assemble(int n_seq, int n_detect, int C, int cap, co
                                      const int64_t* t_ids, const int64_t* t_dis, const float* class_embed,
                                      const float* det_embed, const float* det_refer, float* x, float* refer_logit,
                                      float* pos, int64_t* ids, int64_t* dis, int32_t* row_offsets, int64_t rows_pad,
-                                     int num_pos_feats, float temperature, int32_t* ctrl, moyolo_stream_t stream) {
+                                     int num_pos_feats, float temperature, int32_t* ctrl, float* refer_sig,
+                                     void* x_lp, void* xq_lp, int lp_dtype, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(n_tracks && t_ref && t_qpos && t_label && t_ids && t_dis && class_embed && det_embed && det_refer &&
                      x && refer_logit && pos && ids && dis && row_offsets,
                  MOYOLO_ERR_BAD_ARG, "frame_assemble: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && n_detect >= 0 && C > 0 && cap > 0 && rows_pad > 0, MOYOLO_ERR_BAD_SHAPE,
                  "frame_assemble: bad sizes");
   MOYOLO_REQUIRE(C == 4 * num_pos_feats, MOYOLO_ERR_BAD_SHAPE, "frame_assemble: C must equal 4*num_pos_feats");
+  MOYOLO_REQUIRE(lp_dtype == MOYOLO_BF16 || lp_dtype == MOYOLO_F32, MOYOLO_ERR_UNSUPPORTED,
+                 "frame_assemble: lp_dtype must be F32 or BF16");
   const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
   launch_k(frame_assemble_kernel, dim3(static_cast<unsigned>(rows_pad)), dim3(threads), 0, static_cast<cudaStream_t>(stream), 
       n_seq, n_detect, C, cap, n_tracks, t_ref, t_qpos, t_label, t_ids, t_dis, class_embed, det_embed, det_refer, x,
-      refer_logit, pos, ids, dis, row_offsets, num_pos_feats, temperature, static_cast<int>(rows_pad), ctrl);
+      refer_logit, pos, ids, dis, row_offsets, num_pos_feats, temperature, static_cast<int>(rows_pad), ctrl,
+      refer_sig, x_lp, xq_lp, lp_dtype == MOYOLO_BF16 ? 1 : 0);
   return check_launch("frame_assemble_kernel");
 }
 
@@ -281,26 +330,31 @@ extern "C" int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* ro
                                     const float* pos, const float* hs, const float* boxes, int32_t* n_active,
                                     int32_t* active_index, float* c_ref, float* c_pos, float* c_hs, float* c_box,
                                     int32_t* t_label, int64_t* t_ids, int64_t* t_dis, const int32_t* ctrl,
-                                    moyolo_stream_t stream) {
+                                    void* q_qk_lp, void* q_tgt_lp, int lp_dtype, int num_pos_feats,
+                                    float temperature, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(row_offsets && ids && dis && labels && refer_logit && pos && hs && boxes && n_active &&
                      active_index && c_ref && c_pos && c_hs && c_box && t_label && t_ids && t_dis,
                  MOYOLO_ERR_BAD_ARG, "frame_compact: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_compact: bad sizes");
+  MOYOLO_REQUIRE((q_qk_lp == nullptr && q_tgt_lp == nullptr) || C == 4 * num_pos_feats, MOYOLO_ERR_BAD_SHAPE,
+                 "frame_compact: QIM operands need C == 4*num_pos_feats");
   launch_k(frame_compact_kernel, dim3(n_seq), dim3(1024), 0, static_cast<cudaStream_t>(stream), 
       C, cap, row_offsets, ids, dis, labels, refer_logit, pos, hs, boxes, n_active, active_index, c_ref, c_pos, c_hs,
-      c_box, t_label, t_ids, t_dis, ctrl);
+      c_box, t_label, t_ids, t_dis, ctrl, q_qk_lp, q_tgt_lp, lp_dtype == MOYOLO_BF16 ? 1 : 0, num_pos_feats,
+      temperature);
   return check_launch("frame_compact_kernel");
 }
 
 extern "C" int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,
                                       const float* new_qpos, const float* c_box, float* t_qpos, float* t_ref,
-                                      int32_t* n_tracks, const int32_t* ctrl, moyolo_stream_t stream) {
+                                      int32_t* n_tracks, const int32_t* ctrl, int32_t* info,
+                                      moyolo_stream_t stream) {
   MOYOLO_REQUIRE(row_offsets && n_active && new_qpos && c_box && t_qpos && t_ref && n_tracks, MOYOLO_ERR_BAD_ARG,
                  "frame_writeback: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_writeback: bad sizes");
   dim3 grid(n_seq, 8);
   launch_k(frame_writeback_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), C, cap, row_offsets, n_active, new_qpos,
-                                                                             c_box, t_qpos, t_ref, n_tracks, ctrl);
+                                                                             c_box, t_qpos, t_ref, n_tracks, ctrl, info);
   return check_launch("frame_writeback_kernel");
 }
 

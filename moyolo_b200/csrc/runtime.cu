@@ -1,0 +1,45 @@
+// Host-side frame runtime: everything the host does per frame, in ONE call.
+//
+// A frame of the tracker is a captured CUDA graph plus a handful of stream operations around it
+// (input copies into the device ring on a copy stream, event hand-offs, result copies to pinned host
+// memory). Issued from Python these ~12 driver calls cost more host time than the GPU needs for the
+// frame itself; here they are one C call. No reference counterpart: the reference's frame loop
+// (MOTRtrack/val.py:288-291 -> TrackingModel.predict, ultralytics/nn/tasks.py:513) is eager PyTorch.
+#include "common.cuh"
+
+using namespace moyolo;
+
+#define RT_CHECK(call, what)                                                                 \
+  do {                                                                                       \
+    cudaError_t e_ = (call);                                                                 \
+    if (e_ != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "frame_submit: %s: %s", what, cudaGetErrorString(e_)); \
+  } while (0)
+
+extern "C" int moyolo_frame_submit(const moyolo_frame_submit_t* d) {
+  MOYOLO_REQUIRE(d != nullptr && d->main_stream_valid == 1, MOYOLO_ERR_BAD_ARG, "frame_submit: null descriptor");
+  MOYOLO_REQUIRE(d->n_inputs >= 0 && d->n_inputs <= MOYOLO_SUBMIT_MAX_COPIES && d->n_outputs >= 0 &&
+                     d->n_outputs <= MOYOLO_SUBMIT_MAX_COPIES,
+                 MOYOLO_ERR_BAD_ARG, "frame_submit: too many copies");
+  cudaStream_t cs = static_cast<cudaStream_t>(d->copy_stream);
+  cudaStream_t ms = static_cast<cudaStream_t>(d->main_stream);
+  if (d->n_inputs > 0) {
+    // the ring slot is free once the frame that last read it has finished
+    if (d->ev_slot_free != nullptr) RT_CHECK(cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(d->ev_slot_free), 0), "wait slot");
+    if (d->sync_inputs) {  // inputs still being produced on the main stream
+      MOYOLO_REQUIRE(d->ev_scratch != nullptr, MOYOLO_ERR_BAD_ARG, "frame_submit: sync_inputs needs ev_scratch");
+      RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_scratch), ms), "record scratch");
+      RT_CHECK(cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(d->ev_scratch), 0), "wait scratch");
+    }
+    for (int i = 0; i < d->n_inputs; ++i)
+      RT_CHECK(cudaMemcpyAsync(d->in_dst[i], d->in_src[i], static_cast<size_t>(d->in_bytes[i]), cudaMemcpyDefault, cs),
+               "input copy");
+    RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_copy), cs), "record copy");
+    RT_CHECK(cudaStreamWaitEvent(ms, static_cast<cudaEvent_t>(d->ev_copy), 0), "wait copy");
+  }
+  if (d->graph_exec != nullptr) RT_CHECK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(d->graph_exec), ms), "graph launch");
+  for (int i = 0; i < d->n_outputs; ++i)
+    RT_CHECK(cudaMemcpyAsync(d->out_dst[i], d->out_src[i], static_cast<size_t>(d->out_bytes[i]), cudaMemcpyDefault, ms),
+             "result copy");
+  if (d->ev_done != nullptr) RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_done), ms), "record done");
+  return MOYOLO_OK;
+}

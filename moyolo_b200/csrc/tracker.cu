@@ -13,6 +13,7 @@ namespace moyolo {
 
 constexpr int kTrkThreads = 1024;
 constexpr int kTrkMaxN = 4096;
+constexpr int kSuppSmemWords = 10240;  // 40 KiB: the bit matrix of up to ~570 active tracks
 
 // Block-wide exclusive scan of one int per thread; returns exclusive prefix, total via *total.
 __device__ int block_exclusive_scan(int v, int* total, int* s_warp /* [33] */) {
@@ -80,6 +81,9 @@ __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
   pdl_trigger();
   pdl_wait();
   __shared__ int s_warp[33];
+  __shared__ uint32_t s_zmask[kTrkMaxN / 32];    // rows with a non-empty suppression set
+  __shared__ uint32_t s_removed[kTrkMaxN / 32];  // rows dropped by the greedy filter
+  __shared__ uint32_t s_supp[kSuppSmemWords];    // suppression bit matrix when it fits (else workspace)
   if (ctrl != nullptr && ctrl[0] != 0) return;  // aborted speculative frame (see frame.cu): ID counters untouched
   if (row_offsets != nullptr) {  // batched: one CTA per sequence, rows [row_offsets[s], row_offsets[s+1])
     const int seq = blockIdx.x;
@@ -132,17 +136,26 @@ __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
   __syncthreads();
 
   // ---- C. pairwise suppression bits, then the greedy sweep (head.py:1155-1171) ----
+  // supp[i] has bit j set iff j > i and IoU(i, j) > thr. Row i only matters to the sweep when it is
+  // non-empty (s_zmask), and because its bits all lie above i, "removed by a kept earlier row" is
+  // simply the OR of the kept non-empty rows: the sequential part visits the (few) non-empty rows only.
   const int words = static_cast<int>(trk_words(n_active));
+  uint32_t* supp = (n_active * words <= kSuppSmemWords) ? s_supp : ws.supp;
+  for (int t = threadIdx.x; t < kTrkMaxN / 32; t += kTrkThreads) { s_zmask[t] = 0u; s_removed[t] = 0u; }
+  __syncthreads();
   for (int t = threadIdx.x; t < n_active * words; t += kTrkThreads) {
     const int i = t / words, wj = t % words;
     uint32_t bits = 0;
-    const float* bi = boxes + static_cast<int64_t>(ws.active_idx[i]) * 4;
-    for (int bpos = 0; bpos < 32; ++bpos) {
-      const int j = wj * 32 + bpos;
-      if (j > i && j < n_active && iou_gt(bi, boxes + static_cast<int64_t>(ws.active_idx[j]) * 4, iou_thresh))
-        bits |= 1u << bpos;
+    if (wj * 32 + 31 > i) {
+      const float* bi = boxes + static_cast<int64_t>(ws.active_idx[i]) * 4;
+      for (int bpos = 0; bpos < 32; ++bpos) {
+        const int j = wj * 32 + bpos;
+        if (j > i && j < n_active && iou_gt(bi, boxes + static_cast<int64_t>(ws.active_idx[j]) * 4, iou_thresh))
+          bits |= 1u << bpos;
+      }
     }
-    ws.supp[t] = bits;
+    supp[t] = bits;
+    if (bits != 0u) atomicOr(&s_zmask[i >> 5], 1u << (i & 31));
   }
   __syncthreads();
   if (threadIdx.x < 32) {
@@ -151,24 +164,34 @@ __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
     uint32_t removed[kSlots];
 #pragma unroll
     for (int s = 0; s < kSlots; ++s) removed[s] = 0u;
-    for (int i = 0; i < n_active; ++i) {
-      const int wi = i >> 5, owner = wi & 31, slot = wi >> 5;
-      uint32_t wv = 0u;
+    for (int wz = 0; wz < words; ++wz) {
+      uint32_t zm = s_zmask[wz];  // warp-uniform
+      while (zm != 0u) {
+        const int i = wz * 32 + (__ffs(zm) - 1);
+        zm &= zm - 1u;
+        const int wi = i >> 5, owner = wi & 31, slot = wi >> 5;
+        uint32_t wv = 0u;
 #pragma unroll
-      for (int s = 0; s < kSlots; ++s) wv = (s == slot) ? removed[s] : wv;
-      wv = __shfl_sync(0xffffffffu, wv, owner);
-      const bool kept = ((wv >> (i & 31)) & 1u) == 0u;
-      if (lane == 0) ws.keep[i] = kept ? 1 : 0;
-      if (kept) {
+        for (int s = 0; s < kSlots; ++s) wv = (s == slot) ? removed[s] : wv;
+        wv = __shfl_sync(0xffffffffu, wv, owner);
+        const bool kept = ((wv >> (i & 31)) & 1u) == 0u;
+        if (kept) {
 #pragma unroll
-        for (int s = 0; s < kSlots; ++s) {
-          const int w = lane + 32 * s;
-          if (w < words) removed[s] |= ws.supp[i * words + w];
+          for (int s = 0; s < kSlots; ++s) {
+            const int w = lane + 32 * s;
+            if (w < words) removed[s] |= supp[i * words + w];
+          }
         }
       }
     }
+#pragma unroll
+    for (int s = 0; s < kSlots; ++s) {
+      const int w = lane + 32 * s;
+      if (w < words) s_removed[w] = removed[s];
+    }
   }
   __syncthreads();
+  for (int a = threadIdx.x; a < n_active; a += kTrkThreads) ws.keep[a] = ((s_removed[a >> 5] >> (a & 31)) & 1u) ? 0 : 1;
 
   // ---- D. renumbering side effect on the counters (head.py:1268-1282) ----
   // kept rows with id > max_obj_id_pre become max_obj_id_pre+1, +2, ... in order; the new
@@ -179,7 +202,7 @@ __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
   int n_renum_local = 0;
   long long max_old_local = -1;
   for (int a = ab; a < ae; ++a) {
-    if (!ws.keep[a]) continue;
+    if ((s_removed[a >> 5] >> (a & 31)) & 1u) continue;
     const int64_t id = obj_idxes[ws.active_idx[a]];
     if (id > max_obj_id_pre) ++n_renum_local;
     else max_old_local = max(max_old_local, static_cast<long long>(id));

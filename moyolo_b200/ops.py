@@ -354,30 +354,38 @@ def track_assign_batched(scores, boxes, ids, dis, counters, row_offsets, n_seq: 
 
 def frame_assemble(n_seq, n_detect, C, cap, n_tracks, t_ref, t_qpos, t_label, t_ids, t_dis, class_embed, det_embed,
                    det_refer, x, refer_logit, pos, ids, dis, row_offsets, rows_pad, num_pos_feats=64,
-                   temperature=10000.0, ctrl=None) -> None:
+                   temperature=10000.0, ctrl=None, refer_sig=None, x_lp=None, xq_lp=None) -> None:
+    """Optional fused outputs: refer_sig = sigmoid(refer_logit), x_lp = x and xq_lp = x + pos as GEMM operands."""
+    lp = x_lp if x_lp is not None else xq_lp
     _count(1)
     _lib.check(_lib.lib().moyolo_frame_assemble(
         n_seq, n_detect, C, cap, n_tracks.data_ptr(), t_ref.data_ptr(), t_qpos.data_ptr(), t_label.data_ptr(),
         t_ids.data_ptr(), t_dis.data_ptr(), class_embed.data_ptr(), det_embed.data_ptr(), det_refer.data_ptr(),
         x.data_ptr(), refer_logit.data_ptr(), pos.data_ptr(), ids.data_ptr(), dis.data_ptr(), row_offsets.data_ptr(),
-        rows_pad, num_pos_feats, float(temperature), _ptr(ctrl), _stream()))
+        rows_pad, num_pos_feats, float(temperature), _ptr(ctrl), _ptr(refer_sig), _ptr(x_lp), _ptr(xq_lp),
+        _dt(lp) if lp is not None else F32, _stream()))
 
 
 def frame_compact(n_seq, C, cap, row_offsets, ids, dis, labels, refer_logit, pos, hs, boxes, n_active, active_index,
-                  c_ref, c_pos, c_hs, c_box, t_label, t_ids, t_dis, ctrl=None) -> None:
+                  c_ref, c_pos, c_hs, c_box, t_label, t_ids, t_dis, ctrl=None, q_qk_lp=None, q_tgt_lp=None,
+                  num_pos_feats=64, temperature=10000.0) -> None:
+    """Optional fused QIM operands: q_qk_lp = c_hs + pos2posemb(c_ref), q_tgt_lp = c_hs (qim.py:255,271)."""
+    lp = q_qk_lp if q_qk_lp is not None else q_tgt_lp
     _count(1)
     _lib.check(_lib.lib().moyolo_frame_compact(
         n_seq, C, cap, row_offsets.data_ptr(), ids.data_ptr(), dis.data_ptr(), labels.data_ptr(),
         refer_logit.data_ptr(), pos.data_ptr(), hs.data_ptr(), boxes.data_ptr(), n_active.data_ptr(),
         active_index.data_ptr(), c_ref.data_ptr(), c_pos.data_ptr(), c_hs.data_ptr(), c_box.data_ptr(),
-        t_label.data_ptr(), t_ids.data_ptr(), t_dis.data_ptr(), _ptr(ctrl), _stream()))
+        t_label.data_ptr(), t_ids.data_ptr(), t_dis.data_ptr(), _ptr(ctrl), _ptr(q_qk_lp), _ptr(q_tgt_lp),
+        _dt(lp) if lp is not None else F32, num_pos_feats, float(temperature), _stream()))
 
 
-def frame_writeback(n_seq, C, cap, row_offsets, n_active, new_qpos, c_box, t_qpos, t_ref, n_tracks, ctrl=None) -> None:
+def frame_writeback(n_seq, C, cap, row_offsets, n_active, new_qpos, c_box, t_qpos, t_ref, n_tracks, ctrl=None,
+                    info=None) -> None:
     _count(1)
     _lib.check(_lib.lib().moyolo_frame_writeback(
         n_seq, C, cap, row_offsets.data_ptr(), n_active.data_ptr(), new_qpos.data_ptr(), c_box.data_ptr(),
-        t_qpos.data_ptr(), t_ref.data_ptr(), n_tracks.data_ptr(), _ptr(ctrl), _stream()))
+        t_qpos.data_ptr(), t_ref.data_ptr(), n_tracks.data_ptr(), _ptr(ctrl), _ptr(info), _stream()))
 
 
 def frame_emit(n_seq, rows_pad, row_offsets, ids, boxes, scores, labels, n_active, active_index, seq_ids, frame_rows,

@@ -29,10 +29,13 @@ Execution model (DESIGN.md "Frame pipeline"):
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Dict, List, Optional
 
 import torch
 
+from . import _lib
 from . import executor as ex
 from . import ops
 from .synthetic import DecoderSpec, level_sizes
@@ -142,7 +145,7 @@ class FrameWorkspace:
 
 class _FramePlan:
     """Workspace (and optionally the captured CUDA graph) of one (padded frame size, input slot)."""
-    __slots__ = ("rows_pad", "slot", "graph", "ws", "n_launch")
+    __slots__ = ("rows_pad", "slot", "graph", "ws", "n_launch", "desc")
 
 
 class TrackEngine:
@@ -190,6 +193,15 @@ class TrackEngine:
         self._h_info = torch.zeros(self.DEPTH, S + 8, dtype=torch.int32).pin_memory()
         self._h_rows = torch.zeros(self.DEPTH, self._max_rows, 8).pin_memory()
         self._plans: Dict[tuple, _FramePlan] = {}
+        # native submission (moyolo_frame_submit): raw handles of the streams / events above. torch creates
+        # the underlying cudaEvent lazily on the first record, so every event is recorded once here.
+        self._ev_scratch = torch.cuda.Event()
+        for e in (*self._ev_done, *self._ev_copy, self._ev_scratch):
+            e.record(self._main)
+        torch.cuda.synchronize(dev)
+        self._native = use_graphs and os.environ.get("MOYOLO_NATIVE_SUBMIT", "1") != "0"
+        self._keep = [None, None]            # inputs of the two newest frames (alive until their copies ran)
+        self._h_info_np = self._h_info.numpy()
         self._host_reset()
 
     # ---- host-side bookkeeping ---------------------------------------------------------------
@@ -267,13 +279,11 @@ class TrackEngine:
                        engine=ex._GEMM_ENGINE)
         ops.frame_assemble(S, nd, C, self.cap, self.n_tracks, self.t_ref, self.t_qpos, self.t_label, self.t_ids,
                            self.t_dis, W.class_embed, self.det_embed_in[p.slot], self.det_refer_in[p.slot], ws.x,
-                           ws.refer_logit, ws.pos, ws.ids, ws.dis, ws.ro, R, ctrl=self.ctrl)
+                           ws.refer_logit, ws.pos, ws.ids, ws.dis, ws.ro, R, ctrl=self.ctrl,
+                           refer_sig=ws.refer[0],                            # transformer.py:690
+                           x_lp=None if dt == torch.float32 else ws.x_lp, xq_lp=ws.xq_lp)
         # host-side bound of the device offsets, used for grid sizing only: sum_s ceil(N_s/16) <= R/16 + S
         ro_host = [16 * i for i in range(S)] + [16 * S + R]
-        ops.sigmoid(ws.refer_logit, out=ws.refer[0])                      # transformer.py:690
-        if dt != torch.float32:
-            ops.add_cast(ws.x, None, dt, out=ws.x_lp)
-        ops.add_cast(ws.x, ws.pos, dt, out=ws.xq_lp)
         for i, pk in enumerate(W.layers):
             last = i + 1 == n_l
             value_view = self.values[:, :, i * C:(i + 1) * C]
@@ -302,14 +312,23 @@ class TrackEngine:
                                  mt, it, ctrl=self.ctrl)
         ops.frame_compact(S, C, self.cap, ws.ro, ws.ids, ws.dis, ws.labels, ws.refer_logit, ws.pos, ws.x, boxes,
                           ws.n_active, ws.active_index, ws.c_ref, ws.c_pos, ws.c_hs, ws.c_box, self.t_label,
-                          self.t_ids, self.t_dis, ctrl=self.ctrl)
-        ops.frame_emit(S, R, ws.ro, ws.ids, boxes, ws.scores, ws.labels, ws.n_active, ws.active_index, self.seq_ids,
-                       ws.frame_rows, self.table, self.ctrl)
+                          self.t_ids, self.t_dis, ctrl=self.ctrl, q_qk_lp=ws.q_qk_lp,            # qim.py:255, 271
+                          q_tgt_lp=None if dt == torch.float32 else ws.q_tgt_lp)
+        # the frame's result rows / track-table append are not needed by the QIM update: side branch
+        if fork:
+            self._s_box.wait_stream(cur)
+            with torch.cuda.stream(self._s_box):
+                ops.frame_emit(S, R, ws.ro, ws.ids, boxes, ws.scores, ws.labels, ws.n_active, ws.active_index,
+                               self.seq_ids, ws.frame_rows, self.table, self.ctrl)
+        else:
+            ops.frame_emit(S, R, ws.ro, ws.ids, boxes, ws.scores, ws.labels, ws.n_active, ws.active_index,
+                           self.seq_ids, ws.frame_rows, self.table, self.ctrl)
         self._qim_update(ws, ro_host)
+        # write-back also stores what the host reads back after the frame: [n_active | ctrl]
         ops.frame_writeback(S, C, self.cap, ws.ro, ws.n_active, ws.q_new, ws.c_box, self.t_qpos, self.t_ref,
-                            self.n_tracks, ctrl=self.ctrl)
-        ws.info[:S].copy_(ws.n_active, non_blocking=True)   # what the host reads back after the frame
-        ws.info[S:].copy_(self.ctrl, non_blocking=True)
+                            self.n_tracks, ctrl=self.ctrl, info=ws.info)
+        if fork:
+            cur.wait_stream(self._s_box)
 
     def _qim_update(self, ws: FrameWorkspace, ro_host) -> None:
         """QueryInteractionModule._update_track_embedding (MOTR/models/qim.py:251-301) for the active
@@ -320,10 +339,7 @@ class TrackEngine:
         C = self.spec.d_model
         dt, q, H = W.dt, W.qim, 8  # nn.MultiheadAttention(dim_in, 8, ...) qim.py:88
         eng = ex._GEMM_ENGINE
-        ops.pos2posemb(ws.c_ref, out=ws.q_pos)                                       # qim.py:255
-        ops.add_cast(ws.q_pos, ws.c_hs, dt, out=ws.q_qk_lp)                          # :271 q = k = tgt + query_pos
-        if dt != torch.float32:
-            ops.add_cast(ws.c_hs, None, dt, out=ws.q_tgt_lp)
+        # q = k = tgt + pos2posemb(ref_pts), v = tgt (qim.py:255, 271): operands written by frame_compact
         ex.qkv_proj(ws.q_qk_lp, ws.q_tgt_lp, q["qkv_w"], q["qkv_b"], ws.qkv, C, eng)
         ops.self_attention(ws.qkv[:, :C], ws.qkv[:, C:2 * C], ws.qkv[:, 2 * C:], ws.ro, ro_host, H, out=ws.att,
                            seg_len=ws.n_active)
@@ -362,7 +378,7 @@ class TrackEngine:
         if p is not None:
             return p
         p = _FramePlan()
-        p.rows_pad, p.slot, p.graph, p.n_launch = rows_pad, slot, None, 0
+        p.rows_pad, p.slot, p.graph, p.n_launch, p.desc = rows_pad, slot, None, 0, None
         other = self._plans.get((rows_pad, slot ^ 1))
         # both input slots of one size share a workspace: frames are serialised on the main stream
         p.ws = other.ws if other is not None else FrameWorkspace(rows_pad, self.n_seq, self.spec, self.W.dt, self.dev,
@@ -382,12 +398,55 @@ class TrackEngine:
             with torch.cuda.graph(g):
                 self._body(p)
             p.graph = g
+            p.desc = self._make_desc(p)
             p.n_launch = ops.LAUNCHES - before  # kernels replayed by every graph launch
             ops.LAUNCHES = before
             self._state_restore(snap)  # capture does not execute, but keep the invariant explicit
             torch.cuda.synchronize(self.dev)
         self._plans[(rows_pad, slot)] = p
         return p
+
+    def _make_desc(self, p: _FramePlan):
+        """Pre-filled moyolo_frame_submit_t of a plan: only the per-frame fields change at submit time."""
+        d = _lib.FrameSubmit()
+        d.copy_stream, d.main_stream, d.main_stream_valid = self._copy.cuda_stream, self._main.cuda_stream, 1
+        d.ev_scratch = self._ev_scratch.cuda_event
+        d.ev_copy = self._ev_copy[p.slot].cuda_event
+        d.graph_exec = p.graph.raw_cuda_graph_exec()
+        d.n_inputs = 3
+        for i, t in enumerate((self.feats_in[p.slot], self.det_embed_in[p.slot], self.det_refer_in[p.slot])):
+            d.in_dst[i] = t.data_ptr()
+            d.in_bytes[i] = t.numel() * t.element_size()
+        d.out_src[0], d.out_bytes[0] = p.ws.info.data_ptr(), p.ws.info.numel() * 4
+        d.out_src[1], d.out_bytes[1] = p.ws.frame_rows.data_ptr(), p.rows_pad * 8 * 4
+        return d
+
+    def _submit_native(self, t: int, rows_pad: int, feats, det_embed, det_refer, want_rows: bool,
+                       sync_inputs: bool) -> dict:
+        """Input copies, graph launch, result copies and event hand-offs of one frame as ONE C call."""
+        slot, h = t % 2, t % self.DEPTH
+        p = self._plan(rows_pad, slot)
+        d = p.desc
+        d.ev_slot_free = self._ev_done[(t - 2) % self.DEPTH].cuda_event if t >= 2 else None
+        d.sync_inputs = 1 if sync_inputs else 0
+        d.ev_done = self._ev_done[h].cuda_event
+        d.in_src[0], d.in_src[1], d.in_src[2] = feats.data_ptr(), det_embed.data_ptr(), det_refer.data_ptr()
+        d.out_dst[0] = self._h_info[h].data_ptr()
+        d.out_dst[1] = self._h_rows[h].data_ptr()
+        d.n_outputs = 2 if want_rows else 1
+        self._keep[slot] = (feats, det_embed, det_refer)
+        _lib.check(_lib.lib().moyolo_frame_submit(ctypes.byref(d)))
+        ops.LAUNCHES += p.n_launch
+        self._last_plan = p
+        return {"frame": t, "plan": p, "rows_pad": rows_pad, "want_rows": want_rows}
+
+    def _native_ok(self, feats, det_embed, det_refer) -> bool:
+        f = self.feats_in[0]
+        return (self._native and feats.dtype == f.dtype and feats.is_contiguous() and det_embed.is_contiguous() and
+                det_refer.is_contiguous() and det_embed.dtype == torch.float32 and det_refer.dtype == torch.float32 and
+                feats.numel() == f.numel() and det_embed.numel() == self.det_embed_in[0].numel() and
+                det_refer.numel() == self.det_refer_in[0].numel() and
+                all(x.is_cuda or x.is_pinned() for x in (feats, det_embed, det_refer)))
 
     def prepare(self, max_tracks_per_seq: int) -> int:
         """Pre-capture the frame graphs for every padded size up to `max_tracks_per_seq` tracks per
@@ -460,12 +519,12 @@ class TrackEngine:
             if not block and not ev.query():
                 return
             ev.synchronize()
-            info = self._h_info[rec["frame"] % self.DEPTH]
+            info = self._h_info_np[rec["frame"] % self.DEPTH]
             if int(info[self.n_seq + CTRL_ABORT]) != 0:
                 self._recover()
                 continue
             self._inflight.pop(0)
-            self._T = [int(v) for v in info[:self.n_seq].tolist()]
+            self._T = info[:self.n_seq].tolist()
             self._known = rec["frame"]
             self._T_before[rec["frame"] + 1] = list(self._T)
             self._T_before.pop(rec["frame"] - self.DEPTH, None)
@@ -495,12 +554,15 @@ class TrackEngine:
         t = self._next
         self._harvest(t - 2, block=True)    # at most two frames in flight
         self._harvest(t - 1, block=False)   # use the newest counts if they are already here
-        self._load_inputs(t % 2, feats, det_embed, det_refer, t, sync_inputs)
         rows = sum(self._T) + self.n_seq * self.n_detect
         exact = self._known == t - 1
         rows_pad = self._round(rows if exact else rows + self.margin)
         rows_pad = min(rows_pad, self._max_rows)
-        self._inflight.append(self._launch(t, rows_pad, want_rows))
+        if self._native_ok(feats, det_embed, det_refer):
+            self._inflight.append(self._submit_native(t, rows_pad, feats, det_embed, det_refer, want_rows, sync_inputs))
+        else:
+            self._load_inputs(t % 2, feats, det_embed, det_refer, t, sync_inputs)
+            self._inflight.append(self._launch(t, rows_pad, want_rows))
         self._next = t + 1
         self.frame_idx = self._next
         return t
