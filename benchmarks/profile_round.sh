@@ -1,6 +1,6 @@
 #!/bin/bash
 # Profiling pass run under gpurun (one GPU). Outputs land in gpurun_out/; summaries are copied to profiles/ by hand.
-#   $1 = tag (e.g. r01c)   $2.. = extra bench.py flags
+#   $1 = tag (e.g. r01e)   $2.. = extra bench.py flags
 TAG=${1:-r01}
 shift
 mkdir -p gpurun_out
@@ -8,8 +8,8 @@ BENCH="python bench.py --steps 12 --warmup 3 --no-cpu-baseline --max-tracks 32 -
 # (1) launch list of the timed `value` leg only (graph kernel nodes are profiled individually; cold-cache, serialised)
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_launches_bench.log 2>&1
-# (2) full capture of the dominant kernels (3 launches each, from the middle of the timed leg)
-for K in msda_gather self_attention gemm_tcgen05 add_layernorm; do
-  ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:${K} -s 30 -c 3 -f \
+# (2) full capture of the dominant kernels (a few launches each, from the middle of the timed leg)
+for K in msda_gather self_attention gemm_stream gemm_tcgen05; do
+  ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:${K} -s 8 -c 4 -f \
       -o gpurun_out/${TAG}_${K} $BENCH > gpurun_out/${TAG}_${K}.log 2>&1
 done

@@ -20,6 +20,8 @@
 //
 // The value tensor is read channel-last ([B, Lv, heads, head_dim], arbitrary position stride), i.e.
 // straight out of the value_proj GEMM — no NCHW transposes, no [B*H, Dh, Q, L*P] temporaries.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -107,78 +109,161 @@ __device__ __forceinline__ void fused_location(const MsdaParams& p, int64_t row,
   }
 }
 
+// acc[0..7] += w * (8 bf16 channels of v): four packed fp32x2 FMAs (sm_100 FFMA2; bit-identical to eight
+// scalar round-to-nearest FMAs).
+__device__ __forceinline__ void fma_bf16x8(float (&a)[8], const uint4& v, float w) {
+  const float2 w2 = make_float2(w, w);
+  float2 t;
+  t = __ffma2_rn(w2, bf16x2_to_float2(v.x), make_float2(a[0], a[1])); a[0] = t.x; a[1] = t.y;
+  t = __ffma2_rn(w2, bf16x2_to_float2(v.y), make_float2(a[2], a[3])); a[2] = t.x; a[3] = t.y;
+  t = __ffma2_rn(w2, bf16x2_to_float2(v.z), make_float2(a[4], a[5])); a[4] = t.x; a[5] = t.y;
+  t = __ffma2_rn(w2, bf16x2_to_float2(v.w), make_float2(a[6], a[7])); a[6] = t.x; a[7] = t.y;
+}
+__device__ __forceinline__ void fma_f32x4(float (&a)[4], const uint4& v, float w) {
+  const float2 w2 = make_float2(w, w);
+  float2 t;
+  t = __ffma2_rn(w2, make_float2(__uint_as_float(v.x), __uint_as_float(v.y)), make_float2(a[0], a[1])); a[0] = t.x; a[1] = t.y;
+  t = __ffma2_rn(w2, make_float2(__uint_as_float(v.z), __uint_as_float(v.w)), make_float2(a[2], a[3])); a[2] = t.x; a[3] = t.y;
+}
+
+// 128-bit read-only load that is skipped (result = zeros) when `valid` is false, WITHOUT a branch:
+// grid_sample's zero padding for corners outside the map (the address is then never dereferenced).
+__device__ __forceinline__ uint4 ldg128_if(const void* ptr, bool valid) {
+  uint4 v;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b32 %0, 0;\n\t"
+      "mov.b32 %1, 0;\n\t"
+      "mov.b32 %2, 0;\n\t"
+      "mov.b32 %3, 0;\n\t"
+      "@p ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];\n\t"
+      "}"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(ptr), "r"(static_cast<int>(valid)));
+  return v;
+}
+
 // U = corner rounds kept in flight per loop trip (all of them when 4*L*P == U*32/G).
-template <typename VT, int DH, bool FUSED, int U>
+// NH / NP / NL: n_heads / n_points / n_levels as compile-time constants (0 = read from the parameters):
+// the index arithmetic of the hot configurations then has no integer or float division and each lane
+// handles exactly ceil(L*P/32) sampling points. All element offsets are 32-bit
+// (the host falls back to the generic kernel when a tensor has >= 2^31 elements).
+template <typename VT, int DH, bool FUSED, int U, int NH, int NP, int NL>
 __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaParams p) {
-  pdl_trigger();
-  pdl_wait();
   constexpr int G = DH * static_cast<int>(sizeof(VT)) / 16;  // lanes per value row
   constexpr int CH = 16 / static_cast<int>(sizeof(VT));      // channels per lane
   constexpr int NSG = 32 / G;                                // sub-groups per warp
   static_assert(G >= 4 && G <= 16 && CH >= NSG, "head row must be 64..256 bytes");
+  pdl_trigger();
 
   extern __shared__ __align__(16) int smem_i[];
-  const int LP = p.lv.n * p.n_points;
+  constexpr int kPts = NL ? (NL * NP + 31) / 32 : kMaxPointsPerLane;  // sampling points per lane
+  const int n_heads = NH ? NH : p.n_heads;
+  const int n_points = NP ? NP : p.n_points;
+  const int LP = (NL ? NL : p.lv.n) * n_points;
   const int NU = LP * 4;
   const int NUp = (NU + NSG * U - 1) / (NSG * U) * (NSG * U);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t item = static_cast<int64_t>(blockIdx.x) * kGatherWarps + warp;
-  if (item >= p.rows * p.n_heads) return;  // warp-uniform
-  const int64_t row = item / p.n_heads;
-  const int head = static_cast<int>(item % p.n_heads);
+  const int item = static_cast<int>(blockIdx.x) * kGatherWarps + warp;
+  const int n_rows = static_cast<int>(p.rows);
+  if (item >= n_rows * n_heads) return;  // warp-uniform
+  const int row = item / n_heads;
+  const int head = item - row * n_heads;
 
-  int* s_pos = smem_i + warp * NUp * 2;
-  float* s_w = reinterpret_cast<float*>(s_pos + NUp);
+  int* s_off = smem_i + warp * NUp * 2;                   // element offset of the corner row | -1
+  float* s_w = reinterpret_cast<float*>(s_off + NUp);     // bilinear x attention weight
+  const int ps = static_cast<int>(p.value_pos_stride);
+  pdl_wait();
 
   // ---------------- phase 1: lane `l` owns sampling points l and l + 32 ----------------
-  float aw[kMaxPointsPerLane];
+  // Every global operand of the phase (logit, offset pair, reference box | location, weight) is
+  // requested up front so the softmax shuffles overlap ONE memory round trip instead of following it.
+  float aw[kPts], lx[kPts], ly[kPts];
   if (FUSED) {
-    float lg[kMaxPointsPerLane];
+    float lg[kPts];
+    float2 off[kPts];
+    float rx[kPts], ry[kPts], rw[kPts], rh[kPts];
+    const float* lrow = p.logits + static_cast<int64_t>(row) * p.logits_row_stride + head * LP;
+    const float2* orow = reinterpret_cast<const float2*>(p.offsets + static_cast<int64_t>(row) * p.offsets_row_stride) +
+                         head * LP;
+    const float* rrow = p.refer + static_cast<int64_t>(row) * (p.ref_levels * p.ref_dim);
+#pragma unroll
+    for (int i = 0; i < kPts; ++i) {
+      const int pt = lane + i * 32;
+      const bool ok = pt < LP;
+      const int level = ok ? pt / n_points : 0;
+      lg[i] = ok ? __ldg(lrow + pt) : -INFINITY;
+      off[i] = ok ? __ldg(orow + pt) : make_float2(0.0f, 0.0f);
+      const float* r = rrow + (p.ref_levels == 1 ? 0 : level) * p.ref_dim;
+      if (p.ref_dim == 4) {
+        const float4 r4 = __ldg(reinterpret_cast<const float4*>(r));  // 16-byte aligned: checked by the host
+        rx[i] = r4.x; ry[i] = r4.y; rw[i] = r4.z; rh[i] = r4.w;
+      } else {
+        const float2 r2 = __ldg(reinterpret_cast<const float2*>(r));
+        rx[i] = r2.x; ry[i] = r2.y; rw[i] = rh[i] = 0.0f;
+      }
+    }
     float m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < kMaxPointsPerLane; ++i) {
-      const int pt = lane + i * 32;
-      lg[i] = pt < LP ? __ldg(p.logits + row * p.logits_row_stride + head * LP + pt) : -INFINITY;
-      m = fmaxf(m, lg[i]);
-    }
+    for (int i = 0; i < kPts; ++i) m = fmaxf(m, lg[i]);
     m = warp_max(m);
     if (p.softmax_mode == MOYOLO_SOFTMAX_PLUS1) m = 0.0f;  // exp(x)/(1+sum exp(x)), no shift
-    float s = 0.0f;
+    float sum = 0.0f;
 #pragma unroll
-    for (int i = 0; i < kMaxPointsPerLane; ++i) {
+    for (int i = 0; i < kPts; ++i) {
       const int pt = lane + i * 32;
       aw[i] = pt < LP ? expf(lg[i] - m) : 0.0f;
-      s += aw[i];
+      sum += aw[i];
     }
-    s = warp_sum(s);
-    if (p.softmax_mode == MOYOLO_SOFTMAX_PLUS1) s += 1.0f;
-    const float inv = 1.0f / s;
+    sum = warp_sum(sum);
+    if (p.softmax_mode == MOYOLO_SOFTMAX_PLUS1) sum += 1.0f;
+    const float inv = 1.0f / sum;
+    const float fnp = static_cast<float>(n_points);
 #pragma unroll
-    for (int i = 0; i < kMaxPointsPerLane; ++i) aw[i] *= inv;
+    for (int i = 0; i < kPts; ++i) {
+      aw[i] *= inv;
+      const int pt = lane + i * 32;
+      const int level = pt < LP ? pt / n_points : 0;
+      // sampling location (transformer.py:276-282)
+      if (p.ref_dim == 4) {
+        lx[i] = rx[i] + off[i].x / fnp * rw[i] * 0.5f;
+        ly[i] = ry[i] + off[i].y / fnp * rh[i] * 0.5f;
+      } else {
+        lx[i] = rx[i] + off[i].x / static_cast<float>(p.lv.w[level]);
+        ly[i] = ry[i] + off[i].y / static_cast<float>(p.lv.h[level]);
+      }
+    }
+  } else {
+    const int64_t ibase = static_cast<int64_t>(item) * LP;
+#pragma unroll
+    for (int i = 0; i < kPts; ++i) {
+      const int pt = lane + i * 32;
+      if (pt < LP) {
+        const float2 l2 = __ldg(reinterpret_cast<const float2*>(p.loc) + ibase + pt);
+        lx[i] = l2.x;
+        ly[i] = l2.y;
+        aw[i] = __ldg(static_cast<const float*>(p.weights) + ibase + pt);
+      } else {
+        lx[i] = ly[i] = aw[i] = 0.0f;
+      }
+    }
   }
 #pragma unroll
-  for (int i = 0; i < kMaxPointsPerLane; ++i) {
+  for (int i = 0; i < kPts; ++i) {
     const int pt = lane + i * 32;
     if (pt < LP) {
-      const int level = pt / p.n_points;
-      float lx, ly, a;
-      if (FUSED) {
-        fused_location(p, row, head, pt, level, &lx, &ly);
-        a = aw[i];
-      } else {
-        const int64_t idx = (row * p.n_heads + head) * LP + pt;
-        const float2 l2 = __ldg(reinterpret_cast<const float2*>(p.loc) + idx);
-        lx = l2.x;
-        ly = l2.y;
-        a = __ldg(static_cast<const float*>(p.weights) + idx);
-      }
-      const Corners c = make_corners(lx, ly, p.lv.h[level], p.lv.w[level], p.lv.start[level], a);
-      *reinterpret_cast<int4*>(s_pos + pt * 4) = make_int4(c.pos[0], c.pos[1], c.pos[2], c.pos[3]);
+      const int level = pt / n_points;
+      const Corners c = make_corners(lx[i], ly[i], p.lv.h[level], p.lv.w[level], p.lv.start[level], aw[i]);
+      *reinterpret_cast<int4*>(s_off + pt * 4) =
+          make_int4(c.pos[0] < 0 ? -1 : c.pos[0] * ps, c.pos[1] < 0 ? -1 : c.pos[1] * ps,
+                    c.pos[2] < 0 ? -1 : c.pos[2] * ps, c.pos[3] < 0 ? -1 : c.pos[3] * ps);
       *reinterpret_cast<float4*>(s_w + pt * 4) = make_float4(c.w[0], c.w[1], c.w[2], c.w[3]);
     }
   }
-  for (int u = NU + lane; u < NUp; u += 32) { s_pos[u] = -1; s_w[u] = 0.0f; }
+  for (int u = NU + lane; u < NUp; u += 32) { s_off[u] = -1; s_w[u] = 0.0f; }
   __syncwarp();
 
   // ---------------- phase 2: gather, sub-group sg takes corners sg, sg + NSG, ... ----------------
@@ -187,39 +272,23 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaP
   for (int k = 0; k < CH; ++k) acc[k] = 0.0f;
 
   const int sg = lane / G, sub = lane % G;
-  const int b = batch_of_row(row, p.row_offsets, p.batch, p.rows_per_batch);
+  const int b = p.batch == 1 ? 0 : batch_of_row(row, p.row_offsets, p.batch, p.rows_per_batch);
   const VT* base = static_cast<const VT*>(p.value) + static_cast<int64_t>(b) * p.value_batch_stride +
                    head * DH + sub * CH;
-  const int64_t ps = p.value_pos_stride;
 
   for (int u0 = sg; u0 < NUp; u0 += NSG * U) {
     uint4 v[U];
     float w[U];
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-      const int pos = s_pos[u0 + i * NSG];
+      const int eo = s_off[u0 + i * NSG];
       w[i] = s_w[u0 + i * NSG];
-      v[i] = (pos >= 0) ? ldg128(base + pos * ps) : make_uint4(0u, 0u, 0u, 0u);
+      v[i] = ldg128_if(base + eo, eo >= 0);
     }
 #pragma unroll
     for (int i = 0; i < U; ++i) {
-      if constexpr (sizeof(VT) == 2) {
-        const float2 a0 = bf16x2_to_float2(v[i].x), a1 = bf16x2_to_float2(v[i].y);
-        const float2 a2 = bf16x2_to_float2(v[i].z), a3 = bf16x2_to_float2(v[i].w);
-        acc[0] = fmaf(w[i], a0.x, acc[0]);
-        acc[1] = fmaf(w[i], a0.y, acc[1]);
-        acc[2] = fmaf(w[i], a1.x, acc[2]);
-        acc[3] = fmaf(w[i], a1.y, acc[3]);
-        acc[4] = fmaf(w[i], a2.x, acc[4]);
-        acc[5] = fmaf(w[i], a2.y, acc[5]);
-        acc[6] = fmaf(w[i], a3.x, acc[6]);
-        acc[7] = fmaf(w[i], a3.y, acc[7]);
-      } else {
-        acc[0] = fmaf(w[i], __uint_as_float(v[i].x), acc[0]);
-        acc[1] = fmaf(w[i], __uint_as_float(v[i].y), acc[1]);
-        acc[2] = fmaf(w[i], __uint_as_float(v[i].z), acc[2]);
-        acc[3] = fmaf(w[i], __uint_as_float(v[i].w), acc[3]);
-      }
+      if constexpr (sizeof(VT) == 2) fma_bf16x8(acc, v[i], w[i]);
+      else fma_f32x4(acc, v[i], w[i]);
     }
   }
 
@@ -245,7 +314,7 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaP
     }
   }
   constexpr int NF = CH / NSG;  // finished channels per lane: 1 or 2
-  VT* o = static_cast<VT*>(p.out) + row * p.out_row_stride + head * DH + sub * CH + ch;
+  VT* o = static_cast<VT*>(p.out) + static_cast<int64_t>(row) * p.out_row_stride + head * DH + sub * CH + ch;
   if constexpr (sizeof(VT) == 2) {
     if constexpr (NF == 1) {
       const float hi = __shfl_xor_sync(0xffffffffu, acc[0], G);  // odd-channel partner (last round's bit)
@@ -258,6 +327,165 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaP
       *o = acc[0];
     } else {
       *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Two work items per warp for L*P <= 16 (the decoder's 3 levels x 4 points): heads 2k and 2k+1 of one
+// query row. Phase 1 then runs ONCE for both items with lanes 0..15 / 16..31 owning the points of the
+// two heads (segmented 16-lane softmax), which removes ~40 % of the per-item instructions of the
+// one-item kernel above (where only 12 of 32 lanes had a point) — the kernel is issue-bound at large
+// batch — and keeps 12 corner rows per lane in flight. FUSED mode, 8 heads, head_dim 32.
+// ------------------------------------------------------------------------------------------------
+template <typename VT, int NP, int NL>
+__global__ void __launch_bounds__(kGatherThreads) msda_gather_pair_kernel(const MsdaParams p) {
+  constexpr int DH = 32, NH = 8;
+  constexpr int G = DH * static_cast<int>(sizeof(VT)) / 16;
+  constexpr int CH = 16 / static_cast<int>(sizeof(VT));
+  constexpr int NSG = 32 / G;
+  constexpr int LP = NP * NL;
+  static_assert(LP <= 16, "one point per lane of a 16-lane half");
+  constexpr int NU = LP * 4;
+  constexpr int R = (NU + NSG - 1) / NSG;  // corner rounds per sub-group and item
+  constexpr int NUp = R * NSG;
+  pdl_trigger();
+
+  extern __shared__ __align__(16) int smem_i[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pairi = static_cast<int>(blockIdx.x) * kGatherWarps + warp;
+  if (pairi >= static_cast<int>(p.rows) * (NH / 2)) return;  // warp-uniform
+  const int row = pairi / (NH / 2);
+  const int hp = pairi % (NH / 2);
+  int* s_off = smem_i + warp * (4 * NUp);                    // [2][NUp] element offsets | -1
+  float* s_w = reinterpret_cast<float*>(s_off + 2 * NUp);    // [2][NUp] bilinear x attention weights
+  const int ps = static_cast<int>(p.value_pos_stride);
+  pdl_wait();
+
+  // ---------------- phase 1: lane (half, pl) owns point pl of head 2*hp + half ----------------
+  {
+    const int half = lane >> 4, pl = lane & 15;
+    const int head = hp * 2 + half;
+    const bool ok = pl < LP;
+    const int level = ok ? pl / NP : 0;
+    const float* lrow = p.logits + static_cast<int64_t>(row) * p.logits_row_stride + head * LP;
+    const float2* orow = reinterpret_cast<const float2*>(p.offsets + static_cast<int64_t>(row) * p.offsets_row_stride) +
+                         head * LP;
+    const float* r = p.refer + static_cast<int64_t>(row) * (p.ref_levels * p.ref_dim) +
+                     (p.ref_levels == 1 ? 0 : level) * p.ref_dim;
+    const float lg = ok ? __ldg(lrow + pl) : -INFINITY;
+    const float2 off = ok ? __ldg(orow + pl) : make_float2(0.0f, 0.0f);
+    float rx, ry, rw = 0.0f, rh = 0.0f;
+    if (p.ref_dim == 4) {
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(r));
+      rx = r4.x; ry = r4.y; rw = r4.z; rh = r4.w;
+    } else {
+      const float2 r2 = __ldg(reinterpret_cast<const float2*>(r));
+      rx = r2.x; ry = r2.y;
+    }
+    float m = lg;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (p.softmax_mode == MOYOLO_SOFTMAX_PLUS1) m = 0.0f;
+    float aw = ok ? expf(lg - m) : 0.0f;
+    float sum = aw;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (p.softmax_mode == MOYOLO_SOFTMAX_PLUS1) sum += 1.0f;
+    aw *= 1.0f / sum;
+    float lx, ly;
+    if (p.ref_dim == 4) {
+      lx = rx + off.x / static_cast<float>(NP) * rw * 0.5f;
+      ly = ry + off.y / static_cast<float>(NP) * rh * 0.5f;
+    } else {
+      lx = rx + off.x / static_cast<float>(p.lv.w[level]);
+      ly = ry + off.y / static_cast<float>(p.lv.h[level]);
+    }
+    if (ok) {
+      const Corners c = make_corners(lx, ly, p.lv.h[level], p.lv.w[level], p.lv.start[level], aw);
+      *reinterpret_cast<int4*>(s_off + half * NUp + pl * 4) =
+          make_int4(c.pos[0] < 0 ? -1 : c.pos[0] * ps, c.pos[1] < 0 ? -1 : c.pos[1] * ps,
+                    c.pos[2] < 0 ? -1 : c.pos[2] * ps, c.pos[3] < 0 ? -1 : c.pos[3] * ps);
+      *reinterpret_cast<float4*>(s_w + half * NUp + pl * 4) = make_float4(c.w[0], c.w[1], c.w[2], c.w[3]);
+    }
+    if constexpr (NUp > NU) {
+      for (int u = NU + pl; u < NUp; u += 16) { s_off[half * NUp + u] = -1; s_w[half * NUp + u] = 0.0f; }
+    }
+  }
+  __syncwarp();
+
+  // ---------------- phase 2: both items' corner rows in flight, then the FMAs ----------------
+  const int sg = lane / G, sub = lane % G;
+  const int b = p.batch == 1 ? 0 : batch_of_row(row, p.row_offsets, p.batch, p.rows_per_batch);
+  const VT* base = static_cast<const VT*>(p.value) + static_cast<int64_t>(b) * p.value_batch_stride +
+                   hp * 2 * DH + sub * CH;
+  float acc[2][CH];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < CH; ++k) acc[h][k] = 0.0f;
+
+  auto accumulate = [&](float (&a)[CH], const uint4& v, float w) {
+    if constexpr (sizeof(VT) == 2) fma_bf16x8(a, v, w);
+    else fma_f32x4(a, v, w);
+  };
+  if constexpr (R <= 6) {
+    uint4 v[2][R];
+    float w[2][R];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int eo = s_off[h * NUp + sg + i * NSG];
+        w[h][i] = s_w[h * NUp + sg + i * NSG];
+        v[h][i] = ldg128_if(base + h * DH + eo, eo >= 0);
+      }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int i = 0; i < R; ++i) accumulate(acc[h], v[h][i], w[h][i]);
+  } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 v[R];
+      float w[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int eo = s_off[h * NUp + sg + i * NSG];
+        w[i] = s_w[h * NUp + sg + i * NSG];
+        v[i] = ldg128_if(base + h * DH + eo, eo >= 0);
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i) accumulate(acc[h], v[i], w[i]);
+    }
+  }
+
+  // ---------------- phase 3: recursive-halving reduction per item, coalesced stores ----------------
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    int ch = 0, n = CH;
+#pragma unroll
+    for (int off = 16; off >= G; off >>= 1) {
+      n >>= 1;
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < CH / 2; ++i) {
+        if (i < n) {
+          const float send = up ? acc[h][i] : acc[h][i + n];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+          acc[h][i] = (up ? acc[h][i + n] : acc[h][i]) + recv;
+        }
+      }
+      ch += up ? n : 0;
+    }
+    constexpr int NF = CH / NSG;  // finished channels per lane: 1
+    static_assert(NF == 1, "head_dim 32: one finished channel per lane");
+    VT* o = static_cast<VT*>(p.out) + static_cast<int64_t>(row) * p.out_row_stride + (hp * 2 + h) * DH + sub * CH + ch;
+    if constexpr (sizeof(VT) == 2) {
+      const float hi = __shfl_xor_sync(0xffffffffu, acc[h][0], G);
+      if ((lane & G) == 0) *reinterpret_cast<uint32_t*>(o) = float2_to_bf16x2(acc[h][0], hi);
+    } else {
+      *o = acc[h][0];
     }
   }
 }
@@ -333,7 +561,7 @@ __global__ void msda_generic_kernel(const MsdaParams p, int head_dim) {
 }
 
 
-template <typename VT, int DH, bool FUSED, int U>
+template <typename VT, int DH, bool FUSED, int U, int NH, int NP, int NL>
 static int launch_fast_u(const MsdaParams& p, cudaStream_t st) {
   constexpr int G = DH * static_cast<int>(sizeof(VT)) / 16;
   constexpr int NSG = 32 / G;
@@ -343,17 +571,50 @@ static int launch_fast_u(const MsdaParams& p, cudaStream_t st) {
   const int64_t items = p.rows * p.n_heads;
   const int64_t blocks = (items + kGatherWarps - 1) / kGatherWarps;
   if (blocks == 0) return MOYOLO_OK;
-  launch_k(msda_gather_kernel<VT, DH, FUSED, U>, dim3(static_cast<unsigned>(blocks)), dim3(kGatherThreads), smem, st, p);
+  launch_k(msda_gather_kernel<VT, DH, FUSED, U, NH, NP, NL>, dim3(static_cast<unsigned>(blocks)), dim3(kGatherThreads), smem,
+           st, p);
   return check_launch("msda_gather_kernel");
+}
+
+template <typename VT, int DH, bool FUSED, int U>
+static int launch_fast_hp(const MsdaParams& p, cudaStream_t st) {
+  // compile-time n_heads / n_points / n_levels for the decoder's configurations:
+  // yolo_track.yaml (8 heads, 3 levels x 4 points) and the L=4, P=8 point of the C5 sweep
+  if (p.n_heads == 8 && p.n_points == 4 && p.lv.n == 3) return launch_fast_u<VT, DH, FUSED, U, 8, 4, 3>(p, st);
+  if (p.n_heads == 8 && p.n_points == 8 && p.lv.n == 4) return launch_fast_u<VT, DH, FUSED, U, 8, 8, 4>(p, st);
+  return launch_fast_u<VT, DH, FUSED, U, 0, 0, 0>(p, st);
+}
+
+template <typename VT, int NP, int NL>
+static int launch_pair(const MsdaParams& p, cudaStream_t st) {
+  constexpr int NSG = 32 / (32 * static_cast<int>(sizeof(VT)) / 16);
+  constexpr int NUp = (NP * NL * 4 + NSG - 1) / NSG * NSG;
+  const size_t smem = static_cast<size_t>(kGatherWarps) * 4 * NUp * 4;
+  const int64_t pairs = p.rows * 4;
+  const int64_t blocks = (pairs + kGatherWarps - 1) / kGatherWarps;
+  if (blocks == 0) return MOYOLO_OK;
+  launch_k(msda_gather_pair_kernel<VT, NP, NL>, dim3(static_cast<unsigned>(blocks)), dim3(kGatherThreads), smem, st, p);
+  return check_launch("msda_gather_pair_kernel");
+}
+
+static bool pair_enabled() {
+  static const bool on = [] { const char* e = getenv("MOYOLO_GATHER_PAIR"); return !(e && e[0] == '0'); }();
+  return on;
 }
 
 template <typename VT, int DH, bool FUSED>
 static int launch_fast(const MsdaParams& p, cudaStream_t st) {
+  if constexpr (FUSED && DH == 32) {
+    // two items per warp pay off once the launch is throughput- rather than latency-bound
+    // (measured cross-over between 382 and 3056 rows on B200; see profiles/)
+    if (pair_enabled() && p.rows >= 1024 && p.n_heads == 8 && p.n_points == 4 && p.lv.n == 3)
+      return launch_pair<VT, 4, 3>(p, st);
+  }
   constexpr int NSG = 32 / (DH * static_cast<int>(sizeof(VT)) / 16);
   const int rounds = (p.lv.n * p.n_points * 4 + NSG - 1) / NSG;  // corner rounds per sub-group
   // keep every round in flight when there are few (6 at L=3,P=4 bf16); otherwise trips of 8
-  if (rounds % 6 == 0 && rounds <= 12) return launch_fast_u<VT, DH, FUSED, 6>(p, st);
-  return launch_fast_u<VT, DH, FUSED, 8>(p, st);
+  if (rounds % 6 == 0 && rounds <= 12) return launch_fast_hp<VT, DH, FUSED, 6>(p, st);
+  return launch_fast_hp<VT, DH, FUSED, 8>(p, st);
 }
 
 template <bool FUSED>
@@ -364,7 +625,13 @@ static int dispatch(const MsdaParams& p, int value_dtype, int aux_dtype, int hea
                        (head_dim == 32 || head_dim == 64) && aligned16(p.value) && aligned16(p.out) &&
                        (p.value_pos_stride * esz) % 16 == 0 && (p.value_batch_stride * esz) % 16 == 0 &&
                        (p.out_row_stride * esz) % 16 == 0 && LP <= 32 * kMaxPointsPerLane &&
-                       (FUSED || (reinterpret_cast<uintptr_t>(p.loc) & 7u) == 0);
+                       (FUSED ? ((reinterpret_cast<uintptr_t>(p.offsets) & 7u) == 0 && p.offsets_row_stride % 2 == 0 &&
+                                 (reinterpret_cast<uintptr_t>(p.refer) & (p.ref_dim == 4 ? 15u : 7u)) == 0)
+                              : (reinterpret_cast<uintptr_t>(p.loc) & 7u) == 0) &&
+                       // 32-bit element offsets inside one batch slice and 32-bit item indices
+                       p.lv.start[p.lv.n - 1] + static_cast<int64_t>(p.lv.h[p.lv.n - 1]) * p.lv.w[p.lv.n - 1] <=
+                           (INT32_MAX - 4096) / (p.value_pos_stride > 0 ? p.value_pos_stride : 1) &&
+                       p.rows * p.n_heads * LP < INT32_MAX;
   if (fast_ok) {
     if (value_dtype == MOYOLO_BF16) {
       return head_dim == 32 ? launch_fast<__nv_bfloat16, 32, FUSED>(p, st)

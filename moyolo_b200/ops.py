@@ -42,6 +42,9 @@ def _stream() -> int:
 LAUNCHES = 0
 # optional (pre, post) callables invoked around every deformable-gather launch (bench.py roofline leg)
 GATHER_HOOK = None
+# the roofline leg repeats each (idempotent) gather launch this many times between one event pair so the
+# event-node overhead (~5 us per pair inside a graph) is amortised; 1 everywhere else
+GATHER_REPEAT = 1
 
 
 def _count(n: int = 1) -> None:
@@ -112,11 +115,12 @@ def msda_fused(value: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch
     hook = GATHER_HOOK
     if hook is not None:
         hook[0](B, Lv, Cc, R, n_heads, L, n_points, value.element_size())
-    _lib.check(_lib.lib().moyolo_msda_fused_forward(
-        value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, n_heads, Dh, n_points,
-        offsets.data_ptr(), offsets.stride(0), logits.data_ptr(), logits.stride(0), refer.data_ptr(),
-        refer.shape[1], refer.shape[2], softmax_mode, R, _ptr(row_offsets), out.data_ptr(), out.stride(0),
-        _stream()))
+    for _ in range(GATHER_REPEAT if hook is not None else 1):
+        _lib.check(_lib.lib().moyolo_msda_fused_forward(
+            value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, n_heads, Dh, n_points,
+            offsets.data_ptr(), offsets.stride(0), logits.data_ptr(), logits.stride(0), refer.data_ptr(),
+            refer.shape[1], refer.shape[2], softmax_mode, R, _ptr(row_offsets), out.data_ptr(), out.stride(0),
+            _stream()))
     if hook is not None:
         hook[1]()
     return out
