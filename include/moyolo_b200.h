@@ -177,10 +177,11 @@ int moyolo_box_refine(const void* h, int64_t ldh, int h_dtype, const float* w3, 
                       const float* ref, float* new_ref, int64_t rows, int K, moyolo_stream_t stream);
 
 /* logits[R,nc] = x[R,K] . w[nc,K]^T + b; scores[R] = max_c sigmoid(logits) (head.py:310),
- * labels[R] = argmax_c logits (first maximum, torch.max semantics). scores/labels may be NULL. */
+ * labels[R] = argmax_c logits (first maximum, torch.max semantics), max_logit[R] = max_c logits
+ * (the top-k key of head.py:1048). logits/scores/labels/max_logit may be NULL. */
 int moyolo_score_head(const void* x, int64_t ldx, int x_dtype, const float* w, const float* b,
                       float* logits, float* scores, int32_t* labels, int64_t rows, int K, int nc,
-                      moyolo_stream_t stream);
+                      float* max_logit, moyolo_stream_t stream);
 
 /* refer_sig[R,4] = sigmoid(refer_logit[R,4]) (transformer.py:690) */
 int moyolo_sigmoid(const float* x, float* y, int64_t n, moyolo_stream_t stream);
@@ -280,6 +281,40 @@ int moyolo_frame_emit(int n_seq, int64_t rows_pad, const int32_t* row_offsets, c
                       const float* boxes, const float* scores, const int32_t* labels, const int32_t* n_active,
                       const int32_t* active_index, const int32_t* seq_ids, float* frame_rows, float* table,
                       int64_t table_cap, int32_t* ctrl, moyolo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Encoder-side query selection of MYDecoder (ultralytics/nn/modules/head.py:993-1113), SURVEY.md 8(f1).
+ *
+ * moyolo_enc_output_scores: f = LayerNorm((zero_in_rows[r] ? 0 : x[r]) . w^T + bias) * gamma + beta (head.py:1039,
+ *   `enc_output` on valid_mask * feats), logits = f . score_w^T + score_b (:1041), max_logit = max_c logits (:1048).
+ *   x [M,256] bf16 (row stride ldx), w [256,256] bf16; out_f32 [M,256] fp32, out_lp [M,256] bf16, logits [M,nc],
+ *   max_logit [M] (any output may be NULL); nc <= 8. One tcgen05 kernel, 128 rows per CTA.
+ * moyolo_topk: per row of scores [batch, n] (row stride given) the indices of the k largest values, ordered as
+ *   torch.topk(sorted=True): descending value, equal values by ascending index. k <= 1024.
+ * moyolo_select_gather: embed[b,j] = features[b, idx[b,j]] (fp32 [batch,k,C] and, if embed_lp != NULL, the same as
+ *   `lp_dtype`), enc_scores[b,j] = logits[b, idx[b,j]] (head.py:1092, 1104). features [batch, len_v, C] fp32.
+ * moyolo_anchor_box: refer[r] = h[r] . w3^T + b3 + anchor(idx[r]) (head.py:1044, 1053): h = the two hidden layers of
+ *   enc_bbox_head on the selected rows, anchors per head.py:993-1010 (cell centres, wh = grid_size * 2^level, logit
+ *   space, +inf where a coordinate leaves (eps, 1-eps); the reference divides (x, y) by (H, W) -- reproduced).
+ * moyolo_anchor_invalid: invalid[p] = 1 where the anchor of pyramid position p is masked (valid_mask == False).
+ * moyolo_mask_rows: out[r] = zero_rows[r % period] ? 0 : x[r] (fp32 path of valid_mask * feats).
+ * -------------------------------------------------------------------------------------------*/
+int moyolo_enc_output_scores(const void* x, int64_t ldx, const void* w, const float* bias, const float* gamma,
+                             const float* beta, float eps, const uint8_t* zero_in_rows, const float* score_w,
+                             const float* score_b, int nc, int64_t M, float* out_f32, void* out_lp, float* logits,
+                             float* max_logit, moyolo_stream_t stream);
+int moyolo_topk(const float* scores, int64_t row_stride, int n, int batch, int k, int32_t* idx_out, float* val_out,
+                moyolo_stream_t stream);
+int moyolo_select_gather(const float* features, const float* logits, const int32_t* idx, int batch, int k,
+                         int64_t len_v, int C, int nc, float* embed, void* embed_lp, int lp_dtype, float* enc_scores,
+                         moyolo_stream_t stream);
+int moyolo_anchor_box(const void* h, int64_t ldh, int h_dtype, const float* w3, const float* b3, const int32_t* idx,
+                      const int32_t* shapes_hw_host, int n_levels, int64_t len_v, float grid_size, float eps,
+                      float* refer, int64_t rows, int K, moyolo_stream_t stream);
+int moyolo_anchor_invalid(const int32_t* shapes_hw_host, int n_levels, int64_t len_v, float grid_size, float eps,
+                          uint8_t* invalid, moyolo_stream_t stream);
+int moyolo_mask_rows(const float* x, const uint8_t* zero_rows, int64_t period, float* out, int64_t rows, int C,
+                     moyolo_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-side frame submission: the stream operations around one captured frame graph as ONE call

@@ -44,7 +44,13 @@ SIGNATURES = {
     "moyolo_add_layernorm": (_i, [_p, _p, _p, _p, _f, _l, _i, _p, _p, _p, _p, _i, _p]),
     "moyolo_add_cast": (_i, [_p, _p, _p, _i, _l, _p]),
     "moyolo_box_refine": (_i, [_p, _l, _i, _p, _p, _p, _p, _l, _i, _p]),
-    "moyolo_score_head": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _l, _i, _i, _p]),
+    "moyolo_score_head": (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _l, _i, _i, _p, _p]),
+    "moyolo_enc_output_scores": (_i, [_p, _l, _p, _p, _p, _p, _f, _p, _p, _p, _i, _l, _p, _p, _p, _p, _p]),
+    "moyolo_topk": (_i, [_p, _l, _i, _i, _i, _p, _p, _p]),
+    "moyolo_select_gather": (_i, [_p, _p, _p, _i, _i, _l, _i, _i, _p, _p, _i, _p, _p]),
+    "moyolo_anchor_box": (_i, [_p, _l, _i, _p, _p, _p, _p, _i, _l, _f, _f, _p, _l, _i, _p]),
+    "moyolo_anchor_invalid": (_i, [_p, _i, _l, _f, _f, _p, _p]),
+    "moyolo_mask_rows": (_i, [_p, _p, _l, _p, _l, _i, _p]),
     "moyolo_sigmoid": (_i, [_p, _p, _l, _p]),
     "moyolo_inverse_sigmoid": (_i, [_p, _p, _l, _p]),
     "moyolo_pos2posemb": (_i, [_p, _p, _l, _i, _i, _f, _p]),

@@ -103,6 +103,23 @@ __device__ __forceinline__ float from_float<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
+// Arguments of the tall Linear(256->256) + LayerNorm + class-score kernel (gemm_tcgen05.cu, selector.cu).
+struct RowLnArgs {
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  const uint8_t* zero_acc_rows;  // rows whose INPUT is treated as zero (valid_mask * feats)
+  const float* score_w;          // [nc, 256] or NULL
+  const float* score_b;
+  int nc;
+  int64_t M;
+  float* out_f32;                // [M, 256] or NULL
+  void* out_lp;                  // [M, 256] bf16 or NULL
+  float* logits;                 // [M, nc] or NULL
+  float* max_logit;              // [M] or NULL
+};
+
 // batch index of a row for dense (row_offsets == nullptr) or ragged batches.
 __device__ __forceinline__ int batch_of_row(int64_t row, const int32_t* __restrict__ row_offsets,
                                             int batch, int64_t rows_per_batch) {

@@ -215,7 +215,7 @@ template <typename XT>
 __global__ void __launch_bounds__(kRowWarps * 32) score_head_kernel(
     const XT* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ b,
     float* __restrict__ logits, float* __restrict__ scores, int32_t* __restrict__ labels, int64_t rows,
-    int K, int nc) {
+    int K, int nc, float* __restrict__ max_logit) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31;
@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) score_head_kernel(
   if (lane == 0) {
     if (scores) scores[row] = sigmoidf_(best);
     if (labels) labels[row] = best_c;
+    if (max_logit) max_logit[row] = best;
   }
 }
 
@@ -363,17 +364,17 @@ extern "C" int moyolo_box_refine(const void* h, int64_t ldh, int h_dtype, const 
 
 extern "C" int moyolo_score_head(const void* x, int64_t ldx, int x_dtype, const float* w, const float* b,
                                  float* logits, float* scores, int32_t* labels, int64_t rows, int K, int nc,
-                                 moyolo_stream_t stream) {
+                                 float* max_logit, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(x && w && b, MOYOLO_ERR_BAD_ARG, "score_head: null pointer");
   MOYOLO_REQUIRE(rows >= 0 && K > 0 && nc > 0 && ldx >= K, MOYOLO_ERR_BAD_SHAPE, "score_head: bad sizes");
   if (rows == 0) return MOYOLO_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (x_dtype == MOYOLO_BF16)
     launch_k(score_head_kernel<__nv_bfloat16>, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st, 
-        static_cast<const __nv_bfloat16*>(x), ldx, w, b, logits, scores, labels, rows, K, nc);
+        static_cast<const __nv_bfloat16*>(x), ldx, w, b, logits, scores, labels, rows, K, nc, max_logit);
   else if (x_dtype == MOYOLO_F32)
     launch_k(score_head_kernel<float>, dim3(row_blocks(rows)), dim3(kRowWarps * 32), 0, st, 
-        static_cast<const float*>(x), ldx, w, b, logits, scores, labels, rows, K, nc);
+        static_cast<const float*>(x), ldx, w, b, logits, scores, labels, rows, K, nc, max_logit);
   else
     return fail(MOYOLO_ERR_UNSUPPORTED, "score_head: unsupported x_dtype %d", x_dtype);
   return check_launch("score_head_kernel");

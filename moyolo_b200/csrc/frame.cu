@@ -143,7 +143,12 @@ __device__ int block_exclusive_scan_f(int v, int* total, int* s_warp) {
   return s_warp[warp] + inc - v;
 }
 
-// grid = n_seq, 1024 threads: select ids >= 0 in order, then copy every field the next frame needs.
+// grid = (n_seq, kCompactChunks), 1024 threads: select ids >= 0 in order, then copy every field the next
+// frame needs. Every CTA of a sequence repeats the (cheap) selection scan into shared memory and then
+// copies the compact rows j = blockIdx.y, blockIdx.y + gridDim.y, ...; CTA y == 0 also writes the selection.
+constexpr int kCompactChunks = 8;
+constexpr int kCompactMaxRows = 4096;
+
 __global__ void __launch_bounds__(1024) frame_compact_kernel(
     int C, int cap, const int32_t* __restrict__ row_offsets, const int64_t* __restrict__ ids,
     const int64_t* __restrict__ dis, const int32_t* __restrict__ labels, const float* __restrict__ refer_logit,
@@ -155,10 +160,12 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
   pdl_trigger();
   pdl_wait();
   __shared__ int s_warp[33];
+  __shared__ int16_t s_sel[kCompactMaxRows];  // row (within the sequence) of the j-th active track
   if (ctrl != nullptr && ctrl[kCtrlAbort] != 0) return;  // aborted frame: leave the track state untouched
   const int s = blockIdx.x;
+  const bool first = blockIdx.y == 0;
   const int off = row_offsets[s];
-  const int n = row_offsets[s + 1] - off;
+  const int n = min(row_offsets[s + 1] - off, kCompactMaxRows);
   const int per = (n + blockDim.x - 1) / blockDim.x;
   const int begin = min(static_cast<int>(threadIdx.x) * per, n);
   const int end = min(begin + per, n);
@@ -169,21 +176,25 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
   total = min(total, cap);
   for (int i = begin; i < end; ++i)
     if (ids[off + i] >= 0) {
-      if (rank < cap) active_index[off + rank] = i;
+      if (rank < cap) {
+        s_sel[rank] = static_cast<int16_t>(i);
+        if (first) active_index[off + rank] = i;
+      }
       ++rank;
     }
-  if (threadIdx.x == 0) n_active[s] = total;
+  if (first && threadIdx.x == 0) n_active[s] = total;
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int j = warp; j < total; j += nwarps) {
-    const int64_t src = off + active_index[off + j];
+  const bool want_q = q_qk_lp != nullptr || q_tgt_lp != nullptr;
+  for (int j = blockIdx.y * nwarps + warp; j < total; j += gridDim.y * nwarps) {
+    const int64_t src = off + s_sel[j];
     const int64_t dst = off + j;  // compact rows keep the frame layout: sequence s starts at row_offsets[s]
     for (int c = lane; c < C; c += 32) {
       c_pos[dst * C + c] = pos[src * C + c];
       const float h = hs[src * C + c];
       c_hs[dst * C + c] = h;
       // QIM operands (qim.py:255, 271): q = k = tgt + pos2posemb(ref_pts), v = tgt
-      if (q_qk_lp != nullptr || q_tgt_lp != nullptr) {
+      if (want_q) {
         const int coord = c / num_pos_feats, i = c % num_pos_feats;
         const float p = refer_logit[src * 4 + coord] * 6.283185307179586f;
         const float e = p / powf(temperature, static_cast<float>(2 * (i / 2)) / static_cast<float>(num_pos_feats));
@@ -338,7 +349,7 @@ extern "C" int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* ro
   MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_compact: bad sizes");
   MOYOLO_REQUIRE((q_qk_lp == nullptr && q_tgt_lp == nullptr) || C == 4 * num_pos_feats, MOYOLO_ERR_BAD_SHAPE,
                  "frame_compact: QIM operands need C == 4*num_pos_feats");
-  launch_k(frame_compact_kernel, dim3(n_seq), dim3(1024), 0, static_cast<cudaStream_t>(stream), 
+  launch_k(frame_compact_kernel, dim3(n_seq, kCompactChunks), dim3(1024), 0, static_cast<cudaStream_t>(stream), 
       C, cap, row_offsets, ids, dis, labels, refer_logit, pos, hs, boxes, n_active, active_index, c_ref, c_pos, c_hs,
       c_box, t_label, t_ids, t_dis, ctrl, q_qk_lp, q_tgt_lp, lp_dtype == MOYOLO_BF16 ? 1 : 0, num_pos_feats,
       temperature);

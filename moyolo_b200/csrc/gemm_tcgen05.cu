@@ -611,6 +611,175 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------
+// Tall Linear(256 -> 256) + LayerNorm with a fused class-score head, one CTA per 128 rows (BN = 256: the
+// whole LayerNorm row sits in one thread's TMEM lane, no cluster exchange). The encoder-side
+// `enc_output` + `enc_score_head` of the query selection (ultralytics/nn/modules/head.py:1039-1041):
+//   f = LayerNorm((valid ? x : 0) . w^T + b) * gamma + beta;  logits = f . ws^T + bs;  max_logit = max_c logits
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowLnMaxNc = 8;
+
+struct RowLnCtl {
+  uint64_t full[4];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+  float bias[kLnCols], gamma[kLnCols], beta[kLnCols];
+  float ws[kRowLnMaxNc][kLnCols];
+  float bs[kRowLnMaxNc];
+};
+
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_rowln_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const RowLnArgs a) {
+  constexpr uint32_t kABytes = kBM * kBK * 2;       // 16 KiB
+  constexpr uint32_t kBBytes = kLnCols * kBK * 2;   // 32 KiB
+  constexpr int kKB = 4;                            // K = 256
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = base;
+  uint8_t* smem_b = base + kKB * kABytes;
+  RowLnCtl* ctl = reinterpret_cast<RowLnCtl*>(smem_b + kKB * kBBytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+    for (int s = 0; s < kKB; ++s) mbar_init(smem_u32(&ctl->full[s]), 2);
+    mbar_init(smem_u32(&ctl->tmem_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int kb = 0; kb < kKB; ++kb) {  // weights: immutable, requested before the dependency wait
+      const uint32_t full = smem_u32(&ctl->full[kb]);
+      mbar_expect_tx(full, kBBytes);
+      tma_load_2d(smem_u32(smem_b + kb * kBBytes), &tmap_w, full, kb * kBK, 0);
+    }
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                 "r"(256)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < kLnCols; i += kGemmThreads - 64) {
+      ctl->bias[i] = a.bias ? __ldg(a.bias + i) : 0.0f;
+      ctl->gamma[i] = __ldg(a.gamma + i);
+      ctl->beta[i] = __ldg(a.beta + i);
+      for (int c = 0; c < a.nc; ++c) ctl->ws[c][i] = __ldg(a.score_w + c * kLnCols + i);
+    }
+    if (threadIdx.x - 64 < a.nc) ctl->bs[threadIdx.x - 64] = a.score_b ? __ldg(a.score_b + threadIdx.x - 64) : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_trigger();
+  const uint32_t tmem_acc = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      pdl_wait();
+      for (int kb = 0; kb < kKB; ++kb) {
+        const uint32_t full = smem_u32(&ctl->full[kb]);
+        mbar_expect_tx(full, kABytes);
+        tma_load_2d(smem_u32(smem_a + kb * kABytes), &tmap_x, full, kb * kBK, m0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(kBM, kLnCols);
+      for (int kb = 0; kb < kKB; ++kb) {
+        mbar_wait(smem_u32(&ctl->full[kb]), 0);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + kb * kABytes));
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b + kb * kBBytes));
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) umma_bf16(tmem_acc, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(smem_u32(&ctl->tmem_full));
+    }
+    __syncwarp();
+  } else {
+    const int quad = warp & 3;
+    const int64_t row = static_cast<int64_t>(m0) + quad * 32 + lane;
+    const bool row_ok = row < a.M;
+    const uint32_t tbase = tmem_acc + (static_cast<uint32_t>(quad * 32) << 16);
+    pdl_wait();
+    const float keep = (row_ok && a.zero_acc_rows != nullptr && a.zero_acc_rows[row] != 0) ? 0.0f : 1.0f;
+    mbar_wait(smem_u32(&ctl->tmem_full), 0);
+    tc_fence_after();
+    // pass 1: mean
+    float sum = 0.0f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kLnCols; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tbase + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) sum += fmaf(keep, __uint_as_float(r[j]), ctl->bias[c0 + j]);
+    }
+    const float mean = sum * (1.0f / kLnCols);
+    // pass 2: centred variance
+    float sq = 0.0f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kLnCols; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tbase + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float d = fmaf(keep, __uint_as_float(r[j]), ctl->bias[c0 + j]) - mean;
+        sq = fmaf(d, d, sq);
+      }
+    }
+    const float rstd = rsqrtf(sq * (1.0f / kLnCols) + a.eps);
+    // pass 3: normalise, store, class scores
+    float dot[kRowLnMaxNc];
+#pragma unroll
+    for (int c = 0; c < kRowLnMaxNc; ++c) dot[c] = 0.0f;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kLnCols; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tbase + c0, r);
+      tmem_ld_wait();
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        v[j] = (fmaf(keep, __uint_as_float(r[j]), ctl->bias[c0 + j]) - mean) * rstd * ctl->gamma[c0 + j] + ctl->beta[c0 + j];
+#pragma unroll
+      for (int c = 0; c < kRowLnMaxNc; ++c) {
+        if (c < a.nc) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) dot[c] = fmaf(v[j], ctl->ws[c][c0 + j], dot[c]);
+        }
+      }
+      if (row_ok) {
+        if (a.out_f32 != nullptr) store16<float>(a.out_f32 + row * kLnCols + c0, v, true);
+        if (a.out_lp != nullptr) store16<__nv_bfloat16>(static_cast<__nv_bfloat16*>(a.out_lp) + row * kLnCols + c0, v, true);
+      }
+    }
+    if (row_ok && a.nc > 0) {
+      float best = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < kRowLnMaxNc; ++c) {
+        if (c < a.nc) {
+          const float l = dot[c] + ctl->bs[c];
+          if (a.logits != nullptr) a.logits[row * a.nc + c] = l;
+          best = fmaxf(best, l);
+        }
+      }
+      if (a.max_logit != nullptr) a.max_logit[row] = best;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "r"(256) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -791,6 +960,26 @@ int linear_ln_tcgen05(const void* x, int64_t ldx, const void* w, const float* bi
   e.residual = residual; e.gamma = gamma; e.beta = beta; e.eps = eps;
   e.out_f32 = out_f32; e.out_lp = out_lp; e.pos = pos; e.out_pos_lp = out_pos_lp;
   return launch_gemm<32, __nv_bfloat16, true>(tx, tx, tw, e, st);
+}
+
+// Tall Linear(256->256) + LayerNorm (+ class scores): see gemm_rowln_kernel.
+int linear_rowln_tcgen05(const void* x, int64_t ldx, const void* w, const RowLnArgs& a, cudaStream_t st) {
+  constexpr size_t smem = 4 * (kBM * kBK * 2 + kLnCols * kBK * 2) + sizeof(RowLnCtl) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_rowln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+    if (err != cudaSuccess)
+      return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(rowln smem=%zu): %s", smem, cudaGetErrorString(err));
+    configured = true;
+  }
+  CUtensorMap tx, tw;
+  int rc = make_tmap(&tx, x, a.M, kLnCols, ldx, kBM);
+  if (rc != MOYOLO_OK) return rc;
+  rc = make_tmap(&tw, w, kLnCols, kLnCols, kLnCols, 256);
+  if (rc != MOYOLO_OK) return rc;
+  launch_k(gemm_rowln_kernel, dim3(static_cast<unsigned>((a.M + kBM - 1) / kBM)), dim3(kGemmThreads), smem, st, tx, tw, a);
+  return check_launch("gemm_rowln_kernel");
 }
 
 }  // namespace moyolo

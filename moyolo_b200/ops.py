@@ -250,8 +250,9 @@ def box_refine(h: torch.Tensor, w3: torch.Tensor, b3: torch.Tensor, ref: torch.T
     return out
 
 
-def score_head(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_scores: bool = True, out=None):
-    """out: optional (logits [R,nc] f32, scores [R] f32, labels [R] i32) pre-allocated."""
+def score_head(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_scores: bool = True, out=None,
+               max_logit: Optional[torch.Tensor] = None):
+    """out: optional (logits [R,nc] f32, scores [R] f32, labels [R] i32) pre-allocated; max_logit [R] f32 optional."""
     _cuda(x, w, b)
     R, K = x.shape
     nc = w.shape[0]
@@ -263,7 +264,8 @@ def score_head(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_scores: b
         labels = torch.empty(R, dtype=torch.int32, device=x.device) if want_scores else None
     _count(1)
     _lib.check(_lib.lib().moyolo_score_head(x.data_ptr(), x.stride(0), _dt(x), w.data_ptr(), b.data_ptr(),
-                                            logits.data_ptr(), _ptr(scores), _ptr(labels), R, K, nc, _stream()))
+                                            logits.data_ptr(), _ptr(scores), _ptr(labels), R, K, nc, _ptr(max_logit),
+                                            _stream()))
     return logits, scores, labels
 
 
@@ -400,3 +402,77 @@ def frame_emit(n_seq, rows_pad, row_offsets, ids, boxes, scores, labels, n_activ
         n_seq, rows_pad, row_offsets.data_ptr(), ids.data_ptr(), boxes.data_ptr(), scores.data_ptr(),
         labels.data_ptr(), n_active.data_ptr(), active_index.data_ptr(), seq_ids.data_ptr(), frame_rows.data_ptr(),
         table.data_ptr(), table.shape[0], ctrl.data_ptr(), _stream()))
+
+
+# ---- encoder-side query selection (head.py:993-1113) ----------------------------------------------------------
+def enc_output_scores(x: torch.Tensor, w: torch.Tensor, b, gamma, beta, eps: float, zero_in_rows, score_w, score_b,
+                      out_f32=None, out_lp=None, logits=None, max_logit=None) -> None:
+    """LayerNorm(Linear(mask * x)) + class-score head over all rows in one tcgen05 kernel (bf16 operands)."""
+    _cuda(x, w, b, gamma, beta, zero_in_rows, score_w, score_b, out_f32, out_lp, logits, max_logit)
+    M = x.shape[0]
+    nc = 0 if score_w is None else score_w.shape[0]
+    _count(1)
+    _lib.check(_lib.lib().moyolo_enc_output_scores(
+        x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), gamma.data_ptr(), beta.data_ptr(), float(eps),
+        _ptr(zero_in_rows), _ptr(score_w), _ptr(score_b), nc, M, _ptr(out_f32), _ptr(out_lp), _ptr(logits),
+        _ptr(max_logit), _stream()))
+
+
+def topk(scores: torch.Tensor, k: int, out: Optional[torch.Tensor] = None, vals: Optional[torch.Tensor] = None):
+    """Indices (int32 [batch, k]) of the k largest entries of every row of scores [batch, n] fp32, ordered as
+    torch.topk(sorted=True) (descending; ties by ascending index)."""
+    _cuda(scores, out, vals)
+    B, n = scores.shape
+    if scores.stride(1) != 1 or scores.dtype != torch.float32:
+        raise ValueError("topk: scores must be fp32 with contiguous columns")
+    if out is None:
+        out = torch.empty(B, k, dtype=torch.int32, device=scores.device)
+    _count(1)
+    _lib.check(_lib.lib().moyolo_topk(scores.data_ptr(), scores.stride(0), n, B, int(k), out.data_ptr(), _ptr(vals),
+                                      _stream()))
+    return out
+
+
+def select_gather(features: torch.Tensor, logits, idx: torch.Tensor, embed: torch.Tensor, embed_lp=None,
+                  enc_scores=None) -> None:
+    _cuda(features, logits, idx, embed, embed_lp, enc_scores)
+    B, Lv, Cc = features.shape
+    k = idx.shape[1]
+    nc = 0 if logits is None else logits.shape[-1]
+    _count(1)
+    _lib.check(_lib.lib().moyolo_select_gather(
+        features.data_ptr(), _ptr(logits), idx.data_ptr(), B, k, Lv, Cc, nc, embed.data_ptr(), _ptr(embed_lp),
+        _dt(embed_lp) if embed_lp is not None else F32, _ptr(enc_scores), _stream()))
+
+
+def anchor_box(h: torch.Tensor, w3: torch.Tensor, b3: torch.Tensor, idx: torch.Tensor, shapes, len_v: int,
+               out: torch.Tensor, grid_size: float = 0.05, eps: float = 1e-2) -> torch.Tensor:
+    _cuda(h, w3, b3, idx, out)
+    R, K = h.shape
+    arr, L = _shapes_arr(shapes)
+    _count(1)
+    _lib.check(_lib.lib().moyolo_anchor_box(h.data_ptr(), h.stride(0), _dt(h), w3.data_ptr(), b3.data_ptr(),
+                                            idx.data_ptr(), arr, L, len_v, float(grid_size), float(eps), out.data_ptr(),
+                                            R, K, _stream()))
+    return out
+
+
+def anchor_invalid(shapes, len_v: int, device, grid_size: float = 0.05, eps: float = 1e-2) -> torch.Tensor:
+    """uint8 [len_v]: 1 where the anchor of a pyramid position is masked out (head.py:1006)."""
+    arr, L = _shapes_arr(shapes)
+    out = torch.empty(len_v, dtype=torch.uint8, device=device)
+    _count(1)
+    _lib.check(_lib.lib().moyolo_anchor_invalid(arr, L, len_v, float(grid_size), float(eps), out.data_ptr(), _stream()))
+    return out
+
+
+def mask_rows(x: torch.Tensor, zero_rows: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = 0 where zero_rows[r % len(zero_rows)] else x[r]; x fp32 [R, C] contiguous."""
+    _cuda(x, zero_rows, out)
+    R, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    _count(1)
+    _lib.check(_lib.lib().moyolo_mask_rows(x.data_ptr(), zero_rows.data_ptr(), zero_rows.numel(), out.data_ptr(), R, Cc,
+                                           _stream()))
+    return out

@@ -112,6 +112,36 @@ def make_decoder_state(spec: DecoderSpec, seed: int = 0) -> Dict[str, torch.Tens
     return sd
 
 
+def make_selector_state(spec: DecoderSpec, ch: Sequence[int] = (256, 512, 512), seed: int = 0) -> Dict[str, torch.Tensor]:
+    """Random-init weights of the encoder-side query selection of MYDecoder (head.py:839-863) with the
+    reference's key names: `input_proj.{l}.0.weight` (1x1 conv, no bias), `input_proj.{l}.1.*` (BatchNorm2d incl.
+    running statistics), `enc_output.{0,1}.*` (Linear + LayerNorm), `enc_score_head.*`, `enc_bbox_head.layers.{j}.*`.
+    Separate generator from make_decoder_state so existing goldens keep their weights."""
+    g = _gen(7919 + seed)
+    d = spec.d_model
+    sd: Dict[str, torch.Tensor] = {}
+    for l, c in enumerate(ch):
+        sd[f"input_proj.{l}.0.weight"] = torch.randn(d, c, 1, 1, generator=g) / math.sqrt(c)
+        sd[f"input_proj.{l}.1.weight"] = 1.0 + 0.1 * torch.randn(d, generator=g)
+        sd[f"input_proj.{l}.1.bias"] = 0.05 * torch.randn(d, generator=g)
+        sd[f"input_proj.{l}.1.running_mean"] = 0.1 * torch.randn(d, generator=g)
+        sd[f"input_proj.{l}.1.running_var"] = 0.5 + torch.rand(d, generator=g)
+    sd["enc_output.0.weight"], sd["enc_output.0.bias"] = _lin(g, d, d)
+    sd["enc_output.1.weight"], sd["enc_output.1.bias"] = _ln(g, d)
+    w, _ = _lin(g, spec.nc, d, w_std=0.15)
+    sd["enc_score_head.weight"], sd["enc_score_head.bias"] = w, torch.full((spec.nc,), -2.0)
+    sd["enc_bbox_head.layers.0.weight"], sd["enc_bbox_head.layers.0.bias"] = _lin(g, d, d)
+    sd["enc_bbox_head.layers.1.weight"], sd["enc_bbox_head.layers.1.bias"] = _lin(g, d, d)
+    sd["enc_bbox_head.layers.2.weight"], sd["enc_bbox_head.layers.2.bias"] = _lin(g, 4, d, w_std=0.3 / math.sqrt(d))
+    return sd
+
+
+def make_pyramid_maps(seed: int, B: int, shapes, ch: Sequence[int] = (256, 512, 512)) -> list:
+    """Neck outputs [B, C_l, H_l, W_l] (fp32, NCHW as the reference's Conv2d takes them)."""
+    g = _gen(seed)
+    return [torch.randn(B, c, int(h), int(w), generator=g) for c, (h, w) in zip(ch, shapes)]
+
+
 def sub_state(sd: Dict[str, torch.Tensor], prefix: str) -> Dict[str, torch.Tensor]:
     return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
 

@@ -89,7 +89,7 @@ class FrameWorkspace:
     """Every intermediate tensor of one frame for a padded row count R (allocated once, outside any
     graph capture; kernels write through `out=` so a frame performs no allocation)."""
 
-    def __init__(self, R: int, S: int, spec: DecoderSpec, dt: torch.dtype, dev, d_qim: int):
+    def __init__(self, R: int, S: int, spec: DecoderSpec, dt: torch.dtype, dev, d_qim: int, rows_per_seq: int = 0):
         C, F, nl = spec.d_model, spec.d_ffn, spec.n_layers
         f32 = dict(dtype=torch.float32, device=dev)
         lp = dict(dtype=dt, device=dev)
@@ -123,7 +123,8 @@ class FrameWorkspace:
         self.logits = z(R, spec.nc, **f32)
         self.scores = z(R, **f32)
         self.labels = z(R, dtype=torch.int32, device=dev)
-        self.assign_ws = z(S * ops.track_workspace_bytes(R), dtype=torch.uint8, device=dev)
+        self.rows_per_seq = min(R, rows_per_seq) if rows_per_seq > 0 else R   # bound of one sequence's rows
+        self.assign_ws = z(S * ops.track_workspace_bytes(self.rows_per_seq), dtype=torch.uint8, device=dev)
         self.n_active = z(S, dtype=torch.int32, device=dev)
         self.active_index = z(R, dtype=torch.int32, device=dev)
         self.c_ref = z(R, 4, **f32)
@@ -308,7 +309,7 @@ class TrackEngine:
         boxes = ws.refer[n_l]
         ops.score_head(ws.x_lp, W.score_w, W.score_b, out=(ws.logits, ws.scores, ws.labels))
         st, ft, mt, it = self.thr
-        ops.track_assign_batched(ws.scores, boxes, ws.ids, ws.dis, self.counters, ws.ro, S, R, ws.assign_ws, st, ft,
+        ops.track_assign_batched(ws.scores, boxes, ws.ids, ws.dis, self.counters, ws.ro, S, ws.rows_per_seq, ws.assign_ws, st, ft,
                                  mt, it, ctrl=self.ctrl)
         ops.frame_compact(S, C, self.cap, ws.ro, ws.ids, ws.dis, ws.labels, ws.refer_logit, ws.pos, ws.x, boxes,
                           ws.n_active, ws.active_index, ws.c_ref, ws.c_pos, ws.c_hs, ws.c_box, self.t_label,
@@ -382,7 +383,7 @@ class TrackEngine:
         other = self._plans.get((rows_pad, slot ^ 1))
         # both input slots of one size share a workspace: frames are serialised on the main stream
         p.ws = other.ws if other is not None else FrameWorkspace(rows_pad, self.n_seq, self.spec, self.W.dt, self.dev,
-                                                                 self.W.qim["l1_w"].shape[0])
+                                                                 self.W.qim["l1_w"].shape[0], self.n_detect + self.cap)
         if self.use_graphs:
             torch.cuda.synchronize(self.dev)
             snap = self._state_snapshot()

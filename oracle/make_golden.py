@@ -234,6 +234,32 @@ def gen_qim(qim, structures):
              pred_boxes=boxes, new_query_pos=o.query_pos, new_ref_pts=o.ref_pts)
 
 
+def gen_selection(head):
+    """Encoder-side query selection of the reference MYDecoder (head.py:1012-1029, 993-1010, 1031-1113), eval mode,
+    first-frame path (no carried tracks): feats, detect embeddings, logit-space boxes, encoder scores."""
+    for name, pyr, B, nq, nc, seed in (("select_tiny", "tiny", 2, 48, 1, 81), ("select_c1", "C1", 1, 300, 1, 82),
+                                       ("select_kitti_nc5", "KITTI", 1, 300, 5, 83)):
+        spec = syn.DecoderSpec(nc=nc)
+        shapes = [list(x) for x in syn.PYRAMIDS[pyr]]
+        sd = syn.make_selector_state(spec, (256, 512, 512), WEIGHT_SEED)
+        maps = syn.make_pyramid_maps(seed, B, shapes)
+        m = head.MYDecoder(nc=nc, ch=(256, 512, 512), nq=nq)
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all(not k.startswith(("input_proj", "enc_")) for k in missing), (missing, unexpected)
+        m.eval()
+        with torch.no_grad():
+            feats, shp = m._get_encoder_input(maps)
+            embed, refer, enc_bboxes, enc_scores, _, query_pos = m._get_decoder_input(feats, shp, None, None, None,
+                                                                                      is_first=True)
+        assert shp == shapes
+        # feats is [B, Lv, 256]: the full tensor for the tiny case, every 37th row (+ a checksum) otherwise
+        step = 1 if pyr == "tiny" else 37
+        save(name, dict(pyramid=pyr, B=B, nq=nq, nc=nc, seed=seed, weight_seed=WEIGHT_SEED, shapes=shapes,
+                        checksum=syn.checksum(*maps), feats_row_step=step, feats_checksum=syn.checksum(feats),
+                        source="head.py:1012-1113"),
+             feats=feats[:, ::step].contiguous(), embed=embed, refer=refer, enc_scores=enc_scores, query_pos=query_pos)
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     torch.set_num_threads(8)
@@ -249,6 +275,7 @@ def main():
     gen_kat0()
     gen_tracker(head, structures)
     gen_qim(qim, structures)
+    gen_selection(head)
 
 
 if __name__ == "__main__":

@@ -209,3 +209,55 @@ def qim_update(sd: Dict[str, Tensor], ref_pts: Tensor, query_pos: Tensor, out_em
                   p["linear_feat2.weight"], p["linear_feat2.bias"])                             # :290
     new_query_pos = _ln(p, "norm_feat", query_pos + f2)                                         # :294-298
     return new_query_pos, inverse_sigmoid(pred_boxes[:, :4].detach().clone())                   # :300
+
+
+def generate_anchors(shapes, grid_size: float = 0.05, dtype=torch.float32, eps: float = 1e-2):
+    """ultralytics/nn/modules/head.py:993-1010: cell-centre anchors (cx, cy, w, h) with w = h = 0.05 * 2^level in
+    logit space, `inf` where any coordinate falls outside (eps, 1 - eps). Returns ([1, Lv, 4], [1, Lv, 1] bool)."""
+    anchors = []
+    for i, (h, w) in enumerate(shapes):
+        gy, gx = torch.meshgrid(torch.arange(end=h, dtype=dtype), torch.arange(end=w, dtype=dtype), indexing="ij")
+        grid_xy = torch.stack([gx, gy], -1)
+        valid_wh = torch.tensor([h, w], dtype=dtype)  # sic: the reference divides (x, y) by (h, w), head.py:1000-1001
+        grid_xy = (grid_xy.unsqueeze(0) + 0.5) / valid_wh
+        wh = torch.ones_like(grid_xy) * grid_size * (2.0 ** i)
+        anchors.append(torch.cat([grid_xy, wh], -1).view(-1, h * w, 4))
+    anchors = torch.cat(anchors, 1)
+    valid = ((anchors > eps) * (anchors < 1 - eps)).all(-1, keepdim=True)
+    anchors = torch.log(anchors / (1 - anchors))
+    anchors = anchors.masked_fill(~valid, float("inf"))
+    return anchors, valid
+
+
+def encoder_input(sd: Dict[str, Tensor], maps) -> tuple:
+    """head.py:1012-1029 `_get_encoder_input`: per level 1x1 conv (no bias) + BatchNorm2d (eval, eps 1e-5,
+    head.py:839-840), flattened to [B, H*W, C] and concatenated over levels."""
+    feats, shapes = [], []
+    for l, m in enumerate(maps):
+        p = f"input_proj.{l}."
+        y = F.conv2d(m, sd[p + "0.weight"])
+        y = F.batch_norm(y, sd[p + "1.running_mean"], sd[p + "1.running_var"], sd[p + "1.weight"], sd[p + "1.bias"],
+                         False, 0.0, 1e-5)
+        h, w = y.shape[2:]
+        feats.append(y.flatten(2).permute(0, 2, 1))
+        shapes.append([int(h), int(w)])
+    return torch.cat(feats, 1), shapes
+
+
+def query_selection(sd: Dict[str, Tensor], feats: Tensor, shapes, num_queries: int) -> Dict[str, Tensor]:
+    """head.py:1031-1113 `_get_decoder_input`, the detect-query part (is_first / no carried tracks, eval, no
+    denoising, learnt_init_query False): enc_output on valid_mask * feats (:1039), score head (:1041), bbox head +
+    anchors (:1044), top-k by max-class logit (:1048), gathers (:1053, :1092, :1104)."""
+    bs = feats.shape[0]
+    anchors, valid = generate_anchors(shapes, dtype=feats.dtype)
+    x = valid * feats
+    features = F.layer_norm(F.linear(x, sd["enc_output.0.weight"], sd["enc_output.0.bias"]), (x.shape[-1],),
+                            sd["enc_output.1.weight"], sd["enc_output.1.bias"], 1e-5)
+    scores = F.linear(features, sd["enc_score_head.weight"], sd["enc_score_head.bias"])
+    bboxes = mlp_forward(sd, features, 3, "enc_bbox_head.") + anchors
+    topk = torch.topk(scores.max(-1).values, num_queries, dim=1).indices
+    bi = torch.arange(bs).unsqueeze(-1).repeat(1, num_queries).view(-1)
+    ti = topk.view(-1)
+    return {"features": features, "scores": scores, "topk": topk,
+            "refer": bboxes[bi, ti].view(bs, num_queries, -1), "embed": features[bi, ti].view(bs, num_queries, -1),
+            "enc_scores": scores[bi, ti].view(bs, num_queries, -1)}

@@ -123,3 +123,27 @@ def test_qim_port(name):
         qp, rp = tp.qim_update(sd, t["ref_pts"], t["query_pos"], t["out_embed"], t["pred_boxes"])
     assert rel_rms(qp.numpy(), g["new_query_pos"]) < FP32_TOL
     assert np.array_equal(rp.numpy(), g["new_ref_pts"])
+
+
+@pytest.mark.parametrize("name", ["select_tiny", "select_c1", "select_kitti_nc5"])
+def test_query_selection_restatement(name):
+    """oracle encoder_input / generate_anchors / query_selection (head.py:993-1113) against the reference MYDecoder."""
+    meta, g = load_golden(name)
+    spec = syn.DecoderSpec(nc=meta["nc"])
+    sd = syn.make_selector_state(spec, (256, 512, 512), meta["weight_seed"])
+    maps = syn.make_pyramid_maps(meta["seed"], meta["B"], meta["shapes"])
+    assert abs(syn.checksum(*maps) - meta["checksum"]) < 1e-6 * max(1.0, abs(meta["checksum"]))
+    with torch.no_grad():
+        feats, shapes = tp.encoder_input(sd, maps)
+        sel = tp.query_selection(sd, feats, shapes, meta["nq"])
+    assert shapes == meta["shapes"]
+    assert rel_rms(feats[:, ::meta["feats_row_step"]].numpy(), g["feats"]) < 1e-6
+    # the selected set and its ORDER (torch.topk, descending) are part of the contract: IDs follow query order
+    assert rel_rms(sel["enc_scores"].numpy(), g["enc_scores"]) < 1e-6
+    assert rel_rms(sel["embed"].numpy(), g["embed"]) < 1e-6
+    ref, got = g["refer"], sel["refer"].numpy()
+    fin = np.isfinite(ref)
+    assert np.array_equal(fin, np.isfinite(got))  # anchors outside (eps, 1-eps) are +inf (head.py:1006-1009)
+    assert rel_rms(got[fin], ref[fin]) < 1e-6
+    assert rel_rms(tp.pos2posemb(sel["refer"]).nan_to_num(0.0, 0.0, 0.0).numpy(),
+                   np.nan_to_num(g["query_pos"], nan=0.0, posinf=0.0, neginf=0.0)) < 1e-5
