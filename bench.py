@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=12, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-tracks", type=int, default=160, help="pre-capture frame graphs up to this many tracks/seq")
+    ap.add_argument("--no-selection", action="store_true", help="skip the query-selection (f1) leg")
     ap.add_argument("--profiler-range", action="store_true",
                     help="cudaProfilerStart/Stop around the timed `value` leg (ncu --profile-from-start off)")
     return ap.parse_args()
@@ -341,13 +342,76 @@ def run_moyolo(args):
             "roofline": roof,
             "clocks": clocks,
         }
+        cpu_src = [tuple(x[0].float().cpu() for x in b) for b in dev_batches[:args.cpu_frames]]
+        if world == 1 and not args.no_selection:
+            del dev_batches, host_batches
+            torch.cuda.empty_cache()
+            line["with_query_selection"] = selection_leg(args, sd, spec, syn, shapes, device, S, min(K, 200), Wm)
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline(args, sd, spec, shapes, [tuple(x[0] for x in b) for b in dev_batches])
+            line["cpu_baseline"] = cpu_baseline(args, sd, spec, shapes, cpu_src)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ f1 leg
+def selection_leg(args, sd, spec, syn, shapes, device, S, K, Wm):
+    """The same frame with the encoder-side query selection inside the frame graph: the step
+    starts from the neck's channels-last maps (1x1 conv + BN, enc_output + scores over all Lv positions, top-k,
+    box head + anchors) instead of from ready-made feats / detect queries. Rank-local, no gather."""
+    from moyolo_b200.selector import QuerySelector
+    from moyolo_b200.tracker import TrackEngine
+    ch = (256, 512, 512)
+    lp = torch.bfloat16 if args.precision == "bf16" else torch.float32
+    sd2 = dict(sd)
+    sd2.update(syn.make_selector_state(spec, ch, 0))
+    g = torch.Generator(device=device).manual_seed(4242)
+    cur = [torch.randn(S, h, w, c, generator=g, device=device) for (h, w), c in zip(shapes, ch)]
+    frames = []
+    for _ in range(K):   # temporally coherent maps so that tracks persist, appear and die
+        cur = [m + 0.05 * torch.randn(m.shape, generator=g, device=device) for m in cur]
+        frames.append(tuple(m.to(lp).contiguous() for m in cur))
+
+    def engine(state):
+        sel = QuerySelector(state, spec, shapes, ch, device, args.precision, args.n_detect, S)
+        return TrackEngine(state, spec, shapes, device, args.precision, args.n_detect, S, selector=sel)
+
+    eng = engine(sd2)
+    out = eng.step(*frames[0])[0]
+    sd2 = syn.calibrate_score_bias(sd2, out["logits"], spec, 0.035)
+    del eng
+    eng = engine(sd2)
+    eng.prepare(args.max_tracks)
+    res = {}
+    host = [tuple(x.cpu().pin_memory() for x in f) for f in frames]
+    for name, src, rows in (("value", frames, False), ("e2e", host, True)):
+        eng.reset()
+        for t in range(Wm):
+            eng.submit(*src[t % len(src)], want_rows=rows)
+            if rows and t > 0:
+                eng.collect(t - 1)
+        eng.reset()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        chk = 0.0
+        e0.record()
+        for t in range(K):
+            eng.submit(*src[t], want_rows=rows)
+            if rows and t > 0:
+                chk += float(eng.collect(t - 1)[0]["scores"].sum())
+        eng.drain()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        res[name] = {"value": round(K * S / (ms * 1e-3), 2), "ms_per_step": round(ms / K, 4)}
+    res["unit"] = UNIT
+    res["h2d_bytes_per_step"] = int(sum(x.numel() * x.element_size() for x in frames[0]))
+    res["tracks_carried_end"] = eng.n_tracks_host()
+    res["note"] = ("frame = input_proj of the neck maps + query selection (top-k of all Lv positions) + the decoder frame; "
+                   "value: maps resident in HBM, e2e: pinned host maps, H2D inside the timed region")
+    return res
 
 
 # ------------------------------------------------------------------------------------------ CPU arms

@@ -4,7 +4,7 @@
 TAG=${1:-r01}
 shift
 mkdir -p gpurun_out
-BENCH="python bench.py --steps 12 --warmup 3 --no-cpu-baseline --max-tracks 32 --profiler-range $*"
+BENCH="python bench.py --steps 12 --warmup 3 --no-cpu-baseline --no-selection --max-tracks 32 --profiler-range $*"
 # (1) launch list of the timed `value` leg only (graph kernel nodes are profiled individually; cold-cache, serialised)
 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
     --log-file gpurun_out/${TAG}_launches.csv $BENCH > gpurun_out/${TAG}_launches_bench.log 2>&1

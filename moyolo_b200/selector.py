@@ -76,13 +76,22 @@ class QuerySelector:
         """maps[l]: [S, H_l, W_l, C_l] of the GEMM dtype, contiguous. Writes feats [S, Lv, 256] (GEMM dtype),
         det_embed [S, nq, 256] fp32 and det_refer [S, nq, 4] fp32 (logit space); `self.enc_scores` / `self.idx`
         hold the selected class logits and pyramid positions."""
-        S, Lv, C, nq = self.S, self.Lv, self.spec.d_model, self.nq
+        self.project(maps, feats)
+        self.select(feats, det_embed, det_refer)
+
+    def project(self, maps: Sequence[torch.Tensor], feats: torch.Tensor) -> None:
+        """input_proj (head.py:1012-1029): per level and sequence one GEMM with the folded conv + BatchNorm."""
         eng = ex._GEMM_ENGINE
         for l, (h, w) in enumerate(self.shapes):
             pw, pb = self.proj[l]
-            for s in range(S):
+            for s in range(self.S):
                 ops.linear(maps[l][s].view(h * w, self.ch[l]), pw, pb, out=feats[s, self.starts[l]:self.starts[l + 1]],
                            engine=eng)
+
+    def select(self, feats: torch.Tensor, det_embed: torch.Tensor, det_refer: torch.Tensor) -> None:
+        """enc_output + scores over all positions, top-k, gathers, box head + anchors (head.py:1031-1113)."""
+        S, Lv, C, nq = self.S, self.Lv, self.spec.d_model, self.nq
+        eng = ex._GEMM_ENGINE
         rows = feats.view(S * Lv, C)
         if self.dt == torch.bfloat16 and eng != _lib.GEMM_SIMT:
             ops.enc_output_scores(rows, self.enc_w, self.enc_b, self.enc_g, self.enc_beta, 1e-5, self.invalid,

@@ -157,7 +157,7 @@ class TrackEngine:
     def __init__(self, sd, spec: DecoderSpec, shapes, device, precision: str = "bf16", n_detect: int = 300,
                  n_seq: int = 1, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, iou_thresh=0.8,
                  weights: Optional[DecoderWeights] = None, cap: int = 512, bucket: int = 64, margin: int = 32,
-                 use_graphs: bool = True, table_rows: int = 1 << 18, branches: bool = True):
+                 use_graphs: bool = True, table_rows: int = 1 << 18, branches: bool = True, selector=None):
         self.dev = torch.device(device)
         self.spec, self.shapes, self.n_detect, self.n_seq = spec, [list(s) for s in shapes], n_detect, n_seq
         self.Lv = level_sizes(shapes)
@@ -178,9 +178,21 @@ class TrackEngine:
         self.seq_ids = torch.arange(S, dtype=torch.int32, device=dev)
         self.table = torch.zeros(table_rows, 9, device=dev)
         # 2-deep input ring (graphs read these) and the all-layers value tensor shared by every plan
-        self.feats_in = [torch.zeros(S, self.Lv, C, dtype=self.W.dt, device=dev) for _ in range(2)]
-        self.det_embed_in = [torch.zeros(S, n_detect, C, device=dev) for _ in range(2)]
-        self.det_refer_in = [torch.zeros(S, n_detect, 4, device=dev) for _ in range(2)]
+        # `selector` (moyolo_b200.selector.QuerySelector): the frame then starts from the neck's
+        # channels-last maps; feats / detect queries are produced inside the frame graph.
+        self.selector = selector
+        if selector is None:
+            self.feats_in = [torch.zeros(S, self.Lv, C, dtype=self.W.dt, device=dev) for _ in range(2)]
+            self.det_embed_in = [torch.zeros(S, n_detect, C, device=dev) for _ in range(2)]
+            self.det_refer_in = [torch.zeros(S, n_detect, 4, device=dev) for _ in range(2)]
+            self._ring = [[self.feats_in[i], self.det_embed_in[i], self.det_refer_in[i]] for i in range(2)]
+        else:
+            assert selector.S == S and selector.nq == n_detect and selector.dt == self.W.dt
+            self.feats_in = [torch.zeros(S, self.Lv, C, dtype=self.W.dt, device=dev)] * 2
+            self.det_embed_in = [torch.zeros(S, n_detect, C, device=dev)] * 2
+            self.det_refer_in = [torch.zeros(S, n_detect, 4, device=dev)] * 2
+            self._ring = [[torch.zeros(shp, dtype=self.W.dt, device=dev) for shp in selector.map_shapes()]
+                          for _ in range(2)]
         self.values = torch.zeros(S, self.Lv, spec.n_layers * C, dtype=self.W.dt, device=dev)
         # streams / events
         self._main = torch.cuda.current_stream(dev)
@@ -268,6 +280,8 @@ class TrackEngine:
         cur = torch.cuda.current_stream(self.dev)
         feats = self.feats_in[p.slot].view(S * self.Lv, C)
         fork = self.branches
+        if self.selector is not None:  # input projection of the neck maps -> feats (head.py:1012-1029)
+            self.selector.project(self._ring[p.slot], self.feats_in[p.slot])
         # side branch: value projection of ALL layers in one GEMM (transformer.py:264; feats is the same
         # tensor in every layer, transformer.py:705)
         if fork:
@@ -278,6 +292,8 @@ class TrackEngine:
         else:
             ops.linear(feats, W.value_proj.w, W.value_proj.b, out=self.values.view(S * self.Lv, n_l * C),
                        engine=ex._GEMM_ENGINE)
+        if self.selector is not None:  # detect queries of this frame (head.py:1031-1113)
+            self.selector.select(self.feats_in[p.slot], self.det_embed_in[p.slot], self.det_refer_in[p.slot])
         ops.frame_assemble(S, nd, C, self.cap, self.n_tracks, self.t_ref, self.t_qpos, self.t_label, self.t_ids,
                            self.t_dis, W.class_embed, self.det_embed_in[p.slot], self.det_refer_in[p.slot], ws.x,
                            ws.refer_logit, ws.pos, ws.ids, ws.dis, ws.ro, R, ctrl=self.ctrl,
@@ -415,7 +431,7 @@ class TrackEngine:
         d.ev_copy = self._ev_copy[p.slot].cuda_event
         d.graph_exec = p.graph.raw_cuda_graph_exec()
         d.n_inputs = 3
-        for i, t in enumerate((self.feats_in[p.slot], self.det_embed_in[p.slot], self.det_refer_in[p.slot])):
+        for i, t in enumerate(self._ring[p.slot]):
             d.in_dst[i] = t.data_ptr()
             d.in_bytes[i] = t.numel() * t.element_size()
         d.out_src[0], d.out_bytes[0] = p.ws.info.data_ptr(), p.ws.info.numel() * 4
@@ -442,12 +458,9 @@ class TrackEngine:
         return {"frame": t, "plan": p, "rows_pad": rows_pad, "want_rows": want_rows}
 
     def _native_ok(self, feats, det_embed, det_refer) -> bool:
-        f = self.feats_in[0]
-        return (self._native and feats.dtype == f.dtype and feats.is_contiguous() and det_embed.is_contiguous() and
-                det_refer.is_contiguous() and det_embed.dtype == torch.float32 and det_refer.dtype == torch.float32 and
-                feats.numel() == f.numel() and det_embed.numel() == self.det_embed_in[0].numel() and
-                det_refer.numel() == self.det_refer_in[0].numel() and
-                all(x.is_cuda or x.is_pinned() for x in (feats, det_embed, det_refer)))
+        return self._native and all(x.dtype == r.dtype and x.is_contiguous() and x.numel() == r.numel() and
+                                    (x.is_cuda or x.is_pinned())
+                                    for x, r in zip((feats, det_embed, det_refer), self._ring[0]))
 
     def prepare(self, max_tracks_per_seq: int) -> int:
         """Pre-capture the frame graphs for every padded size up to `max_tracks_per_seq` tracks per
@@ -481,13 +494,11 @@ class TrackEngine:
             if t.is_cuda:
                 t.record_stream(cs)  # the caller may drop its reference before the async copy has run
         with torch.cuda.stream(cs):
-            dst = self.feats_in[slot]
-            if feats.dtype == dst.dtype or not feats.is_cuda:
-                dst.copy_(feats.reshape(dst.shape), non_blocking=True)
-            else:  # dtype conversion on device through the library's own cast kernel
-                ops.add_cast(feats.reshape(-1).float().contiguous(), None, dst.dtype, out=dst.view(-1))
-            self.det_embed_in[slot].copy_(det_embed.reshape(self.det_embed_in[slot].shape), non_blocking=True)
-            self.det_refer_in[slot].copy_(det_refer.reshape(self.det_refer_in[slot].shape), non_blocking=True)
+            for src, dst in zip((feats, det_embed, det_refer), self._ring[slot]):
+                if src.dtype == dst.dtype or not src.is_cuda:
+                    dst.copy_(src.reshape(dst.shape), non_blocking=True)
+                else:  # dtype conversion on device through the library's own cast kernel
+                    ops.add_cast(src.reshape(-1).float().contiguous(), None, dst.dtype, out=dst.view(-1))
             self._ev_copy[slot].record(cs)
 
     def _launch(self, frame: int, rows_pad: int, want_rows: bool) -> dict:
@@ -548,7 +559,8 @@ class TrackEngine:
                want_rows: bool = True, sync_inputs: bool = False) -> int:
         """Enqueue the next frame without waiting for it. feats [n_seq, Lv, C] (GEMM dtype or fp32;
         device or pinned host), det_embed [n_seq, nd, C] fp32, det_refer [n_seq, nd, 4] fp32 logit-space
-        boxes. Unless sync_inputs is set the tensors must be complete when submit() is called (their copy
+        boxes. With a `selector` the three arguments are instead the neck's channels-last maps
+        [n_seq, H_l, W_l, C_l] of the three pyramid levels (GEMM dtype). Unless sync_inputs is set the tensors must be complete when submit() is called (their copy
         runs on the engine's copy stream, which is then not ordered after the caller's stream), and they
         must not be modified until the frame after next has been submitted. Returns the frame index for
         `collect`."""

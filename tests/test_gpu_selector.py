@@ -92,3 +92,40 @@ def test_query_selection_vs_reference_golden(dev, name, precision, tol):
     fin = np.isfinite(obox)
     assert np.array_equal(fin, np.isfinite(got))
     assert rel_rms(got[fin], obox[fin]) < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_frames_from_neck_maps_equal_frames_from_selected_queries(dev, precision):
+    """TrackEngine with the query selection inside the frame graph (inputs = neck maps) must produce exactly the
+    tracks of the decoder-only engine fed with the standalone selector's outputs (same kernels, same order)."""
+    from moyolo_b200.selector import QuerySelector
+    from moyolo_b200.tracker import TrackEngine
+    spec = syn.DecoderSpec()
+    shapes = [list(s) for s in syn.PYRAMIDS["tiny"]]
+    ch, nd, S, n_frames = (256, 512, 512), 48, 2, 5
+    sd = dict(syn.make_decoder_state(spec, 7))
+    sd.update(syn.make_selector_state(spec, ch, 0))
+    sd[f"dec_score_head.{spec.n_layers - 1}.bias"] = sd[f"dec_score_head.{spec.n_layers - 1}.bias"] + 3.0  # some tracks are born
+    dt = torch.bfloat16 if precision == "bf16" else torch.float32
+    Lv = syn.level_sizes(shapes)
+    sel_a = QuerySelector(sd, spec, shapes, ch, dev, precision, nd, S)
+    sel_b = QuerySelector(sd, spec, shapes, ch, dev, precision, nd, S)
+    eng_maps = TrackEngine(sd, spec, shapes, dev, precision, nd, S, selector=sel_a)
+    eng_dec = TrackEngine(sd, spec, shapes, dev, precision, nd, S)
+    base = [m.permute(0, 2, 3, 1).contiguous() for m in syn.make_pyramid_maps(5, S, shapes, ch)]
+    g = torch.Generator().manual_seed(11)
+    born = 0
+    for t in range(n_frames):
+        maps = [(m + 0.05 * t * torch.randn(m.shape, generator=g)).to(dev).to(dt).contiguous() for m in base]
+        feats = torch.zeros(S, Lv, 256, dtype=dt, device=dev)
+        de, dr = torch.zeros(S, nd, 256, device=dev), torch.zeros(S, nd, 4, device=dev)
+        sel_b.run(maps, feats, de, dr)
+        a = eng_maps.step(*maps)
+        a = [{k: v.clone() for k, v in o.items()} for o in a]
+        b = eng_dec.step(feats, de, dr)
+        for s in range(S):
+            for k in ("ids", "boxes", "scores", "labels"):
+                assert torch.equal(a[s][k], b[s][k]), (t, s, k)
+            born += int((a[s]["ids"] >= 0).sum())
+    assert born > 0, "no object was ever tracked"
+    assert torch.equal(eng_maps.track_table(), eng_dec.track_table())
