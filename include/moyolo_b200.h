@@ -226,6 +226,12 @@ int moyolo_track_assign_batched(const float* scores, const float* boxes, int64_t
                                 int n_seq, int64_t max_rows_per_seq, float score_thresh, float filter_thresh,
                                 int miss_tolerance, float iou_thresh, void* workspace, const int32_t* ctrl,
                                 moyolo_stream_t stream);
+/* Second half of the batched update only: the duplicate filter + renumbering (head.py:1155-1196, 1268-1282) on ids
+ * that were already updated (moyolo_frame_assign_compact). It changes nothing but `counters`, so a frame runs it
+ * off its critical path. */
+int moyolo_track_suppress_batched(const float* boxes, int64_t* obj_idxes, int64_t* counters,
+                                  const int32_t* row_offsets, int n_seq, int64_t max_rows_per_seq,
+                                  float iou_thresh, void* workspace, const int32_t* ctrl, moyolo_stream_t stream);
 int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,
                          int32_t* active_index, const void* const* src_host, void* const* dst_host,
                          const int64_t* row_bytes_host, int n_fields, moyolo_stream_t stream);
@@ -244,6 +250,12 @@ int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,
  *   QIM inputs gathered to frame-layout compact buffers c_* (sequence s at row_offsets[s]) and
  *   t_label/t_ids/t_dis written straight to the state arrays. Optional (NULL = skip) QIM operands as `lp_dtype`:
  *   q_qk_lp = c_hs + pos2posemb(c_ref) (qim.py:255,271), q_tgt_lp = c_hs.
+ * moyolo_frame_assign_compact: the ID assignment of RuntimeTrackerBase.update (head.py:1232-1243: in query order
+ *   id==-1 && score>=score_thresh -> id = max_obj_id++ with max_obj_id = counters[2*s]; id>=0 &&
+ *   score<filter_thresh -> disappear_time++, id = -1 at >= miss_tolerance) fused with moyolo_frame_compact on the
+ *   updated ids, one launch. ids_in/dis_in (from frame_assemble) are read-only; the updated values go to
+ *   ids_out/dis_out [rows_pad] (must not alias; padding rows get -1 / 0). counters is NOT modified: follow with
+ *   moyolo_track_suppress_batched (any time before the next frame) for the reference's counter side effects.
  * moyolo_frame_writeback: t_qpos <- new_qpos rows, t_ref <- inverse_sigmoid(c_box), n_tracks <- n_active
  *   (MOTR/models/qim.py:298-300); optional info int32 [n_seq+8] = (n_active | ctrl), the frame summary a host reads.
  * moyolo_frame_emit: the frame's results. frame_rows [rows_pad, 8] fp32 = (id, cx, cy, w, h, score, label,
@@ -274,6 +286,15 @@ int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* row_offsets, 
                          int32_t* t_label, int64_t* t_ids, int64_t* t_dis, const int32_t* ctrl,
                          void* q_qk_lp, void* q_tgt_lp, int lp_dtype, int num_pos_feats, float temperature,
                          moyolo_stream_t stream);
+int moyolo_frame_assign_compact(int n_seq, int C, int cap, int64_t rows_pad, const int32_t* row_offsets,
+                                const float* scores, const int64_t* ids_in, const int64_t* dis_in,
+                                const int64_t* counters, float score_thresh, float filter_thresh,
+                                int miss_tolerance, int64_t* ids_out, int64_t* dis_out, const int32_t* labels,
+                                const float* refer_logit, const float* pos, const float* hs, const float* boxes,
+                                int32_t* n_active, int32_t* active_index, float* c_ref, float* c_pos, float* c_hs,
+                                float* c_box, int32_t* t_label, int64_t* t_ids, int64_t* t_dis, const int32_t* ctrl,
+                                void* q_qk_lp, void* q_tgt_lp, int lp_dtype, int num_pos_feats, float temperature,
+                                moyolo_stream_t stream);
 int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,
                            const float* new_qpos, const float* c_box, float* t_qpos, float* t_ref,
                            int32_t* n_tracks, const int32_t* ctrl, int32_t* info, moyolo_stream_t stream);

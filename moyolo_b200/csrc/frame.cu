@@ -221,6 +221,126 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
   }
 }
 
+// grid = (n_seq, kCompactChunks), 1024 threads. The ID assignment of RuntimeTrackerBase.update
+// (head.py:1232-1243) fused with the active-track compaction: every CTA of a sequence repeats the (cheap,
+// deterministic) assignment scan -- `max_obj_id++` in query order == exclusive prefix count of the new rows; the
+// packed scan carries the count of active rows in its high half -- and then copies the compact rows
+// j = blockIdx.y*32 + warp, ...; CTA y == 0 also writes the updated ids / disappear counters (to separate output
+// arrays: the other CTAs still read the inputs) and the selection. The duplicate filter + renumbering of the
+// reference only changes the ID counters (its filtered copy is dropped, head.py:1268-1283): it runs afterwards,
+// off the critical path, as moyolo_track_suppress_batched.
+__global__ void __launch_bounds__(1024) frame_assign_compact_kernel(
+    int C, int cap, int rows_pad, const int32_t* __restrict__ row_offsets, const float* __restrict__ scores,
+    const int64_t* __restrict__ ids_in, const int64_t* __restrict__ dis_in, const int64_t* __restrict__ counters,
+    float score_thresh, float filter_thresh, int miss_tolerance, int64_t* __restrict__ ids_out,
+    int64_t* __restrict__ dis_out, const int32_t* __restrict__ labels, const float* __restrict__ refer_logit,
+    const float* __restrict__ pos, const float* __restrict__ hs, const float* __restrict__ boxes,
+    int32_t* __restrict__ n_active, int32_t* __restrict__ active_index, float* __restrict__ c_ref,
+    float* __restrict__ c_pos, float* __restrict__ c_hs, float* __restrict__ c_box, int32_t* __restrict__ t_label,
+    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis, const int32_t* __restrict__ ctrl,
+    void* __restrict__ q_qk_lp, void* __restrict__ q_tgt_lp, int lp_bf16, int num_pos_feats, float temperature) {
+  pdl_trigger();
+  __shared__ int s_warp[33];
+  __shared__ int16_t s_sel[kCompactMaxRows];  // row (within the sequence) of the j-th active track
+  __shared__ float s_dimt[256];               // pos2posemb denominators (transformer.py:185-186)
+  for (int i = threadIdx.x; i < num_pos_feats; i += blockDim.x)
+    s_dimt[i] = powf(temperature, static_cast<float>(2 * (i / 2)) / static_cast<float>(num_pos_feats));
+  pdl_wait();
+  if (ctrl != nullptr && ctrl[kCtrlAbort] != 0) return;  // aborted frame: leave the track state untouched
+  const int s = blockIdx.x;
+  const bool first = blockIdx.y == 0;
+  const int off = row_offsets[s];
+  const int n = min(row_offsets[s + 1] - off, kCompactMaxRows);
+  const int64_t max_obj_id = counters[2 * s];
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int begin = min(static_cast<int>(threadIdx.x) * per, n);
+  const int end = min(begin + per, n);
+  // packed per-thread counts: low 16 bits = new objects, high bits = rows that are active after the update
+  int local = 0;
+  for (int i = begin; i < end; ++i) {
+    const int64_t id = ids_in[off + i];
+    const float sc = scores[off + i];
+    const bool is_new = id == -1 && sc >= score_thresh;
+    const bool dies = id >= 0 && sc < filter_thresh && dis_in[off + i] + 1 >= miss_tolerance;
+    const bool alive = is_new || (id >= 0 && !dies);
+    local += (is_new ? 1 : 0) + (alive ? 65536 : 0);
+  }
+  int total;
+  const int rank = block_exclusive_scan_f(local, &total, s_warp);
+  int new_rank = rank & 0xffff, act_rank = rank >> 16;
+  const int n_act = min(total >> 16, cap);
+  for (int i = begin; i < end; ++i) {
+    int64_t id = ids_in[off + i];
+    int64_t dt = dis_in[off + i];
+    const float sc = scores[off + i];
+    if (id == -1 && sc >= score_thresh) {
+      id = max_obj_id + new_rank++;
+    } else if (id >= 0 && sc < filter_thresh) {
+      dt += 1;
+      if (dt >= miss_tolerance) id = -1;
+    }
+    if (first) { ids_out[off + i] = id; dis_out[off + i] = dt; }
+    if (id >= 0) {
+      if (act_rank < cap) {
+        s_sel[act_rank] = static_cast<int16_t>(i);
+        if (first) {
+          active_index[off + act_rank] = i;
+          const int64_t st = static_cast<int64_t>(s) * cap + act_rank;
+          t_label[st] = labels[off + i];
+          t_ids[st] = id;
+          t_dis[st] = dt;
+        }
+      }
+      ++act_rank;
+    }
+  }
+  if (first && threadIdx.x == 0) n_active[s] = n_act;
+  if (first && s == static_cast<int>(gridDim.x) - 1)  // padding rows of the frame: never an object
+    for (int r = row_offsets[s + 1] + threadIdx.x; r < rows_pad; r += blockDim.x) { ids_out[r] = -1; dis_out[r] = 0; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const bool want_q = q_qk_lp != nullptr || q_tgt_lp != nullptr;
+  for (int j = blockIdx.y * nwarps + warp; j < n_act; j += gridDim.y * nwarps) {
+    const int64_t src = off + s_sel[j];
+    const int64_t dst = off + j;  // compact rows keep the frame layout: sequence s starts at row_offsets[s]
+    const float4 rl = *reinterpret_cast<const float4*>(refer_logit + src * 4);
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 pv = *reinterpret_cast<const float4*>(pos + src * C + c);
+      const float4 hv = *reinterpret_cast<const float4*>(hs + src * C + c);
+      *reinterpret_cast<float4*>(c_pos + dst * C + c) = pv;
+      *reinterpret_cast<float4*>(c_hs + dst * C + c) = hv;
+      // QIM operands (qim.py:255, 271): q = k = tgt + pos2posemb(ref_pts), v = tgt
+      if (want_q) {
+        const float h4[4] = {hv.x, hv.y, hv.z, hv.w};
+        float qk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int cc = c + u, coord = cc / num_pos_feats, i = cc % num_pos_feats;
+          const float r = coord == 0 ? rl.x : (coord == 1 ? rl.y : (coord == 2 ? rl.z : rl.w));
+          const float p = r * 6.283185307179586f;
+          const float e = p / s_dimt[i];
+          qk[u] = ((i & 1) ? cosf(e) : sinf(e)) + h4[u];
+        }
+        if (lp_bf16) {
+          if (q_qk_lp)
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(q_qk_lp) + dst * C + c) =
+                make_uint2(float2_to_bf16x2(qk[0], qk[1]), float2_to_bf16x2(qk[2], qk[3]));
+          if (q_tgt_lp)
+            *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(q_tgt_lp) + dst * C + c) =
+                make_uint2(float2_to_bf16x2(h4[0], h4[1]), float2_to_bf16x2(h4[2], h4[3]));
+        } else {
+          if (q_qk_lp) *reinterpret_cast<float4*>(static_cast<float*>(q_qk_lp) + dst * C + c) = make_float4(qk[0], qk[1], qk[2], qk[3]);
+          if (q_tgt_lp) *reinterpret_cast<float4*>(static_cast<float*>(q_tgt_lp) + dst * C + c) = hv;
+        }
+      }
+    }
+    if (lane == 0) {
+      *reinterpret_cast<float4*>(c_ref + dst * 4) = rl;
+      *reinterpret_cast<float4*>(c_box + dst * 4) = *reinterpret_cast<const float4*>(boxes + src * 4);
+    }
+  }
+}
+
 // grid = (n_seq, chunks): t_qpos[s, j] = new_qpos[off_s + j]; t_ref[s, j] = inverse_sigmoid(c_box[off_s + j]).
 __global__ void frame_writeback_kernel(int C, int cap, const int32_t* __restrict__ row_offsets,
                                        const int32_t* __restrict__ n_active, const float* __restrict__ new_qpos,
@@ -354,6 +474,37 @@ extern "C" int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* ro
       c_box, t_label, t_ids, t_dis, ctrl, q_qk_lp, q_tgt_lp, lp_dtype == MOYOLO_BF16 ? 1 : 0, num_pos_feats,
       temperature);
   return check_launch("frame_compact_kernel");
+}
+
+extern "C" int moyolo_frame_assign_compact(int n_seq, int C, int cap, int64_t rows_pad, const int32_t* row_offsets,
+                                           const float* scores, const int64_t* ids_in, const int64_t* dis_in,
+                                           const int64_t* counters, float score_thresh, float filter_thresh,
+                                           int miss_tolerance, int64_t* ids_out, int64_t* dis_out,
+                                           const int32_t* labels, const float* refer_logit, const float* pos,
+                                           const float* hs, const float* boxes, int32_t* n_active,
+                                           int32_t* active_index, float* c_ref, float* c_pos, float* c_hs,
+                                           float* c_box, int32_t* t_label, int64_t* t_ids, int64_t* t_dis,
+                                           const int32_t* ctrl, void* q_qk_lp, void* q_tgt_lp, int lp_dtype,
+                                           int num_pos_feats, float temperature, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(row_offsets && scores && ids_in && dis_in && counters && ids_out && dis_out && labels &&
+                     refer_logit && pos && hs && boxes && n_active && active_index && c_ref && c_pos && c_hs &&
+                     c_box && t_label && t_ids && t_dis,
+                 MOYOLO_ERR_BAD_ARG, "frame_assign_compact: null pointer");
+  MOYOLO_REQUIRE(ids_in != ids_out && dis_in != dis_out, MOYOLO_ERR_BAD_ARG,
+                 "frame_assign_compact: ids/dis outputs must not alias the inputs");
+  MOYOLO_REQUIRE(n_seq > 0 && C > 0 && C % 4 == 0 && cap > 0 && rows_pad > 0, MOYOLO_ERR_BAD_SHAPE,
+                 "frame_assign_compact: bad sizes");
+  MOYOLO_REQUIRE(C == 4 * num_pos_feats && num_pos_feats <= 256, MOYOLO_ERR_BAD_SHAPE,
+                 "frame_assign_compact: C must equal 4*num_pos_feats (<= 1024)");
+  MOYOLO_REQUIRE(aligned16(refer_logit) && aligned16(pos) && aligned16(hs) && aligned16(boxes) && aligned16(c_ref) &&
+                     aligned16(c_pos) && aligned16(c_hs) && aligned16(c_box) && aligned16(q_qk_lp) && aligned16(q_tgt_lp),
+                 MOYOLO_ERR_ALIGNMENT, "frame_assign_compact: row buffers must be 16-byte aligned");
+  launch_k(frame_assign_compact_kernel, dim3(n_seq, kCompactChunks), dim3(1024), 0, static_cast<cudaStream_t>(stream),
+      C, cap, static_cast<int>(rows_pad), row_offsets, scores, ids_in, dis_in, counters, score_thresh, filter_thresh,
+      miss_tolerance, ids_out, dis_out, labels, refer_logit, pos, hs, boxes, n_active, active_index, c_ref, c_pos,
+      c_hs, c_box, t_label, t_ids, t_dis, ctrl, q_qk_lp, q_tgt_lp, lp_dtype == MOYOLO_BF16 ? 1 : 0, num_pos_feats,
+      temperature);
+  return check_launch("frame_assign_compact_kernel");
 }
 
 extern "C" int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
     const float* __restrict__ scores, const float* __restrict__ boxes, int64_t* __restrict__ obj_idxes,
     int64_t* __restrict__ disappear_time, int64_t* __restrict__ counters, int n, float score_thresh,
     float filter_thresh, int miss_tolerance, float iou_thresh, void* workspace,
-    const int32_t* __restrict__ row_offsets, int64_t ws_stride, const int32_t* __restrict__ ctrl) {
+    const int32_t* __restrict__ row_offsets, int64_t ws_stride, const int32_t* __restrict__ ctrl, int do_assign) {
   pdl_trigger();
   pdl_wait();
   __shared__ int s_warp[33];
@@ -105,23 +105,27 @@ __global__ void __launch_bounds__(kTrkThreads) track_assign_kernel(
   const int64_t max_obj_id_pre = counters[1];
 
   // ---- A. ID assignment in query order (head.py:1232-1243) ----
+  // (do_assign == 0: the ids were already updated by frame_assign_compact; only the counters' side effects follow)
   int n_new_local = 0;
-  for (int i = begin; i < end; ++i)
-    n_new_local += (obj_idxes[i] == -1 && scores[i] >= score_thresh) ? 1 : 0;
-  int n_new_total;
-  int new_rank = block_exclusive_scan(n_new_local, &n_new_total, s_warp);
+  if (do_assign)
+    for (int i = begin; i < end; ++i)
+      n_new_local += (obj_idxes[i] == -1 && scores[i] >= score_thresh) ? 1 : 0;
+  int n_new_total = 0;
+  int new_rank = do_assign ? block_exclusive_scan(n_new_local, &n_new_total, s_warp) : 0;
   int n_act_local = 0;
   for (int i = begin; i < end; ++i) {
     int64_t id = obj_idxes[i];
-    const float s = scores[i];
-    if (id == -1 && s >= score_thresh) {
-      id = max_obj_id + new_rank++;
-    } else if (id >= 0 && s < filter_thresh) {
-      const int64_t dt = disappear_time[i] + 1;
-      disappear_time[i] = dt;
-      if (dt >= miss_tolerance) id = -1;
+    if (do_assign) {
+      const float s = scores[i];
+      if (id == -1 && s >= score_thresh) {
+        id = max_obj_id + new_rank++;
+      } else if (id >= 0 && s < filter_thresh) {
+        const int64_t dt = disappear_time[i] + 1;
+        disappear_time[i] = dt;
+        if (dt >= miss_tolerance) id = -1;
+      }
+      obj_idxes[i] = id;
     }
-    obj_idxes[i] = id;
     n_act_local += id >= 0 ? 1 : 0;
   }
   // ---- B. active subset, in order (head.py:1245-1250) ----
@@ -279,7 +283,7 @@ extern "C" int moyolo_track_assign(const float* scores, const float* boxes, int6
   if (n == 0) return MOYOLO_OK;
   launch_k(track_assign_kernel, dim3(1), dim3(kTrkThreads), 0, static_cast<cudaStream_t>(stream), 
       scores, boxes, obj_idxes, disappear_time, counters, static_cast<int>(n), score_thresh, filter_thresh,
-      miss_tolerance, iou_thresh, workspace, nullptr, 0, nullptr);
+      miss_tolerance, iou_thresh, workspace, nullptr, 0, nullptr, 1);
   return check_launch("track_assign_kernel");
 }
 
@@ -294,8 +298,22 @@ extern "C" int moyolo_track_assign_batched(const float* scores, const float* box
                  "track_assign_batched: max_rows_per_seq must be in (0, %d]", kTrkMaxN);
   launch_k(track_assign_kernel, dim3(n_seq), dim3(kTrkThreads), 0, static_cast<cudaStream_t>(stream), 
       scores, boxes, obj_idxes, disappear_time, counters, 0, score_thresh, filter_thresh, miss_tolerance, iou_thresh,
-      workspace, row_offsets, moyolo_track_workspace_bytes(max_rows_per_seq), ctrl);
+      workspace, row_offsets, moyolo_track_workspace_bytes(max_rows_per_seq), ctrl, 1);
   return check_launch("track_assign_kernel(batched)");
+}
+
+extern "C" int moyolo_track_suppress_batched(const float* boxes, int64_t* obj_idxes, int64_t* counters,
+                                             const int32_t* row_offsets, int n_seq, int64_t max_rows_per_seq,
+                                             float iou_thresh, void* workspace, const int32_t* ctrl,
+                                             moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(boxes && obj_idxes && counters && row_offsets && workspace, MOYOLO_ERR_BAD_ARG,
+                 "track_suppress_batched: null pointer");
+  MOYOLO_REQUIRE(n_seq > 0 && max_rows_per_seq > 0 && max_rows_per_seq <= kTrkMaxN, MOYOLO_ERR_BAD_SHAPE,
+                 "track_suppress_batched: max_rows_per_seq must be in (0, %d]", kTrkMaxN);
+  launch_k(track_assign_kernel, dim3(n_seq), dim3(kTrkThreads), 0, static_cast<cudaStream_t>(stream),
+      nullptr, boxes, obj_idxes, nullptr, counters, 0, 0.0f, 0.0f, 0, iou_thresh, workspace, row_offsets,
+      moyolo_track_workspace_bytes(max_rows_per_seq), ctrl, 0);
+  return check_launch("track_assign_kernel(suppress)");
 }
 
 extern "C" int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,

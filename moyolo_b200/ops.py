@@ -386,6 +386,35 @@ def frame_compact(n_seq, C, cap, row_offsets, ids, dis, labels, refer_logit, pos
         _dt(lp) if lp is not None else F32, num_pos_feats, float(temperature), _stream()))
 
 
+def frame_assign_compact(n_seq, C, cap, rows_pad, row_offsets, scores, ids_in, dis_in, counters, ids_out, dis_out,
+                         labels, refer_logit, pos, hs, boxes, n_active, active_index, c_ref, c_pos, c_hs, c_box,
+                         t_label, t_ids, t_dis, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, ctrl=None,
+                         q_qk_lp=None, q_tgt_lp=None, num_pos_feats=64, temperature=10000.0) -> None:
+    """ID assignment (head.py:1232-1243) + active-track compaction in one launch; `counters` is only read
+    (follow with track_suppress_batched)."""
+    lp = q_qk_lp if q_qk_lp is not None else q_tgt_lp
+    _count(1)
+    _lib.check(_lib.lib().moyolo_frame_assign_compact(
+        n_seq, C, cap, rows_pad, row_offsets.data_ptr(), scores.data_ptr(), ids_in.data_ptr(), dis_in.data_ptr(),
+        counters.data_ptr(), float(score_thresh), float(filter_thresh), int(miss_tolerance), ids_out.data_ptr(),
+        dis_out.data_ptr(), labels.data_ptr(), refer_logit.data_ptr(), pos.data_ptr(), hs.data_ptr(), boxes.data_ptr(),
+        n_active.data_ptr(), active_index.data_ptr(), c_ref.data_ptr(), c_pos.data_ptr(), c_hs.data_ptr(),
+        c_box.data_ptr(), t_label.data_ptr(), t_ids.data_ptr(), t_dis.data_ptr(), _ptr(ctrl), _ptr(q_qk_lp),
+        _ptr(q_tgt_lp), _dt(lp) if lp is not None else F32, num_pos_feats, float(temperature), _stream()))
+
+
+def track_suppress_batched(boxes, ids, counters, row_offsets, n_seq: int, max_rows_per_seq: int, workspace,
+                           iou_thresh=0.8, ctrl=None) -> None:
+    """Duplicate filter + renumbering side effects on `counters` (head.py:1155-1196, 1268-1282) for ids that
+    frame_assign_compact already updated."""
+    _cuda(boxes, ids, counters, row_offsets, workspace)
+    assert workspace.numel() * workspace.element_size() >= n_seq * track_workspace_bytes(max_rows_per_seq)
+    _count(1)
+    _lib.check(_lib.lib().moyolo_track_suppress_batched(
+        boxes.data_ptr(), ids.data_ptr(), counters.data_ptr(), row_offsets.data_ptr(), n_seq, max_rows_per_seq,
+        float(iou_thresh), workspace.data_ptr(), _ptr(ctrl), _stream()))
+
+
 def frame_writeback(n_seq, C, cap, row_offsets, n_active, new_qpos, c_box, t_qpos, t_ref, n_tracks, ctrl=None,
                     info=None) -> None:
     _count(1)

@@ -99,7 +99,9 @@ class FrameWorkspace:
         self.x = z(R, C, **f32)              # residual stream
         self.refer_logit = z(R, 4, **f32)
         self.pos = z(R, C, **f32)
-        self.ids = z(R, dtype=torch.int64, device=dev)
+        self.ids0 = z(R, dtype=torch.int64, device=dev)    # as assembled (previous frame's ids | -1)
+        self.dis0 = z(R, dtype=torch.int64, device=dev)
+        self.ids = z(R, dtype=torch.int64, device=dev)     # after this frame's ID assignment
         self.dis = z(R, dtype=torch.int64, device=dev)
         self.ro = z(S + 1, dtype=torch.int32, device=dev)
         self.refer = [z(R, 4, **f32) for _ in range(nl + 1)]   # sigmoid(refer) and the refined boxes per layer
@@ -296,7 +298,7 @@ class TrackEngine:
             self.selector.select(self.feats_in[p.slot], self.det_embed_in[p.slot], self.det_refer_in[p.slot])
         ops.frame_assemble(S, nd, C, self.cap, self.n_tracks, self.t_ref, self.t_qpos, self.t_label, self.t_ids,
                            self.t_dis, W.class_embed, self.det_embed_in[p.slot], self.det_refer_in[p.slot], ws.x,
-                           ws.refer_logit, ws.pos, ws.ids, ws.dis, ws.ro, R, ctrl=self.ctrl,
+                           ws.refer_logit, ws.pos, ws.ids0, ws.dis0, ws.ro, R, ctrl=self.ctrl,
                            refer_sig=ws.refer[0],                            # transformer.py:690
                            x_lp=None if dt == torch.float32 else ws.x_lp, xq_lp=ws.xq_lp)
         # host-side bound of the device offsets, used for grid sizing only: sum_s ceil(N_s/16) <= R/16 + S
@@ -325,21 +327,27 @@ class TrackEngine:
         boxes = ws.refer[n_l]
         ops.score_head(ws.x_lp, W.score_w, W.score_b, out=(ws.logits, ws.scores, ws.labels))
         st, ft, mt, it = self.thr
-        ops.track_assign_batched(ws.scores, boxes, ws.ids, ws.dis, self.counters, ws.ro, S, ws.rows_per_seq, ws.assign_ws, st, ft,
-                                 mt, it, ctrl=self.ctrl)
-        ops.frame_compact(S, C, self.cap, ws.ro, ws.ids, ws.dis, ws.labels, ws.refer_logit, ws.pos, ws.x, boxes,
-                          ws.n_active, ws.active_index, ws.c_ref, ws.c_pos, ws.c_hs, ws.c_box, self.t_label,
-                          self.t_ids, self.t_dis, ctrl=self.ctrl, q_qk_lp=ws.q_qk_lp,            # qim.py:255, 271
-                          q_tgt_lp=None if dt == torch.float32 else ws.q_tgt_lp)
-        # the frame's result rows / track-table append are not needed by the QIM update: side branch
+        # ID assignment (head.py:1232-1243) + active-track selection/compaction (qim.py:184-187) in one launch
+        ops.frame_assign_compact(S, C, self.cap, R, ws.ro, ws.scores, ws.ids0, ws.dis0, self.counters, ws.ids, ws.dis,
+                                 ws.labels, ws.refer_logit, ws.pos, ws.x, boxes, ws.n_active, ws.active_index,
+                                 ws.c_ref, ws.c_pos, ws.c_hs, ws.c_box, self.t_label, self.t_ids, self.t_dis, st, ft, mt,
+                                 ctrl=self.ctrl, q_qk_lp=ws.q_qk_lp,                                 # qim.py:255, 271
+                                 q_tgt_lp=None if dt == torch.float32 else ws.q_tgt_lp)
+
+        def side():
+            # neither the duplicate filter (it only moves the ID counters, head.py:1268-1283) nor the frame's result
+            # rows / track-table append are needed by the QIM update
+            ops.track_suppress_batched(boxes, ws.ids, self.counters, ws.ro, S, ws.rows_per_seq, ws.assign_ws, it,
+                                       ctrl=self.ctrl)
+            ops.frame_emit(S, R, ws.ro, ws.ids, boxes, ws.scores, ws.labels, ws.n_active, ws.active_index,
+                           self.seq_ids, ws.frame_rows, self.table, self.ctrl)
+
         if fork:
             self._s_box.wait_stream(cur)
             with torch.cuda.stream(self._s_box):
-                ops.frame_emit(S, R, ws.ro, ws.ids, boxes, ws.scores, ws.labels, ws.n_active, ws.active_index,
-                               self.seq_ids, ws.frame_rows, self.table, self.ctrl)
+                side()
         else:
-            ops.frame_emit(S, R, ws.ro, ws.ids, boxes, ws.scores, ws.labels, ws.n_active, ws.active_index,
-                           self.seq_ids, ws.frame_rows, self.table, self.ctrl)
+            side()
         self._qim_update(ws, ro_host)
         # write-back also stores what the host reads back after the frame: [n_active | ctrl]
         ops.frame_writeback(S, C, self.cap, ws.ro, ws.n_active, ws.q_new, ws.c_box, self.t_qpos, self.t_ref,

@@ -455,3 +455,82 @@ def test_pipelined_submit_equals_synchronous_steps(dev):
         want[:, 0] = torch.where(ref_table[:, 0] == 0, torch.tensor(5.0), torch.tensor(9.0))
         assert torch.equal(table, want), margin
         assert ref.n_tracks_host() == eng.n_tracks_host()
+
+
+def test_frame_assign_compact_equals_two_step(dev):
+    """moyolo_frame_assign_compact + moyolo_track_suppress_batched (the frame path: ID assignment fused with the
+    compaction, counters updated off the critical path) against moyolo_track_assign_batched +
+    moyolo_frame_compact, which test_track_assign_bit_exact pins to the reference: every output bit-identical,
+    on ragged lock-step sequences including one with no active row and one that overflows `cap`."""
+    m, ops, syn, mg, tp = _mods()
+    g = torch.Generator().manual_seed(11)
+    C, cap, S = 256, 48, 4
+    ns = [37, 300, 1, 420]
+    R = 832
+    ro_host = [0]
+    for n in ns:
+        ro_host.append(ro_host[-1] + n)
+    ro = torch.tensor(ro_host, dtype=torch.int32, device=dev)
+    scores = torch.rand(R, generator=g)
+    scores[ro_host[2]:ro_host[3]] = 0.1                       # sequence 2: nothing becomes active
+    ids0 = torch.full((R,), -1, dtype=torch.int64)
+    dis0 = torch.zeros(R, dtype=torch.int64)
+    for s, n in enumerate(ns):                                # a carried prefix with ids and disappear counters
+        k = n // 3 if s != 2 else 0
+        ids0[ro_host[s]:ro_host[s] + k] = torch.randperm(100, generator=g)[:k] if k <= 100 else torch.arange(k)
+        dis0[ro_host[s]:ro_host[s] + k] = torch.randint(0, 6, (k,), generator=g)
+    boxes = torch.rand(R, 4, generator=g) * 0.5
+    boxes[5] = boxes[4]                                       # exact duplicates exercise the IoU filter
+    boxes[ro_host[1] + 7] = boxes[ro_host[1] + 3]
+    labels = torch.randint(0, 5, (R,), generator=g, dtype=torch.int32)
+    refer_logit, pos, hs = torch.randn(R, 4, generator=g), torch.randn(R, C, generator=g), torch.randn(R, C, generator=g)
+    counters0 = torch.tensor([[100, 99], [7, 6], [0, 0], [1000, 999]], dtype=torch.int64)
+    to = lambda *ts: [t.to(dev) for t in ts]  # noqa: E731
+    scores, boxes, labels, refer_logit, pos, hs = to(scores, boxes, labels, refer_logit, pos, hs)
+    z = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+
+    def outputs():
+        return dict(n_active=z(S, dtype=torch.int32), active_index=z(R, dtype=torch.int32), c_ref=z(R, 4), c_pos=z(R, C),
+                    c_hs=z(R, C), c_box=z(R, 4), t_label=z(S, cap, dtype=torch.int32), t_ids=z(S, cap, dtype=torch.int64),
+                    t_dis=z(S, cap, dtype=torch.int64), q_qk=z(R, C, dtype=torch.bfloat16), q_tgt=z(R, C, dtype=torch.bfloat16))
+
+    aws = torch.zeros(S * ops.track_workspace_bytes(512), dtype=torch.uint8, device=dev)
+    # two-step path (in place)
+    a = outputs()
+    ids_a, dis_a, cnt_a = ids0.to(dev), dis0.to(dev), counters0.to(dev)
+    ops.track_assign_batched(scores, boxes, ids_a, dis_a, cnt_a, ro, S, 512, aws)
+    ops.frame_compact(S, C, cap, ro, ids_a, dis_a, labels, refer_logit, pos, hs, boxes, a["n_active"], a["active_index"],
+                      a["c_ref"], a["c_pos"], a["c_hs"], a["c_box"], a["t_label"], a["t_ids"], a["t_dis"],
+                      q_qk_lp=a["q_qk"], q_tgt_lp=a["q_tgt"])
+    # fused path
+    b = outputs()
+    ids_in, dis_in, cnt_b = ids0.to(dev), dis0.to(dev), counters0.to(dev)
+    ids_b, dis_b = z(R, dtype=torch.int64), z(R, dtype=torch.int64)
+    ops.frame_assign_compact(S, C, cap, R, ro, scores, ids_in, dis_in, cnt_b, ids_b, dis_b, labels, refer_logit, pos, hs,
+                             boxes, b["n_active"], b["active_index"], b["c_ref"], b["c_pos"], b["c_hs"], b["c_box"],
+                             b["t_label"], b["t_ids"], b["t_dis"], q_qk_lp=b["q_qk"], q_tgt_lp=b["q_tgt"])
+    assert torch.equal(cnt_b, counters0.to(dev)), "frame_assign_compact must not touch the counters"
+    ops.track_suppress_batched(boxes, ids_b, cnt_b, ro, S, 512, aws)
+    torch.cuda.synchronize()
+    n_rows = ro_host[-1]
+    assert torch.equal(ids_a[:n_rows], ids_b[:n_rows]) and torch.equal(dis_a[:n_rows], dis_b[:n_rows])
+    assert bool((ids_b[n_rows:] == -1).all()) and bool((dis_b[n_rows:] == 0).all())
+    assert torch.equal(cnt_a, cnt_b), (cnt_a.tolist(), cnt_b.tolist())
+    na = a["n_active"].tolist()
+    assert na == b["n_active"].tolist() and na[2] == 0 and na[3] == cap, na
+    for s in range(S):
+        lo, k = ro_host[s], na[s]
+        for key in ("active_index", "c_ref", "c_pos", "c_hs", "c_box", "q_qk", "q_tgt"):
+            assert torch.equal(a[key][lo:lo + k], b[key][lo:lo + k]), (s, key)
+        for key in ("t_label", "t_ids", "t_dis"):
+            assert torch.equal(a[key][s, :k], b[key][s, :k]), (s, key)
+    # and the integer logic against the numpy restatement of RuntimeTrackerBase.update
+    from oracle.tracker_port import TrackerPort
+    for s in range(S):
+        port = TrackerPort()
+        port.max_obj_id, port.max_obj_id_pre = int(counters0[s, 0]), int(counters0[s, 1])
+        lo, hi = ro_host[s], ro_host[s + 1]
+        ids_p, dis_p = ids0[lo:hi].numpy().copy(), dis0[lo:hi].numpy().copy()
+        port.update(scores[lo:hi].cpu().numpy(), boxes[lo:hi].cpu().numpy(), ids_p, dis_p)
+        assert np.array_equal(ids_p, ids_b[lo:hi].cpu().numpy()) and np.array_equal(dis_p, dis_b[lo:hi].cpu().numpy()), s
+        assert [port.max_obj_id, port.max_obj_id_pre] == cnt_b[s].tolist(), s
