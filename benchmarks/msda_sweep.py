@@ -96,6 +96,15 @@ def main():
                             rec["refcuda_max_abs_diff"] = err
                             rec["refcuda_warm_us"] = round(time_warm(rk), 2)
                             rec["refcuda_cold_us"] = round(time_cold(rk), 2)
+                        # backward: ours vs the reference's col2im kernel, both incl. the zero-fill
+                        go = torch.randn(B, Q, C, generator=g).to(dev)
+                        bw = lambda: ops.msda_sampled_backward(v4, shapes, loc, w, go)  # noqa: E731
+                        rec["bwd_warm_us"] = round(time_warm(bw, n=5), 2)
+                        if ref_cuda.available():
+                            rbw = lambda: ref_cuda.msda_col2im(v4, shapes, loc, w, go)  # noqa: E731
+                            rec["refcuda_bwd_warm_us"] = round(time_warm(rbw, n=5), 2)
+                            rec["refcuda_bwd_max_rel_diff"] = max(
+                                float((x - y).abs().max() / (y.pow(2).mean().sqrt() + 1e-30)) for x, y in zip(bw(), rbw()))
                         if B * Q <= 4800:
                             pt = lambda: tp.msda_core_gridsample(v4, shapes, loc, w)  # noqa: E731
                             rec["torch_gridsample_warm_us"] = round(time_warm(pt, n=3, reps=3), 2)

@@ -13,6 +13,8 @@
  *         MOTR/models/ops/src/vision.cpp:13-16, MOTR/models/ops/src/ms_deform_attn.h:20-40,
  *         MOTR/models/ops/src/cuda/ms_deform_attn_cuda.cu:20-80 (the legacy FFI), and the
  *         Python core `multi_scale_deformable_attn_pytorch`, ultralytics/nn/modules/utils.py:41-78
+ *   - moyolo_msda_sampled_backward <-  pybind `ms_deform_attn_backward`, MOTR/models/ops/src/vision.cpp:15,
+ *         MOTR/models/ops/src/cuda/ms_deform_attn_cuda.cu:83-153
  *   - moyolo_msda_fused_forward    <-  ultralytics/nn/modules/transformer.py:268-285
  *         (softmax over L*P, sampling-location arithmetic, grid_sample gather, weighted sum)
  *   - moyolo_linear                <-  nn.Linear call sites transformer.py:264,268,269,286
@@ -97,6 +99,20 @@ int moyolo_msda_sampled_forward(const void* value, int value_dtype, int64_t valu
                                 int n_points, const void* loc, const void* weights, int aux_dtype,
                                 int64_t rows, const int32_t* row_offsets, void* out,
                                 int64_t out_row_stride, moyolo_stream_t stream);
+
+/* Backward of the pre-normalised mode: replaces pybind `ms_deform_attn_backward`
+ * (MOTR/models/ops/src/vision.cpp:15, ms_deform_attn.h:42-61, cuda/ms_deform_attn_cuda.cu:83-153, kernels
+ * cuda/ms_deform_im2col_cuda.cuh:88-159, 301-920) and the autograd of multi_scale_deformable_attn_pytorch.
+ *   grad_out     [R, n_heads*head_dim] (row stride `grad_out_row_stride` elements),
+ *   grad_value   [B, Lv, n_heads, head_dim] contiguous, ACCUMULATED into (the caller zero-fills it),
+ *   grad_loc     [R, n_heads, n_levels, n_points, 2], grad_weights [R, n_heads, n_levels, n_points] (overwritten).
+ * Gradients, loc and weights are fp32 for fp32 / bf16 `value` and fp64 for fp64 `value` (`aux_dtype`). */
+int moyolo_msda_sampled_backward(const void* value, int value_dtype, int64_t value_batch_stride,
+                                 int64_t value_pos_stride, const int32_t* shapes_hw_host, int n_levels,
+                                 int batch, int64_t len_v, int n_heads, int head_dim, int n_points,
+                                 const void* loc, const void* weights, int aux_dtype, const void* grad_out,
+                                 int64_t grad_out_row_stride, int64_t rows, const int32_t* row_offsets,
+                                 void* grad_value, void* grad_loc, void* grad_weights, moyolo_stream_t stream);
 
 /* Fused mode (transformer.py:268-285): raw Linear outputs in, no intermediate tensors.
  *   offsets [R, n_heads, n_levels, n_points, 2] fp32, row stride `offsets_row_stride` elements,

@@ -35,6 +35,8 @@ SIGNATURES = {
     "moyolo_last_error": (C.c_char_p, []),
     "moyolo_device_supported": (_i, []),
     "moyolo_msda_sampled_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _p, _i, _l, _p, _p, _l, _p]),
+    "moyolo_msda_sampled_backward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _p, _i, _p, _l, _l, _p, _p,
+                                          _p, _p, _p]),
     "moyolo_msda_fused_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _l, _p, _i, _i, _i,
                                        _l, _p, _p, _l, _p]),
     "moyolo_linear": (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _i, _p]),

@@ -40,10 +40,49 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return ops.msda_sampled(value, shapes, sampling_loc, attn_weight)
 
 
+def _check_legacy(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, extra=()):
+    for name, t in (("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), *extra):
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")  # ms_deform_attn_cuda.cu:28-32, 92-97
+        if not t.is_cuda:
+            raise RuntimeError("Not implemented on the CPU" if name == "value" else
+                               f"{name} must be a CUDA tensor")  # ms_deform_attn.h:36,57, .cu:34-38, 99-104
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                             im2col_step):
-    raise NotImplementedError("moyolo_b200 implements the inference (forward) path only; "
-                              "ms_deform_attn_backward is SURVEY.md §8(f4)")
+    """-> [grad_value, grad_sampling_loc, grad_attn_weight], each of its input's shape and dtype
+    (MOTR/models/ops/src/cuda/ms_deform_attn_cuda.cu:83-153)."""
+    _check_legacy(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, (("grad_output", grad_output),))
+    batch = value.shape[0]
+    step = min(batch, int(im2col_step))
+    if step <= 0 or batch % step != 0:
+        raise RuntimeError(f"batch({batch}) must divide im2col_step({step})")  # .cu:116-118
+    gv, gl, gw = ops.msda_sampled_backward(value, spatial_shapes.tolist(), sampling_loc, attn_weight, grad_output)
+    return [gv.to(value.dtype), gl.to(sampling_loc.dtype), gw.to(attn_weight.dtype)]
+
+
+class MSDeformAttnFunction(torch.autograd.Function):
+    """Same call signature as the reference's autograd function
+    (MOTR/models/ops/functions/ms_deform_attn_func.py:24-41), forward and backward in libmoyolo_b200."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step):
+        ctx.im2col_step = im2col_step
+        output = ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                                        attention_weights, im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, start, loc, aw = ctx.saved_tensors
+        gv, gl, gw = ms_deform_attn_backward(value, shapes, start, loc, aw, grad_output.contiguous(), ctx.im2col_step)
+        return gv, None, None, gl, gw, None
 
 
 def install(name: str = "MultiScaleDeformableAttention") -> None:

@@ -84,6 +84,38 @@ def msda_sampled(value: torch.Tensor, shapes, loc: torch.Tensor, weights: torch.
     return out
 
 
+def msda_sampled_backward(value: torch.Tensor, shapes, loc: torch.Tensor, weights: torch.Tensor,
+                          grad_out: torch.Tensor, row_offsets: Optional[torch.Tensor] = None):
+    """Gradients of msda_sampled w.r.t. (value, loc, weights) -- the legacy ms_deform_attn_backward
+    (MOTR/models/ops/src/cuda/ms_deform_attn_cuda.cu:83-153). grad_out [B, Q, H*Dh].
+    Returns (grad_value [B, Lv, H, Dh], grad_loc like loc, grad_weights like weights); fp32 for fp32 / bf16
+    value, fp64 for fp64 value."""
+    _cuda(value, loc, weights, grad_out)
+    B, Lv, H, Dh = value.shape
+    if value.stride(3) != 1 or value.stride(2) != Dh:
+        value = value.contiguous()
+    gdt = torch.float64 if value.dtype == torch.float64 else torch.float32
+    loc, weights = loc.contiguous().to(gdt), weights.contiguous().to(gdt)
+    _, Q, _, L, P, _ = loc.shape
+    arr, n_levels = _shapes_arr(shapes)
+    if n_levels != L:
+        raise ValueError(f"value_shapes has {n_levels} levels but sampling locations have {L}")
+    grad_out = grad_out.reshape(B * Q, H * Dh).to(gdt)
+    if grad_out.stride(1) != 1:
+        grad_out = grad_out.contiguous()
+    grad_value = torch.zeros(B, Lv, H, Dh, dtype=gdt, device=value.device)
+    grad_loc = torch.zeros_like(loc)
+    grad_w = torch.zeros_like(weights)
+    if B * Q == 0:
+        return grad_value, grad_loc, grad_w
+    _count(1)
+    _lib.check(_lib.lib().moyolo_msda_sampled_backward(
+        value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, H, Dh, P, loc.data_ptr(),
+        weights.data_ptr(), _dt(loc), grad_out.data_ptr(), grad_out.stride(0), B * Q, _ptr(row_offsets),
+        grad_value.data_ptr(), grad_loc.data_ptr(), grad_w.data_ptr(), _stream()))
+    return grad_value, grad_loc, grad_w
+
+
 def msda_fused(value: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch.Tensor, refer: torch.Tensor,
                n_heads: int, n_points: int, batch: int, softmax_mode: int = _lib.SOFTMAX,
                row_offsets: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -169,6 +169,23 @@ def make_core_inputs(seed: int, B: int, Q: int, n_heads: int, head_dim: int, sha
     return value, loc, w
 
 
+def make_core_grad_inputs(seed: int, B: int, Q: int, n_heads: int, head_dim: int, shapes, n_points: int,
+                          outside_frac: float = 0.1):
+    """Inputs of the core op's backward: as make_core_inputs but WITHOUT the exact-border / pixel-centre
+    specials (the location gradient is discontinuous where a pixel coordinate is an integer, so two correct fp32
+    implementations may legitimately pick different one-sided derivatives there) plus the output gradient."""
+    g = _gen(seed)
+    Lv, L = level_sizes(shapes), len(shapes)
+    value = torch.randn(B, Lv, n_heads, head_dim, generator=g)
+    loc = torch.rand(B, Q, n_heads, L, n_points, 2, generator=g)
+    far = torch.rand(B, Q, n_heads, L, n_points, 1, generator=g) < outside_frac
+    loc = torch.where(far, loc * 1.6 - 0.3, loc)
+    w = torch.rand(B, Q, n_heads, L, n_points, generator=g) + 1e-5
+    w = w / w.sum((-1, -2), keepdim=True)
+    grad_out = torch.randn(B, Q, n_heads * head_dim, generator=g)
+    return value, loc, w, grad_out
+
+
 def make_module_inputs(seed: int, B: int, Q: int, d_model: int, shapes, ref_dim: int = 4, ref_levels: int = 1):
     """Inputs of MSDeformAttn.forward / a decoder layer: query, refer_bbox (sigmoid space), feats, query_pos."""
     g = _gen(seed)

@@ -6,6 +6,7 @@ compute); each file stores the reference outputs, the seeds/config and a checksu
 a consumer can detect RNG drift. Reference entry points executed:
   kat0      MOTR/models/ops/functions/ms_deform_attn_func.py:44-64 on the case of MOTR/models/ops/test.py:21-60
   core_*    ultralytics/nn/modules/utils.py:41-78   multi_scale_deformable_attn_pytorch
+  core_grad_*  torch.autograd through the same function (the gradients ms_deform_attn_backward returns)
   msda_*    ultralytics/nn/modules/transformer.py:193-287  MSDeformAttn
   layer_*   transformer.py:394-450 DeformableTransformerDecoderLayer, :515-652 MOTRDecoderLayer
   decoder_* transformer.py:453-510 DeformableTransformerDecoder, :663-728 MOTRTransformerDecoder
@@ -92,6 +93,28 @@ def gen_core(U):
         o64 = U.multi_scale_deformable_attn_pytorch(value.double(), c["shapes"], loc.double(), w.double())
         save(c["name"], dict(c, shapes=[list(s) for s in c["shapes"]], checksum=syn.checksum(value, loc, w)),
              out_f32=o32, out_f64=o64)
+
+
+GRAD_CASES = [
+    dict(name="core_grad_a", seed=51, B=2, Q=24, H=8, D=32, shapes=syn.PYRAMIDS["tiny"], P=4),
+    dict(name="core_grad_b", seed=52, B=1, Q=19, H=4, D=64, shapes=[(5, 7), (3, 2)], P=8),
+    dict(name="core_grad_c", seed=53, B=3, Q=9, H=2, D=6, shapes=[(6, 4), (3, 2), (5, 7), (1, 1)], P=2),
+]
+
+
+def gen_core_grad(U):
+    """Autograd of the reference's multi_scale_deformable_attn_pytorch (what MSDeformAttnFunction.backward /
+    ms_deform_attn_backward compute, MOTR/models/ops/functions/ms_deform_attn_func.py:33-41), fp32 and fp64."""
+    for c in GRAD_CASES:
+        value, loc, w, go = syn.make_core_grad_inputs(c["seed"], c["B"], c["Q"], c["H"], c["D"], c["shapes"], c["P"])
+        out = {}
+        for tag, dt in (("f32", torch.float32), ("f64", torch.float64)):
+            v, l, a = (t.to(dt).clone().requires_grad_(True) for t in (value, loc, w))
+            o = U.multi_scale_deformable_attn_pytorch(v, c["shapes"], l, a)
+            o.backward(go.to(dt))
+            out.update({f"grad_value_{tag}": v.grad, f"grad_loc_{tag}": l.grad, f"grad_w_{tag}": a.grad})
+        save(c["name"], dict(c, shapes=[list(s) for s in c["shapes"]], checksum=syn.checksum(value, loc, w, go),
+                             source="autograd of ultralytics/nn/modules/utils.py:41-78"), **out)
 
 
 def gen_posemb(T, U):
@@ -266,6 +289,7 @@ def main():
     T, U = ref_loader.load_decoder_modules()
     print("decoder-side goldens (light loader)")
     gen_core(U)
+    gen_core_grad(U)
     gen_posemb(T, U)
     gen_msda(T)
     gen_layers(T)

@@ -52,10 +52,10 @@ def test_kat0_legacy_ffi(dev):
         else:
             assert np.allclose(out, ref, rtol=1e-2, atol=1e-3)
             assert rel_rms(out, ref) < FP32_TOL
-    with pytest.raises(NotImplementedError):
-        msda_ext.ms_deform_attn_backward(v, shapes, lsi, loc, aw, out, 2)
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         msda_ext.ms_deform_attn_forward(v.cpu(), shapes, lsi, loc, aw, 2)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        msda_ext.ms_deform_attn_backward(v.cpu(), shapes, lsi, loc, aw, torch.from_numpy(out).to(dev), 2)
 
 
 def test_core_golden(dev):
@@ -534,3 +534,84 @@ def test_frame_assign_compact_equals_two_step(dev):
         port.update(scores[lo:hi].cpu().numpy(), boxes[lo:hi].cpu().numpy(), ids_p, dis_p)
         assert np.array_equal(ids_p, ids_b[lo:hi].cpu().numpy()) and np.array_equal(dis_p, dis_b[lo:hi].cpu().numpy()), s
         assert [port.max_obj_id, port.max_obj_id_pre] == cnt_b[s].tolist(), s
+
+
+# ------------------------------------------------------------------ f4: backward of the gather
+def _legacy_shapes(shapes, dev):
+    t = torch.as_tensor([list(s) for s in shapes], dtype=torch.long, device=dev)
+    return t, torch.cat((t.new_zeros((1,)), t.prod(1).cumsum(0)[:-1]))
+
+
+def test_backward_vs_reference_autograd_golden(dev):
+    """ms_deform_attn_backward through the legacy FFI stand-in against torch.autograd of the reference's
+    multi_scale_deformable_attn_pytorch (tests/golden/core_grad_*.npz): fp32 within 1e-4*rms, fp64 within 1e-10;
+    D=32 / D=64 run the warp kernel, D=6 and fp64 the generic one."""
+    m, ops, syn, mg, tp = _mods()
+    from moyolo_b200 import msda_ext
+    for c in mg.GRAD_CASES:
+        meta, g = load_golden(c["name"])
+        value, loc, w, go = syn.make_core_grad_inputs(c["seed"], c["B"], c["Q"], c["H"], c["D"], c["shapes"], c["P"])
+        assert abs(syn.checksum(value, loc, w, go) - meta["checksum"]) < 1e-6 * max(1.0, abs(meta["checksum"]))
+        shapes, lsi = _legacy_shapes(c["shapes"], dev)
+        for tag, dt, tol in (("f32", torch.float32, FP32_TOL), ("f64", torch.float64, 1e-10)):
+            gv, gl, gw = msda_ext.ms_deform_attn_backward(value.to(dev, dt), shapes, lsi, loc.to(dev, dt), w.to(dev, dt),
+                                                          go.to(dev, dt), 64)
+            assert gv.dtype == dt and gv.shape == value.shape and gl.shape == loc.shape and gw.shape == w.shape
+            for name, t in (("grad_value", gv), ("grad_loc", gl), ("grad_w", gw)):
+                assert rel_rms(t.cpu().numpy(), g[f"{name}_{tag}"]) < tol, (c["name"], tag, name)
+
+
+@pytest.mark.parametrize("B,Q,name", [(1, 300, "C1"), (2, 357, "MOT17")])
+def test_backward_vs_c_oracle_full_size(dev, B, Q, name):
+    """Warp kernel (fp32 and bf16 value) against the plain-C restatement of the col2im arithmetic at the
+    frame's real sizes; plus a size-independent property: the three gradients are linear in grad_out."""
+    m, ops, syn, mg, tp = _mods()
+    from oracle import c_core
+    shapes = [list(s) for s in syn.PYRAMIDS[name]]
+    value, loc, w, go = syn.make_core_grad_inputs(100 + Q, B, Q, 8, 32, shapes, 4)
+    ref = c_core.msda_core_backward(value.numpy(), shapes, loc.numpy(), w.numpy(), go.numpy())
+    v, l, a, g = value.to(dev), loc.to(dev), w.to(dev), go.to(dev)
+    got = ops.msda_sampled_backward(v, shapes, l, a, g)
+    for nm, t, r in zip(("grad_value", "grad_loc", "grad_w"), got, ref):
+        assert rel_rms(t.cpu().numpy(), r) < FP32_TOL, (name, nm)
+    got_bf = ops.msda_sampled_backward(v.to(torch.bfloat16), shapes, l, a, g)
+    ref_bf = c_core.msda_core_backward(value.to(torch.bfloat16).float().numpy(), shapes, loc.numpy(), w.numpy(), go.numpy())
+    for nm, t, r in zip(("grad_value", "grad_loc", "grad_w"), got_bf, ref_bf):
+        assert t.dtype == torch.float32 and rel_rms(t.cpu().numpy(), r) < FP32_TOL, (name, "bf16 value", nm)
+    got2 = ops.msda_sampled_backward(v, shapes, l, a, -2.0 * g)
+    for t, t2 in zip(got, got2):
+        assert rel_rms(t2.cpu().numpy(), -2.0 * t.cpu().numpy()) < 1e-5
+
+
+def test_backward_gradcheck_like_reference_test(dev):
+    """The reference's own gradient test (MOTR/models/ops/test.py:63-79): torch.autograd.gradcheck in double
+    on MSDeformAttnFunction with its sizes (N=1, M=2, L=2, P=2, Lq=2), channels 30 and 32 here."""
+    from moyolo_b200.msda_ext import MSDeformAttnFunction
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.long, device=dev)
+    lsi = torch.cat((shapes.new_zeros((1,)), shapes.prod(1).cumsum(0)[:-1]))
+    S = int(shapes.prod(1).sum())
+    torch.manual_seed(3)
+    for channels in (30, 32):
+        value = (torch.rand(N, S, M, channels, device=dev) * 0.01).double().requires_grad_(True)
+        loc = torch.rand(N, Lq, M, L, P, 2, device=dev).double().requires_grad_(True)
+        aw = torch.rand(N, Lq, M, L, P, device=dev) + 1e-5
+        aw = (aw / aw.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
+        assert torch.autograd.gradcheck(MSDeformAttnFunction.apply, (value, shapes, lsi, loc, aw, 2))
+
+
+def test_backward_vs_reference_cuda_kernel(dev):
+    """Our backward against the REFERENCE's own col2im kernel (ms_deform_im2col_cuda.cuh:956-1130) compiled for
+    sm_100a into oracle/_ref (both accumulate grad_value with atomics in arbitrary order -> tolerance, not bits)."""
+    from oracle import ref_cuda
+    if not ref_cuda.available() or not hasattr(__import__("ctypes").CDLL(str(ref_cuda._SO)), "ref_msda_col2im_f32"):
+        pytest.skip("oracle/_ref/libmsda_ref_cuda.so (with the backward wrapper) not built")
+    m, ops, syn, mg, tp = _mods()
+    for name, B, Q in (("tiny", 2, 50), ("MOT17", 1, 357)):
+        shapes = [list(s) for s in syn.PYRAMIDS[name]]
+        value, loc, w, go = syn.make_core_grad_inputs(7 + Q, B, Q, 8, 32, shapes, 4)
+        v, l, a, g = value.to(dev), loc.to(dev), w.to(dev), go.to(dev)
+        ref = ref_cuda.msda_col2im(v, shapes, l, a, g)
+        got = ops.msda_sampled_backward(v, shapes, l, a, g)
+        for nm, t, r in zip(("grad_value", "grad_loc", "grad_w"), got, ref):
+            assert rel_rms(t.cpu().numpy(), r.cpu().numpy()) < FP32_TOL, (name, nm)

@@ -48,6 +48,21 @@ def test_core_restatements(case):
     assert rel_rms(o64, g["out_f64"]) < 1e-12
 
 
+@pytest.mark.parametrize("case", mg.GRAD_CASES, ids=lambda c: c["name"])
+def test_core_backward_restatement(case):
+    """oracle/msda_core.c backward (col2im arithmetic, ms_deform_im2col_cuda.cuh:88-159) against
+    torch.autograd of the reference's multi_scale_deformable_attn_pytorch."""
+    meta, g = load_golden(case["name"])
+    value, loc, w, go = syn.make_core_grad_inputs(case["seed"], case["B"], case["Q"], case["H"], case["D"],
+                                                  case["shapes"], case["P"])
+    assert abs(syn.checksum(value, loc, w, go) - meta["checksum"]) < 1e-6 * max(1.0, abs(meta["checksum"]))
+    for tag, dt, tol in (("f32", np.float32, FP32_TOL), ("f64", np.float64, 1e-12)):
+        got = c_core.msda_core_backward(value.numpy().astype(dt), meta["shapes"], loc.numpy().astype(dt),
+                                        w.numpy().astype(dt), go.numpy().astype(dt))
+        for name, a in zip(("grad_value", "grad_loc", "grad_w"), got):
+            assert rel_rms(a, g[f"{name}_{tag}"]) < tol, (tag, name)
+
+
 def test_posemb_and_inverse_sigmoid():
     _, g = load_golden("posemb")
     assert rel_rms(tp.pos2posemb(torch.from_numpy(g["pos"])).numpy(), g["emb"]) < 1e-6
