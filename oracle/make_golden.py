@@ -13,6 +13,7 @@ a consumer can detect RNG drift. Reference entry points executed:
   posemb    transformer.py:183-190 pos2posemb; utils.py:34-38 inverse_sigmoid
   tracker_* ultralytics/nn/modules/head.py:1143-1283 RuntimeTrackerBase on MOTR Instances
   qim_*     MOTR/models/qim.py:251-301 QueryInteractionModule._update_track_embedding
+  formats   MOTR/submit_dance.py:410-419 Detector.write_results; ultralytics/engine/results.py:475-512 save_txt
 """
 from __future__ import annotations
 
@@ -283,6 +284,46 @@ def gen_selection(head):
              feats=feats[:, ::step].contiguous(), embed=embed, refer=refer, enc_scores=enc_scores, query_pos=query_pos)
 
 
+def gen_formats():
+    """Output text of the reference's own writers on a seeded track table:
+    Detector.write_results (MOTR/submit_dance.py:410-419) and TrackResults.save_txt
+    (ultralytics/engine/results.py:475-512)."""
+    import importlib
+    import os
+    import tempfile
+    sys.path.insert(0, str(ref_loader.REF / "MOTR"))
+    sd = importlib.import_module("MOTR.submit_dance")
+    res = importlib.import_module("ultralytics.engine.results")
+    g = torch.Generator().manual_seed(61)
+    n, img_w, img_h = 40, 1088, 608
+    table = torch.zeros(n, 9)
+    table[:, 1] = torch.arange(n) // 8                       # 5 frames
+    table[:, 2] = torch.randint(-1, 30, (n,), generator=g).float()
+    table[:, 3:5] = torch.rand(n, 2, generator=g) * 0.8 + 0.1
+    table[:, 5:7] = torch.rand(n, 2, generator=g) * 0.2 + 0.01
+    table[:, 7] = torch.rand(n, generator=g)
+    table[:, 8] = torch.randint(0, 5, (n,), generator=g).float()
+    cx, cy, w, h = table[:, 3], table[:, 4], table[:, 5], table[:, 6]
+    xyxy = torch.stack([cx - 0.5 * w, cy - 0.5 * h, cx + 0.5 * w, cy + 0.5 * h], 1) * torch.tensor(
+        [img_w, img_h, img_w, img_h], dtype=torch.float32)
+    mot, txt, txt_conf = [], {}, {}
+    for f in range(5):
+        m = table[:, 1] == f
+        with tempfile.TemporaryDirectory() as d:
+            p = os.path.join(d, "mot.txt")
+            sd.Detector.write_results(p, f + 1, xyxy[m].numpy(), table[m, 2].long().numpy())
+            mot.append(open(p).read() if os.path.exists(p) else "")
+            boxes6 = torch.cat([xyxy[m], table[m, 7:8], table[m, 8:9]], 1)
+            r = res.TrackResults(np.zeros((img_h, img_w, 3), np.uint8), "x.jpg", {i: str(i) for i in range(5)},
+                                 boxes=boxes6, track_id=table[m, 2].long())
+            for conf, store in ((False, txt), (True, txt_conf)):
+                q = os.path.join(d, f"l{int(conf)}.txt")
+                r.save_txt(q, save_conf=conf)
+                store[f] = open(q).read()
+    save("formats", dict(seed=61, img_w=img_w, img_h=img_h, mot="".join(mot), save_txt=txt, save_txt_conf=txt_conf,
+                         source="MOTR/submit_dance.py:410-419; ultralytics/engine/results.py:475-512"), table=table)
+
+
 def main():
     assert ref_loader.available(), "needs /root/reference"
     torch.set_num_threads(8)
@@ -300,6 +341,7 @@ def main():
     gen_tracker(head, structures)
     gen_qim(qim, structures)
     gen_selection(head)
+    gen_formats()
 
 
 if __name__ == "__main__":
