@@ -19,7 +19,7 @@
 //    residual-add + LayerNorm (+ "+pos" operand of the next GEMM) of the post-norm blocks
 //    (transformer.py:640-641, 646-647, 578-579) fused into the epilogue. A LayerNorm row spans the
 //    256/BN CTAs of a thread-block cluster; row statistics are exchanged through distributed shared
-//    memory (two-pass mean / centred variance, two cluster barriers).
+//    memory (per-slab mean / centred sum of squares merged with the parallel-variance formula, one exchange).
 //  * gemm_stream_kernel — persistent, weight-resident kernel for the tall value projection
 //    (M = S*Lv ~ 10^4..10^5 rows, K = 256): every CTA keeps its [128 x 256] weight slab in shared
 //    memory, streams x-tiles through a 6-deep TMA ring, double-buffers the accumulator in TMEM so the
@@ -359,35 +359,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           v[16 + j] += __uint_as_float(r1[j]) + ctl->bias[16 + j];
         }
       }
-      // pass 1: row mean over the 256 columns held by the NC CTAs of the cluster
+      // Row statistics over the 256 columns held by the NC CTAs of the cluster in ONE exchange: every CTA
+      // computes the mean and the centred sum of squares of its own 32-column slab (two passes, in registers)
+      // and the slabs are merged with the parallel-variance formula (Chan et al.):
+      //   mean = sum_i m_i / NC,   M2 = sum_i M2_i + BN * sum_i (m_i - mean)^2
+      // -- as robust as a global two-pass, one cluster barrier and one DSMEM round fewer.
       float ps = 0.0f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) ps += v[j];
-      cluster_wait();  // #0
-      const uint32_t slot0 = smem_u32(&ctl->red[0][my_rank][rl]);
-#pragma unroll
-      for (int p = 0; p < NC; ++p) st_cluster_f32(slot0, p, ps);
-      cluster_arrive();
-      cluster_wait();  // #1
-      float tot = 0.0f;
-#pragma unroll
-      for (int p = 0; p < NC; ++p) tot += ctl->red[0][p][rl];
-      const float mean = tot * (1.0f / kLnCols);
+      const float m_loc = ps * (1.0f / BN);
       float pq = 0.0f;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        v[j] -= mean;
-        pq = fmaf(v[j], v[j], pq);
+        const float d = v[j] - m_loc;
+        pq = fmaf(d, d, pq);
       }
+      cluster_wait();  // #0
+      const uint32_t slot0 = smem_u32(&ctl->red[0][my_rank][rl]);
       const uint32_t slot1 = smem_u32(&ctl->red[1][my_rank][rl]);
 #pragma unroll
-      for (int p = 0; p < NC; ++p) st_cluster_f32(slot1, p, pq);
+      for (int p = 0; p < NC; ++p) {
+        st_cluster_f32(slot0, p, m_loc);
+        st_cluster_f32(slot1, p, pq);
+      }
       cluster_arrive();
-      cluster_wait();  // #2
-      float sq = 0.0f;
+      cluster_wait();  // #1
+      float msum = 0.0f, sq = 0.0f;
 #pragma unroll
-      for (int p = 0; p < NC; ++p) sq += ctl->red[1][p][rl];
+      for (int p = 0; p < NC; ++p) {
+        msum += ctl->red[0][p][rl];
+        sq += ctl->red[1][p][rl];
+      }
+      const float mean = msum * (1.0f / NC);
+#pragma unroll
+      for (int p = 0; p < NC; ++p) {
+        const float d = ctl->red[0][p][rl] - mean;
+        sq = fmaf(static_cast<float>(BN) * d, d, sq);
+      }
       const float rstd = rsqrtf(sq * (1.0f / kLnCols) + e.eps);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] -= mean;
       if (row_ok) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = v[j] * rstd * ctl->gamma[j] + ctl->beta[j];
@@ -416,9 +427,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
   }
   if constexpr (LN) {
-    if (warp < 2) {  // producer / MMA warps take part in the three cluster barriers
-      cluster_wait();
-      cluster_arrive();
+    if (warp < 2) {  // producer / MMA warps take part in the two cluster barriers
       cluster_wait();
       cluster_arrive();
       cluster_wait();
