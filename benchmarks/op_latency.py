@@ -89,6 +89,18 @@ def main():
     gout = torch.empty(R, C, dtype=bf, device=dev)
     res["msda_fused"] = timed(lambda: ops.msda_fused(values[:, :, :C], shapes, ol[:, :192], ol[:, 192:], refer, H, 4, S,
                                                      row_offsets=ro if S > 1 else None, out=gout))
+    wol = (rn(288, 256) / 16).to(bf); bol = rn(288)
+    xq = rn(R, 256).to(bf)
+    olo = torch.empty(R, 288, device=dev)
+
+    def two_launch():
+        ops.linear(xq, wol, bol, out=olo)
+        ops.msda_fused(values[:, :, :C], shapes, olo[:, :192], olo[:, 192:], refer, H, 4, S,
+                       row_offsets=ro if S > 1 else None, out=gout)
+    res["offlog_gemm+msda_fused (2 launches)"] = timed(two_launch)
+    if ops.proj_fused_supported(bf, H, 32, 3, 4, R):
+        res["msda_proj_fused (1 launch)"] = timed(lambda: ops.msda_proj_fused(
+            values[:, :, :C], shapes, xq, wol, bol, refer, H, 4, S, row_offsets=ro if S > 1 else None, out=gout))
     # heads
     w3, b3 = rn(4, C) * 0.05, rn(4)
     refb = torch.rand(R, 4, generator=g).to(dev)

@@ -100,6 +100,21 @@ int moyolo_msda_sampled_forward(const void* value, int value_dtype, int64_t valu
                                 int64_t rows, const int32_t* row_offsets, void* out,
                                 int64_t out_row_stride, moyolo_stream_t stream);
 
+/* Fused mode with the sampling_offsets | attention_weights projection inside the gather kernel
+ * (transformer.py:268-285 in ONE launch): offsets|logits = xq . w_offlog^T + b_offlog is computed per
+ * (8 rows, head) CTA on mma.sync and never leaves shared memory.
+ *   xq       [R, 256] bf16 (row stride `xq_row_stride` elements): the query operand (x + pos),
+ *   w_offlog [n_heads*L*P*3, 256] bf16 = rows of sampling_offsets.weight followed by attention_weights.weight,
+ *   b_offlog fp32, same stacking. Serves bf16 value, 8 heads x 32, 3 levels x 4 points (the decoder's
+ *   configuration); returns MOYOLO_ERR_UNSUPPORTED otherwise. */
+int moyolo_msda_proj_fused_forward(const void* value, int value_dtype, int64_t value_batch_stride,
+                                   int64_t value_pos_stride, const int32_t* shapes_hw_host, int n_levels,
+                                   int batch, int64_t len_v, int n_heads, int head_dim, int n_points,
+                                   const void* xq, int64_t xq_row_stride, const void* w_offlog,
+                                   const float* b_offlog, const float* refer, int ref_levels, int ref_dim,
+                                   int softmax_mode, int64_t rows, const int32_t* row_offsets, void* out,
+                                   int64_t out_row_stride, moyolo_stream_t stream);
+
 /* Backward of the pre-normalised mode: replaces pybind `ms_deform_attn_backward`
  * (MOTR/models/ops/src/vision.cpp:15, ms_deform_attn.h:42-61, cuda/ms_deform_attn_cuda.cu:83-153, kernels
  * cuda/ms_deform_im2col_cuda.cuh:88-159, 301-920) and the autograd of multi_scale_deformable_attn_pytorch.

@@ -39,6 +39,8 @@ SIGNATURES = {
                                           _p, _p, _p]),
     "moyolo_msda_fused_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _l, _p, _i, _i, _i,
                                        _l, _p, _p, _l, _p]),
+    "moyolo_msda_proj_fused_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _p, _p, _i, _i, _i,
+                                            _l, _p, _p, _l, _p]),
     "moyolo_linear": (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _i, _p]),
     "moyolo_linear_dual": (_i, [_p, _l, _p, _l, _i, _p, _p, _p, _l, _l, _i, _i, _i, _p]),
     "moyolo_linear_add_layernorm": (_i, [_p, _l, _p, _p, _p, _p, _p, _f, _l, _i, _i, _p, _p, _p, _p, _p]),

@@ -45,6 +45,11 @@ struct MsdaParams {
   int ref_levels;
   int ref_dim;
   int softmax_mode;
+  // projection fused into the gather (msda_gather_proj_kernel): offsets|logits = xq . w^T + bias
+  const void* xq;            // bf16 [rows, n_heads*head_dim], row stride xq_row_stride elements
+  int64_t xq_row_stride;
+  const void* w_offlog;      // bf16 [n_heads*L*P*3, n_heads*head_dim] = [sampling_offsets ; attention_weights]
+  const float* b_offlog;     // fp32 [n_heads*L*P*3]
   // pre-normalised inputs
   const void* loc;
   const void* weights;
@@ -143,6 +148,77 @@ __device__ __forceinline__ uint4 ldg128_if(const void* ptr, bool valid) {
       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
       : "l"(ptr), "r"(static_cast<int>(valid)));
   return v;
+}
+
+// Phases 2 and 3 of a (row, head) item, shared by the gather kernels: sub-group sg of the warp walks the staged
+// corners sg, sg + NSG, ... (U of them in flight per trip), then the sub-groups' partial sums are merged.
+template <typename VT, int DH, int U>
+__device__ __forceinline__ void gather_reduce_store(const MsdaParams& p, const int* s_off, const float* s_w, int NUp,
+                                                    int b, int row, int head, int lane) {
+  constexpr int G = DH * static_cast<int>(sizeof(VT)) / 16;  // lanes per value row
+  constexpr int CH = 16 / static_cast<int>(sizeof(VT));      // channels per lane
+  constexpr int NSG = 32 / G;                                // sub-groups per warp
+  // ---------------- phase 2: gather, sub-group sg takes corners sg, sg + NSG, ... ----------------
+  float acc[CH];
+#pragma unroll
+  for (int k = 0; k < CH; ++k) acc[k] = 0.0f;
+
+  const int sg = lane / G, sub = lane % G;
+  const VT* base = static_cast<const VT*>(p.value) + static_cast<int64_t>(b) * p.value_batch_stride +
+                   head * DH + sub * CH;
+  for (int u0 = sg; u0 < NUp; u0 += NSG * U) {
+    uint4 v[U];
+    float w[U];
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      const int eo = s_off[u0 + i * NSG];
+      w[i] = s_w[u0 + i * NSG];
+      v[i] = ldg128_if(base + eo, eo >= 0);
+    }
+#pragma unroll
+    for (int i = 0; i < U; ++i) {
+      if constexpr (sizeof(VT) == 2) fma_bf16x8(acc, v[i], w[i]);
+      else fma_f32x4(acc, v[i], w[i]);
+    }
+  }
+
+  // ---------------- phase 3: recursive-halving reduction across the sub-groups ----------------
+  // Each round the lane keeps one half of its channels and receives the partner's partial sums for
+  // that half, so after log2(NSG) rounds every lane holds CH/NSG finished channels.
+  int ch = 0;
+  {
+    int n = CH;
+#pragma unroll
+    for (int off = 16; off >= G; off >>= 1) {
+      n >>= 1;
+      const bool up = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < CH / 2; ++i) {
+        if (i < n) {
+          const float send = up ? acc[i] : acc[i + n];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+          acc[i] = (up ? acc[i + n] : acc[i]) + recv;
+        }
+      }
+      ch += up ? n : 0;
+    }
+  }
+  constexpr int NF = CH / NSG;  // finished channels per lane: 1 or 2
+  VT* o = static_cast<VT*>(p.out) + static_cast<int64_t>(row) * p.out_row_stride + head * DH + sub * CH + ch;
+  if constexpr (sizeof(VT) == 2) {
+    if constexpr (NF == 1) {
+      const float hi = __shfl_xor_sync(0xffffffffu, acc[0], G);  // odd-channel partner (last round's bit)
+      if ((lane & G) == 0) *reinterpret_cast<uint32_t*>(o) = float2_to_bf16x2(acc[0], hi);
+    } else {
+      *reinterpret_cast<uint32_t*>(o) = float2_to_bf16x2(acc[0], acc[1]);
+    }
+  } else {
+    if constexpr (NF == 1) {
+      *o = acc[0];
+    } else {
+      *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
+    }
+  }
 }
 
 // U = corner rounds kept in flight per loop trip (all of them when 4*L*P == U*32/G).
@@ -266,69 +342,8 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_kernel(const MsdaP
   for (int u = NU + lane; u < NUp; u += 32) { s_off[u] = -1; s_w[u] = 0.0f; }
   __syncwarp();
 
-  // ---------------- phase 2: gather, sub-group sg takes corners sg, sg + NSG, ... ----------------
-  float acc[CH];
-#pragma unroll
-  for (int k = 0; k < CH; ++k) acc[k] = 0.0f;
-
-  const int sg = lane / G, sub = lane % G;
   const int b = p.batch == 1 ? 0 : batch_of_row(row, p.row_offsets, p.batch, p.rows_per_batch);
-  const VT* base = static_cast<const VT*>(p.value) + static_cast<int64_t>(b) * p.value_batch_stride +
-                   head * DH + sub * CH;
-
-  for (int u0 = sg; u0 < NUp; u0 += NSG * U) {
-    uint4 v[U];
-    float w[U];
-#pragma unroll
-    for (int i = 0; i < U; ++i) {
-      const int eo = s_off[u0 + i * NSG];
-      w[i] = s_w[u0 + i * NSG];
-      v[i] = ldg128_if(base + eo, eo >= 0);
-    }
-#pragma unroll
-    for (int i = 0; i < U; ++i) {
-      if constexpr (sizeof(VT) == 2) fma_bf16x8(acc, v[i], w[i]);
-      else fma_f32x4(acc, v[i], w[i]);
-    }
-  }
-
-  // ---------------- phase 3: recursive-halving reduction across the sub-groups ----------------
-  // Each round the lane keeps one half of its channels and receives the partner's partial sums for
-  // that half, so after log2(NSG) rounds every lane holds CH/NSG finished channels.
-  int ch = 0;
-  {
-    int n = CH;
-#pragma unroll
-    for (int off = 16; off >= G; off >>= 1) {
-      n >>= 1;
-      const bool up = (lane & off) != 0;
-#pragma unroll
-      for (int i = 0; i < CH / 2; ++i) {
-        if (i < n) {
-          const float send = up ? acc[i] : acc[i + n];
-          const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-          acc[i] = (up ? acc[i + n] : acc[i]) + recv;
-        }
-      }
-      ch += up ? n : 0;
-    }
-  }
-  constexpr int NF = CH / NSG;  // finished channels per lane: 1 or 2
-  VT* o = static_cast<VT*>(p.out) + static_cast<int64_t>(row) * p.out_row_stride + head * DH + sub * CH + ch;
-  if constexpr (sizeof(VT) == 2) {
-    if constexpr (NF == 1) {
-      const float hi = __shfl_xor_sync(0xffffffffu, acc[0], G);  // odd-channel partner (last round's bit)
-      if ((lane & G) == 0) *reinterpret_cast<uint32_t*>(o) = float2_to_bf16x2(acc[0], hi);
-    } else {
-      *reinterpret_cast<uint32_t*>(o) = float2_to_bf16x2(acc[0], acc[1]);
-    }
-  } else {
-    if constexpr (NF == 1) {
-      *o = acc[0];
-    } else {
-      *reinterpret_cast<float2*>(o) = make_float2(acc[0], acc[1]);
-    }
-  }
+  gather_reduce_store<VT, DH, U>(p, s_off, s_w, NUp, b, row, head, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -488,6 +503,150 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_pair_kernel(const 
       *o = acc[h][0];
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gather with the sampling_offsets | attention_weights projection fused in (transformer.py:268-269 + 271-285):
+// one CTA = 8 query rows x ONE head. The head's 3*L*P projection rows (24 offset + 12 logit rows of the
+// [288, 256] weight at L=3, P=4; 18 KB of bf16) are immutable, so they are requested with cp.async BEFORE the
+// programmatic-dependency wait; after it the 8 activation rows (4 KB) arrive in one round trip, five warps
+// run the [8(16) x 256] x [256 x 40] product on mma.sync.m16n8k16 (tiles far below a tcgen05 128-row tile),
+// and the 8 warps then run the usual phases 1-3 for (row, head) items with offsets / logits read from shared
+// memory. Removes one dependent launch (and the fp32 [R, 288] round trip through L2) per decoder layer.
+// bf16 value, head_dim 32, 8 heads, d_model 256.
+// ------------------------------------------------------------------------------------------------
+constexpr int kProjRows = 8;
+
+template <int NP, int NL>
+__global__ void __launch_bounds__(kGatherThreads) msda_gather_proj_kernel(const MsdaParams p) {
+  using VT = __nv_bfloat16;
+  constexpr int DH = 32, NH = 8, K = NH * DH, PITCH = K + 8;
+  constexpr int LP = NP * NL, NO = LP * 3, NT = (NO + 7) / 8, NOp = NT * 8;
+  constexpr int G = 4, NSG = 8, NU = LP * 4, U = 6;
+  constexpr int NUp = (NU + NSG * U - 1) / (NSG * U) * (NSG * U);
+  static_assert(LP <= 32 && K / 32 == kGatherWarps && kProjRows == kGatherWarps, "one point per lane, one K slice per warp");
+  pdl_trigger();
+  extern __shared__ __align__(16) int smem_i[];
+  __nv_bfloat16* sW = reinterpret_cast<__nv_bfloat16*>(smem_i);      // [NOp][PITCH]
+  __nv_bfloat16* sX = sW + NOp * PITCH;                               // [8][PITCH]
+  float* sB = reinterpret_cast<float*>(sX + kProjRows * PITCH);       // [NOp]
+  float* sOL = sB + NOp;                                              // [8][NOp]
+  float* sP = sOL + kProjRows * NOp;                                  // [8 warps][8][NOp] K-slice partial sums
+  int* sStage = reinterpret_cast<int*>(sP + kGatherWarps * kProjRows * NOp);  // per warp: [NUp] offsets, [NUp] weights
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int head = blockIdx.y;
+  const int row0 = static_cast<int>(blockIdx.x) * kProjRows;
+  const int n_rows = static_cast<int>(p.rows);
+  // projection row n of this head -> row of the stacked [offsets ; logits] weight
+  auto src_row = [&](int n) { return n < 2 * LP ? head * 2 * LP + n : NH * 2 * LP + head * LP + (n - 2 * LP); };
+  {
+    const __nv_bfloat16* w = static_cast<const __nv_bfloat16*>(p.w_offlog);
+    for (int i = threadIdx.x; i < NO * (K / 8); i += kGatherThreads) {
+      const int n = i / (K / 8), c = i % (K / 8);
+      cp_async16(smem_addr(sW + n * PITCH + c * 8), w + static_cast<int64_t>(src_row(n)) * K + c * 8, true);
+    }
+    for (int i = threadIdx.x; i < (NOp - NO) * (K / 8); i += kGatherThreads) {
+      const int n = NO + i / (K / 8), c = i % (K / 8);
+      *reinterpret_cast<uint4*>(sW + n * PITCH + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    if (threadIdx.x < NOp) sB[threadIdx.x] = threadIdx.x < NO ? __ldg(p.b_offlog + src_row(threadIdx.x)) : 0.0f;
+    cp_async_commit();
+  }
+  pdl_wait();
+  {
+    const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(p.xq);
+    for (int i = threadIdx.x; i < kProjRows * (K / 8); i += kGatherThreads) {
+      const int r = i / (K / 8), c = i % (K / 8);
+      const bool ok = row0 + r < n_rows;
+      cp_async16(smem_addr(sX + r * PITCH + c * 8), x + static_cast<int64_t>(ok ? row0 + r : 0) * p.xq_row_stride + c * 8, ok);
+    }
+    cp_async_commit();
+  }
+  // this warp's item: reference box requested now, consumed after the projection
+  const int row = row0 + warp;
+  const bool item_ok = row < n_rows;
+  const int level = lane < LP ? lane / NP : 0;
+  float rx = 0.0f, ry = 0.0f, rw = 0.0f, rh = 0.0f;
+  if (item_ok) {
+    const float* r = p.refer + static_cast<int64_t>(row) * (p.ref_levels * p.ref_dim) + (p.ref_levels == 1 ? 0 : level) * p.ref_dim;
+    if (p.ref_dim == 4) {
+      const float4 r4 = __ldg(reinterpret_cast<const float4*>(r));
+      rx = r4.x; ry = r4.y; rw = r4.z; rh = r4.w;
+    } else {
+      const float2 r2 = __ldg(reinterpret_cast<const float2*>(r));
+      rx = r2.x; ry = r2.y;
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- projection: warp w owns the K slice [32w, 32w+32) for all NT n-tiles (independent accumulators, two
+  // MMAs each); rows 8..15 of the m16 tile mirror rows 0..7. The 8 partial [8 x NOp] tiles are summed through
+  // shared memory together with the bias.
+  {
+    uint32_t a0[4], a1[4];
+    ldmatrix_x4(smem_addr(sX + (lane & 7) * PITCH + warp * 32 + (lane >> 4) * 8), a0);
+    ldmatrix_x4(smem_addr(sX + (lane & 7) * PITCH + warp * 32 + 16 + (lane >> 4) * 8), a1);
+    float c[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      uint32_t kb[4];
+      ldmatrix_x4(smem_addr(sW + (j * 8 + (lane & 7)) * PITCH + warp * 32 + (lane >> 3) * 8), kb);
+      c[j][0] = c[j][1] = c[j][2] = c[j][3] = 0.0f;
+      mma_bf16_16816(c[j], a0, kb[0], kb[1]);
+      mma_bf16_16816(c[j], a1, kb[2], kb[3]);
+    }
+    const int g = lane >> 2, t = lane & 3;
+    float* part = sP + (warp * kProjRows + g) * NOp + 2 * t;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) *reinterpret_cast<float2*>(part + j * 8) = make_float2(c[j][0], c[j][1]);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < kProjRows * NOp; o += kGatherThreads) {
+    float acc = sB[o % NOp];
+#pragma unroll
+    for (int w8 = 0; w8 < kGatherWarps; ++w8) acc += sP[w8 * kProjRows * NOp + o];
+    sOL[o] = acc;
+  }
+  __syncthreads();
+  if (!item_ok) return;  // warp-uniform, after the last block-wide barrier
+
+  // ---------------- phase 1: lane pt owns sampling point pt ----------------
+  int* s_off = sStage + warp * NUp * 2;
+  float* s_w = reinterpret_cast<float*>(s_off + NUp);
+  const int ps = static_cast<int>(p.value_pos_stride);
+  {
+    const bool ok = lane < LP;
+    const float* ol = sOL + warp * NOp;
+    const float lg = ok ? ol[2 * LP + lane] : -INFINITY;
+    const float2 off = ok ? *reinterpret_cast<const float2*>(ol + 2 * lane) : make_float2(0.0f, 0.0f);
+    float m = warp_max(lg);
+    if (p.softmax_mode == MOYOLO_SOFTMAX_PLUS1) m = 0.0f;
+    float aw = ok ? expf(lg - m) : 0.0f;
+    float sum = warp_sum(aw);
+    if (p.softmax_mode == MOYOLO_SOFTMAX_PLUS1) sum += 1.0f;
+    aw *= 1.0f / sum;
+    float lx, ly;
+    if (p.ref_dim == 4) {
+      lx = rx + off.x / static_cast<float>(NP) * rw * 0.5f;
+      ly = ry + off.y / static_cast<float>(NP) * rh * 0.5f;
+    } else {
+      lx = rx + off.x / static_cast<float>(p.lv.w[level]);
+      ly = ry + off.y / static_cast<float>(p.lv.h[level]);
+    }
+    if (ok) {
+      const Corners c = make_corners(lx, ly, p.lv.h[level], p.lv.w[level], p.lv.start[level], aw);
+      *reinterpret_cast<int4*>(s_off + lane * 4) =
+          make_int4(c.pos[0] < 0 ? -1 : c.pos[0] * ps, c.pos[1] < 0 ? -1 : c.pos[1] * ps,
+                    c.pos[2] < 0 ? -1 : c.pos[2] * ps, c.pos[3] < 0 ? -1 : c.pos[3] * ps);
+      *reinterpret_cast<float4*>(s_w + lane * 4) = make_float4(c.w[0], c.w[1], c.w[2], c.w[3]);
+    }
+    for (int u = NU + lane; u < NUp; u += 32) { s_off[u] = -1; s_w[u] = 0.0f; }
+  }
+  __syncwarp();
+  const int b = p.batch == 1 ? 0 : batch_of_row(row, p.row_offsets, p.batch, p.rows_per_batch);
+  gather_reduce_store<VT, DH, U>(p, s_off, s_w, NUp, b, row, head, lane);
+  (void)G;
 }
 
 // Generic kernel: any head_dim / dtype (incl. fp64 for the legacy FFI known-answer test,
@@ -740,4 +899,48 @@ extern "C" int moyolo_msda_fused_forward(const void* value, int value_dtype, int
   p.ref_dim = ref_dim;
   p.softmax_mode = softmax_mode;
   return dispatch<true>(p, value_dtype, MOYOLO_F32, head_dim, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int moyolo_msda_proj_fused_forward(const void* value, int value_dtype, int64_t value_batch_stride,
+                                              int64_t value_pos_stride, const int32_t* shapes_hw_host, int n_levels,
+                                              int batch, int64_t len_v, int n_heads, int head_dim, int n_points,
+                                              const void* xq, int64_t xq_row_stride, const void* w_offlog,
+                                              const float* b_offlog, const float* refer, int ref_levels, int ref_dim,
+                                              int softmax_mode, int64_t rows, const int32_t* row_offsets, void* out,
+                                              int64_t out_row_stride, moyolo_stream_t stream) {
+  MsdaParams p{};
+  int rc = fill_common(&p, value, value_dtype, value_batch_stride, value_pos_stride, shapes_hw_host,
+                       n_levels, batch, len_v, n_heads, head_dim, n_points, rows, row_offsets, out,
+                       out_row_stride);
+  if (rc != MOYOLO_OK) return rc;
+  MOYOLO_REQUIRE(xq && w_offlog && b_offlog && refer, MOYOLO_ERR_BAD_ARG, "null xq/w_offlog/b_offlog/refer pointer");
+  MOYOLO_REQUIRE(value_dtype == MOYOLO_BF16 && n_heads == 8 && head_dim == 32 && n_points == 4 && n_levels == 3,
+                 MOYOLO_ERR_UNSUPPORTED,
+                 "msda_proj_fused_forward serves bf16, 8 heads x 32, 3 levels x 4 points (use moyolo_linear + "
+                 "moyolo_msda_fused_forward otherwise)");
+  MOYOLO_REQUIRE(ref_dim == 2 || ref_dim == 4, MOYOLO_ERR_BAD_SHAPE,
+                 "Last dim of reference_points must be 2 or 4, but got %d.", ref_dim);
+  MOYOLO_REQUIRE(ref_levels == 1 || ref_levels == n_levels, MOYOLO_ERR_BAD_SHAPE,
+                 "refer_bbox level dim must be 1 or n_levels (%d), got %d", n_levels, ref_levels);
+  MOYOLO_REQUIRE(softmax_mode == MOYOLO_SOFTMAX || softmax_mode == MOYOLO_SOFTMAX_PLUS1, MOYOLO_ERR_BAD_ARG,
+                 "bad softmax_mode %d", softmax_mode);
+  MOYOLO_REQUIRE(aligned16(value) && aligned16(out) && aligned16(xq) && aligned16(w_offlog) &&
+                     (value_pos_stride * 2) % 16 == 0 && (value_batch_stride * 2) % 16 == 0 &&
+                     (out_row_stride * 2) % 16 == 0 && (xq_row_stride * 2) % 16 == 0 &&
+                     (reinterpret_cast<uintptr_t>(refer) & (ref_dim == 4 ? 15u : 7u)) == 0,
+                 MOYOLO_ERR_ALIGNMENT, "msda_proj_fused_forward: operands must be 16-byte aligned");
+  MOYOLO_REQUIRE(p.lv.start[p.lv.n - 1] + static_cast<int64_t>(p.lv.h[p.lv.n - 1]) * p.lv.w[p.lv.n - 1] <=
+                         (INT32_MAX - 4096) / (p.value_pos_stride > 0 ? p.value_pos_stride : 1) &&
+                     rows < (1 << 24),
+                 MOYOLO_ERR_UNSUPPORTED, "msda_proj_fused_forward: tensor too large for 32-bit offsets");
+  p.xq = xq; p.xq_row_stride = xq_row_stride; p.w_offlog = w_offlog; p.b_offlog = b_offlog;
+  p.refer = refer; p.ref_levels = ref_levels; p.ref_dim = ref_dim; p.softmax_mode = softmax_mode;
+  if (rows == 0) return MOYOLO_OK;
+  constexpr int K = 256, PITCH = K + 8, NOp = 40, NUp = 48;
+  constexpr size_t smem = static_cast<size_t>(NOp + kProjRows) * PITCH * 2 + NOp * 4 + kProjRows * NOp * 4 +
+                          static_cast<size_t>(kGatherWarps) * kProjRows * NOp * 4 + static_cast<size_t>(kGatherWarps) * NUp * 8;
+  static_assert(smem <= 48 * 1024, "fits the default dynamic shared memory limit");
+  const dim3 grid(static_cast<unsigned>((rows + kProjRows - 1) / kProjRows), 8);
+  launch_k(msda_gather_proj_kernel<4, 3>, grid, dim3(kGatherThreads), smem, static_cast<cudaStream_t>(stream), p);
+  return check_launch("msda_gather_proj_kernel");
 }

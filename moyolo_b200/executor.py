@@ -255,11 +255,18 @@ def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offset
                                      out_pos=ws.x1q_lp)
         else:
             ops.linear_add_layernorm(ws.att, pk.o.w, pk.o.b, ws.x, g, b_, e, out_f32=ws.x1, out_lp=ws.x1q_lp)
-        ops.linear(ws.x1q_lp, pkm.offlog.w, pkm.offlog.b, out=ws.ol, engine=eng)
-        if before_gather is not None:
-            before_gather()
-        ops.msda_fused(value_view, shapes, ws.ol[:, :pkm.n_off], ws.ol[:, pkm.n_off:], refer, pkm.n_heads,
-                       pkm.n_points, batch, pkm.softmax_mode, row_offsets, out=ws.g)
+        if ops.proj_fused_supported(dt, pkm.n_heads, C // pkm.n_heads, pkm.n_levels, pkm.n_points, ws.R):
+            # offsets|logits projection inside the gather kernel: one launch for transformer.py:268-285
+            if before_gather is not None:
+                before_gather()
+            ops.msda_proj_fused(value_view, shapes, ws.x1q_lp, pkm.offlog.w, pkm.offlog.b, refer, pkm.n_heads,
+                                pkm.n_points, batch, pkm.softmax_mode, row_offsets, out=ws.g)
+        else:
+            ops.linear(ws.x1q_lp, pkm.offlog.w, pkm.offlog.b, out=ws.ol, engine=eng)
+            if before_gather is not None:
+                before_gather()
+            ops.msda_fused(value_view, shapes, ws.ol[:, :pkm.n_off], ws.ol[:, pkm.n_off:], refer, pkm.n_heads,
+                           pkm.n_points, batch, pkm.softmax_mode, row_offsets, out=ws.g)
         g, b_, e = pk.norms[1]
         ops.linear_add_layernorm(ws.g, pkm.out.w, pkm.out.b, ws.x1, g, b_, e, out_f32=ws.x2, out_lp=ws.x2_lp)
         ops.linear(ws.x2_lp, pk.ffn1.w, pk.ffn1.b, relu=True, out=ws.h, engine=eng)

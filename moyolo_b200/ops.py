@@ -45,6 +45,10 @@ GATHER_HOOK = None
 # the roofline leg repeats each (idempotent) gather launch this many times between one event pair so the
 # event-node overhead (~5 us per pair inside a graph) is amortised; 1 everywhere else
 GATHER_REPEAT = 1
+# offsets|logits projection inside the gather kernel (MOYOLO_PROJ_FUSED=0 disables; row bound see proj_fused_supported)
+import os as _os  # noqa: E402
+PROJ_FUSED = _os.environ.get("MOYOLO_PROJ_FUSED", "1") != "0"
+PROJ_FUSED_MAX_ROWS = int(_os.environ.get("MOYOLO_PROJ_FUSED_MAX_ROWS", "1024"))
 
 
 def _count(n: int = 1) -> None:
@@ -156,6 +160,47 @@ def msda_fused(value: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch
     if hook is not None:
         hook[1]()
     return out
+
+
+def msda_proj_fused(value: torch.Tensor, shapes, xq: torch.Tensor, w_offlog: torch.Tensor, b_offlog: torch.Tensor,
+                    refer: torch.Tensor, n_heads: int, n_points: int, batch: int,
+                    softmax_mode: int = _lib.SOFTMAX, row_offsets: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """msda_fused with the offsets|logits projection (xq . w_offlog^T + b_offlog) inside the gather kernel:
+    transformer.py:268-285 in one launch. bf16, 8 heads x 32, 3 levels x 4 points."""
+    _cuda(value, xq, w_offlog, b_offlog, refer)
+    B, Lv, Cc = value.shape
+    if B != batch or value.stride(2) != 1:
+        raise ValueError("value must be [B, Lv, C] with contiguous channels")
+    R = xq.shape[0]
+    arr, L = _shapes_arr(shapes)
+    if xq.stride(1) != 1 or xq.dtype != torch.bfloat16 or w_offlog.dtype != torch.bfloat16 or not w_offlog.is_contiguous():
+        raise ValueError("xq / w_offlog must be bf16 with contiguous columns")
+    refer = refer.contiguous()
+    if out is None:
+        out = torch.empty(R, Cc, dtype=value.dtype, device=value.device)
+    if R == 0:
+        return out
+    _count(1)
+    hook = GATHER_HOOK
+    if hook is not None:
+        hook[0](B, Lv, Cc, R, n_heads, L, n_points, value.element_size())
+    for _ in range(GATHER_REPEAT if hook is not None else 1):
+        _lib.check(_lib.lib().moyolo_msda_proj_fused_forward(
+            value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, n_heads, Cc // n_heads,
+            n_points, xq.data_ptr(), xq.stride(0), w_offlog.data_ptr(), b_offlog.data_ptr(), refer.data_ptr(),
+            refer.shape[1], refer.shape[2], softmax_mode, R, _ptr(row_offsets), out.data_ptr(), out.stride(0),
+            _stream()))
+    if hook is not None:
+        hook[1]()
+    return out
+
+
+def proj_fused_supported(value_dtype, n_heads: int, head_dim: int, n_levels: int, n_points: int, rows: int) -> bool:
+    """Configurations served by msda_proj_fused; beyond ~1k rows the per-CTA re-read of the projection weights
+    costs more than the saved launch (the tcgen05 GEMM + pair gather then win)."""
+    return (PROJ_FUSED and value_dtype == torch.bfloat16 and n_heads == 8 and head_dim == 32 and n_levels == 3
+            and n_points == 4 and rows <= PROJ_FUSED_MAX_ROWS)
 
 
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out_dtype: torch.dtype = None,

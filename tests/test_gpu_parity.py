@@ -615,3 +615,46 @@ def test_backward_vs_reference_cuda_kernel(dev):
         got = ops.msda_sampled_backward(v, shapes, l, a, g)
         for nm, t, r in zip(("grad_value", "grad_loc", "grad_w"), got, ref):
             assert rel_rms(t.cpu().numpy(), r.cpu().numpy()) < FP32_TOL, (name, nm)
+
+
+@pytest.mark.parametrize("B,Q,name,ref_dim", [(1, 382, "MOT17", 4), (2, 77, "tiny", 4), (1, 9, "tiny", 2)])
+def test_msda_proj_fused_equals_gemm_plus_gather(dev, B, Q, name, ref_dim):
+    """The gather with the sampling_offsets|attention_weights projection fused in (one launch) against the
+    two-launch path it replaces (tcgen05 GEMM -> fused gather), and both against the fp32 oracle of
+    MSDeformAttn's middle section (transformer.py:268-285) on the same bf16 operands. Ragged rows included."""
+    m, ops, syn, mg, tp = _mods()
+    H, D, L, P, C = 8, 32, 3, 4, 256
+    shapes = [list(s) for s in syn.PYRAMIDS[name]]
+    Lv = syn.level_sizes(shapes)
+    g = torch.Generator().manual_seed(5 + Q)
+    R = B * Q
+    value = torch.randn(B, Lv, C, generator=g).to(dev, torch.bfloat16)
+    xq = torch.randn(R, C, generator=g).to(dev, torch.bfloat16)
+    w = (torch.randn(H * L * P * 3, C, generator=g) * 0.05).to(dev, torch.bfloat16)
+    bias = (torch.randn(H * L * P * 3, generator=g) * 0.5).to(dev)
+    cxcy = torch.rand(R, 1, 2, generator=g)
+    refer = (torch.cat([cxcy, torch.rand(R, 1, 2, generator=g) * 0.4 + 0.02], -1) if ref_dim == 4 else cxcy).to(dev)
+    ro = None
+    if B == 2:  # ragged: sequence 0 owns 50 rows, sequence 1 the rest
+        ro = torch.tensor([0, 50, R], dtype=torch.int32, device=dev)
+    fused = ops.msda_proj_fused(value, shapes, xq, w, bias, refer, H, P, B, row_offsets=ro)
+    ol = ops.linear(xq, w, bias, out_dtype=torch.float32)
+    n_off = H * L * P * 2
+    two = ops.msda_fused(value, shapes, ol[:, :n_off], ol[:, n_off:], refer, H, P, B, row_offsets=ro)
+    # fp32 oracle on the same (bf16-rounded) operands
+    olr = xq.float().cpu() @ w.float().cpu().T + bias.cpu()
+    off = olr[:, :n_off].view(R, H, L, P, 2)
+    aw = torch.softmax(olr[:, n_off:].view(R, H, L * P), -1).view(R, H, L, P)
+    rf = refer.cpu()
+    if ref_dim == 4:
+        loc = rf[:, :, None, None, :2] + off / P * rf[:, :, None, None, 2:] * 0.5
+    else:
+        norm = torch.tensor([[s[1], s[0]] for s in shapes], dtype=torch.float32).view(1, 1, L, 1, 2)
+        loc = rf[:, :, None, None, :] + off / norm
+    bounds = [0, 50, R] if B == 2 else [0, R]
+    ref = torch.cat([tp.msda_core_gather(value[b:b + 1].float().cpu().view(1, Lv, H, D), shapes,
+                                         loc[bounds[b]:bounds[b + 1]][None], aw[bounds[b]:bounds[b + 1]][None])[0]
+                     for b in range(B)])
+    assert rel_rms(fused.float().cpu().numpy(), ref.numpy()) < BF16_TOL
+    assert rel_rms(two.float().cpu().numpy(), ref.numpy()) < BF16_TOL
+    assert rel_rms(fused.float().cpu().numpy(), two.float().cpu().numpy()) < BF16_TOL
