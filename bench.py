@@ -116,10 +116,63 @@ def make_frames(args, syn, spec, shapes, device, seq_seed, n_frames, lp):
     return frames
 
 
-def gather_bytes(B, Lv, C, R, H, L, P, s_v):
+def gather_bytes(B, Lv, C, R, H, L, P, s_v, proj_fused=False):
     """Compulsory bytes of one deformable-gather launch: value once + raw offsets and
-    logits + reference boxes + output."""
-    return B * Lv * C * s_v + R * H * L * P * 3 * 4 + R * 4 * 4 + R * C * s_v
+    logits + reference boxes + output. With the offsets|logits projection fused into the kernel the fp32
+    [R, H*L*P*3] operand is replaced by the bf16 query rows [R, C] and the projection weight + bias."""
+    common = B * Lv * C * s_v + R * 4 * 4 + R * C * s_v
+    if proj_fused:
+        return common + R * C * 2 + H * L * P * 3 * (C * 2 + 4)
+    return common + R * H * L * P * 3 * 4
+
+
+def batched_gather_roofline(ops, syn, shapes, spec, device, peak, S=16, Q=300):
+    """The same gather in the regime where one launch carries enough bytes to be bandwidth-bound: S lock-step
+    sequences (what a GPU tracking S videos gathers per layer), value laid out as in the frame (one layer's
+    column slice of the all-layers value tensor). warm = back-to-back launches in a CUDA graph with the value
+    slice L2-resident where it fits (how it runs right after the value_proj GEMM); cold = a 256 MB L2 flush
+    before every launch."""
+    H, L, P, C = spec.n_heads, spec.n_levels, spec.n_points, spec.d_model
+    Lv = syn.level_sizes(shapes)
+    g = torch.Generator().manual_seed(123)
+    R = S * Q
+    values = torch.randn(S, Lv, 2 * C, generator=g).to(device, torch.bfloat16)   # two layers' slices side by side
+    value = values[:, :, :C]
+    ol = torch.randn(R, H * L * P * 3, generator=g).to(device)
+    refer = torch.cat([torch.rand(R, 1, 2, generator=g), torch.rand(R, 1, 2, generator=g) * 0.3 + 0.02], -1).to(device)
+    ro = torch.arange(0, R + 1, Q, dtype=torch.int32, device=device)
+    out = torch.empty(R, C, dtype=torch.bfloat16, device=device)
+    n_off = H * L * P * 2
+    fn = lambda: ops.msda_fused(value, shapes, ol[:, :n_off], ol[:, n_off:], refer, H, P, S, row_offsets=ro, out=out)  # noqa: E731
+    fn()
+    torch.cuda.synchronize()
+    N = 20
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for _ in range(N):
+            fn()
+    warm = 1e9
+    for _ in range(5):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); gr.replay(); b.record(); torch.cuda.synchronize()
+        warm = min(warm, a.elapsed_time(b) / N)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    cold = []
+    for _ in range(7):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        cold.append(a.elapsed_time(b))
+    cold.sort()
+    nbytes = gather_bytes(S, Lv, C, R, H, L, P, 2)
+    w_gbs, c_gbs = nbytes / (warm * 1e-3) / 1e9, nbytes / (cold[len(cold) // 2] * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "msda_gather_pair_kernel<bf16,4,3>", "sequences": S, "rows": R,
+            "algorithmic_bytes_per_launch": int(nbytes), "warm_us": round(warm * 1e3, 2),
+            "cold_us": round(cold[len(cold) // 2] * 1e3, 2), "achieved_warm": round(w_gbs, 1),
+            "achieved_cold": round(c_gbs, 1), "peak": peak, "unit": "GB/s", "frac_warm": round(w_gbs / peak, 4),
+            "frac_cold": round(c_gbs / peak, 4),
+            "note": "same gather, 16 lock-step sequences per launch (bandwidth regime); warm = value slice as left in "
+                    "L2 by the preceding launch, cold = L2 flushed before the launch"}
 
 
 def run_moyolo(args):
@@ -224,7 +277,7 @@ def run_moyolo(args):
     # value_proj GEMM) and the event pairs give the device time of each gather launch. The event nodes
     # are full dependencies, so the gather loses its programmatic-launch overlap with its neighbours:
     # the figure is the kernel's own launch-to-completion time.
-    roof = None
+    roof = roof_batched = None
     if rank == 0:
         cur_pairs = []
 
@@ -251,6 +304,8 @@ def run_moyolo(args):
         pairs_of = {key: cur_pairs[i * n_l:(i + 1) * n_l] for i, key in enumerate(eng2._plans.keys())}
         g_ms, n_pairs, nbytes = 0.0, 0, 0
         n_inst = min(K, 60)
+        pf = ops.proj_fused_supported(lp, spec.n_heads, spec.d_model // spec.n_heads, spec.n_levels, spec.n_points,
+                                      S * (args.n_detect + args.max_tracks))
         for t in range(n_inst):
             T_in = sum(eng2.n_tracks_host())
             eng2.submit(*dev_batches[t], want_rows=False)
@@ -263,7 +318,7 @@ def run_moyolo(args):
                 g_ms += a.elapsed_time(b) / REP
                 n_pairs += 1
                 nbytes += gather_bytes(S, eng2.Lv, spec.d_model, T_in + S * args.n_detect, spec.n_heads, spec.n_levels,
-                                       spec.n_points, 2 if args.precision == "bf16" else 4)
+                                       spec.n_points, 2 if args.precision == "bf16" else 4, proj_fused=pf)
         peaks = {}
         pk = ROOT / "MEASURED_PEAKS.json"
         if pk.exists():
@@ -274,19 +329,24 @@ def run_moyolo(args):
         tf = ROOT / "profiles" / "gather_traffic.json"   # dram bytes per launch from the committed ncu --set full capture
         if tf.exists():
             traffic = json.loads(tf.read_text()).get(f"{args.workload}_S{S}_{args.precision}")
-        roof = {"bound": "hbm", "kernel": "msda_gather_kernel<bf16,32,fused>", "achieved": round(ach, 1),
+        kname = ("msda_gather_proj_kernel<4,3> (gather with the offsets|logits projection fused in)" if pf else
+                 ("msda_gather_pair_kernel<bf16,4,3>" if S * args.n_detect >= 1024 else "msda_gather_kernel<bf16,32,fused>"))
+        roof = {"bound": "hbm", "kernel": kname, "achieved": round(ach, 1),
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
                 "launches_timed": n_pairs, "avg_launch_us": round(g_ms * 1e3 / max(n_pairs, 1), 3),
                 "algorithmic_bytes_per_launch": int(nbytes / max(n_pairs, 1)),
-                "note": "compulsory bytes (value slice once + offsets/logits + refs + out for the frame's real rows, "
-                        "SURVEY.md 8(d)) / device time between external CUDA-event nodes placed around each gather "
-                        f"gather inside the captured frame graph (6 per frame; each event pair brackets {REP} identical "
-                        "back-to-back launches of that gather and the time is divided by it, because a pair of event "
-                        "nodes alone costs ~5 us). One sequence per GPU: the launch moves "
+                "note": "compulsory bytes (value slice once + query rows / projection weights (or raw offsets/logits) + "
+                        "refs + out for the frame's real rows, SURVEY.md 8(d)) / device time between external CUDA-event "
+                        f"nodes placed around each gather inside the captured frame graph (6 per frame; each event pair "
+                        f"brackets {REP} identical back-to-back launches of that gather and the time is divided by it, "
+                        "because a pair of event nodes alone costs ~5 us). With ONE sequence per GPU the launch moves "
                         "~7.6 MB in a few microseconds out of L2 (the value slice was just written by the value_proj "
-                        "GEMM); it is a latency chain, not a bandwidth stream. DESIGN.md and profiles/ hold the batch "
-                        "sweep against the roofline"}
+                        "GEMM) and, at <= 1024 rows, also computes the offsets|logits projection: it is a latency "
+                        "chain (dependency release -> query rows -> projection -> corner rows), not a bandwidth "
+                        "stream; `roofline_batched` is the same gather where a launch carries enough bytes"}
+        if S == 1 and args.precision == "bf16":
+            roof_batched = batched_gather_roofline(ops, syn, shapes, spec, device, peak)
         del eng2
 
     # ---------------- leg 3: `e2e` — host buffers, H2D + D2H inside the timed region ----------------
@@ -340,6 +400,7 @@ def run_moyolo(args):
                     "ms_per_step": round(ms_e2e / K, 4)},
             "gpu_launches": int(launches),
             "roofline": roof,
+            "roofline_batched": roof_batched,
             "clocks": clocks,
         }
         cpu_src = [tuple(x[0].float().cpu() for x in b) for b in dev_batches[:args.cpu_frames]]
