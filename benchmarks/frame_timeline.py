@@ -77,6 +77,7 @@ def main():
     for k in range(1, n_total + 1):
         p = _FramePlan()
         p.rows_pad, p.slot, p.ws, p.graph, p.n_launch, p.desc = base.rows_pad, 0, base.ws, None, 0, None
+        p.info, p.frame_rows = base.info, base.frame_rows
         proxy.limit, proxy.count, proxy.names = k, 0, []
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):

@@ -374,6 +374,9 @@ int moyolo_mask_rows(const float* x, const uint8_t* zero_rows, int64_t period, f
  *   on copy_stream: [wait ev_slot_free] [wait for main_stream if sync_inputs] n_inputs x memcpyAsync
  *                   (host-pinned or device sources, UVA) -> record ev_copy
  *   on main_stream: wait ev_copy -> launch graph_exec -> n_outputs x memcpyAsync -> record ev_done
+ *   With out_stream_valid == 1 the result copies leave the main stream: record ev_graph on main_stream, and on
+ *   out_stream: wait ev_graph -> n_outputs x memcpyAsync -> record ev_done -- the next frame's graph then starts
+ *   right behind this one (the caller double-buffers the copied-from buffers per frame parity).
  * All handles are plain CUDA runtime handles (cudaStream_t, cudaEvent_t, cudaGraphExec_t) owned by the
  * caller. With n_inputs == 0 only the main-stream part runs.
  * -------------------------------------------------------------------------------------------*/
@@ -396,6 +399,9 @@ typedef struct {
   const void* out_src[MOYOLO_SUBMIT_MAX_COPIES];
   void* out_dst[MOYOLO_SUBMIT_MAX_COPIES];
   int64_t out_bytes[MOYOLO_SUBMIT_MAX_COPIES];
+  void* out_stream;      /* optional stream for the result copies */
+  int out_stream_valid;  /* 1 = use out_stream / ev_graph */
+  void* ev_graph;
 } moyolo_frame_submit_t;
 int moyolo_frame_submit(const moyolo_frame_submit_t* d);
 

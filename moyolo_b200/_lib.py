@@ -26,7 +26,8 @@ class FrameSubmit(C.Structure):
                 ("ev_slot_free", _p), ("ev_scratch", _p), ("ev_copy", _p), ("ev_done", _p), ("graph_exec", _p),
                 ("n_inputs", _i), ("n_outputs", _i),
                 ("in_src", _p * 4), ("in_dst", _p * 4), ("in_bytes", _l * 4),
-                ("out_src", _p * 4), ("out_dst", _p * 4), ("out_bytes", _l * 4)]
+                ("out_src", _p * 4), ("out_dst", _p * 4), ("out_bytes", _l * 4),
+                ("out_stream", _p), ("out_stream_valid", _i), ("ev_graph", _p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/moyolo_b200.h declares

@@ -37,9 +37,16 @@ extern "C" int moyolo_frame_submit(const moyolo_frame_submit_t* d) {
     RT_CHECK(cudaStreamWaitEvent(ms, static_cast<cudaEvent_t>(d->ev_copy), 0), "wait copy");
   }
   if (d->graph_exec != nullptr) RT_CHECK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(d->graph_exec), ms), "graph launch");
+  cudaStream_t os = ms;
+  if (d->out_stream_valid == 1) {  // result copies off the main stream: the next frame's graph follows this one directly
+    MOYOLO_REQUIRE(d->ev_graph != nullptr, MOYOLO_ERR_BAD_ARG, "frame_submit: out_stream needs ev_graph");
+    os = static_cast<cudaStream_t>(d->out_stream);
+    RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_graph), ms), "record graph");
+    RT_CHECK(cudaStreamWaitEvent(os, static_cast<cudaEvent_t>(d->ev_graph), 0), "wait graph");
+  }
   for (int i = 0; i < d->n_outputs; ++i)
-    RT_CHECK(cudaMemcpyAsync(d->out_dst[i], d->out_src[i], static_cast<size_t>(d->out_bytes[i]), cudaMemcpyDefault, ms),
+    RT_CHECK(cudaMemcpyAsync(d->out_dst[i], d->out_src[i], static_cast<size_t>(d->out_bytes[i]), cudaMemcpyDefault, os),
              "result copy");
-  if (d->ev_done != nullptr) RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_done), ms), "record done");
+  if (d->ev_done != nullptr) RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_done), os), "record done");
   return MOYOLO_OK;
 }

@@ -133,8 +133,6 @@ class FrameWorkspace:
         self.c_pos = z(R, C, **f32)
         self.c_hs = z(R, C, **f32)
         self.c_box = z(R, 4, **f32)
-        self.frame_rows = z(R, 8, **f32)
-        self.info = z(S + 8, dtype=torch.int32, device=dev)
         # QIM
         self.q_pos = z(R, C, **f32)
         self.q_qk_lp = z(R, C, **lp)
@@ -148,7 +146,7 @@ class FrameWorkspace:
 
 class _FramePlan:
     """Workspace (and optionally the captured CUDA graph) of one (padded frame size, input slot)."""
-    __slots__ = ("rows_pad", "slot", "graph", "ws", "n_launch", "desc")
+    __slots__ = ("rows_pad", "slot", "graph", "ws", "n_launch", "desc", "info", "frame_rows")
 
 
 class TrackEngine:
@@ -201,6 +199,7 @@ class TrackEngine:
         self._copy = torch.cuda.Stream(dev)
         self._s_val = torch.cuda.Stream(dev)
         self._s_box = torch.cuda.Stream(dev)
+        self._out = torch.cuda.Stream(dev)      # result copies (device -> pinned host), off the main stream
         self._ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self._ev_copy = [torch.cuda.Event() for _ in range(2)]
         # pinned host rings: [n_active (S) | ctrl (8)] and the packed frame rows
@@ -211,7 +210,8 @@ class TrackEngine:
         # native submission (moyolo_frame_submit): raw handles of the streams / events above. torch creates
         # the underlying cudaEvent lazily on the first record, so every event is recorded once here.
         self._ev_scratch = torch.cuda.Event()
-        for e in (*self._ev_done, *self._ev_copy, self._ev_scratch):
+        self._ev_graph = torch.cuda.Event()
+        for e in (*self._ev_done, *self._ev_copy, self._ev_scratch, self._ev_graph):
             e.record(self._main)
         torch.cuda.synchronize(dev)
         self._native = use_graphs and os.environ.get("MOYOLO_NATIVE_SUBMIT", "1") != "0"
@@ -340,7 +340,7 @@ class TrackEngine:
             ops.track_suppress_batched(boxes, ws.ids, self.counters, ws.ro, S, ws.rows_per_seq, ws.assign_ws, it,
                                        ctrl=self.ctrl)
             ops.frame_emit(S, R, ws.ro, ws.ids, boxes, ws.scores, ws.labels, ws.n_active, ws.active_index,
-                           self.seq_ids, ws.frame_rows, self.table, self.ctrl)
+                           self.seq_ids, p.frame_rows, self.table, self.ctrl)
 
         if fork:
             self._s_box.wait_stream(cur)
@@ -351,7 +351,7 @@ class TrackEngine:
         self._qim_update(ws, ro_host)
         # write-back also stores what the host reads back after the frame: [n_active | ctrl]
         ops.frame_writeback(S, C, self.cap, ws.ro, ws.n_active, ws.q_new, ws.c_box, self.t_qpos, self.t_ref,
-                            self.n_tracks, ctrl=self.ctrl, info=ws.info)
+                            self.n_tracks, ctrl=self.ctrl, info=p.info)
         if fork:
             cur.wait_stream(self._s_box)
 
@@ -408,6 +408,10 @@ class TrackEngine:
         # both input slots of one size share a workspace: frames are serialised on the main stream
         p.ws = other.ws if other is not None else FrameWorkspace(rows_pad, self.n_seq, self.spec, self.W.dt, self.dev,
                                                                  self.W.qim["l1_w"].shape[0], self.n_detect + self.cap)
+        # what the host reads back is double-buffered per input slot (frame parity): the result copies run on their
+        # own stream while the next frame's graph (other slot) is already executing
+        p.info = torch.zeros(self.n_seq + 8, dtype=torch.int32, device=self.dev)
+        p.frame_rows = torch.zeros(rows_pad, 8, device=self.dev)
         if self.use_graphs:
             torch.cuda.synchronize(self.dev)
             snap = self._state_snapshot()
@@ -442,8 +446,9 @@ class TrackEngine:
         for i, t in enumerate(self._ring[p.slot]):
             d.in_dst[i] = t.data_ptr()
             d.in_bytes[i] = t.numel() * t.element_size()
-        d.out_src[0], d.out_bytes[0] = p.ws.info.data_ptr(), p.ws.info.numel() * 4
-        d.out_src[1], d.out_bytes[1] = p.ws.frame_rows.data_ptr(), p.rows_pad * 8 * 4
+        d.out_src[0], d.out_bytes[0] = p.info.data_ptr(), p.info.numel() * 4
+        d.out_src[1], d.out_bytes[1] = p.frame_rows.data_ptr(), p.rows_pad * 8 * 4
+        d.out_stream, d.out_stream_valid, d.ev_graph = self._out.cuda_stream, 1, self._ev_graph.cuda_event
         return d
 
     def _submit_native(self, t: int, rows_pad: int, feats, det_embed, det_refer, want_rows: bool,
@@ -523,9 +528,9 @@ class TrackEngine:
                 self._body(p)
             # the frame's host-visible results: [active-track counts | control block] and, optionally, the
             # packed rows -- one small device->host copy each
-            self._h_info[h].copy_(p.ws.info, non_blocking=True)
+            self._h_info[h].copy_(p.info, non_blocking=True)
             if want_rows:
-                self._h_rows[h, :rows_pad].copy_(p.ws.frame_rows, non_blocking=True)
+                self._h_rows[h, :rows_pad].copy_(p.frame_rows, non_blocking=True)
             self._ev_done[h].record(main)
         self._last_plan = p
         return {"frame": frame, "plan": p, "rows_pad": rows_pad, "want_rows": want_rows}
