@@ -44,6 +44,7 @@ class Proxy:
 
 def main():
     S = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    branches = len(sys.argv) > 2 and sys.argv[2] == "branch"   # keep the side branches: deltas = critical-path growth
     reps = 15
     spec = syn.DecoderSpec()
     shapes = [list(s) for s in syn.PYRAMIDS["MOT17"]]
@@ -56,7 +57,7 @@ def main():
     W = DecoderWeights(sd, spec, dev, "bf16")
     gens = [syn.SequenceGenerator(syn.SequenceSpec("MOT17", 41, 300, 1 + s, shapes=shapes), spec.d_model, dev)
             for s in range(S)]
-    eng = TrackEngine(sd, spec, shapes, dev, "bf16", 300, S, weights=W, branches=False)
+    eng = TrackEngine(sd, spec, shapes, dev, "bf16", 300, S, weights=W, branches=branches)
     eng.prepare(160)
     last = None
     for _ in range(41):
@@ -104,12 +105,12 @@ def main():
     agg = {}
     for r in rows_out:
         agg[r["call"]] = round(agg.get(r["call"], 0.0) + r["delta_us"], 2)
-    res = {"S": S, "rows_pad": base.rows_pad, "tracks": eng.n_tracks_host(), "launches": n_total,
+    res = {"S": S, "branches": branches, "rows_pad": base.rows_pad, "tracks": eng.n_tracks_host(), "launches": n_total,
            "note": "prefix-graph replay medians; delta = time the k-th launch adds inside the (branch-free) frame graph; "
                    "the first entry includes the graph-launch overhead",
            "by_call_us": dict(sorted(agg.items(), key=lambda kv: -kv[1])), "timeline": rows_out}
     (ROOT / "gpurun_out").mkdir(exist_ok=True)
-    (ROOT / "gpurun_out" / f"frame_timeline_S{S}.json").write_text(json.dumps(res, indent=1))
+    (ROOT / "gpurun_out" / f"frame_timeline_S{S}{'_branch' if branches else ''}.json").write_text(json.dumps(res, indent=1))
     print(json.dumps({k: v for k, v in res.items() if k != "timeline"}, indent=1))
     for r in rows_out:
         print(f"{r['k']:3d} {r['call']:28s} {r['delta_us']:7.2f} {r['cum_us']:8.2f}")

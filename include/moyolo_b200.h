@@ -156,6 +156,14 @@ int moyolo_linear(const void* x, int64_t ldx, const void* w, const float* bias, 
                   int64_t ldy, int64_t M, int N, int K, int in_dtype, int out_dtype, int epilogue,
                   const uint8_t* zero_rows, int engine, moyolo_stream_t stream);
 
+/* The persistent, weight-resident tcgen05 kernel for TALL x (value_proj over all pyramid positions,
+ * transformer.py:264) with an explicit CTA budget: y[M,N] = x[M,256] . w[N,256]^T + bias as bf16, rows with
+ * zero_rows != 0 written as zeros. max_ctas > 0 bounds the grid (0 = one CTA per SM): a frame runs the layers'
+ * value projections NEXT TO its latency-bound main chain, which needs some SMs left free. bf16, K == 256,
+ * N % 128 == 0, 16-byte aligned operands and row strides. */
+int moyolo_linear_tall(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy,
+                       int64_t M, int N, int K, const uint8_t* zero_rows, int max_ctas, moyolo_stream_t stream);
+
 /* Two A operands in ONE launch: y[:, :n_split] = x1 . w[:n_split]^T, y[:, n_split:] = x2 . w[n_split:]^T (+ bias).
  * The packed in-projection of nn.MultiheadAttention with q = k = x + pos, v = x (transformer.py:637-638):
  * x1 = x + pos, x2 = x, n_split = 2C. bf16 operands, tcgen05 engine only; n_split % 64 == 0. */
@@ -402,8 +410,32 @@ typedef struct {
   void* out_stream;      /* optional stream for the result copies */
   int out_stream_valid;  /* 1 = use out_stream / ev_graph */
   void* ev_graph;
+  /* optional value projection AHEAD of the frame graph (vp_valid == 1): on vp_stream, wait ev_copy and
+   * ev_tail_prev (recorded by the previous frame's graph once its last decoder layer is issued; NULL for the
+   * first frame), run moyolo_linear_tall(vp_x -> vp_y) on at most vp_max_ctas SMs, record ev_vp; main_stream
+   * waits ev_vp before the graph launch. The projection then fills the SMs the previous frame's tail leaves idle. */
+  void* vp_stream;
+  int vp_valid;
+  void* ev_tail_prev;
+  void* ev_vp;
+  const void* vp_x;
+  int64_t vp_ldx;
+  const void* vp_w;
+  const float* vp_bias;
+  void* vp_y;
+  int64_t vp_ldy;
+  int64_t vp_M;
+  int vp_N;
+  int vp_max_ctas;
 } moyolo_frame_submit_t;
 int moyolo_frame_submit(const moyolo_frame_submit_t* d);
+
+/* Raw CUDA events that may be recorded inside a captured graph and waited on from outside it (ev_tail_prev above):
+ * moyolo_event_record uses cudaEventRecordExternal while `stream` is capturing, a plain record otherwise. */
+void* moyolo_event_create(void);
+int moyolo_event_destroy(void* ev);
+int moyolo_event_record(void* ev, moyolo_stream_t stream);
+int moyolo_stream_wait_event(moyolo_stream_t stream, void* ev);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

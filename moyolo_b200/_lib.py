@@ -27,7 +27,10 @@ class FrameSubmit(C.Structure):
                 ("n_inputs", _i), ("n_outputs", _i),
                 ("in_src", _p * 4), ("in_dst", _p * 4), ("in_bytes", _l * 4),
                 ("out_src", _p * 4), ("out_dst", _p * 4), ("out_bytes", _l * 4),
-                ("out_stream", _p), ("out_stream_valid", _i), ("ev_graph", _p)]
+                ("out_stream", _p), ("out_stream_valid", _i), ("ev_graph", _p),
+                ("vp_stream", _p), ("vp_valid", _i), ("ev_tail_prev", _p), ("ev_vp", _p),
+                ("vp_x", _p), ("vp_ldx", _l), ("vp_w", _p), ("vp_bias", _p), ("vp_y", _p), ("vp_ldy", _l),
+                ("vp_M", _l), ("vp_N", _i), ("vp_max_ctas", _i)]
 
 
 # name -> (restype, argtypes); must list every symbol include/moyolo_b200.h declares
@@ -43,6 +46,7 @@ SIGNATURES = {
     "moyolo_msda_proj_fused_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _p, _p, _i, _i, _i,
                                             _l, _p, _p, _l, _p]),
     "moyolo_linear": (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _i, _p]),
+    "moyolo_linear_tall": (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _p, _i, _p]),
     "moyolo_linear_dual": (_i, [_p, _l, _p, _l, _i, _p, _p, _p, _l, _l, _i, _i, _i, _p]),
     "moyolo_linear_add_layernorm": (_i, [_p, _l, _p, _p, _p, _p, _p, _f, _l, _i, _i, _p, _p, _p, _p, _p]),
     "moyolo_self_attention": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
@@ -73,6 +77,10 @@ SIGNATURES = {
                                          _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p]),
     "moyolo_frame_writeback": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "moyolo_frame_submit": (_i, [C.POINTER(FrameSubmit)]),
+    "moyolo_event_create": (_p, []),
+    "moyolo_event_destroy": (_i, [_p]),
+    "moyolo_event_record": (_i, [_p, _p]),
+    "moyolo_stream_wait_event": (_i, [_p, _p]),
     "moyolo_frame_emit": (_i, [_i, _l, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _l, _p, _p]),
 }
 

@@ -26,6 +26,7 @@
 //    epilogue of tile i overlaps the MMAs of tile i+1, and writes bf16 through swizzled shared-memory
 //    slabs with TMA stores (full-line writes instead of one row per thread).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <mutex>
 
@@ -446,35 +447,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 // Persistent weight-resident kernel for tall x (value projection). K == 256, N % 128 == 0.
 // CTA c owns output-column tile (c % n_tiles) and walks the row tiles group, group + n_groups, ...
 // ------------------------------------------------------------------------------------------------
-constexpr int kSBN = 128;
+// BN = output columns per CTA: 256 when N allows it (every x-tile is then read by N/256 instead of N/128 CTAs,
+// which halves the dominant L2 -> SM traffic; the two 256-column accumulators fill the SM's 512 TMEM columns),
+// else 128.
 constexpr int kSK = 256;
 constexpr int kSKB = kSK / kBK;   // 4 k-blocks
-constexpr int kSStages = 6;       // x-tile ring: 6 x 16 KiB
 constexpr int kSlabBytes = 32 * 128;  // one epilogue slab: 32 rows x 64 bf16
+template <int BN>
+struct StreamCfg {
+  static constexpr int kStages = BN == 256 ? 4 : 6;  // x-tile ring of 16 KiB stages (shared memory budget)
+  static constexpr int kSlabs = BN == 256 ? 2 : 4;   // output slabs per epilogue warp (TMA stores in flight)
+};
 
+template <int BN>
 struct StreamCtl {
-  uint64_t full[kSStages];
-  uint64_t empty[kSStages];
+  uint64_t full[StreamCfg<BN>::kStages];
+  uint64_t empty[StreamCfg<BN>::kStages];
   uint64_t b_full;
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
   uint32_t tmem_base;
-  float bias[kSBN];
+  float bias[BN];
 };
 
+template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_y, const float* __restrict__ bias,
                    const uint8_t* __restrict__ zero_rows, int64_t M, int n_tiles, int n_groups) {
+  constexpr int kSBN = BN;
+  constexpr int kSStages = StreamCfg<BN>::kStages;
   constexpr uint32_t kABytes = kBM * kBK * 2;   // 16 KiB
-  constexpr uint32_t kBBytes = kSBN * kBK * 2;  // 16 KiB per k-block
+  constexpr uint32_t kBBytes = kSBN * kBK * 2;  // 16 / 32 KiB per k-block
   constexpr uint32_t kTmemCols = 2 * kSBN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* smem_b = base;                                  // 4 x 16 KiB, resident
-  uint8_t* smem_a = smem_b + kSKB * kBBytes;               // 6 x 16 KiB ring
+  uint8_t* smem_b = base;                                  // 4 k-blocks of the weight slab, resident
+  uint8_t* smem_a = smem_b + kSKB * kBBytes;               // ring of 16 KiB x-tile stages
   uint8_t* smem_o = smem_a + kSStages * kABytes;           // 4 warps x 2 slabs x 4 KiB
-  StreamCtl* ctl = reinterpret_cast<StreamCtl*>(smem_o + 8 * kSlabBytes);
+  constexpr int kSlabs = StreamCfg<BN>::kSlabs;
+  StreamCtl<BN>* ctl = reinterpret_cast<StreamCtl<BN>*>(smem_o + 4 * kSlabs * kSlabBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x % n_tiles;
@@ -559,7 +571,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   } else {
     // epilogue warp `quad` owns rows [quad*32, quad*32+32) of every tile and two private 4 KiB slabs
     const int quad = warp & 3;
-    uint8_t* slab = smem_o + quad * 2 * kSlabBytes;
+    uint8_t* slab = smem_o + quad * kSlabs * kSlabBytes;
     pdl_wait();
     int n_store = 0;
     for (int t = 0; t < my_tiles; ++t) {
@@ -571,19 +583,23 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * kSBN + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint8_t* sl = slab + (n_store & 1) * kSlabBytes;
-        // the TMA store issued two slabs ago must have finished READING this slab
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      for (int half = 0; half < kSBN / 64; ++half) {
+        uint8_t* sl = slab + (n_store % kSlabs) * kSlabBytes;
+        // the TMA store issued kSlabs slabs ago must have finished READING this slab
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kSlabs - 1) : "memory");
         __syncwarp();
+        // all 64 columns of the slab are requested from TMEM before the single wait (one TMEM round trip per
+        // slab instead of four: the epilogue, not the MMAs, bounds this kernel)
+        uint32_t r[4][16];
 #pragma unroll
-        for (int c = 0; c < 64; c += 16) {
-          uint32_t r[16];
-          tmem_ld16(tacc + half * 64 + c, r);
-          tmem_ld_wait();
+        for (int q = 0; q < 4; ++q) tmem_ld16(tacc + half * 64 + q * 16, r[q]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int c = q * 16;
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = zero ? 0.0f : __uint_as_float(r[j]) + ctl->bias[half * 64 + c + j];
+          for (int j = 0; j < 16; ++j) v[j] = zero ? 0.0f : __uint_as_float(r[q][j]) + ctl->bias[half * 64 + c + j];
           uint4 a, b;
           a.x = float2_to_bf16x2(v[0], v[1]);   a.y = float2_to_bf16x2(v[2], v[3]);
           a.z = float2_to_bf16x2(v[4], v[5]);   a.w = float2_to_bf16x2(v[6], v[7]);
@@ -870,13 +886,17 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tx2, const CUte
   return check_launch("gemm_tcgen05_kernel");
 }
 
-static int launch_stream(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy, int64_t M,
-                         int N, const uint8_t* zero_rows, cudaStream_t st) {
-  constexpr size_t smem = kSKB * kSBN * kBK * 2 + kSStages * kBM * kBK * 2 + 8 * kSlabBytes + sizeof(StreamCtl) + 1024;
+template <int BN>
+static int launch_stream_bn(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy, int64_t M,
+                            int N, const uint8_t* zero_rows, int max_ctas, cudaStream_t st) {
+  constexpr size_t smem = kSKB * BN * kBK * 2 + StreamCfg<BN>::kStages * kBM * kBK * 2 +
+                          4 * StreamCfg<BN>::kSlabs * kSlabBytes +
+                          sizeof(StreamCtl<BN>) + 1024;
+  static_assert(smem <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt in to");
   static bool configured = false;
   static int n_sm = 0;
   if (!configured) {
-    cudaError_t err = cudaFuncSetAttribute(gemm_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t err = cudaFuncSetAttribute(gemm_stream_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem));
     if (err != cudaSuccess)
       return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(stream smem=%zu): %s", smem, cudaGetErrorString(err));
@@ -888,18 +908,43 @@ static int launch_stream(const void* x, int64_t ldx, const void* w, const float*
   CUtensorMap tx, tw, ty;
   int rc = make_tmap(&tx, x, M, kSK, ldx, kBM);
   if (rc != MOYOLO_OK) return rc;
-  rc = make_tmap(&tw, w, N, kSK, kSK, kSBN);
+  rc = make_tmap(&tw, w, N, kSK, kSK, BN);
   if (rc != MOYOLO_OK) return rc;
   rc = make_tmap(&ty, y, M, N, ldy, 32);
   if (rc != MOYOLO_OK) return rc;
-  const int n_tiles = N / kSBN;
+  const int n_tiles = N / BN;
   const int m_tiles = static_cast<int>((M + kBM - 1) / kBM);
-  int n_groups = n_sm / n_tiles;
+  int n_groups = (max_ctas > 0 && max_ctas < n_sm ? max_ctas : n_sm) / n_tiles;
+  {
+    // MOYOLO_STREAM_GROUPS caps the row-tile groups (CTAs = groups * N/BN): leaving some SMs free lets the short
+    // query GEMMs of the frame's main chain run next to the value projection instead of queueing behind it
+    static const int cap = [] { const char* e = getenv("MOYOLO_STREAM_GROUPS"); return e ? atoi(e) : 0; }();
+    if (cap > 0 && n_groups > cap) n_groups = cap;
+  }
   if (n_groups < 1) n_groups = 1;
   if (n_groups > m_tiles) n_groups = m_tiles;
-  launch_k(gemm_stream_kernel, dim3(n_tiles * n_groups), dim3(kGemmThreads), smem, st, tx, tw, ty, bias, zero_rows, M,
+  launch_k(gemm_stream_kernel<BN>, dim3(n_tiles * n_groups), dim3(kGemmThreads), smem, st, tx, tw, ty, bias, zero_rows, M,
            n_tiles, n_groups);
   return check_launch("gemm_stream_kernel");
+}
+
+static int launch_stream(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy, int64_t M,
+                         int N, const uint8_t* zero_rows, int max_ctas, cudaStream_t st) {
+  // 128-column tiles by default (measured equal or faster than 256 on B200 for K = 256: the kernel is bound by
+  // its epilogue / store path, not by re-reading x); MOYOLO_STREAM_BN=256 selects the wide variant
+  static const bool wide = [] { const char* e = getenv("MOYOLO_STREAM_BN"); return e && atoi(e) == 256; }();
+  if (wide && N % 256 == 0) return launch_stream_bn<256>(x, ldx, w, bias, y, ldy, M, N, zero_rows, max_ctas, st);
+  return launch_stream_bn<128>(x, ldx, w, bias, y, ldy, M, N, zero_rows, max_ctas, st);
+}
+
+bool linear_tall_supported(const void* x, int64_t ldx, const void* w, const void* y, int64_t ldy, int64_t M, int N, int K) {
+  return M > 0 && M < (1ll << 31) && K == kSK && N % 128 == 0 && aligned16(x) && aligned16(w) && aligned16(y) &&
+         (ldx * 2) % 16 == 0 && (ldy * 2) % 16 == 0;
+}
+
+int linear_tall(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy, int64_t M, int N,
+                const uint8_t* zero_rows, int max_ctas, cudaStream_t st) {
+  return launch_stream(x, ldx, w, bias, y, ldy, M, N, zero_rows, max_ctas, st);
 }
 
 // x2 / n_split: optional second A operand for output columns >= n_split (n_split % 64 == 0).
@@ -909,9 +954,9 @@ int linear_tcgen05(const void* x, int64_t ldx, const void* x2, int64_t ldx2, int
   MOYOLO_REQUIRE(out_dtype == MOYOLO_F32 || out_dtype == MOYOLO_BF16, MOYOLO_ERR_UNSUPPORTED,
                  "tcgen05 engine writes fp32 or bf16");
   // tall x, K == 256: persistent weight-resident kernel (value projection)
-  if (x2 == nullptr && M >= 4096 && K == kSK && N % kSBN == 0 && out_dtype == MOYOLO_BF16 && !relu && aligned16(y) &&
+  if (x2 == nullptr && M >= 4096 && K == kSK && N % 128 == 0 && out_dtype == MOYOLO_BF16 && !relu && aligned16(y) &&
       (ldy * 2) % 16 == 0)
-    return launch_stream(x, ldx, w, bias, y, ldy, M, N, zero_rows, st);
+    return launch_stream(x, ldx, w, bias, y, ldy, M, N, zero_rows, 0, st);
   // Tile width: narrow tiles spread the few-hundred-row query GEMMs over more SMs (latency-bound).
   int bn;
   if (M > 2048 && N % 256 == 0) bn = 256;

@@ -100,6 +100,9 @@ int linear_simt(const void* x, int64_t ldx, const void* w, const float* bias, vo
 }
 
 // implemented in gemm_tcgen05.cu
+bool linear_tall_supported(const void* x, int64_t ldx, const void* w, const void* y, int64_t ldy, int64_t M, int N, int K);
+int linear_tall(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy, int64_t M, int N,
+                const uint8_t* zero_rows, int max_ctas, cudaStream_t st);
 int linear_tcgen05(const void* x, int64_t ldx, const void* x2, int64_t ldx2, int n_split, const void* w,
                    const float* bias, void* y, int64_t ldy, int64_t M, int N, int K, int out_dtype, int relu,
                    const uint8_t* zero_rows, cudaStream_t st);
@@ -136,6 +139,19 @@ extern "C" int moyolo_linear(const void* x, int64_t ldx, const void* w, const fl
   }
   MOYOLO_REQUIRE(engine == MOYOLO_GEMM_SIMT, MOYOLO_ERR_BAD_ARG, "moyolo_linear: bad engine %d", engine);
   return linear_simt(x, ldx, w, bias, y, ldy, M, N, K, in_dtype, out_dtype, relu, zero_rows, st);
+}
+
+extern "C" int moyolo_linear_tall(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy,
+                                  int64_t M, int N, int K, const uint8_t* zero_rows, int max_ctas,
+                                  moyolo_stream_t stream) {
+  using namespace moyolo;
+  MOYOLO_REQUIRE(x && w && y, MOYOLO_ERR_BAD_ARG, "moyolo_linear_tall: null x/w/y pointer");
+  MOYOLO_REQUIRE(M >= 0 && N > 0 && K > 0 && ldx >= K && ldy >= N && max_ctas >= 0, MOYOLO_ERR_BAD_SHAPE,
+                 "moyolo_linear_tall: bad sizes");
+  if (M == 0) return MOYOLO_OK;
+  MOYOLO_REQUIRE(linear_tall_supported(x, ldx, w, y, ldy, M, N, K), MOYOLO_ERR_UNSUPPORTED,
+                 "moyolo_linear_tall: needs bf16, K == 256, N %% 128 == 0, 16B-aligned x/w/y and row strides");
+  return linear_tall(x, ldx, w, bias, y, ldy, M, N, zero_rows, max_ctas, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int moyolo_linear_dual(const void* x1, int64_t ldx1, const void* x2, int64_t ldx2, int n_split,

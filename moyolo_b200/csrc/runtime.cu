@@ -12,7 +12,7 @@ using namespace moyolo;
 #define RT_CHECK(call, what)                                                                 \
   do {                                                                                       \
     cudaError_t e_ = (call);                                                                 \
-    if (e_ != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "frame_submit: %s: %s", what, cudaGetErrorString(e_)); \
+    if (e_ != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "runtime: %s: %s", what, cudaGetErrorString(e_)); \
   } while (0)
 
 extern "C" int moyolo_frame_submit(const moyolo_frame_submit_t* d) {
@@ -36,6 +36,19 @@ extern "C" int moyolo_frame_submit(const moyolo_frame_submit_t* d) {
     RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_copy), cs), "record copy");
     RT_CHECK(cudaStreamWaitEvent(ms, static_cast<cudaEvent_t>(d->ev_copy), 0), "wait copy");
   }
+  if (d->vp_valid == 1) {
+    MOYOLO_REQUIRE(d->ev_vp != nullptr && d->vp_x && d->vp_w && d->vp_y, MOYOLO_ERR_BAD_ARG,
+                   "frame_submit: value projection needs ev_vp and x / w / y");
+    cudaStream_t vs = static_cast<cudaStream_t>(d->vp_stream);
+    if (d->n_inputs > 0) RT_CHECK(cudaStreamWaitEvent(vs, static_cast<cudaEvent_t>(d->ev_copy), 0), "vp wait copy");
+    if (d->ev_tail_prev != nullptr)
+      RT_CHECK(cudaStreamWaitEvent(vs, static_cast<cudaEvent_t>(d->ev_tail_prev), 0), "vp wait previous tail");
+    const int rc = moyolo_linear_tall(d->vp_x, d->vp_ldx, d->vp_w, d->vp_bias, d->vp_y, d->vp_ldy, d->vp_M, d->vp_N, 256,
+                                      nullptr, d->vp_max_ctas, d->vp_stream);
+    if (rc != MOYOLO_OK) return rc;
+    RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_vp), vs), "record vp");
+    RT_CHECK(cudaStreamWaitEvent(ms, static_cast<cudaEvent_t>(d->ev_vp), 0), "wait vp");
+  }
   if (d->graph_exec != nullptr) RT_CHECK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(d->graph_exec), ms), "graph launch");
   cudaStream_t os = ms;
   if (d->out_stream_valid == 1) {  // result copies off the main stream: the next frame's graph follows this one directly
@@ -48,5 +61,39 @@ extern "C" int moyolo_frame_submit(const moyolo_frame_submit_t* d) {
     RT_CHECK(cudaMemcpyAsync(d->out_dst[i], d->out_src[i], static_cast<size_t>(d->out_bytes[i]), cudaMemcpyDefault, os),
              "result copy");
   if (d->ev_done != nullptr) RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_done), os), "record done");
+  return MOYOLO_OK;
+}
+
+// Raw event helpers for the one event that is recorded INSIDE captured frame graphs and waited on from outside
+// (the "tail reached" signal that gates the next frame's value projection). Inside a stream capture the record
+// becomes an external event-record node (cudaEventRecordExternal is only valid there); outside it is a plain record.
+extern "C" void* moyolo_event_create(void) {
+  cudaEvent_t ev = nullptr;
+  if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return ev;
+}
+
+extern "C" int moyolo_event_destroy(void* ev) {
+  if (ev != nullptr) RT_CHECK(cudaEventDestroy(static_cast<cudaEvent_t>(ev)), "event destroy");
+  return MOYOLO_OK;
+}
+
+extern "C" int moyolo_event_record(void* ev, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(ev != nullptr, MOYOLO_ERR_BAD_ARG, "event_record: null event");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  RT_CHECK(cudaStreamIsCapturing(st, &cs), "capture status");
+  RT_CHECK(cudaEventRecordWithFlags(static_cast<cudaEvent_t>(ev), st,
+                                    cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault),
+           "event record");
+  return MOYOLO_OK;
+}
+
+extern "C" int moyolo_stream_wait_event(moyolo_stream_t stream, void* ev) {
+  MOYOLO_REQUIRE(ev != nullptr, MOYOLO_ERR_BAD_ARG, "stream_wait_event: null event");
+  RT_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), static_cast<cudaEvent_t>(ev), 0), "stream wait event");
   return MOYOLO_OK;
 }

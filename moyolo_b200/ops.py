@@ -226,6 +226,22 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out_dtyp
     return out
 
 
+def linear_tall(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out: torch.Tensor,
+                zero_rows: Optional[torch.Tensor] = None, max_ctas: int = 0) -> torch.Tensor:
+    """y = x . w^T + b for tall x [M, 256] (bf16) through the persistent weight-resident kernel, on at most
+    `max_ctas` SMs (0 = all)."""
+    _cuda(x, w, b, out)
+    M, K = x.shape
+    N = w.shape[0]
+    if x.stride(1) != 1 or out.stride(1) != 1 or not w.is_contiguous() or x.dtype != torch.bfloat16 or \
+            out.dtype != torch.bfloat16:
+        raise ValueError("linear_tall: bf16 x / w / out with contiguous columns")
+    _count(1)
+    _lib.check(_lib.lib().moyolo_linear_tall(x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), out.data_ptr(),
+                                             out.stride(0), M, N, K, _ptr(zero_rows), int(max_ctas), _stream()))
+    return out
+
+
 def linear_dual(x1: torch.Tensor, x2: torch.Tensor, n_split: int, w: torch.Tensor, b: Optional[torch.Tensor],
                 out: torch.Tensor) -> torch.Tensor:
     """out[:, :n_split] = x1 . w[:n_split]^T, out[:, n_split:] = x2 . w[n_split:]^T (+ b) in one launch

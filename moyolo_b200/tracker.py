@@ -165,6 +165,10 @@ class TrackEngine:
         self.thr = (score_thresh, filter_thresh, miss_tolerance, iou_thresh)
         self.cap, self.bucket, self.margin, self.use_graphs = cap, bucket, margin, use_graphs
         self.branches = branches
+        # split value projection (see _body): bf16 tcgen05 path with the persistent kernel's shape constraints
+        self._vp_split = (self.W.dt == torch.bfloat16 and spec.d_model == 256 and ex._GEMM_ENGINE != _lib.GEMM_SIMT and
+                          n_seq * self.Lv >= 4096 and os.environ.get("MOYOLO_VP_SPLIT", "1") != "0")
+        self._vp_ctas = int(os.environ.get("MOYOLO_VP_CTAS", "72" if n_seq <= 2 else "0"))
         S, C, dev = n_seq, spec.d_model, self.dev
         # device-resident track state (fixed capacity)
         self.n_tracks = torch.zeros(S, dtype=torch.int32, device=dev)
@@ -193,7 +197,15 @@ class TrackEngine:
             self.det_refer_in = [torch.zeros(S, n_detect, 4, device=dev)] * 2
             self._ring = [[torch.zeros(shp, dtype=self.W.dt, device=dev) for shp in selector.map_shapes()]
                           for _ in range(2)]
-        self.values = torch.zeros(S, self.Lv, spec.n_layers * C, dtype=self.W.dt, device=dev)
+        # Value projection AHEAD of the frame (bf16 tall path, frame inputs = feats): it is not captured in the frame
+        # graph but launched at submit time on its own stream, gated on an event the PREVIOUS frame's graph records
+        # when its last decoder layer has been issued -- so it runs on the SMs the previous frame's tail (ID
+        # assignment, QIM: a chain of tiny kernels) leaves idle instead of in front of this frame's first gather.
+        # Needs the all-layers value tensor double-buffered by frame parity.
+        self._vp_ahead = (selector is None and self._vp_split and os.environ.get("MOYOLO_VP_AHEAD", "1") != "0")
+        n_val = 2 if self._vp_ahead else 1
+        self.values_buf = [torch.zeros(S, self.Lv, spec.n_layers * C, dtype=self.W.dt, device=dev) for _ in range(n_val)]
+        self.values = self.values_buf[0]
         # streams / events
         self._main = torch.cuda.current_stream(dev)
         self._copy = torch.cuda.Stream(dev)
@@ -202,6 +214,10 @@ class TrackEngine:
         self._out = torch.cuda.Stream(dev)      # result copies (device -> pinned host), off the main stream
         self._ev_done = [torch.cuda.Event() for _ in range(self.DEPTH)]
         self._ev_copy = [torch.cuda.Event() for _ in range(2)]
+        self._ev_vp = [torch.cuda.Event() for _ in range(2)]                 # value projection of slot done
+        # recorded INSIDE the frame graphs, waited on from outside: raw events of the library (an external
+        # event-record node while capturing, a plain record otherwise)
+        self._ev_tail = [_lib.lib().moyolo_event_create() for _ in range(2)]
         # pinned host rings: [n_active (S) | ctrl (8)] and the packed frame rows
         self._max_rows = self._round(S * (n_detect + cap))
         self._h_info = torch.zeros(self.DEPTH, S + 8, dtype=torch.int32).pin_memory()
@@ -211,13 +227,20 @@ class TrackEngine:
         # the underlying cudaEvent lazily on the first record, so every event is recorded once here.
         self._ev_scratch = torch.cuda.Event()
         self._ev_graph = torch.cuda.Event()
-        for e in (*self._ev_done, *self._ev_copy, self._ev_scratch, self._ev_graph):
+        for e in (*self._ev_done, *self._ev_copy, self._ev_scratch, self._ev_graph, *self._ev_vp):
             e.record(self._main)
         torch.cuda.synchronize(dev)
         self._native = use_graphs and os.environ.get("MOYOLO_NATIVE_SUBMIT", "1") != "0"
         self._keep = [None, None]            # inputs of the two newest frames (alive until their copies ran)
         self._h_info_np = self._h_info.numpy()
         self._host_reset()
+
+    def __del__(self):
+        try:
+            for e in getattr(self, "_ev_tail", []):
+                _lib.lib().moyolo_event_destroy(e)
+        except Exception:  # interpreter shutdown
+            pass
 
     # ---- host-side bookkeeping ---------------------------------------------------------------
     def _host_reset(self):
@@ -284,16 +307,33 @@ class TrackEngine:
         fork = self.branches
         if self.selector is not None:  # input projection of the neck maps -> feats (head.py:1012-1029)
             self.selector.project(self._ring[p.slot], self.feats_in[p.slot])
-        # side branch: value projection of ALL layers in one GEMM (transformer.py:264; feats is the same
-        # tensor in every layer, transformer.py:705)
+        # side branch: value projection of ALL layers (transformer.py:264; feats is the same tensor in every layer,
+        # transformer.py:705). With the persistent tcgen05 kernel it is issued as two launches: layer 0's column
+        # slice on every SM (the first gather waits for nothing else), then layers 1.. on a CTA budget that leaves
+        # SMs free for the latency-bound main chain running next to it (they are needed one layer later).
+        values = self.values_buf[p.slot % len(self.values_buf)]
+        values2d = values.view(S * self.Lv, n_l * C)
+        split = self._vp_split and n_l > 1
+        self._ev_v0 = None
+
+        def value_proj():
+            if self._vp_ahead:   # launched at submit time (see _value_ahead), not part of the frame graph
+                return
+            if split:
+                ops.linear_tall(feats, W.value_proj.w[:C], W.value_proj.b[:C], values2d[:, :C])
+                if fork:
+                    self._ev_v0 = torch.cuda.Event()
+                    self._ev_v0.record(torch.cuda.current_stream(self.dev))
+                ops.linear_tall(feats, W.value_proj.w[C:], W.value_proj.b[C:], values2d[:, C:], max_ctas=self._vp_ctas)
+            else:
+                ops.linear(feats, W.value_proj.w, W.value_proj.b, out=values2d, engine=ex._GEMM_ENGINE)
+
         if fork:
             self._s_val.wait_stream(cur)
             with torch.cuda.stream(self._s_val):
-                ops.linear(feats, W.value_proj.w, W.value_proj.b, out=self.values.view(S * self.Lv, n_l * C),
-                           engine=ex._GEMM_ENGINE)
+                value_proj()
         else:
-            ops.linear(feats, W.value_proj.w, W.value_proj.b, out=self.values.view(S * self.Lv, n_l * C),
-                       engine=ex._GEMM_ENGINE)
+            value_proj()
         if self.selector is not None:  # detect queries of this frame (head.py:1031-1113)
             self.selector.select(self.feats_in[p.slot], self.det_embed_in[p.slot], self.det_refer_in[p.slot])
         ops.frame_assemble(S, nd, C, self.cap, self.n_tracks, self.t_ref, self.t_qpos, self.t_label, self.t_ids,
@@ -305,14 +345,19 @@ class TrackEngine:
         ro_host = [16 * i for i in range(S)] + [16 * S + R]
         for i, pk in enumerate(W.layers):
             last = i + 1 == n_l
-            value_view = self.values[:, :, i * C:(i + 1) * C]
+            value_view = values[:, :, i * C:(i + 1) * C]
 
             def before_gather(i=i):
                 if not fork:
                     return
                 if i == 0:
-                    cur.wait_stream(self._s_val)
+                    if self._ev_v0 is not None:
+                        cur.wait_event(self._ev_v0)   # layer 0's value slice only
+                    else:
+                        cur.wait_stream(self._s_val)
                 else:
+                    if i == 1 and self._ev_v0 is not None:
+                        cur.wait_stream(self._s_val)  # the other layers' slices
                     cur.wait_stream(self._s_box)   # refer[i] comes from the box head of layer i-1
 
             ex.run_layer_ws(pk, ws, ws.refer[i].view(R, 1, 4), value_view, self.shapes, S, ws.ro, ro_host,
@@ -324,6 +369,8 @@ class TrackEngine:
                     ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
             else:
                 ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
+        if self._vp_ahead:  # the next frame's value projection may start now: only the tail is left
+            _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
         boxes = ws.refer[n_l]
         ops.score_head(ws.x_lp, W.score_w, W.score_b, out=(ws.logits, ws.scores, ws.labels))
         st, ft, mt, it = self.thr
@@ -449,6 +496,14 @@ class TrackEngine:
         d.out_src[0], d.out_bytes[0] = p.info.data_ptr(), p.info.numel() * 4
         d.out_src[1], d.out_bytes[1] = p.frame_rows.data_ptr(), p.rows_pad * 8 * 4
         d.out_stream, d.out_stream_valid, d.ev_graph = self._out.cuda_stream, 1, self._ev_graph.cuda_event
+        if self._vp_ahead:
+            S, C, n_l = self.n_seq, self.spec.d_model, self.spec.n_layers
+            d.vp_valid, d.vp_stream = 1, self._s_val.cuda_stream
+            d.ev_vp = self._ev_vp[p.slot].cuda_event
+            d.vp_x, d.vp_ldx = self.feats_in[p.slot].data_ptr(), C
+            d.vp_w, d.vp_bias = self.W.value_proj.w.data_ptr(), self.W.value_proj.b.data_ptr()
+            d.vp_y, d.vp_ldy = self.values_buf[p.slot].data_ptr(), n_l * C
+            d.vp_M, d.vp_N, d.vp_max_ctas = S * self.Lv, n_l * C, self._vp_ctas
         return d
 
     def _submit_native(self, t: int, rows_pad: int, feats, det_embed, det_refer, want_rows: bool,
@@ -460,13 +515,14 @@ class TrackEngine:
         d.ev_slot_free = self._ev_done[(t - 2) % self.DEPTH].cuda_event if t >= 2 else None
         d.sync_inputs = 1 if sync_inputs else 0
         d.ev_done = self._ev_done[h].cuda_event
+        d.ev_tail_prev = self._ev_tail[(t - 1) % 2] if (self._vp_ahead and t > 0) else None
         d.in_src[0], d.in_src[1], d.in_src[2] = feats.data_ptr(), det_embed.data_ptr(), det_refer.data_ptr()
         d.out_dst[0] = self._h_info[h].data_ptr()
         d.out_dst[1] = self._h_rows[h].data_ptr()
         d.n_outputs = 2 if want_rows else 1
         self._keep[slot] = (feats, det_embed, det_refer)
         _lib.check(_lib.lib().moyolo_frame_submit(ctypes.byref(d)))
-        ops.LAUNCHES += p.n_launch
+        ops.LAUNCHES += p.n_launch + (1 if self._vp_ahead else 0)
         self._last_plan = p
         return {"frame": t, "plan": p, "rows_pad": rows_pad, "want_rows": want_rows}
 
@@ -513,6 +569,23 @@ class TrackEngine:
                 else:  # dtype conversion on device through the library's own cast kernel
                     ops.add_cast(src.reshape(-1).float().contiguous(), None, dst.dtype, out=dst.view(-1))
             self._ev_copy[slot].record(cs)
+        self._value_ahead(slot, frame)
+
+    def _value_ahead(self, slot: int, frame: int) -> None:
+        """Value projection of the frame whose inputs were just enqueued for ring slot `slot` (python path; the
+        native submission does the same inside moyolo_frame_submit)."""
+        if not self._vp_ahead:
+            return
+        vs = self._s_val
+        vs.wait_event(self._ev_copy[slot])
+        if frame > 0:
+            _lib.check(_lib.lib().moyolo_stream_wait_event(vs.cuda_stream, self._ev_tail[(frame - 1) % 2]))
+        S, C, n_l = self.n_seq, self.spec.d_model, self.spec.n_layers
+        with torch.cuda.stream(vs):
+            ops.linear_tall(self.feats_in[slot].view(S * self.Lv, C), self.W.value_proj.w, self.W.value_proj.b,
+                            self.values_buf[slot].view(S * self.Lv, n_l * C), max_ctas=self._vp_ctas)
+            self._ev_vp[slot].record(vs)
+        self._main.wait_event(self._ev_vp[slot])
 
     def _launch(self, frame: int, rows_pad: int, want_rows: bool) -> dict:
         slot = frame % 2
