@@ -72,6 +72,22 @@ def main():
         gam, bet = rn(256), rn(256)
         o32 = torch.empty(R, 256, device=dev); olp = torch.empty(R, 256, dtype=bf, device=dev); opl = torch.empty(R, 256, dtype=bf, device=dev)
         res[f"gemm_ln_K{K}"] = timed(lambda: ops.linear_add_layernorm(xin, wl, bl, rs, gam, bet, 1e-5, out_f32=o32, out_lp=olp, pos=ps, out_pos=opl))
+    # FFN block: two launches vs the one-launch cluster kernel
+    for F in (1024, 256):
+        w1 = (rn(F, 256) / 16).to(bf); b1 = rn(F)
+        w2 = (rn(256, F) / F ** 0.5).to(bf); b2 = rn(256)
+        xin = rn(R, 256).to(bf)
+        hbuf = torch.empty(R, F, dtype=bf, device=dev)
+        rs, ps = rn(R, 256), rn(R, 256)
+        gam, bet = rn(256), rn(256)
+        o32 = torch.empty(R, 256, device=dev); olp = torch.empty(R, 256, dtype=bf, device=dev); opl = torch.empty(R, 256, dtype=bf, device=dev)
+
+        def two():
+            ops.linear(xin, w1, b1, relu=True, out=hbuf)
+            ops.linear_add_layernorm(hbuf, w2, b2, rs, gam, bet, 1e-5, out_f32=o32, out_lp=olp, pos=ps, out_pos=opl)
+        res[f"ffn_F{F} (2 launches)"] = timed(two)
+        res[f"ffn_F{F} fused (1 launch)"] = timed(lambda: ops.ffn_add_layernorm(xin, w1, b1, w2, b2, hbuf, rs, gam, bet, 1e-5,
+                                                                                out_f32=o32, out_lp=olp, pos=ps, out_pos=opl))
     # attention
     qkv = rn(R, 3 * C).to(bf)
     per = R // S

@@ -181,6 +181,17 @@ int moyolo_linear_add_layernorm(const void* x, int64_t ldx, const void* w, const
                                 int64_t M, int N, int K, float* out_f32, void* out_lp, const float* pos,
                                 void* out_pos_lp, moyolo_stream_t stream);
 
+/* The whole post-norm FFN block in one launch (transformer.py:576-580; QIM qim.py:280-282, 290-298):
+ *   out = LayerNorm(residual + relu(x[M,C] . w1[F,C]^T + b1) . w2[C,F]^T + b2) * gamma + beta,  C == 256, F in {256, 1024}
+ * outputs as moyolo_linear_add_layernorm. h: bf16 [M, F] scratch (row stride F) that carries the hidden activations
+ * between the two GEMM phases of the kernel (one thread-block cluster of 8 CTAs per 128 rows; each CTA computes F/8
+ * hidden columns, a cluster barrier publishes them, then each CTA contracts the full hidden row tile for its 32
+ * output columns and the cluster normalises the row). Bit-identical to moyolo_linear(relu) + moyolo_linear_add_layernorm. */
+int moyolo_ffn_add_layernorm(const void* x, int64_t ldx, const void* w1, const float* b1, const void* w2,
+                             const float* b2, void* h, int F, const float* residual, const float* gamma,
+                             const float* beta, float eps, int64_t M, int C, float* out_f32, void* out_lp,
+                             const float* pos, void* out_pos_lp, moyolo_stream_t stream);
+
 /* Query self-attention over ragged sequences (transformer.py:637-641 with nn.MultiheadAttention
  * semantics: scores = (q/sqrt(head_dim)) . k^T, softmax over all keys of the same sequence, . v).
  * q, k, v: [R, n_heads*head_dim] slices with row strides ldq/ldk/ldv (elements) of dtype `dtype`;

@@ -444,6 +444,310 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 }
 
 // ------------------------------------------------------------------------------------------------
+// The whole post-norm FFN block in ONE launch (transformer.py:576-580; QIM qim.py:280-282, 290-298):
+//   out = LayerNorm(residual + W2 . relu(W1 . x + b1) + b2)
+// A thread-block cluster of 8 CTAs owns 128 rows. Phase 1: CTA r computes the hidden slab
+// H[:, r*BN1 : (r+1)*BN1] = relu(x . W1_r^T + b1_r) (tcgen05, accumulator in TMEM) and writes it as bf16 to the
+// global scratch `h`. A cluster barrier (release/acquire, with generic->async proxy fences around it) makes the
+// eight slabs visible; phase 2 streams the full H row tile [128 x F] back through TMA as the A operand of the
+// second GEMM (CTA r: output columns [32r, 32r+32), its W2 slab resident in shared memory since before the
+// dependency wait), and the epilogue is the cluster LayerNorm of gemm_tcgen05_kernel<32, ., true>.
+// Saves one dependent launch per FFN block; the arithmetic (operand rounding, K order) is that of the two-launch
+// path, so results are bit-identical to it.
+// ------------------------------------------------------------------------------------------------
+template <int BN1>
+struct FfnCtl {
+  uint64_t full[kStages];
+  uint64_t empty[kStages];
+  uint64_t w2_full;
+  uint64_t acc1_full;
+  uint64_t acc2_full;
+  uint32_t tmem_base;
+  float bias1[BN1];
+  float bias2[32];
+  float gamma[32];
+  float beta[32];
+  float red[2][kLnCols / 32][kBM];  // [mean | M2][peer CTA][row]
+};
+
+struct FfnArgs {
+  const float* b1;
+  const float* b2;
+  void* h;          // bf16 [M, F] scratch (row stride F)
+  int F;            // hidden width = 8 * BN1
+  int64_t M;
+  const float* residual;
+  const float* gamma;
+  const float* beta;
+  float eps;
+  float* out_f32;
+  void* out_lp;
+  const float* pos;
+  void* out_pos_lp;
+};
+
+template <int BN1>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_ffn_ln_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
+                   const __grid_constant__ CUtensorMap tmap_h, const __grid_constant__ CUtensorMap tmap_w2,
+                   const FfnArgs e) {
+  constexpr int NC = kLnCols / 32;                   // 8 CTAs per cluster
+  constexpr uint32_t kABytes = kBM * kBK * 2;        // 16 KiB
+  constexpr uint32_t kB1Bytes = BN1 * kBK * 2;       // W1 k-block of this CTA's hidden slab
+  constexpr uint32_t kB2Bytes = 32 * kBK * 2;        // W2 k-block of this CTA's 32 output columns (4 KiB)
+  constexpr uint32_t kTmemCols = BN1 + 32 <= 64 ? 64 : 256;
+  constexpr int kKB1 = kLnCols / kBK;                // K of phase 1 = d_model = 256 -> 4 k-blocks
+  static_assert(kKB1 == kStages, "phase 1 fills the ring exactly once");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = base;                                   // ring: x tiles (phase 1), then H tiles (phase 2)
+  uint8_t* smem_b1 = smem_a + kStages * kABytes;            // W1 slab, 4 k-blocks
+  uint8_t* smem_w2 = smem_b1 + kStages * kB1Bytes;          // W2 slab, F/64 k-blocks, resident
+  const int num_kb2 = e.F / kBK;
+  using Ctl = FfnCtl<BN1>;
+  Ctl* ctl = reinterpret_cast<Ctl*>(smem_w2 + static_cast<size_t>(num_kb2) * kB2Bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t my_rank = cluster_ctarank();
+  const int m0 = blockIdx.y * kBM;
+  const int n1 = static_cast<int>(my_rank) * BN1;   // hidden columns of phase 1
+  const int n2 = static_cast<int>(my_rank) * 32;    // output columns of phase 2
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w1)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_w2)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_x)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmap_h)) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(smem_u32(&ctl->full[s]), 2);
+      mbar_init(smem_u32(&ctl->empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ctl->w2_full), 1);
+    mbar_init(smem_u32(&ctl->acc1_full), 1);
+    mbar_init(smem_u32(&ctl->acc2_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // weights are immutable during a frame: both slabs are requested before waiting on the previous kernel
+    for (int kb = 0; kb < kKB1; ++kb) {
+      const uint32_t full = smem_u32(&ctl->full[kb]);
+      mbar_expect_tx(full, kB1Bytes);
+      tma_load_2d(smem_u32(smem_b1 + kb * kB1Bytes), &tmap_w1, full, kb * kBK, n1);
+    }
+    const uint32_t wf = smem_u32(&ctl->w2_full);
+    mbar_expect_tx(wf, static_cast<uint32_t>(num_kb2) * kB2Bytes);
+    for (int kb = 0; kb < num_kb2; ++kb) tma_load_2d(smem_u32(smem_w2 + kb * kB2Bytes), &tmap_w2, wf, kb * kBK, n2);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&ctl->tmem_base)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN1; i += kGemmThreads - 64) ctl->bias1[i] = e.b1 ? __ldg(e.b1 + n1 + i) : 0.0f;
+    if (threadIdx.x - 64 < 32) {
+      const int i = threadIdx.x - 64;
+      ctl->bias2[i] = e.b2 ? __ldg(e.b2 + n2 + i) : 0.0f;
+      ctl->gamma[i] = __ldg(e.gamma + n2 + i);
+      ctl->beta[i] = __ldg(e.beta + n2 + i);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_trigger();
+  const uint32_t tmem_acc1 = ctl->tmem_base;         // BN1 columns
+  const uint32_t tmem_acc2 = ctl->tmem_base + BN1;   // 32 columns
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      pdl_wait();
+      for (int kb = 0; kb < kKB1; ++kb) {  // phase 1: x tiles (the W1 halves of these stages are already in flight)
+        const uint32_t full = smem_u32(&ctl->full[kb]);
+        mbar_expect_tx(full, kABytes);
+        tma_load_2d(smem_u32(smem_a + kb * kABytes), &tmap_x, full, kb * kBK, m0);
+      }
+    }
+    __syncwarp();
+    cluster_arrive();  // #H: every CTA of the cluster has written its hidden slab
+    cluster_wait();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of H (acquired above) -> async-proxy reads
+      for (int kb = 0; kb < num_kb2; ++kb) {  // phase 2: H tiles; W2 is resident
+        const int it = kKB1 + kb, s = it % kStages;
+        const uint32_t full = smem_u32(&ctl->full[s]);
+        mbar_wait(smem_u32(&ctl->empty[s]), ((it / kStages) & 1) ^ 1);
+        mbar_arrive(full);  // the stage's second arrival (no B operand to wait for in this phase)
+        mbar_expect_tx(full, kABytes);
+        tma_load_2d(smem_u32(smem_a + s * kABytes), &tmap_h, full, kb * kBK, m0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc1 = make_idesc(kBM, BN1);
+      for (int kb = 0; kb < kKB1; ++kb) {
+        mbar_wait(smem_u32(&ctl->full[kb]), 0);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + kb * kABytes));
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_b1 + kb * kB1Bytes));
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) umma_bf16(tmem_acc1, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&ctl->empty[kb]));
+      }
+      umma_commit(smem_u32(&ctl->acc1_full));
+    }
+    __syncwarp();
+    cluster_arrive();  // #H
+    cluster_wait();
+    if (lane == 0) {
+      constexpr uint32_t idesc2 = make_idesc(kBM, 32);
+      mbar_wait(smem_u32(&ctl->w2_full), 0);
+      for (int kb = 0; kb < num_kb2; ++kb) {
+        const int it = kKB1 + kb, s = it % kStages;
+        mbar_wait(smem_u32(&ctl->full[s]), (it / kStages) & 1);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(smem_u32(smem_a + s * kABytes));
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem_w2 + kb * kB2Bytes));
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) umma_bf16(tmem_acc2, adesc + 2 * k, bdesc + 2 * k, idesc2, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&ctl->empty[s]));
+      }
+      umma_commit(smem_u32(&ctl->acc2_full));
+    }
+    __syncwarp();
+  } else {
+    // ===== epilogue warps 2..5: TMEM lane quadrant = warp % 4, one row per thread =====
+    const int quad = warp & 3;
+    const int rl = quad * 32 + lane;
+    const int64_t row = static_cast<int64_t>(m0) + rl;
+    const bool row_ok = row < e.M;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    pdl_wait();
+    // ---- phase 1 epilogue: hidden slab -> bias + ReLU -> bf16 -> global scratch ----
+    mbar_wait(smem_u32(&ctl->acc1_full), 0);
+    tc_fence_after();
+    {
+      __nv_bfloat16* hrow = static_cast<__nv_bfloat16*>(e.h) + row * e.F + n1;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN1; c0 += 32) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(tmem_acc1 + lane_base + c0, r0);
+        tmem_ld16(tmem_acc1 + lane_base + c0 + 16, r1);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r0[j]) + ctl->bias1[c0 + j], 0.0f);
+        store16<__nv_bfloat16>(hrow + c0, v, true);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = fmaxf(__uint_as_float(r1[j]) + ctl->bias1[c0 + 16 + j], 0.0f);
+        store16<__nv_bfloat16>(hrow + c0 + 16, v, true);
+      }
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");  // H is read back through TMA (async proxy) by every CTA
+    tc_fence_before();
+    cluster_arrive();  // #H (release: the slab is visible to the cluster)
+    // residual row slab (and the +pos operand) prefetched while the peers finish and phase 2 runs
+    float v[32], pv[32];
+    const int64_t goff = row * kLnCols + n2;
+    const bool want_pos = e.out_pos_lp != nullptr;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f), p4 = r4;
+      if (row_ok && e.residual != nullptr) r4 = *reinterpret_cast<const float4*>(e.residual + goff + 4 * j);
+      if (row_ok && want_pos) p4 = *reinterpret_cast<const float4*>(e.pos + goff + 4 * j);
+      v[4 * j] = r4.x; v[4 * j + 1] = r4.y; v[4 * j + 2] = r4.z; v[4 * j + 3] = r4.w;
+      pv[4 * j] = p4.x; pv[4 * j + 1] = p4.y; pv[4 * j + 2] = p4.z; pv[4 * j + 3] = p4.w;
+    }
+    cluster_wait();
+    // ---- phase 2 epilogue: + bias + residual, cluster LayerNorm ----
+    mbar_wait(smem_u32(&ctl->acc2_full), 0);
+    tc_fence_after();
+    {
+      uint32_t r0[16], r1[16];
+      tmem_ld16(tmem_acc2 + lane_base, r0);
+      tmem_ld16(tmem_acc2 + lane_base + 16, r1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] += __uint_as_float(r0[j]) + ctl->bias2[j];
+        v[16 + j] += __uint_as_float(r1[j]) + ctl->bias2[16 + j];
+      }
+    }
+    float ps = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) ps += v[j];
+    const float m_loc = ps * (1.0f / 32);
+    float pq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float d = v[j] - m_loc;
+      pq = fmaf(d, d, pq);
+    }
+    const uint32_t slot0 = smem_u32(&ctl->red[0][my_rank][rl]);
+    const uint32_t slot1 = smem_u32(&ctl->red[1][my_rank][rl]);
+#pragma unroll
+    for (int p = 0; p < NC; ++p) {
+      st_cluster_f32(slot0, p, m_loc);
+      st_cluster_f32(slot1, p, pq);
+    }
+    cluster_arrive();
+    cluster_wait();  // #LN
+    float msum = 0.0f, sq = 0.0f;
+#pragma unroll
+    for (int p = 0; p < NC; ++p) {
+      msum += ctl->red[0][p][rl];
+      sq += ctl->red[1][p][rl];
+    }
+    const float mean = msum * (1.0f / NC);
+#pragma unroll
+    for (int p = 0; p < NC; ++p) {
+      const float d = ctl->red[0][p][rl] - mean;
+      sq = fmaf(32.0f * d, d, sq);
+    }
+    const float rstd = rsqrtf(sq * (1.0f / kLnCols) + e.eps);
+    if (row_ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean) * rstd * ctl->gamma[j] + ctl->beta[j];
+      if (e.out_f32 != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(e.out_f32 + goff + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      if (e.out_lp != nullptr) {
+        __nv_bfloat16* d = static_cast<__nv_bfloat16*>(e.out_lp) + goff;
+        float h0[16], h1[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { h0[j] = v[j]; h1[j] = v[16 + j]; }
+        store16<__nv_bfloat16>(d, h0, true);
+        store16<__nv_bfloat16>(d + 16, h1, true);
+      }
+      if (want_pos) {
+        __nv_bfloat16* d = static_cast<__nv_bfloat16*>(e.out_pos_lp) + goff;
+        float h0[16], h1[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { h0[j] = v[j] + pv[j]; h1[j] = v[16 + j] + pv[16 + j]; }
+        store16<__nv_bfloat16>(d, h0, true);
+        store16<__nv_bfloat16>(d + 16, h1, true);
+      }
+    }
+  }
+  if (warp < 2) {  // producer / MMA warps take part in the LayerNorm barrier
+    cluster_arrive();
+    cluster_wait();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(ctl->tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Persistent weight-resident kernel for tall x (value projection). K == 256, N % 128 == 0.
 // CTA c owns output-column tile (c % n_tiles) and walks the row tiles group, group + n_groups, ...
 // ------------------------------------------------------------------------------------------------
@@ -1014,6 +1318,51 @@ int linear_ln_tcgen05(const void* x, int64_t ldx, const void* w, const float* bi
   e.residual = residual; e.gamma = gamma; e.beta = beta; e.eps = eps;
   e.out_f32 = out_f32; e.out_lp = out_lp; e.pos = pos; e.out_pos_lp = out_pos_lp;
   return launch_gemm<32, __nv_bfloat16, true>(tx, tx, tw, e, st);
+}
+
+bool ffn_ln_tcgen05_supported(const void* x, int64_t ldx, const void* w1, const void* w2, const void* h, int64_t M, int C,
+                              int F) {
+  return C == kLnCols && (F == 1024 || F == 256) && M > 0 && M < (1ll << 31) && aligned16(x) && aligned16(w1) &&
+         aligned16(w2) && aligned16(h) && (ldx * 2) % 16 == 0;
+}
+
+template <int BN1>
+static int launch_ffn_ln(const CUtensorMap& tx, const CUtensorMap& tw1, const CUtensorMap& th, const CUtensorMap& tw2,
+                         const FfnArgs& e, cudaStream_t st) {
+  const size_t smem = kStages * (kBM * kBK * 2 + BN1 * kBK * 2) + static_cast<size_t>(e.F / kBK) * 32 * kBK * 2 +
+                      sizeof(FfnCtl<BN1>) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t err = cudaFuncSetAttribute(gemm_ffn_ln_kernel<BN1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+    if (err != cudaSuccess)
+      return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(ffn smem=%zu): %s", smem, cudaGetErrorString(err));
+    configured = true;
+  }
+  dim3 grid(kLnCols / 32, static_cast<unsigned>((e.M + kBM - 1) / kBM));
+  launch_cluster(gemm_ffn_ln_kernel<BN1>, grid, dim3(kGemmThreads), smem, st, kLnCols / 32, tx, tw1, th, tw2, e);
+  return check_launch("gemm_ffn_ln_kernel");
+}
+
+// out = LayerNorm(residual + relu(x . w1^T + b1) . w2^T + b2) * gamma + beta; x [M,256], w1 [F,256], w2 [256,F],
+// h = bf16 [M,F] scratch.
+int ffn_ln_tcgen05(const void* x, int64_t ldx, const void* w1, const float* b1, const void* w2, const float* b2, void* h,
+                   int F, const float* residual, const float* gamma, const float* beta, float eps, int64_t M,
+                   float* out_f32, void* out_lp, const float* pos, void* out_pos_lp, cudaStream_t st) {
+  CUtensorMap tx, tw1, th, tw2;
+  const int bn1 = F / (kLnCols / 32);
+  int rc = make_tmap(&tx, x, M, kLnCols, ldx, kBM);
+  if (rc != MOYOLO_OK) return rc;
+  rc = make_tmap(&tw1, w1, F, kLnCols, kLnCols, bn1);
+  if (rc != MOYOLO_OK) return rc;
+  rc = make_tmap(&th, h, M, F, F, kBM);
+  if (rc != MOYOLO_OK) return rc;
+  rc = make_tmap(&tw2, w2, kLnCols, F, F, 32);
+  if (rc != MOYOLO_OK) return rc;
+  FfnArgs e{};
+  e.b1 = b1; e.b2 = b2; e.h = h; e.F = F; e.M = M; e.residual = residual; e.gamma = gamma; e.beta = beta; e.eps = eps;
+  e.out_f32 = out_f32; e.out_lp = out_lp; e.pos = pos; e.out_pos_lp = out_pos_lp;
+  return bn1 == 128 ? launch_ffn_ln<128>(tx, tw1, th, tw2, e, st) : launch_ffn_ln<32>(tx, tw1, th, tw2, e, st);
 }
 
 // Tall Linear(256->256) + LayerNorm (+ class scores): see gemm_rowln_kernel.

@@ -100,6 +100,11 @@ int linear_simt(const void* x, int64_t ldx, const void* w, const float* bias, vo
 }
 
 // implemented in gemm_tcgen05.cu
+bool ffn_ln_tcgen05_supported(const void* x, int64_t ldx, const void* w1, const void* w2, const void* h, int64_t M, int C,
+                              int F);
+int ffn_ln_tcgen05(const void* x, int64_t ldx, const void* w1, const float* b1, const void* w2, const float* b2, void* h,
+                   int F, const float* residual, const float* gamma, const float* beta, float eps, int64_t M,
+                   float* out_f32, void* out_lp, const float* pos, void* out_pos_lp, cudaStream_t st);
 bool linear_tall_supported(const void* x, int64_t ldx, const void* w, const void* y, int64_t ldy, int64_t M, int N, int K);
 int linear_tall(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy, int64_t M, int N,
                 const uint8_t* zero_rows, int max_ctas, cudaStream_t st);
@@ -186,4 +191,24 @@ extern "C" int moyolo_linear_add_layernorm(const void* x, int64_t ldx, const voi
                  MOYOLO_ERR_ALIGNMENT, "moyolo_linear_add_layernorm: row buffers must be 16-byte aligned");
   return linear_ln_tcgen05(x, ldx, w, bias, residual, gamma, beta, eps, M, K, out_f32, out_lp, pos, out_pos_lp,
                            static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int moyolo_ffn_add_layernorm(const void* x, int64_t ldx, const void* w1, const float* b1, const void* w2,
+                                        const float* b2, void* h, int F, const float* residual, const float* gamma,
+                                        const float* beta, float eps, int64_t M, int C, float* out_f32, void* out_lp,
+                                        const float* pos, void* out_pos_lp, moyolo_stream_t stream) {
+  using namespace moyolo;
+  MOYOLO_REQUIRE(x && w1 && w2 && h && gamma && beta, MOYOLO_ERR_BAD_ARG, "moyolo_ffn_add_layernorm: null pointer");
+  MOYOLO_REQUIRE(out_pos_lp == nullptr || pos != nullptr, MOYOLO_ERR_BAD_ARG,
+                 "moyolo_ffn_add_layernorm: out_pos_lp requested without pos");
+  MOYOLO_REQUIRE(M >= 0 && C > 0 && F > 0 && ldx >= C, MOYOLO_ERR_BAD_SHAPE, "moyolo_ffn_add_layernorm: bad sizes");
+  if (M == 0) return MOYOLO_OK;
+  MOYOLO_REQUIRE(ffn_ln_tcgen05_supported(x, ldx, w1, w2, h, M, C, F), MOYOLO_ERR_UNSUPPORTED,
+                 "moyolo_ffn_add_layernorm: needs d_model == 256, hidden in {256, 1024} and 16B-aligned bf16 operands");
+  MOYOLO_REQUIRE((residual == nullptr || aligned16(residual)) && (out_f32 == nullptr || aligned16(out_f32)) &&
+                     (out_lp == nullptr || aligned16(out_lp)) && (pos == nullptr || aligned16(pos)) &&
+                     (out_pos_lp == nullptr || aligned16(out_pos_lp)),
+                 MOYOLO_ERR_ALIGNMENT, "moyolo_ffn_add_layernorm: row buffers must be 16-byte aligned");
+  return ffn_ln_tcgen05(x, ldx, w1, b1, w2, b2, h, F, residual, gamma, beta, eps, M, out_f32, out_lp, pos, out_pos_lp,
+                        static_cast<cudaStream_t>(stream));
 }

@@ -269,8 +269,13 @@ def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offset
                            pkm.n_points, batch, pkm.softmax_mode, row_offsets, out=ws.g)
         g, b_, e = pk.norms[1]
         ops.linear_add_layernorm(ws.g, pkm.out.w, pkm.out.b, ws.x1, g, b_, e, out_f32=ws.x2, out_lp=ws.x2_lp)
-        ops.linear(ws.x2_lp, pk.ffn1.w, pk.ffn1.b, relu=True, out=ws.h, engine=eng)
         g, b_, e = pk.norms[2]
+        if ops.ffn_fused_supported(dt, C, pk.ffn1.w.shape[0]):   # FFN1 + FFN2 + residual + LayerNorm in one launch
+            ops.ffn_add_layernorm(ws.x2_lp, pk.ffn1.w, pk.ffn1.b, pk.ffn2.w, pk.ffn2.b, ws.h, ws.x2, g, b_, e,
+                                  out_f32=ws.x, out_lp=ws.x_lp, pos=pos_next,
+                                  out_pos=ws.xq_lp if pos_next is not None else None)
+            return
+        ops.linear(ws.x2_lp, pk.ffn1.w, pk.ffn1.b, relu=True, out=ws.h, engine=eng)
         ops.linear_add_layernorm(ws.h, pk.ffn2.w, pk.ffn2.b, ws.x2, g, b_, e, out_f32=ws.x, out_lp=ws.x_lp,
                                  pos=pos_next, out_pos=ws.xq_lp if pos_next is not None else None)
         return

@@ -278,6 +278,39 @@ def linear_add_layernorm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Ten
         float(eps), M, N, K, _ptr(out_f32), _ptr(out_lp), _ptr(pos), _ptr(out_pos), _stream()))
 
 
+# One-launch FFN block (moyolo_ffn_add_layernorm). Correct and bit-identical to the two launches it replaces, but
+# MEASURED SLOWER on B200 (382 rows: 12.6 us vs 10.7 us for hidden 1024, 8.8 vs 7.8 us for hidden 256): publishing the
+# hidden slab through L2 behind a cluster barrier costs more than the programmatic-dependent-launch boundary it
+# removes. Off by default; MOYOLO_FFN_FUSED=1 selects it.
+FFN_FUSED = _os.environ.get("MOYOLO_FFN_FUSED", "0") == "1"
+
+
+def ffn_fused_supported(dt, C: int, F: int) -> bool:
+    return FFN_FUSED and dt == torch.bfloat16 and C == 256 and F in (256, 1024)
+
+
+def ffn_add_layernorm(x: torch.Tensor, w1: torch.Tensor, b1, w2: torch.Tensor, b2, h: torch.Tensor,
+                      residual: Optional[torch.Tensor], gamma: torch.Tensor, beta: torch.Tensor, eps: float,
+                      out_f32: Optional[torch.Tensor] = None, out_lp: Optional[torch.Tensor] = None,
+                      pos: Optional[torch.Tensor] = None, out_pos: Optional[torch.Tensor] = None) -> None:
+    """LayerNorm(residual + relu(x . w1^T + b1) . w2^T + b2) in ONE launch (d_model 256, hidden 256 / 1024, bf16
+    operands); h is the bf16 [M, F] scratch for the hidden activations."""
+    _cuda(x, w1, b1, w2, b2, h, residual, gamma, beta, out_f32, out_lp, pos, out_pos)
+    M, Cc = x.shape
+    F = w1.shape[0]
+    if x.stride(1) != 1 or not w1.is_contiguous() or not w2.is_contiguous() or not h.is_contiguous() or \
+            h.shape[0] < M or h.shape[1] != F or w2.shape != (Cc, F):
+        raise ValueError("ffn_add_layernorm: x [M,C] contiguous columns, w1 [F,C], w2 [C,F], h [>=M,F] contiguous")
+    for t in (residual, out_f32, out_lp, pos, out_pos):
+        if t is not None and (not t.is_contiguous() or t.shape != (M, Cc)):
+            raise ValueError("ffn_add_layernorm: row buffers must be contiguous [M, C]")
+    _count(1)
+    _lib.check(_lib.lib().moyolo_ffn_add_layernorm(
+        x.data_ptr(), x.stride(0), w1.data_ptr(), _ptr(b1), w2.data_ptr(), _ptr(b2), h.data_ptr(), F, _ptr(residual),
+        gamma.data_ptr(), beta.data_ptr(), float(eps), M, Cc, _ptr(out_f32), _ptr(out_lp), _ptr(pos), _ptr(out_pos),
+        _stream()))
+
+
 def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, row_offsets: torch.Tensor,
                    row_offsets_host: Sequence[int], n_heads: int, attn_mask: Optional[torch.Tensor] = None,
                    out: Optional[torch.Tensor] = None, seg_len: Optional[torch.Tensor] = None) -> torch.Tensor:

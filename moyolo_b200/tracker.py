@@ -418,6 +418,12 @@ class TrackEngine:
         if ex.fused_epilogues(dt, C) and q["l1_w"].shape[0] % 64 == 0:
             ops.linear_add_layernorm(ws.att, q["o_w"], q["o_b"], ws.c_hs, *q["norm1"], 1e-5, out_f32=ws.q_tgt,   # :277-278
                                      out_lp=ws.q_tgt_lp2)
+            if ops.ffn_fused_supported(dt, C, q["l1_w"].shape[0]):   # each FFN block of the QIM in one launch
+                ops.ffn_add_layernorm(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], q["l2_w"], q["l2_b"], ws.q_h, ws.q_tgt,
+                                      *q["norm2"], 1e-5, out_lp=ws.q_tgt_lp3)                                    # :280-282
+                ops.ffn_add_layernorm(ws.q_tgt_lp3, q["f1_w"], q["f1_b"], q["f2_w"], q["f2_b"], ws.q_h, ws.c_pos,
+                                      *q["norm_feat"], 1e-5, out_f32=ws.q_new)                                   # :290-298
+                return
             ops.linear(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], relu=True, out=ws.q_h, engine=eng)
             ops.linear_add_layernorm(ws.q_h, q["l2_w"], q["l2_b"], ws.q_tgt, *q["norm2"], 1e-5,                  # :280-282
                                      out_lp=ws.q_tgt_lp3)

@@ -153,3 +153,50 @@ def test_linear_add_layernorm(dev, M, K):
     ref2 = torch.nn.functional.layer_norm(torch.nn.functional.linear(x.double(), w.double()), (C,), gamma.double(),
                                           beta.double(), 1e-5)
     assert rel_rms(o2.cpu().numpy(), ref2.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("M,F,with_pos", [(382, 1024, True), (77, 1024, False), (300, 256, False), (129, 256, True),
+                                          (3056, 1024, True)])
+def test_ffn_add_layernorm_fused(dev, M, F, with_pos):
+    """The one-launch FFN block (GEMM -> ReLU -> GEMM -> +residual -> LayerNorm in one cluster kernel) against the
+    two launches it replaces (bit-identical: same operand rounding and K order) and against an fp64 reference of
+    transformer.py:576-580 on the same bf16-rounded operands."""
+    from moyolo_b200 import ops
+    C = 256
+    assert ops.ffn_fused_supported(torch.bfloat16, C, F) in (True, False)  # opt-in (MOYOLO_FFN_FUSED=1): measured slower
+    g = torch.Generator().manual_seed(M + F)
+    x = torch.randn(M, C, generator=g).bfloat16()
+    w1 = (torch.randn(F, C, generator=g) / C ** 0.5).bfloat16()
+    b1 = torch.randn(F, generator=g) * 0.1
+    w2 = (torch.randn(C, F, generator=g) / F ** 0.5).bfloat16()
+    b2 = torch.randn(C, generator=g) * 0.1
+    res = torch.randn(M, C, generator=g)
+    pos = torch.randn(M, C, generator=g)
+    gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    xd, w1d, b1d, w2d, b2d, resd, posd, gd, bd = (t.to(dev) for t in (x, w1, b1, w2, b2, res, pos, gam, bet))
+
+    def outs():
+        return (torch.zeros(M, C, device=dev), torch.zeros(M, C, dtype=torch.bfloat16, device=dev),
+                torch.zeros(M, C, dtype=torch.bfloat16, device=dev) if with_pos else None)
+
+    # two-launch path
+    h2 = torch.zeros(M, F, dtype=torch.bfloat16, device=dev)
+    a32, alp, apos = outs()
+    ops.linear(xd, w1d, b1d, relu=True, out=h2)
+    ops.linear_add_layernorm(h2, w2d, b2d, resd, gd, bd, 1e-5, out_f32=a32, out_lp=alp, pos=posd if with_pos else None,
+                             out_pos=apos)
+    # fused
+    h1 = torch.zeros(M, F, dtype=torch.bfloat16, device=dev)
+    f32, flp, fpos = outs()
+    ops.ffn_add_layernorm(xd, w1d, b1d, w2d, b2d, h1, resd, gd, bd, 1e-5, out_f32=f32, out_lp=flp,
+                          pos=posd if with_pos else None, out_pos=fpos)
+    torch.cuda.synchronize()
+    assert torch.equal(h1, h2), "hidden activations differ"
+    assert torch.equal(f32, a32) and torch.equal(flp, alp)
+    if with_pos:
+        assert torch.equal(fpos, apos)
+    # fp64 reference on the same operands (hidden rounded to bf16 as both device paths do)
+    hid = torch.relu(x.double() @ w1.double().T + b1.double()).bfloat16().double()
+    t = hid @ w2.double().T + b2.double() + res.double()
+    ref = torch.nn.functional.layer_norm(t, (C,), gam.double(), bet.double(), 1e-5)
+    assert rel_rms(f32.cpu().double().numpy(), ref.numpy()) < 5e-3  # bf16 rounding of the hidden layer dominates
