@@ -19,7 +19,8 @@ from moyolo_b200 import _lib, synthetic as syn  # noqa: E402
 from moyolo_b200.tracker import DecoderWeights, TrackEngine, _FramePlan  # noqa: E402
 
 dev = torch.device("cuda:0")
-_NOT_LAUNCH = {"moyolo_last_error", "moyolo_version", "moyolo_track_workspace_bytes", "moyolo_device_supported"}
+_NOT_LAUNCH = {"moyolo_last_error", "moyolo_version", "moyolo_track_workspace_bytes", "moyolo_device_supported",
+               "moyolo_event_record", "moyolo_event_create", "moyolo_event_destroy", "moyolo_stream_wait_event"}
 
 
 class Proxy:

@@ -157,7 +157,8 @@ class TrackEngine:
     def __init__(self, sd, spec: DecoderSpec, shapes, device, precision: str = "bf16", n_detect: int = 300,
                  n_seq: int = 1, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, iou_thresh=0.8,
                  weights: Optional[DecoderWeights] = None, cap: int = 512, bucket: int = 64, margin: int = 32,
-                 use_graphs: bool = True, table_rows: int = 1 << 18, branches: bool = True, selector=None):
+                 use_graphs: bool = True, table_rows: int = 1 << 18, branches: bool = True, selector=None,
+                 value_ahead: Optional[bool] = None):
         self.dev = torch.device(device)
         self.spec, self.shapes, self.n_detect, self.n_seq = spec, [list(s) for s in shapes], n_detect, n_seq
         self.Lv = level_sizes(shapes)
@@ -202,7 +203,10 @@ class TrackEngine:
         # when its last decoder layer has been issued -- so it runs on the SMs the previous frame's tail (ID
         # assignment, QIM: a chain of tiny kernels) leaves idle instead of in front of this frame's first gather.
         # Needs the all-layers value tensor double-buffered by frame parity.
-        self._vp_ahead = (selector is None and self._vp_split and os.environ.get("MOYOLO_VP_AHEAD", "1") != "0")
+        self._vp_ahead = (selector is None and self._vp_split and os.environ.get("MOYOLO_VP_AHEAD", "1") != "0" and
+                          value_ahead is not False)
+        if value_ahead and not self._vp_ahead:
+            raise ValueError("value_ahead needs the bf16 tcgen05 path, frame inputs = feats and S*Lv >= 4096")
         n_val = 2 if self._vp_ahead else 1
         self.values_buf = [torch.zeros(S, self.Lv, spec.n_layers * C, dtype=self.W.dt, device=dev) for _ in range(n_val)]
         self.values = self.values_buf[0]

@@ -658,3 +658,49 @@ def test_msda_proj_fused_equals_gemm_plus_gather(dev, B, Q, name, ref_dim):
     assert rel_rms(fused.float().cpu().numpy(), ref.numpy()) < BF16_TOL
     assert rel_rms(two.float().cpu().numpy(), ref.numpy()) < BF16_TOL
     assert rel_rms(fused.float().cpu().numpy(), two.float().cpu().numpy()) < BF16_TOL
+
+
+def test_value_projection_ahead_equals_in_graph(dev):
+    """The value projection launched AHEAD of the frame graph (own stream, CTA budget, gated on the previous
+    frame's tail event, double-buffered value tensor) must give exactly the rows of the engine that keeps it
+    inside the graph: same kernel, same tiles -> bit-identical IDs, boxes and scores over a pipelined sequence
+    on the C1 pyramid (Lv = 8400, large enough for the persistent kernel), incl. the synchronous step() path."""
+    m, ops, syn, mg, tp = _mods()
+    from moyolo_b200.tracker import DecoderWeights, TrackEngine
+    spec = syn.DecoderSpec()
+    shapes = [list(s) for s in syn.PYRAMIDS["C1"]]
+    sd = syn.make_decoder_state(spec, 3)
+    n_frames, nd, S = 7, 100, 1
+    gen = syn.SequenceGenerator(syn.SequenceSpec(name="C1", n_frames=n_frames, n_detect=nd, seed=5, shapes=shapes),
+                                spec.d_model, dev)
+    frames = [tuple(t.clone() for t in gen.next_frame()) for _ in range(n_frames)]
+    eng0 = TrackEngine(sd, spec, shapes, dev, "bf16", nd, S, value_ahead=False)
+    out0 = eng0.step(frames[0][0][None], frames[0][1][None], frames[0][2][None])[0]
+    sd = syn.calibrate_score_bias(sd, out0["logits"], spec, 0.1)
+    W = DecoderWeights(sd, spec, dev, "bf16")
+    batches = [tuple(x[None].to(torch.bfloat16 if i == 0 else torch.float32).contiguous() for i, x in enumerate(f))
+               for f in frames]
+    results = {}
+    for ahead in (False, True):
+        eng = TrackEngine(sd, spec, shapes, dev, "bf16", nd, S, weights=W, value_ahead=ahead)
+        assert eng._vp_ahead == ahead
+        got = {}
+        for t in range(n_frames):
+            eng.submit(*batches[t], want_rows=True)
+            if t > 0:
+                got[t - 1] = {k: v.clone() for k, v in eng.collect(t - 1)[0].items()}
+        got[n_frames - 1] = {k: v.clone() for k, v in eng.collect(n_frames - 1)[0].items()}
+        results[ahead] = (got, eng.track_table().clone().cpu(), eng.n_tracks_host())
+        # synchronous path on a fresh sequence
+        eng.reset()
+        outs = [eng.step(*batches[t])[0] for t in range(3)]
+        results[(ahead, "step")] = [{k: v.clone().cpu() for k, v in o.items()} for o in outs]
+    a, b = results[False], results[True]
+    assert a[2] == b[2] and max(a[2]) > 0, "no track was carried"
+    assert torch.equal(a[1], b[1])
+    for t in range(n_frames):
+        for k in ("ids", "boxes", "scores", "labels"):
+            assert torch.equal(a[0][t][k], b[0][t][k]), (t, k)
+    for oa, ob in zip(results[(False, "step")], results[(True, "step")]):
+        for k in oa:
+            assert torch.equal(oa[k], ob[k]), ("step", k)
