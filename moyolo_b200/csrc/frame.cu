@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
   }
 }
 
-// grid = (n_seq, kCompactChunks), 1024 threads. The ID assignment of RuntimeTrackerBase.update
+// grid = (n_seq, kCompactChunks), 256 threads. The ID assignment of RuntimeTrackerBase.update
 // (head.py:1232-1243) fused with the active-track compaction: every CTA of a sequence repeats the (cheap,
 // deterministic) assignment scan -- `max_obj_id++` in query order == exclusive prefix count of the new rows; the
 // packed scan carries the count of active rows in its high half -- and then copies the compact rows
@@ -229,7 +229,9 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
 // arrays: the other CTAs still read the inputs) and the selection. The duplicate filter + renumbering of the
 // reference only changes the ID counters (its filtered copy is dropped, head.py:1268-1283): it runs afterwards,
 // off the critical path, as moyolo_track_suppress_batched.
-__global__ void __launch_bounds__(1024) frame_assign_compact_kernel(
+constexpr int kAssignThreads = 256;  // 8 warps: cheap block scans; each thread owns ceil(n/256) consecutive rows
+
+__global__ void __launch_bounds__(kAssignThreads) frame_assign_compact_kernel(
     int C, int cap, int rows_pad, const int32_t* __restrict__ row_offsets, const float* __restrict__ scores,
     const int64_t* __restrict__ ids_in, const int64_t* __restrict__ dis_in, const int64_t* __restrict__ counters,
     float score_thresh, float filter_thresh, int miss_tolerance, int64_t* __restrict__ ids_out,
@@ -499,7 +501,7 @@ extern "C" int moyolo_frame_assign_compact(int n_seq, int C, int cap, int64_t ro
   MOYOLO_REQUIRE(aligned16(refer_logit) && aligned16(pos) && aligned16(hs) && aligned16(boxes) && aligned16(c_ref) &&
                      aligned16(c_pos) && aligned16(c_hs) && aligned16(c_box) && aligned16(q_qk_lp) && aligned16(q_tgt_lp),
                  MOYOLO_ERR_ALIGNMENT, "frame_assign_compact: row buffers must be 16-byte aligned");
-  launch_k(frame_assign_compact_kernel, dim3(n_seq, kCompactChunks), dim3(1024), 0, static_cast<cudaStream_t>(stream),
+  launch_k(frame_assign_compact_kernel, dim3(n_seq, kCompactChunks), dim3(kAssignThreads), 0, static_cast<cudaStream_t>(stream),
       C, cap, static_cast<int>(rows_pad), row_offsets, scores, ids_in, dis_in, counters, score_thresh, filter_thresh,
       miss_tolerance, ids_out, dis_out, labels, refer_logit, pos, hs, boxes, n_active, active_index, c_ref, c_pos,
       c_hs, c_box, t_label, t_ids, t_dis, ctrl, q_qk_lp, q_tgt_lp, lp_dtype == MOYOLO_BF16 ? 1 : 0, num_pos_feats,
