@@ -31,6 +31,25 @@ import torch.distributed as dist  # noqa: E402
 METRIC = "decoder_frames_per_sec"
 UNIT = "frames/s"
 
+# stdout carries exactly ONE line (the JSON result). Libraries write banners to fd 1 (e.g. "NCCL version ..." when
+# NCCL_DEBUG=VERSION): everything else is sent to stderr and the real stdout is restored for the result line.
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -414,7 +433,7 @@ def run_moyolo(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        _emit(line)
 
 
 # ------------------------------------------------------------------------------------------ f1 leg
@@ -541,11 +560,12 @@ def run_reference(args):
                        "baseline_config": "BASELINE.json configs[1]"},
             "cpu_baseline": {"value": round(fps, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": round(fps, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 if __name__ == "__main__":
     a = parse()
+    _quiet_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
