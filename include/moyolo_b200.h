@@ -438,6 +438,10 @@ typedef struct {
   int64_t vp_M;
   int vp_N;
   int vp_max_ctas;
+  /* vp_valid == 2: instead of the value projection alone, launch the captured graph `pre_graph_exec` on vp_stream
+   * (everything of the frame that depends on its inputs only: input projection, value projection, query selection);
+   * same event protocol (wait ev_copy [and ev_tail_prev], record ev_vp, main_stream waits ev_vp). */
+  void* pre_graph_exec;
 } moyolo_frame_submit_t;
 int moyolo_frame_submit(const moyolo_frame_submit_t* d);
 

@@ -30,7 +30,7 @@ class FrameSubmit(C.Structure):
                 ("out_stream", _p), ("out_stream_valid", _i), ("ev_graph", _p),
                 ("vp_stream", _p), ("vp_valid", _i), ("ev_tail_prev", _p), ("ev_vp", _p),
                 ("vp_x", _p), ("vp_ldx", _l), ("vp_w", _p), ("vp_bias", _p), ("vp_y", _p), ("vp_ldy", _l),
-                ("vp_M", _l), ("vp_N", _i), ("vp_max_ctas", _i)]
+                ("vp_M", _l), ("vp_N", _i), ("vp_max_ctas", _i), ("pre_graph_exec", _p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/moyolo_b200.h declares

@@ -36,16 +36,20 @@ extern "C" int moyolo_frame_submit(const moyolo_frame_submit_t* d) {
     RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_copy), cs), "record copy");
     RT_CHECK(cudaStreamWaitEvent(ms, static_cast<cudaEvent_t>(d->ev_copy), 0), "wait copy");
   }
-  if (d->vp_valid == 1) {
-    MOYOLO_REQUIRE(d->ev_vp != nullptr && d->vp_x && d->vp_w && d->vp_y, MOYOLO_ERR_BAD_ARG,
-                   "frame_submit: value projection needs ev_vp and x / w / y");
+  if (d->vp_valid == 1 || d->vp_valid == 2) {
+    MOYOLO_REQUIRE(d->ev_vp != nullptr && (d->vp_valid == 2 ? d->pre_graph_exec != nullptr : (d->vp_x && d->vp_w && d->vp_y)),
+                   MOYOLO_ERR_BAD_ARG, "frame_submit: value projection needs ev_vp and x / w / y (or a prelude graph)");
     cudaStream_t vs = static_cast<cudaStream_t>(d->vp_stream);
     if (d->n_inputs > 0) RT_CHECK(cudaStreamWaitEvent(vs, static_cast<cudaEvent_t>(d->ev_copy), 0), "vp wait copy");
     if (d->ev_tail_prev != nullptr)
       RT_CHECK(cudaStreamWaitEvent(vs, static_cast<cudaEvent_t>(d->ev_tail_prev), 0), "vp wait previous tail");
-    const int rc = moyolo_linear_tall(d->vp_x, d->vp_ldx, d->vp_w, d->vp_bias, d->vp_y, d->vp_ldy, d->vp_M, d->vp_N, 256,
-                                      nullptr, d->vp_max_ctas, d->vp_stream);
-    if (rc != MOYOLO_OK) return rc;
+    if (d->vp_valid == 2) {
+      RT_CHECK(cudaGraphLaunch(static_cast<cudaGraphExec_t>(d->pre_graph_exec), vs), "prelude graph launch");
+    } else {
+      const int rc = moyolo_linear_tall(d->vp_x, d->vp_ldx, d->vp_w, d->vp_bias, d->vp_y, d->vp_ldy, d->vp_M, d->vp_N, 256,
+                                        nullptr, d->vp_max_ctas, d->vp_stream);
+      if (rc != MOYOLO_OK) return rc;
+    }
     RT_CHECK(cudaEventRecord(static_cast<cudaEvent_t>(d->ev_vp), vs), "record vp");
     RT_CHECK(cudaStreamWaitEvent(ms, static_cast<cudaEvent_t>(d->ev_vp), 0), "wait vp");
   }

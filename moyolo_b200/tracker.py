@@ -193,9 +193,17 @@ class TrackEngine:
             self._ring = [[self.feats_in[i], self.det_embed_in[i], self.det_refer_in[i]] for i in range(2)]
         else:
             assert selector.S == S and selector.nq == n_detect and selector.dt == self.W.dt
-            self.feats_in = [torch.zeros(S, self.Lv, C, dtype=self.W.dt, device=dev)] * 2
-            self.det_embed_in = [torch.zeros(S, n_detect, C, device=dev)] * 2
-            self.det_refer_in = [torch.zeros(S, n_detect, 4, device=dev)] * 2
+            # Query selection AHEAD of the frame (see _prelude): input projection, value projection and the top-k
+            # selection of frame t+1 run as their own small graph on a side stream while frame t is still decoding
+            # (the latency-bound decoder leaves most SMs idle); their outputs are then double-buffered by frame parity.
+            self._sel_ahead = (use_graphs and self.W.dt == torch.bfloat16 and value_ahead is not False and
+                               os.environ.get("MOYOLO_SEL_AHEAD", "1") != "0")
+            nb = 2 if self._sel_ahead else 1
+            fi = [torch.zeros(S, self.Lv, C, dtype=self.W.dt, device=dev) for _ in range(nb)]
+            de = [torch.zeros(S, n_detect, C, device=dev) for _ in range(nb)]
+            dr = [torch.zeros(S, n_detect, 4, device=dev) for _ in range(nb)]
+            self.feats_in, self.det_embed_in, self.det_refer_in = [fi[i % nb] for i in range(2)], \
+                [de[i % nb] for i in range(2)], [dr[i % nb] for i in range(2)]
             self._ring = [[torch.zeros(shp, dtype=self.W.dt, device=dev) for shp in selector.map_shapes()]
                           for _ in range(2)]
         # Value projection AHEAD of the frame (bf16 tall path, frame inputs = feats): it is not captured in the frame
@@ -205,9 +213,12 @@ class TrackEngine:
         # Needs the all-layers value tensor double-buffered by frame parity.
         self._vp_ahead = (selector is None and self._vp_split and os.environ.get("MOYOLO_VP_AHEAD", "1") != "0" and
                           value_ahead is not False)
-        if value_ahead and not self._vp_ahead:
-            raise ValueError("value_ahead needs the bf16 tcgen05 path, frame inputs = feats and S*Lv >= 4096")
-        n_val = 2 if self._vp_ahead else 1
+        if selector is None:
+            self._sel_ahead = False
+        if value_ahead and not (self._vp_ahead or self._sel_ahead):
+            raise ValueError("value_ahead needs the bf16 tcgen05 path (and S*Lv >= 4096 when the inputs are feats)")
+        self._pre_graphs = [None, None]   # per input slot: captured prelude graph (selection-ahead mode)
+        n_val = 2 if (self._vp_ahead or self._sel_ahead) else 1
         self.values_buf = [torch.zeros(S, self.Lv, spec.n_layers * C, dtype=self.W.dt, device=dev) for _ in range(n_val)]
         self.values = self.values_buf[0]
         # streams / events
@@ -309,7 +320,7 @@ class TrackEngine:
         cur = torch.cuda.current_stream(self.dev)
         feats = self.feats_in[p.slot].view(S * self.Lv, C)
         fork = self.branches
-        if self.selector is not None:  # input projection of the neck maps -> feats (head.py:1012-1029)
+        if self.selector is not None and not self._sel_ahead:  # input projection of the neck maps -> feats (head.py:1012-1029)
             self.selector.project(self._ring[p.slot], self.feats_in[p.slot])
         # side branch: value projection of ALL layers (transformer.py:264; feats is the same tensor in every layer,
         # transformer.py:705). With the persistent tcgen05 kernel it is issued as two launches: layer 0's column
@@ -321,7 +332,7 @@ class TrackEngine:
         self._ev_v0 = None
 
         def value_proj():
-            if self._vp_ahead:   # launched at submit time (see _value_ahead), not part of the frame graph
+            if self._vp_ahead or self._sel_ahead:   # launched at submit time (see _value_ahead), not part of the frame graph
                 return
             if split:
                 ops.linear_tall(feats, W.value_proj.w[:C], W.value_proj.b[:C], values2d[:, :C])
@@ -338,7 +349,7 @@ class TrackEngine:
                 value_proj()
         else:
             value_proj()
-        if self.selector is not None:  # detect queries of this frame (head.py:1031-1113)
+        if self.selector is not None and not self._sel_ahead:  # detect queries of this frame (head.py:1031-1113)
             self.selector.select(self.feats_in[p.slot], self.det_embed_in[p.slot], self.det_refer_in[p.slot])
         ops.frame_assemble(S, nd, C, self.cap, self.n_tracks, self.t_ref, self.t_qpos, self.t_label, self.t_ids,
                            self.t_dis, W.class_embed, self.det_embed_in[p.slot], self.det_refer_in[p.slot], ws.x,
@@ -506,6 +517,10 @@ class TrackEngine:
         d.out_src[0], d.out_bytes[0] = p.info.data_ptr(), p.info.numel() * 4
         d.out_src[1], d.out_bytes[1] = p.frame_rows.data_ptr(), p.rows_pad * 8 * 4
         d.out_stream, d.out_stream_valid, d.ev_graph = self._out.cuda_stream, 1, self._ev_graph.cuda_event
+        if self._sel_ahead:
+            d.vp_valid, d.vp_stream = 2, self._s_val.cuda_stream
+            d.ev_vp = self._ev_vp[p.slot].cuda_event
+            d.pre_graph_exec = self._prelude(p.slot).raw_cuda_graph_exec()
         if self._vp_ahead:
             S, C, n_l = self.n_seq, self.spec.d_model, self.spec.n_layers
             d.vp_valid, d.vp_stream = 1, self._s_val.cuda_stream
@@ -532,7 +547,7 @@ class TrackEngine:
         d.n_outputs = 2 if want_rows else 1
         self._keep[slot] = (feats, det_embed, det_refer)
         _lib.check(_lib.lib().moyolo_frame_submit(ctypes.byref(d)))
-        ops.LAUNCHES += p.n_launch + (1 if self._vp_ahead else 0)
+        ops.LAUNCHES += p.n_launch + (1 if self._vp_ahead else 0) + (self._pre_launches if self._sel_ahead else 0)
         self._last_plan = p
         return {"frame": t, "plan": p, "rows_pad": rows_pad, "want_rows": want_rows}
 
@@ -581,9 +596,56 @@ class TrackEngine:
             self._ev_copy[slot].record(cs)
         self._value_ahead(slot, frame)
 
+    def _prelude(self, slot: int) -> torch.cuda.CUDAGraph:
+        """Selection-ahead mode: everything of a frame that depends on its INPUTS only -- input projection of the neck
+        maps (head.py:1012-1029), the all-layers value projection (transformer.py:264) and the encoder-side query
+        selection (head.py:1031-1113) -- captured once per input slot as its own graph."""
+        g = self._pre_graphs[slot]
+        if g is not None:
+            return g
+        S, C, n_l, sel = self.n_seq, self.spec.d_model, self.spec.n_layers, self.selector
+
+        def run():
+            cur = torch.cuda.current_stream(self.dev)
+            sel.project(self._ring[slot], self.feats_in[slot])
+            self._s_box.wait_stream(cur)   # value projection next to the selection chain
+            with torch.cuda.stream(self._s_box):
+                ops.linear(self.feats_in[slot].view(S * self.Lv, C), self.W.value_proj.w, self.W.value_proj.b,
+                           out=self.values_buf[slot].view(S * self.Lv, n_l * C), engine=ex._GEMM_ENGINE)
+            sel.select(self.feats_in[slot], self.det_embed_in[slot], self.det_refer_in[slot])
+            cur.wait_stream(self._s_box)
+
+        torch.cuda.synchronize(self.dev)
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):   # eager pass: loads modules, sets kernel attributes
+            run()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        before = ops.LAUNCHES
+        with torch.cuda.graph(g):
+            run()
+        self._pre_launches = ops.LAUNCHES - before
+        ops.LAUNCHES = before
+        torch.cuda.synchronize(self.dev)
+        self._pre_graphs[slot] = g
+        return g
+
     def _value_ahead(self, slot: int, frame: int) -> None:
-        """Value projection of the frame whose inputs were just enqueued for ring slot `slot` (python path; the
-        native submission does the same inside moyolo_frame_submit)."""
+        """Value projection (or, in selection-ahead mode, the whole prelude graph) of the frame whose inputs were
+        just enqueued for ring slot `slot` (python path; the native submission does the same inside
+        moyolo_frame_submit)."""
+        if self._sel_ahead:
+            g = self._prelude(slot)
+            vs = self._s_val
+            vs.wait_event(self._ev_copy[slot])
+            with torch.cuda.stream(vs):
+                g.replay()
+                self._ev_vp[slot].record(vs)
+            ops.LAUNCHES += self._pre_launches
+            self._main.wait_event(self._ev_vp[slot])
+            return
         if not self._vp_ahead:
             return
         vs = self._s_val

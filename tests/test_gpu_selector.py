@@ -129,3 +129,40 @@ def test_frames_from_neck_maps_equal_frames_from_selected_queries(dev, precision
             born += int((a[s]["ids"] >= 0).sum())
     assert born > 0, "no object was ever tracked"
     assert torch.equal(eng_maps.track_table(), eng_dec.track_table())
+
+
+def test_selection_ahead_equals_in_graph_pipelined(dev):
+    """Selection-ahead mode (input projection + value projection + query selection as their own graph on a side
+    stream, overlapping the previous frame) against the in-graph mode over a pipelined submit/collect sequence:
+    bit-identical rows and track table."""
+    from moyolo_b200.selector import QuerySelector
+    from moyolo_b200.tracker import TrackEngine
+    spec = syn.DecoderSpec()
+    shapes = [list(s) for s in syn.PYRAMIDS["tiny"]]
+    ch, nd, S, n_frames = (256, 512, 512), 48, 2, 8
+    sd = dict(syn.make_decoder_state(spec, 7))
+    sd.update(syn.make_selector_state(spec, ch, 0))
+    sd[f"dec_score_head.{spec.n_layers - 1}.bias"] = sd[f"dec_score_head.{spec.n_layers - 1}.bias"] + 3.0
+    base = [m.permute(0, 2, 3, 1).contiguous() for m in syn.make_pyramid_maps(5, S, shapes, ch)]
+    g = torch.Generator().manual_seed(11)
+    frames = [[(m + 0.05 * t * torch.randn(m.shape, generator=g)).to(dev).to(torch.bfloat16).contiguous() for m in base]
+              for t in range(n_frames)]
+    out = {}
+    for ahead in (False, True):
+        sel = QuerySelector(sd, spec, shapes, ch, dev, "bf16", nd, S)
+        eng = TrackEngine(sd, spec, shapes, dev, "bf16", nd, S, selector=sel, value_ahead=ahead)
+        assert eng._sel_ahead == ahead
+        got = {}
+        for t in range(n_frames):
+            eng.submit(*frames[t], want_rows=True)
+            if t > 0:
+                got[t - 1] = [{k: v.clone() for k, v in o.items()} for o in eng.collect(t - 1)]
+        got[n_frames - 1] = [{k: v.clone() for k, v in o.items()} for o in eng.collect(n_frames - 1)]
+        out[ahead] = (got, eng.track_table().clone().cpu(), eng.n_tracks_host())
+    a, b = out[False], out[True]
+    assert a[2] == b[2] and max(a[2]) > 0
+    assert torch.equal(a[1], b[1])
+    for t in range(n_frames):
+        for s in range(S):
+            for k in ("ids", "boxes", "scores", "labels"):
+                assert torch.equal(a[0][t][s][k], b[0][t][s][k]), (t, s, k)
