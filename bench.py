@@ -489,7 +489,8 @@ def selection_leg(args, sd, spec, syn, shapes, device, S, K, Wm):
     res["unit"] = UNIT
     res["h2d_bytes_per_step"] = int(sum(x.numel() * x.element_size() for x in frames[0]))
     res["tracks_carried_end"] = eng.n_tracks_host()
-    res["note"] = ("frame = input_proj of the neck maps + query selection (top-k of all Lv positions) + the decoder frame; "
+    res["note"] = ("frame = input_proj of the neck maps + query selection (top-k of all Lv positions) + the decoder frame "
+                   "(the selection of frame t+1 runs as its own graph on a side stream while frame t decodes); "
                    "value: maps resident in HBM, e2e: pinned host maps, H2D inside the timed region")
     return res
 

@@ -148,10 +148,11 @@ def test_selection_ahead_equals_in_graph_pipelined(dev):
     frames = [[(m + 0.05 * t * torch.randn(m.shape, generator=g)).to(dev).to(torch.bfloat16).contiguous() for m in base]
               for t in range(n_frames)]
     out = {}
-    for ahead in (False, True):
+    for ahead in (False, True, "abort"):   # "abort": ahead mode with mis-speculated padded sizes (device-side abort + re-launch)
         sel = QuerySelector(sd, spec, shapes, ch, dev, "bf16", nd, S)
-        eng = TrackEngine(sd, spec, shapes, dev, "bf16", nd, S, selector=sel, value_ahead=ahead)
-        assert eng._sel_ahead == ahead
+        kw = dict(margin=0, bucket=8) if ahead == "abort" else {}
+        eng = TrackEngine(sd, spec, shapes, dev, "bf16", nd, S, selector=sel, value_ahead=bool(ahead), **kw)
+        assert eng._sel_ahead == bool(ahead)
         got = {}
         for t in range(n_frames):
             eng.submit(*frames[t], want_rows=True)
@@ -159,10 +160,14 @@ def test_selection_ahead_equals_in_graph_pipelined(dev):
                 got[t - 1] = [{k: v.clone() for k, v in o.items()} for o in eng.collect(t - 1)]
         got[n_frames - 1] = [{k: v.clone() for k, v in o.items()} for o in eng.collect(n_frames - 1)]
         out[ahead] = (got, eng.track_table().clone().cpu(), eng.n_tracks_host())
-    a, b = out[False], out[True]
-    assert a[2] == b[2] and max(a[2]) > 0
-    assert torch.equal(a[1], b[1])
-    for t in range(n_frames):
-        for s in range(S):
-            for k in ("ids", "boxes", "scores", "labels"):
-                assert torch.equal(a[0][t][s][k], b[0][t][s][k]), (t, s, k)
+        if ahead == "abort":
+            assert eng.aborts > 0, "the abort / re-launch path was not exercised"
+    a = out[False]
+    for key in (True, "abort"):
+        b = out[key]
+        assert a[2] == b[2] and max(a[2]) > 0
+        assert torch.equal(a[1], b[1]), key
+        for t in range(n_frames):
+            for s in range(S):
+                for k in ("ids", "boxes", "scores", "labels"):
+                    assert torch.equal(a[0][t][s][k], b[0][t][s][k]), (key, t, s, k)
