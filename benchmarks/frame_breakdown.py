@@ -80,6 +80,17 @@ def main():
             ts.append(a.elapsed_time(b) * 1e3)
         ts.sort()
         res[f"{name}_single_replay_us_median"] = round(ts[len(ts) // 2], 1)
+        # 20 replays back to back on one stream (no copies, no event hand-offs, no value projection): what a graph
+        # boundary itself costs
+        eng._state_restore(snap)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(20):
+            p.graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        res[f"{name}_back_to_back_us_per_replay"] = round(a.elapsed_time(b) * 1e3 / 20, 1)
         res[f"{name}_rows_pad"] = p.rows_pad
         res[f"{name}_launches"] = p.n_launch
         del eng

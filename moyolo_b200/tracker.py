@@ -170,6 +170,7 @@ class TrackEngine:
         self._vp_split = (self.W.dt == torch.bfloat16 and spec.d_model == 256 and ex._GEMM_ENGINE != _lib.GEMM_SIMT and
                           n_seq * self.Lv >= 4096 and os.environ.get("MOYOLO_VP_SPLIT", "1") != "0")
         self._vp_ctas = int(os.environ.get("MOYOLO_VP_CTAS", "72" if n_seq <= 2 else "0"))
+        self._vp_gate = os.environ.get("MOYOLO_VP_GATE", "1") != "0"   # gate the ahead projection on the previous tail
         S, C, dev = n_seq, spec.d_model, self.dev
         # device-resident track state (fixed capacity)
         self.n_tracks = torch.zeros(S, dtype=torch.int32, device=dev)
@@ -540,7 +541,7 @@ class TrackEngine:
         d.ev_slot_free = self._ev_done[(t - 2) % self.DEPTH].cuda_event if t >= 2 else None
         d.sync_inputs = 1 if sync_inputs else 0
         d.ev_done = self._ev_done[h].cuda_event
-        d.ev_tail_prev = self._ev_tail[(t - 1) % 2] if (self._vp_ahead and t > 0) else None
+        d.ev_tail_prev = self._ev_tail[(t - 1) % 2] if (self._vp_ahead and self._vp_gate and t > 0) else None
         d.in_src[0], d.in_src[1], d.in_src[2] = feats.data_ptr(), det_embed.data_ptr(), det_refer.data_ptr()
         d.out_dst[0] = self._h_info[h].data_ptr()
         d.out_dst[1] = self._h_rows[h].data_ptr()
@@ -650,7 +651,7 @@ class TrackEngine:
             return
         vs = self._s_val
         vs.wait_event(self._ev_copy[slot])
-        if frame > 0:
+        if frame > 0 and self._vp_gate:
             _lib.check(_lib.lib().moyolo_stream_wait_event(vs.cuda_stream, self._ev_tail[(frame - 1) % 2]))
         S, C, n_l = self.n_seq, self.spec.d_model, self.spec.n_layers
         with torch.cuda.stream(vs):
