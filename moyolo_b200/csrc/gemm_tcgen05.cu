@@ -757,10 +757,15 @@ gemm_ffn_ln_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
 constexpr int kSK = 256;
 constexpr int kSKB = kSK / kBK;   // 4 k-blocks
 constexpr int kSlabBytes = 32 * 128;  // one epilogue slab: 32 rows x 64 bf16
+// The kernel is bound by its EPILOGUE (TMEM -> registers -> bf16 -> swizzled shared memory -> TMA store), not by the
+// MMAs: it runs EIGHT epilogue warps -- two per TMEM lane quadrant, each taking every other 64-column slab of a tile --
+// next to the producer and the MMA warp (320 threads).
+constexpr int kStreamEpiWarps = 8;
+constexpr int kStreamThreads = 64 + kStreamEpiWarps * 32;
 template <int BN>
 struct StreamCfg {
-  static constexpr int kStages = BN == 256 ? 4 : 6;  // x-tile ring of 16 KiB stages (shared memory budget)
-  static constexpr int kSlabs = BN == 256 ? 2 : 4;   // output slabs per epilogue warp (TMA stores in flight)
+  static constexpr int kStages = BN == 256 ? 3 : 6;  // x-tile ring of 16 KiB stages (shared memory budget)
+  static constexpr int kSlabs = BN == 256 ? 1 : 2;   // output slabs per epilogue warp (TMA stores in flight)
 };
 
 template <int BN>
@@ -775,7 +780,7 @@ struct StreamCtl {
 };
 
 template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kStreamThreads, 1)
 gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                    const __grid_constant__ CUtensorMap tmap_y, const float* __restrict__ bias,
                    const uint8_t* __restrict__ zero_rows, int64_t M, int n_tiles, int n_groups) {
@@ -788,9 +793,9 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_b = base;                                  // 4 k-blocks of the weight slab, resident
   uint8_t* smem_a = smem_b + kSKB * kBBytes;               // ring of 16 KiB x-tile stages
-  uint8_t* smem_o = smem_a + kSStages * kABytes;           // 4 warps x 2 slabs x 4 KiB
+  uint8_t* smem_o = smem_a + kSStages * kABytes;           // 8 warps x 2 slabs x 4 KiB
   constexpr int kSlabs = StreamCfg<BN>::kSlabs;
-  StreamCtl<BN>* ctl = reinterpret_cast<StreamCtl<BN>*>(smem_o + 4 * kSlabs * kSlabBytes);
+  StreamCtl<BN>* ctl = reinterpret_cast<StreamCtl<BN>*>(smem_o + kStreamEpiWarps * kSlabs * kSlabBytes);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x % n_tiles;
@@ -810,7 +815,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     mbar_init(smem_u32(&ctl->b_full), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&ctl->acc_full[s]), 1);
-      mbar_init(smem_u32(&ctl->acc_empty[s]), 4);  // one arrive per epilogue warp
+      mbar_init(smem_u32(&ctl->acc_empty[s]), kStreamEpiWarps);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t bf = smem_u32(&ctl->b_full);
@@ -824,7 +829,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < kSBN; i += kGemmThreads - 64) ctl->bias[i] = bias ? __ldg(bias + n0 + i) : 0.0f;
+    for (int i = threadIdx.x - 64; i < kSBN; i += kStreamThreads - 64) ctl->bias[i] = bias ? __ldg(bias + n0 + i) : 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -873,9 +878,11 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     }
     __syncwarp();
   } else {
-    // epilogue warp `quad` owns rows [quad*32, quad*32+32) of every tile and two private 4 KiB slabs
+    // epilogue warp (quad, part): rows [quad*32, quad*32+32) of every tile (its TMEM lane quadrant = warp % 4), the
+    // 64-column slabs part, part + 2, ...; two private 4 KiB staging slabs
     const int quad = warp & 3;
-    uint8_t* slab = smem_o + quad * kSlabs * kSlabBytes;
+    const int part = (warp - 2) >> 2;   // 0 or 1
+    uint8_t* slab = smem_o + (warp - 2) * kSlabs * kSlabBytes;
     pdl_wait();
     int n_store = 0;
     for (int t = 0; t < my_tiles; ++t) {
@@ -887,7 +894,7 @@ gemm_stream_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
       tc_fence_after();
       const uint32_t tacc = tmem_base + as * kSBN + (static_cast<uint32_t>(quad * 32) << 16);
 #pragma unroll 1
-      for (int half = 0; half < kSBN / 64; ++half) {
+      for (int half = part; half < kSBN / 64; half += kStreamEpiWarps / 4) {
         uint8_t* sl = slab + (n_store % kSlabs) * kSlabBytes;
         // the TMA store issued kSlabs slabs ago must have finished READING this slab
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kSlabs - 1) : "memory");
@@ -1194,7 +1201,7 @@ template <int BN>
 static int launch_stream_bn(const void* x, int64_t ldx, const void* w, const float* bias, void* y, int64_t ldy, int64_t M,
                             int N, const uint8_t* zero_rows, int max_ctas, cudaStream_t st) {
   constexpr size_t smem = kSKB * BN * kBK * 2 + StreamCfg<BN>::kStages * kBM * kBK * 2 +
-                          4 * StreamCfg<BN>::kSlabs * kSlabBytes +
+                          kStreamEpiWarps * StreamCfg<BN>::kSlabs * kSlabBytes +
                           sizeof(StreamCtl<BN>) + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt in to");
   static bool configured = false;
@@ -1227,7 +1234,7 @@ static int launch_stream_bn(const void* x, int64_t ldx, const void* w, const flo
   }
   if (n_groups < 1) n_groups = 1;
   if (n_groups > m_tiles) n_groups = m_tiles;
-  launch_k(gemm_stream_kernel<BN>, dim3(n_tiles * n_groups), dim3(kGemmThreads), smem, st, tx, tw, ty, bias, zero_rows, M,
+  launch_k(gemm_stream_kernel<BN>, dim3(n_tiles * n_groups), dim3(kStreamThreads), smem, st, tx, tw, ty, bias, zero_rows, M,
            n_tiles, n_groups);
   return check_launch("gemm_stream_kernel");
 }
