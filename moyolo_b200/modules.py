@@ -86,6 +86,10 @@ class MSDeformAttn(nn.Module):
         self.value_proj = nn.Linear(d_model, d_model)
         self.output_proj = nn.Linear(d_model, d_model)
         self.precision: Optional[str] = None  # None -> executor default
+        # True: forward() builds an autograd graph (training through the op): the four linears, the
+        # softmax and the location arithmetic are torch ops on the GPU, the gather is MSDeformAttnFunction (forward AND
+        # backward kernels of libmoyolo_b200), everything fp32. False (default): the fused inference kernels.
+        self.differentiable = False
         self._reset_parameters()
 
     def _reset_parameters(self):
@@ -118,6 +122,12 @@ class MSDeformAttn(nn.Module):
         num_points = refer_bbox.shape[-1]
         if num_points not in (2, 4):
             raise ValueError(f'Last dim of reference_points must be 2 or 4, but got {num_points}.')
+        if torch.is_grad_enabled():
+            if self.differentiable:
+                return self._forward_autograd(query, refer_bbox, value, value_shapes, value_mask)
+            if query.requires_grad or value.requires_grad or refer_bbox.requires_grad:
+                raise RuntimeError("moyolo_b200.MSDeformAttn runs its inference kernels, which build no autograd graph, "
+                                   "but an input requires grad: set module.differentiable = True for the training path")
         dt = self._dt()
         pk = ex.cached_pack(self, "msda", ex.MsdaPack, dt)
         C = self.d_model
@@ -132,6 +142,42 @@ class MSDeformAttn(nn.Module):
         refer = refer_bbox.reshape(bs * len_q, refer_bbox.shape[2], num_points).float().contiguous()
         out = ex.msda_forward(pk, q_lp, refer, val.view(bs, len_v, C), value_shapes, bs, None, dt)
         return out.view(bs, len_q, C).to(query.dtype)
+
+
+    def _forward_autograd(self, query, refer_bbox, value, value_shapes, value_mask=None):
+        """transformer.py:262-286 as a differentiable graph; the core (utils.py:41-78) is the library's gather with
+        its own backward kernel (msda_ext.MSDeformAttnFunction)."""
+        import torch.nn.functional as F
+        from .msda_ext import MSDeformAttnFunction
+        if not query.is_cuda:
+            raise RuntimeError("Not implemented on the CPU")
+        bs, len_q, C = query.shape
+        len_v = value.shape[1]
+        H, L, P = self.n_heads, self.n_levels, self.n_points
+        v = F.linear(value.float(), self.value_proj.weight, self.value_proj.bias)
+        if value_mask is not None:
+            v = v.masked_fill(value_mask[..., None], 0.0)
+        v = v.view(bs, len_v, H, C // H)
+        q = query.float()
+        off = F.linear(q, self.sampling_offsets.weight, self.sampling_offsets.bias).view(bs, len_q, H, L, P, 2)
+        att = F.linear(q, self.attention_weights.weight, self.attention_weights.bias).view(bs, len_q, H, L * P)
+        if self.my_softmax and type(self).__name__ == "MOTRMSDeformAttn":
+            e = att.exp()
+            att = e / (1.0 + e.sum(-1, keepdim=True))                  # transformer.py:239-244
+        else:
+            att = F.softmax(att, -1)
+        att = att.view(bs, len_q, H, L, P)
+        rb = refer_bbox.float()
+        if rb.shape[-1] == 2:
+            norm = torch.as_tensor([[w, h] for h, w in value_shapes], dtype=torch.float32, device=query.device)
+            loc = rb[:, :, None, :, None, :] + off / norm[None, None, None, :, None, :]
+        else:
+            loc = rb[:, :, None, :, None, :2] + off / P * rb[:, :, None, :, None, 2:] * 0.5
+        shapes_t = torch.as_tensor([list(x) for x in value_shapes], dtype=torch.long, device=query.device)
+        lsi = torch.cat((shapes_t.new_zeros((1,)), shapes_t.prod(1).cumsum(0)[:-1]))
+        core = MSDeformAttnFunction.apply(v.contiguous(), shapes_t, lsi, loc.contiguous(), att.contiguous(),
+                                          self.im2col_step)
+        return F.linear(core, self.output_proj.weight, self.output_proj.bias).to(query.dtype)
 
 
 class MOTRMSDeformAttn(MSDeformAttn):

@@ -704,3 +704,46 @@ def test_value_projection_ahead_equals_in_graph(dev):
     for oa, ob in zip(results[(False, "step")], results[(True, "step")]):
         for k in oa:
             assert torch.equal(oa[k], ob[k]), ("step", k)
+
+
+@pytest.mark.parametrize("ref_dim,with_mask", [(4, False), (2, True)])
+def test_msdeform_attn_module_training_path(dev, ref_dim, with_mask):
+    """MSDeformAttn with `differentiable = True`: output and the gradients w.r.t. every parameter and input against
+    torch.autograd through the fp64 CPU oracle of the module (oracle/torch_port.msdeform_attn_forward, pinned to the
+    reference by msda_*.npz); without the switch an input that requires grad is refused loudly."""
+    m, ops, syn, mg, tp = _mods()
+    spec = syn.DecoderSpec()
+    shapes = [list(s) for s in syn.PYRAMIDS["tiny"]]
+    B, Q = 2, 19
+    attn = m.MSDeformAttn(spec.d_model, spec.n_levels, spec.n_heads, spec.n_points)
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():   # non-degenerate offsets / logits (the default init zeroes those weights)
+        attn.sampling_offsets.weight.copy_(torch.randn(attn.sampling_offsets.weight.shape, generator=g) * 0.02)
+        attn.attention_weights.weight.copy_(torch.randn(attn.attention_weights.weight.shape, generator=g) * 0.05)
+    query, refer, feats, _ = syn.make_module_inputs(3, B, Q, spec.d_model, shapes, ref_dim=ref_dim,
+                                                    ref_levels=1 if ref_dim == 4 else spec.n_levels)
+    mask = (torch.rand(B, feats.shape[1], generator=g) < 0.1) if with_mask else None
+    go = torch.randn(B, Q, spec.d_model, generator=g)
+    # oracle: fp64 CPU autograd
+    p64 = {k: v.detach().double().clone().requires_grad_(True) for k, v in attn.state_dict().items()}
+    q64, v64, r64 = (t.double().clone().requires_grad_(True) for t in (query, feats, refer))
+    out64 = tp.msdeform_attn_forward(p64, q64, r64, v64, shapes, spec.n_heads, spec.n_levels, spec.n_points, mask,
+                                     core=tp.msda_core_gather)
+    out64.backward(go.double())
+    # device: training path
+    attn = attn.to(dev)
+    qd, vd, rd = (t.to(dev).clone().requires_grad_(True) for t in (query, feats, refer))
+    with pytest.raises(RuntimeError, match="differentiable"):
+        attn(qd, rd, vd, shapes, None if mask is None else mask.to(dev))
+    attn.differentiable = True
+    out = attn(qd, rd, vd, shapes, None if mask is None else mask.to(dev))
+    out.backward(go.to(dev))
+    assert rel_rms(out.detach().cpu().numpy(), out64.detach().numpy()) < FP32_TOL
+    for name, got, ref in (("query", qd.grad, q64.grad), ("value", vd.grad, v64.grad), ("refer", rd.grad, r64.grad)):
+        assert rel_rms(got.cpu().numpy(), ref.numpy()) < 5e-4, name
+    for k, prm in attn.named_parameters():
+        assert rel_rms(prm.grad.cpu().numpy(), p64[k].grad.numpy()) < 5e-4, k
+    # and under no_grad the module still runs the fused inference kernels
+    with torch.no_grad():
+        out_inf = attn(qd.detach(), rd.detach(), vd.detach(), shapes, None if mask is None else mask.to(dev))
+    assert rel_rms(out_inf.cpu().numpy(), out64.detach().numpy()) < FP32_TOL
