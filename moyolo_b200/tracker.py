@@ -379,7 +379,8 @@ class TrackEngine:
             ex.run_layer_ws(pk, ws, ws.refer[i].view(R, 1, 4), value_view, self.shapes, S, ws.ro, ro_host,
                             ws.pos, None if last else ws.pos, dt, before_gather)
             # box refinement of this layer (transformer.py:709): only the NEXT layer's gather needs it
-            if fork and not last:
+            # (the last layer's box head runs next to the score head, which only needs the layer output)
+            if fork:
                 self._s_box.wait_stream(cur)
                 with torch.cuda.stream(self._s_box):
                     ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
@@ -389,6 +390,8 @@ class TrackEngine:
             _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
         boxes = ws.refer[n_l]
         ops.score_head(ws.x_lp, W.score_w, W.score_b, out=(ws.logits, ws.scores, ws.labels))
+        if fork:
+            cur.wait_stream(self._s_box)   # final boxes
         st, ft, mt, it = self.thr
         # ID assignment (head.py:1232-1243) + active-track selection/compaction (qim.py:184-187) in one launch
         ops.frame_assign_compact(S, C, self.cap, R, ws.ro, ws.scores, ws.ids0, ws.dis0, self.counters, ws.ids, ws.dis,
