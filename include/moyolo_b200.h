@@ -306,7 +306,9 @@ int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,
  *   updated ids, one launch. ids_in/dis_in (from frame_assemble) are read-only; the updated values go to
  *   ids_out/dis_out [rows_pad] (must not alias; padding rows get -1 / 0). counters is NOT modified: follow with
  *   moyolo_track_suppress_batched (any time before the next frame) for the reference's counter side effects.
- * moyolo_frame_writeback: t_qpos <- new_qpos rows, t_ref <- inverse_sigmoid(c_box), n_tracks <- n_active
+ * moyolo_frame_writeback: t_qpos <- new_qpos rows, t_ref <- inverse_sigmoid(c_box) (or, with c_box == NULL, of
+ *   boxes[row_offsets[s] + active_index[.]]: the frame then passes boxes == NULL to moyolo_frame_assign_compact, which
+ *   no longer has to wait for the last layer's box head), n_tracks <- n_active
  *   (MOTR/models/qim.py:298-300); optional info int32 [n_seq+8] = (n_active | ctrl), the frame summary a host reads.
  * moyolo_frame_emit: the frame's results. frame_rows [rows_pad, 8] fp32 = (id, cx, cy, w, h, score, label,
  *   seq) for every row (padding rows id = -1) -- what a host reads back with one copy -- and the tracked
@@ -347,7 +349,8 @@ int moyolo_frame_assign_compact(int n_seq, int C, int cap, int64_t rows_pad, con
                                 moyolo_stream_t stream);
 int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,
                            const float* new_qpos, const float* c_box, float* t_qpos, float* t_ref,
-                           int32_t* n_tracks, const int32_t* ctrl, int32_t* info, moyolo_stream_t stream);
+                           int32_t* n_tracks, const int32_t* ctrl, int32_t* info, const float* boxes,
+                           const int32_t* active_index, moyolo_stream_t stream);
 int moyolo_frame_emit(int n_seq, int64_t rows_pad, const int32_t* row_offsets, const int64_t* ids,
                       const float* boxes, const float* scores, const int32_t* labels, const int32_t* n_active,
                       const int32_t* active_index, const int32_t* seq_ids, float* frame_rows, float* table,

@@ -76,7 +76,7 @@ SIGNATURES = {
     "moyolo_track_suppress_batched": (_i, [_p, _p, _p, _p, _i, _l, _f, _p, _p, _p]),
     "moyolo_frame_assign_compact": (_i, [_i, _i, _i, _l, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _p, _p, _p,
                                          _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _f, _p]),
-    "moyolo_frame_writeback": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "moyolo_frame_writeback": (_i, [_i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
     "moyolo_frame_submit": (_i, [C.POINTER(FrameSubmit)]),
     "moyolo_event_create": (_p, []),
     "moyolo_event_destroy": (_i, [_p]),

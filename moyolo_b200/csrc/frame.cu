@@ -338,7 +338,9 @@ __global__ void __launch_bounds__(kAssignThreads) frame_assign_compact_kernel(
     }
     if (lane == 0) {
       *reinterpret_cast<float4*>(c_ref + dst * 4) = rl;
-      *reinterpret_cast<float4*>(c_box + dst * 4) = *reinterpret_cast<const float4*>(boxes + src * 4);
+      // boxes == NULL: the caller lets frame_writeback gather the refined boxes itself, so that this kernel does not
+      // have to wait for the last layer's box head
+      if (boxes != nullptr) *reinterpret_cast<float4*>(c_box + dst * 4) = *reinterpret_cast<const float4*>(boxes + src * 4);
     }
   }
 }
@@ -348,7 +350,8 @@ __global__ void frame_writeback_kernel(int C, int cap, const int32_t* __restrict
                                        const int32_t* __restrict__ n_active, const float* __restrict__ new_qpos,
                                        const float* __restrict__ c_box, float* __restrict__ t_qpos,
                                        float* __restrict__ t_ref, int32_t* __restrict__ n_tracks,
-                                       const int32_t* __restrict__ ctrl, int32_t* __restrict__ info) {
+                                       const int32_t* __restrict__ ctrl, int32_t* __restrict__ info,
+                                       const float* __restrict__ boxes, const int32_t* __restrict__ active_index) {
   pdl_trigger();
   pdl_wait();
   // host-visible frame summary: [n_active (n_seq) | ctrl (8)], written even for an aborted frame
@@ -365,7 +368,11 @@ __global__ void frame_writeback_kernel(int C, int cap, const int32_t* __restrict
   for (int j = warp; j < k; j += nwarps) {
     const int64_t src = off + j, dst = static_cast<int64_t>(s) * cap + j;
     for (int c = lane; c < C; c += 32) t_qpos[dst * C + c] = new_qpos[src * C + c];
-    if (lane < 4) t_ref[dst * 4 + lane] = inv_sigmoid_(c_box[src * 4 + lane]);
+    // boxes of the active rows: already compacted (c_box) or gathered here through the selection (boxes, active_index)
+    if (lane < 4) {
+      const float bx = boxes != nullptr ? boxes[(static_cast<int64_t>(off) + active_index[src]) * 4 + lane] : c_box[src * 4 + lane];
+      t_ref[dst * 4 + lane] = inv_sigmoid_(bx);
+    }
   }
   if (blockIdx.y == 0 && threadIdx.x == 0) n_tracks[s] = k;
 }
@@ -489,8 +496,8 @@ extern "C" int moyolo_frame_assign_compact(int n_seq, int C, int cap, int64_t ro
                                            const int32_t* ctrl, void* q_qk_lp, void* q_tgt_lp, int lp_dtype,
                                            int num_pos_feats, float temperature, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(row_offsets && scores && ids_in && dis_in && counters && ids_out && dis_out && labels &&
-                     refer_logit && pos && hs && boxes && n_active && active_index && c_ref && c_pos && c_hs &&
-                     c_box && t_label && t_ids && t_dis,
+                     refer_logit && pos && hs && n_active && active_index && c_ref && c_pos && c_hs &&
+                     (boxes == nullptr || c_box) && t_label && t_ids && t_dis,
                  MOYOLO_ERR_BAD_ARG, "frame_assign_compact: null pointer");
   MOYOLO_REQUIRE(ids_in != ids_out && dis_in != dis_out, MOYOLO_ERR_BAD_ARG,
                  "frame_assign_compact: ids/dis outputs must not alias the inputs");
@@ -511,14 +518,15 @@ extern "C" int moyolo_frame_assign_compact(int n_seq, int C, int cap, int64_t ro
 
 extern "C" int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,
                                       const float* new_qpos, const float* c_box, float* t_qpos, float* t_ref,
-                                      int32_t* n_tracks, const int32_t* ctrl, int32_t* info,
-                                      moyolo_stream_t stream) {
-  MOYOLO_REQUIRE(row_offsets && n_active && new_qpos && c_box && t_qpos && t_ref && n_tracks, MOYOLO_ERR_BAD_ARG,
-                 "frame_writeback: null pointer");
+                                      int32_t* n_tracks, const int32_t* ctrl, int32_t* info, const float* boxes,
+                                      const int32_t* active_index, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(row_offsets && n_active && new_qpos && t_qpos && t_ref && n_tracks &&
+                     (c_box != nullptr || (boxes != nullptr && active_index != nullptr)),
+                 MOYOLO_ERR_BAD_ARG, "frame_writeback: null pointer (needs c_box, or boxes + active_index)");
   MOYOLO_REQUIRE(n_seq > 0 && C > 0 && cap > 0, MOYOLO_ERR_BAD_SHAPE, "frame_writeback: bad sizes");
   dim3 grid(n_seq, 8);
   launch_k(frame_writeback_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), C, cap, row_offsets, n_active, new_qpos,
-                                                                             c_box, t_qpos, t_ref, n_tracks, ctrl, info);
+           c_box, t_qpos, t_ref, n_tracks, ctrl, info, c_box != nullptr ? nullptr : boxes, active_index);
   return check_launch("frame_writeback_kernel");
 }
 

@@ -523,9 +523,9 @@ def frame_assign_compact(n_seq, C, cap, rows_pad, row_offsets, scores, ids_in, d
     _lib.check(_lib.lib().moyolo_frame_assign_compact(
         n_seq, C, cap, rows_pad, row_offsets.data_ptr(), scores.data_ptr(), ids_in.data_ptr(), dis_in.data_ptr(),
         counters.data_ptr(), float(score_thresh), float(filter_thresh), int(miss_tolerance), ids_out.data_ptr(),
-        dis_out.data_ptr(), labels.data_ptr(), refer_logit.data_ptr(), pos.data_ptr(), hs.data_ptr(), boxes.data_ptr(),
+        dis_out.data_ptr(), labels.data_ptr(), refer_logit.data_ptr(), pos.data_ptr(), hs.data_ptr(), _ptr(boxes),
         n_active.data_ptr(), active_index.data_ptr(), c_ref.data_ptr(), c_pos.data_ptr(), c_hs.data_ptr(),
-        c_box.data_ptr(), t_label.data_ptr(), t_ids.data_ptr(), t_dis.data_ptr(), _ptr(ctrl), _ptr(q_qk_lp),
+        _ptr(c_box), t_label.data_ptr(), t_ids.data_ptr(), t_dis.data_ptr(), _ptr(ctrl), _ptr(q_qk_lp),
         _ptr(q_tgt_lp), _dt(lp) if lp is not None else F32, num_pos_feats, float(temperature), _stream()))
 
 
@@ -542,11 +542,13 @@ def track_suppress_batched(boxes, ids, counters, row_offsets, n_seq: int, max_ro
 
 
 def frame_writeback(n_seq, C, cap, row_offsets, n_active, new_qpos, c_box, t_qpos, t_ref, n_tracks, ctrl=None,
-                    info=None) -> None:
+                    info=None, boxes=None, active_index=None) -> None:
+    """c_box None: the boxes of the active rows are gathered from `boxes` through `active_index`."""
     _count(1)
     _lib.check(_lib.lib().moyolo_frame_writeback(
-        n_seq, C, cap, row_offsets.data_ptr(), n_active.data_ptr(), new_qpos.data_ptr(), c_box.data_ptr(),
-        t_qpos.data_ptr(), t_ref.data_ptr(), n_tracks.data_ptr(), _ptr(ctrl), _ptr(info), _stream()))
+        n_seq, C, cap, row_offsets.data_ptr(), n_active.data_ptr(), new_qpos.data_ptr(), _ptr(c_box),
+        t_qpos.data_ptr(), t_ref.data_ptr(), n_tracks.data_ptr(), _ptr(ctrl), _ptr(info), _ptr(boxes),
+        _ptr(active_index), _stream()))
 
 
 def frame_emit(n_seq, rows_pad, row_offsets, ids, boxes, scores, labels, n_active, active_index, seq_ids, frame_rows,

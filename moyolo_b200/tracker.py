@@ -390,14 +390,14 @@ class TrackEngine:
             _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
         boxes = ws.refer[n_l]
         ops.score_head(ws.x_lp, W.score_w, W.score_b, out=(ws.logits, ws.scores, ws.labels))
-        if fork:
-            cur.wait_stream(self._s_box)   # final boxes
         st, ft, mt, it = self.thr
-        # ID assignment (head.py:1232-1243) + active-track selection/compaction (qim.py:184-187) in one launch
+        # ID assignment (head.py:1232-1243) + active-track selection/compaction (qim.py:184-187) in one launch. With
+        # side branches it does not touch the refined boxes (frame_writeback gathers them through the selection), so
+        # neither it nor the QIM update waits for the last layer's box head running on the side branch.
         ops.frame_assign_compact(S, C, self.cap, R, ws.ro, ws.scores, ws.ids0, ws.dis0, self.counters, ws.ids, ws.dis,
-                                 ws.labels, ws.refer_logit, ws.pos, ws.x, boxes, ws.n_active, ws.active_index,
-                                 ws.c_ref, ws.c_pos, ws.c_hs, ws.c_box, self.t_label, self.t_ids, self.t_dis, st, ft, mt,
-                                 ctrl=self.ctrl, q_qk_lp=ws.q_qk_lp,                                 # qim.py:255, 271
+                                 ws.labels, ws.refer_logit, ws.pos, ws.x, None if fork else boxes, ws.n_active,
+                                 ws.active_index, ws.c_ref, ws.c_pos, ws.c_hs, None if fork else ws.c_box, self.t_label,
+                                 self.t_ids, self.t_dis, st, ft, mt, ctrl=self.ctrl, q_qk_lp=ws.q_qk_lp,   # qim.py:255, 271
                                  q_tgt_lp=None if dt == torch.float32 else ws.q_tgt_lp)
 
         def side():
@@ -409,17 +409,18 @@ class TrackEngine:
                            self.seq_ids, p.frame_rows, self.table, self.ctrl)
 
         if fork:
-            self._s_box.wait_stream(cur)
+            self._s_box.wait_stream(cur)   # (the last box head is already queued on this branch)
             with torch.cuda.stream(self._s_box):
                 side()
         else:
             side()
         self._qim_update(ws, ro_host)
-        # write-back also stores what the host reads back after the frame: [n_active | ctrl]
-        ops.frame_writeback(S, C, self.cap, ws.ro, ws.n_active, ws.q_new, ws.c_box, self.t_qpos, self.t_ref,
-                            self.n_tracks, ctrl=self.ctrl, info=p.info)
         if fork:
-            cur.wait_stream(self._s_box)
+            cur.wait_stream(self._s_box)   # final boxes (and the rest of the side branch)
+        # write-back also stores what the host reads back after the frame: [n_active | ctrl]
+        ops.frame_writeback(S, C, self.cap, ws.ro, ws.n_active, ws.q_new, None if fork else ws.c_box, self.t_qpos,
+                            self.t_ref, self.n_tracks, ctrl=self.ctrl, info=p.info, boxes=boxes if fork else None,
+                            active_index=ws.active_index if fork else None)
 
     def _qim_update(self, ws: FrameWorkspace, ro_host) -> None:
         """QueryInteractionModule._update_track_embedding (MOTR/models/qim.py:251-301) for the active
