@@ -171,6 +171,7 @@ class TrackEngine:
                           n_seq * self.Lv >= 4096 and os.environ.get("MOYOLO_VP_SPLIT", "1") != "0")
         self._vp_ctas = int(os.environ.get("MOYOLO_VP_CTAS", "72" if n_seq <= 2 else "0"))
         self._vp_gate = os.environ.get("MOYOLO_VP_GATE", "1") != "0"   # gate the ahead projection on the previous tail
+        self._vp_gate_layer = int(os.environ.get("MOYOLO_VP_GATE_LAYER", str(spec.n_layers)))  # n_layers = the tail
         S, C, dev = n_seq, spec.d_model, self.dev
         # device-resident track state (fixed capacity)
         self.n_tracks = torch.zeros(S, dtype=torch.int32, device=dev)
@@ -376,6 +377,8 @@ class TrackEngine:
                         cur.wait_stream(self._s_val)  # the other layers' slices
                     cur.wait_stream(self._s_box)   # refer[i] comes from the box head of layer i-1
 
+            if self._vp_ahead and i == self._vp_gate_layer:   # experiment knob: release the next projection earlier
+                _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
             ex.run_layer_ws(pk, ws, ws.refer[i].view(R, 1, 4), value_view, self.shapes, S, ws.ro, ro_host,
                             ws.pos, None if last else ws.pos, dt, before_gather)
             # box refinement of this layer (transformer.py:709): only the NEXT layer's gather needs it
@@ -386,7 +389,7 @@ class TrackEngine:
                     ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
             else:
                 ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
-        if self._vp_ahead:  # the next frame's value projection may start now: only the tail is left
+        if self._vp_ahead and self._vp_gate_layer >= n_l:  # the next frame's value projection may start now: only the tail is left
             _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
         boxes = ws.refer[n_l]
         ops.score_head(ws.x_lp, W.score_w, W.score_b, out=(ws.logits, ws.scores, ws.labels))
