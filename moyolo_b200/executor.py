@@ -17,7 +17,7 @@ stay fp32).
 from __future__ import annotations
 
 import os
-from typing import List, Optional, Sequence
+from typing import Sequence
 
 import torch
 

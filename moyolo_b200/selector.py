@@ -15,7 +15,7 @@ reference computes it for all Lv rows and keeps num_queries of them). Maps are t
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import torch
 
