@@ -33,6 +33,11 @@ __global__ void frame_assemble_kernel(int n_seq, int n_detect, int C, int cap, c
                                       int rows_pad, int32_t* __restrict__ ctrl, float* __restrict__ refer_sig,
                                       void* __restrict__ x_lp, void* __restrict__ xq_lp, int lp_bf16) {
   pdl_trigger();
+  // pos2posemb denominators (transformer.py:185-186), one table per CTA, computed before the dependency wait
+  __shared__ float s_dimt[256];
+  for (int i = threadIdx.x; i < num_pos_feats && i < 256; i += blockDim.x)
+    s_dimt[i] = powf(temperature, static_cast<float>(2 * (i / 2)) / static_cast<float>(num_pos_feats));
+  __syncthreads();
   pdl_wait();
   const int row = blockIdx.x;
   // optional fused outputs: sigmoid(refer) (transformer.py:690) and the GEMM operand copies x, x + pos
@@ -106,7 +111,7 @@ __global__ void frame_assemble_kernel(int n_seq, int n_detect, int C, int cap, c
       xr[c] = xv;
       const int coord = c / num_pos_feats, i = c % num_pos_feats;
       const float p = dr[coord] * 6.283185307179586f;
-      const float e = p / powf(temperature, static_cast<float>(2 * (i / 2)) / static_cast<float>(num_pos_feats));
+      const float e = p / s_dimt[i];
       const float pv = (i & 1) ? cosf(e) : sinf(e);
       pr[c] = pv;
       emit_lp(c, xv, pv);
@@ -454,7 +459,8 @@ extern "C" int moyolo_frame_assemble(int n_seq, int n_detect, int C, int cap, co
                  MOYOLO_ERR_BAD_ARG, "frame_assemble: null pointer");
   MOYOLO_REQUIRE(n_seq > 0 && n_detect >= 0 && C > 0 && cap > 0 && rows_pad > 0, MOYOLO_ERR_BAD_SHAPE,
                  "frame_assemble: bad sizes");
-  MOYOLO_REQUIRE(C == 4 * num_pos_feats, MOYOLO_ERR_BAD_SHAPE, "frame_assemble: C must equal 4*num_pos_feats");
+  MOYOLO_REQUIRE(C == 4 * num_pos_feats && num_pos_feats <= 256, MOYOLO_ERR_BAD_SHAPE,
+                 "frame_assemble: C must equal 4*num_pos_feats (<= 1024)");
   MOYOLO_REQUIRE(lp_dtype == MOYOLO_BF16 || lp_dtype == MOYOLO_F32, MOYOLO_ERR_UNSUPPORTED,
                  "frame_assemble: lp_dtype must be F32 or BF16");
   const int threads = C >= 256 ? 256 : (C >= 128 ? 128 : 64);
