@@ -19,7 +19,8 @@
 //    residual-add + LayerNorm (+ "+pos" operand of the next GEMM) of the post-norm blocks
 //    (transformer.py:640-641, 646-647, 578-579) fused into the epilogue. A LayerNorm row spans the
 //    256/BN CTAs of a thread-block cluster; row statistics are exchanged through distributed shared
-//    memory (per-slab mean / centred sum of squares merged with the parallel-variance formula, one exchange).
+//    memory (per-slab mean / centred sum of squares, sent with st.async stores that complete an mbarrier in the
+//    receiving CTA, merged with the parallel-variance formula: one exchange, no cluster-wide barrier after start-up).
 //  * gemm_stream_kernel — persistent, weight-resident kernel for the tall value projection
 //    (M = S*Lv ~ 10^4..10^5 rows, K = 256): every CTA keeps its [128 x 256] weight slab in shared
 //    memory, streams x-tiles through a 6-deep TMA ring, double-buffers the accumulator in TMEM so the
@@ -136,6 +137,17 @@ __device__ __forceinline__ void st_cluster_f32(uint32_t local_addr, uint32_t ran
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
 }
 
+// Asynchronous store into a peer CTA's shared memory that signals (complete_tx) an mbarrier in that CTA when it has
+// landed: the receiver waits on its own mbarrier instead of a cluster-wide barrier.
+__device__ __forceinline__ void st_async_cluster_f32(uint32_t local_addr, uint32_t local_bar, uint32_t rank, float v) {
+  uint32_t raddr, rbar;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(local_addr), "r"(rank));
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(local_bar), "r"(rank));
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(raddr),
+               "r"(__float_as_uint(v)), "r"(rbar)
+               : "memory");
+}
+
 // Everything the epilogues need besides the tensor maps.
 struct GemmEpi {
   const float* bias;
@@ -163,11 +175,12 @@ struct GemmCtl {
   uint64_t full[kStages];
   uint64_t empty[kStages];
   uint64_t tmem_full;
+  uint64_t ln_bar;  // LN: completes when the row statistics of all cluster peers have landed in `red`
   uint32_t tmem_base;
   float bias[BN];
   float gamma[LN ? BN : 1];
   float beta[LN ? BN : 1];
-  float red[LN ? 2 : 1][LN ? kLnCols / BN : 1][LN ? kBM : 1];  // [pass][peer CTA][row]
+  float red[LN ? 2 : 1][LN ? kLnCols / BN : 1][LN ? kBM : 1];  // [mean | M2][peer CTA][row]
 };
 
 template <typename TO>
@@ -222,7 +235,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_init(smem_u32(&ctl->empty[s]), 1);
     }
     mbar_init(smem_u32(&ctl->tmem_full), 1);
+    if constexpr (LN) mbar_init(smem_u32(&ctl->ln_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // LN: every peer sends 2 floats per row (its slab's mean and centred sum of squares)
+    if constexpr (LN) mbar_expect_tx(smem_u32(&ctl->ln_bar), (kLnCols / BN) * kBM * 2 * 4);
     // weights are immutable during a frame: request them before waiting on the previous kernel
     for (int kb = 0; kb < pre; ++kb) {
       const uint32_t full = smem_u32(&ctl->full[kb]);
@@ -375,16 +391,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const float d = v[j] - m_loc;
         pq = fmaf(d, d, pq);
       }
-      cluster_wait();  // #0
+      cluster_wait();  // #0: every peer has initialised its barrier
       const uint32_t slot0 = smem_u32(&ctl->red[0][my_rank][rl]);
       const uint32_t slot1 = smem_u32(&ctl->red[1][my_rank][rl]);
+      const uint32_t lbar = smem_u32(&ctl->ln_bar);
 #pragma unroll
       for (int p = 0; p < NC; ++p) {
-        st_cluster_f32(slot0, p, m_loc);
-        st_cluster_f32(slot1, p, pq);
+        st_async_cluster_f32(slot0, lbar, p, m_loc);
+        st_async_cluster_f32(slot1, lbar, p, pq);
       }
-      cluster_arrive();
-      cluster_wait();  // #1
+      mbar_wait(lbar, 0);  // all NC * 128 * 2 values of the peers (and our own) have landed
       float msum = 0.0f, sq = 0.0f;
 #pragma unroll
       for (int p = 0; p < NC; ++p) {
@@ -428,11 +444,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
   }
   if constexpr (LN) {
-    if (warp < 2) {  // producer / MMA warps take part in the two cluster barriers
-      cluster_wait();
-      cluster_arrive();
-      cluster_wait();
-    }
+    if (warp < 2) cluster_wait();  // producer / MMA warps: the start-up barrier only
   }
 
   tc_fence_before();
