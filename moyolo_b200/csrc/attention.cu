@@ -5,6 +5,8 @@
 // through shared memory in 64-key tiles with an online softmax; fp32 math, exp via expf.
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace moyolo {
@@ -517,12 +519,12 @@ extern "C" int moyolo_self_attention(const void* q, int64_t ldq, const void* k, 
     const __nv_bfloat16 *qq = static_cast<const __nv_bfloat16*>(q), *kk = static_cast<const __nv_bfloat16*>(k),
                         *vv = static_cast<const __nv_bfloat16*>(v);
     if (splitk) {
-      static bool configured = false;
-      if (!configured) {
+      static std::atomic<bool> configured{false};  // benign if two host threads race: the attribute is idempotent
+      if (!configured.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(self_attention_splitk32_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSplitkSmem));
         if (e != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
-        configured = true;
+        configured.store(true, std::memory_order_release);
       }
       launch_k(self_attention_splitk32_kernel, dim3(mgrid), dim3(128), kSplitkSmem, st, qq, ldq, kk, ldk, vv, ldv,
                static_cast<__nv_bfloat16*>(out), ldo, batch, row_offsets, seg_len);
