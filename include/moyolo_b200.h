@@ -181,6 +181,16 @@ int moyolo_linear_add_layernorm(const void* x, int64_t ldx, const void* w, const
                                 int64_t M, int N, int K, float* out_f32, void* out_lp, const float* pos,
                                 void* out_pos_lp, moyolo_stream_t stream);
 
+/* moyolo_linear_add_layernorm with the decoder's class-score head fused behind the LayerNorm (transformer.py:717-721,
+ * head.py:310): logits[M,nc] = bf16(out) . score_w[nc,256]^T + score_b, scores[M] = sigmoid(max_c logits),
+ * labels[M] = argmax_c (first maximum). Each CTA of the cluster sends the partial dot products of its 32 columns to
+ * cluster rank 0 (st.async + mbarrier), which finishes the row. 1 <= nc <= 8; logits / scores / labels may be NULL. */
+int moyolo_linear_add_layernorm_scores(const void* x, int64_t ldx, const void* w, const float* bias,
+                                       const float* residual, const float* gamma, const float* beta, float eps,
+                                       int64_t M, int N, int K, float* out_f32, void* out_lp, const float* score_w,
+                                       const float* score_b, int nc, float* logits, float* scores, int32_t* labels,
+                                       moyolo_stream_t stream);
+
 /* The whole post-norm FFN block in one launch (transformer.py:576-580; QIM qim.py:280-282, 290-298):
  *   out = LayerNorm(residual + relu(x[M,C] . w1[F,C]^T + b1) . w2[C,F]^T + b2) * gamma + beta,  C == 256, F in {256, 1024}
  * outputs as moyolo_linear_add_layernorm. h: bf16 [M, F] scratch (row stride F) that carries the hidden activations

@@ -49,6 +49,8 @@ SIGNATURES = {
     "moyolo_linear_tall": (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _p, _i, _p]),
     "moyolo_linear_dual": (_i, [_p, _l, _p, _l, _i, _p, _p, _p, _l, _l, _i, _i, _i, _p]),
     "moyolo_linear_add_layernorm": (_i, [_p, _l, _p, _p, _p, _p, _p, _f, _l, _i, _i, _p, _p, _p, _p, _p]),
+    "moyolo_linear_add_layernorm_scores": (_i, [_p, _l, _p, _p, _p, _p, _p, _f, _l, _i, _i, _p, _p, _p, _p, _i, _p, _p, _p,
+                                                _p]),
     "moyolo_ffn_add_layernorm": (_i, [_p, _l, _p, _p, _p, _p, _p, _i, _p, _p, _p, _f, _l, _i, _p, _p, _p, _p, _p]),
     "moyolo_self_attention": (_i, [_p, _l, _p, _l, _p, _l, _p, _l, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
     "moyolo_add_layernorm": (_i, [_p, _p, _p, _p, _f, _l, _i, _p, _p, _p, _p, _i, _p]),

@@ -170,7 +170,16 @@ struct GemmEpi {
   void* out_lp;
   const float* pos;
   void* out_pos_lp;
+  // optional class-score head fused behind the LayerNorm (transformer.py:717-721): logits = bf16(out) . score_w^T + b
+  const float* score_w;   // fp32 [score_nc, 256] or NULL
+  const float* score_b;
+  int score_nc;           // 0 = no score head; <= kMaxScoreNc
+  float* logits;          // [M, score_nc]
+  float* scores;          // [M] sigmoid(max logit)
+  int32_t* labels;        // [M] argmax (first maximum)
 };
+
+constexpr int kMaxScoreNc = 8;
 
 template <int BN, bool LN>
 struct GemmCtl {
@@ -178,6 +187,7 @@ struct GemmCtl {
   uint64_t empty[kStages];
   uint64_t tmem_full;
   uint64_t ln_bar;  // LN: completes when the row statistics of all cluster peers have landed in `red`
+  uint64_t sc_bar;  // LN + score head, cluster rank 0: completes when every peer's partial class scores have landed
   uint32_t tmem_base;
   float bias[BN];
   float gamma[LN ? BN : 1];
@@ -237,10 +247,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_init(smem_u32(&ctl->empty[s]), 1);
     }
     mbar_init(smem_u32(&ctl->tmem_full), 1);
-    if constexpr (LN) mbar_init(smem_u32(&ctl->ln_bar), 1);
+    if constexpr (LN) {
+      mbar_init(smem_u32(&ctl->ln_bar), 1);
+      mbar_init(smem_u32(&ctl->sc_bar), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // LN: every peer sends 2 floats per row (its slab's mean and centred sum of squares)
     if constexpr (LN) mbar_expect_tx(smem_u32(&ctl->ln_bar), (kLnCols / BN) * kBM * 2 * 4);
+    if constexpr (LN) {
+      if (e.score_nc > 0 && cluster_ctarank() == 0)
+        mbar_expect_tx(smem_u32(&ctl->sc_bar), static_cast<uint32_t>(e.score_nc) * (kLnCols / BN) * kBM * 4);
+    }
     // weights are immutable during a frame: request them before waiting on the previous kernel
     for (int kb = 0; kb < pre; ++kb) {
       const uint32_t full = smem_u32(&ctl->full[kb]);
@@ -418,9 +435,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       const float rstd = rsqrtf(sq * (1.0f / kLnCols) + e.eps);
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] -= mean;
-      if (row_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = v[j] * rstd * ctl->gamma[j] + ctl->beta[j];
+      for (int j = 0; j < 32; ++j) v[j] = v[j] * rstd * ctl->gamma[j] + ctl->beta[j];
+      if (row_ok) {
         if (e.out_f32 != nullptr) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -441,6 +458,37 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           for (int j = 0; j < 16; ++j) { h0[j] = v[j] + pv[j]; h1[j] = v[16 + j] + pv[16 + j]; }
           store16<TO>(d, h0, true);
           store16<TO>(d + 16, h1, true);
+        }
+      }
+      if (e.score_nc > 0) {
+        // class-score head on the bf16-rounded output row (what the stand-alone score_head kernel reads): this CTA's
+        // partial dot products over its 32 columns go to cluster rank 0, which adds the bias and writes the logits,
+        // sigmoid(max logit) and the arg-max label of the row
+        float* sred = reinterpret_cast<float*>(ctl + 1);   // [score_nc][NC][kBM], dynamic shared memory behind ctl
+        const uint32_t sbar = smem_u32(&ctl->sc_bar);
+        for (int c = 0; c < e.score_nc; ++c) {
+          const float* wc = e.score_w + c * kLnCols + n0;
+          float sdot = 0.0f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sdot = fmaf(__bfloat162float(__float2bfloat16_rn(v[j])), __ldg(wc + j), sdot);
+          st_async_cluster_f32(smem_u32(sred + (c * NC + static_cast<int>(my_rank)) * kBM + rl), sbar, 0, row_ok ? sdot : 0.0f);
+        }
+        if (my_rank == 0) {
+          mbar_wait(sbar, 0);
+          float best = -INFINITY;
+          int best_c = 0;
+          for (int c = 0; c < e.score_nc; ++c) {
+            float d = 0.0f;
+#pragma unroll
+            for (int p = 0; p < NC; ++p) d += sred[(c * NC + p) * kBM + rl];
+            d += __ldg(e.score_b + c);
+            if (row_ok && e.logits != nullptr) e.logits[row * e.score_nc + c] = d;
+            if (d > best) { best = d; best_c = c; }  // first maximum wins, as torch.max
+          }
+          if (row_ok) {
+            if (e.scores != nullptr) e.scores[row] = 1.0f / (1.0f + expf(-best));
+            if (e.labels != nullptr) e.labels[row] = best_c;
+          }
         }
       }
     }
@@ -1194,11 +1242,13 @@ static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 template <int BN, typename TO, bool LN>
 static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tx2, const CUtensorMap& tw, const GemmEpi& e,
                        cudaStream_t st) {
-  constexpr size_t smem = kStages * (kBM * kBK * 2 + BN * kBK * 2) + sizeof(GemmCtl<BN, LN>) + 1024;
+  constexpr size_t smem_base = kStages * (kBM * kBK * 2 + BN * kBK * 2) + sizeof(GemmCtl<BN, LN>) + 1024;
+  constexpr size_t smem_max = smem_base + (LN ? kMaxScoreNc * (kLnCols / BN) * kBM * 4 : 0);
+  const size_t smem = smem_base + (LN ? static_cast<size_t>(e.score_nc) * (kLnCols / BN) * kBM * 4 : 0);
   static std::atomic<bool> configured{false};  // benign if two host threads race: the attribute is idempotent  // per template instantiation
   if (!configured.load(std::memory_order_acquire)) {
     cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, TO, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem));
+                                           static_cast<int>(smem_max));
     if (err != cudaSuccess)
       return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(err));
     configured.store(true, std::memory_order_release);
@@ -1328,7 +1378,8 @@ bool linear_ln_tcgen05_supported(const void* x, int64_t ldx, const void* w, int6
 // out = LayerNorm(x . w^T + bias + residual) * gamma + beta, N == 256, all row-major contiguous [M, 256].
 int linear_ln_tcgen05(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual,
                       const float* gamma, const float* beta, float eps, int64_t M, int K, float* out_f32, void* out_lp,
-                      const float* pos, void* out_pos_lp, cudaStream_t st) {
+                      const float* pos, void* out_pos_lp, const float* score_w, const float* score_b, int score_nc,
+                      float* logits, float* scores, int32_t* labels, cudaStream_t st) {
   CUtensorMap tx, tw;
   int rc = make_tmap(&tx, x, M, K, ldx, kBM);
   if (rc != MOYOLO_OK) return rc;
@@ -1338,6 +1389,8 @@ int linear_ln_tcgen05(const void* x, int64_t ldx, const void* w, const float* bi
   e.bias = bias; e.M = M; e.N = kLnCols; e.K = K; e.n_split = kLnCols;
   e.residual = residual; e.gamma = gamma; e.beta = beta; e.eps = eps;
   e.out_f32 = out_f32; e.out_lp = out_lp; e.pos = pos; e.out_pos_lp = out_pos_lp;
+  e.score_w = score_w; e.score_b = score_b; e.score_nc = score_w != nullptr ? score_nc : 0;
+  e.logits = logits; e.scores = scores; e.labels = labels;
   return launch_gemm<32, __nv_bfloat16, true>(tx, tx, tw, e, st);
 }
 

@@ -115,7 +115,8 @@ bool linear_tcgen05_supported(const void* x, int64_t ldx, const void* w, int64_t
 bool linear_ln_tcgen05_supported(const void* x, int64_t ldx, const void* w, int64_t M, int N, int K);
 int linear_ln_tcgen05(const void* x, int64_t ldx, const void* w, const float* bias, const float* residual,
                       const float* gamma, const float* beta, float eps, int64_t M, int K, float* out_f32, void* out_lp,
-                      const float* pos, void* out_pos_lp, cudaStream_t st);
+                      const float* pos, void* out_pos_lp, const float* score_w, const float* score_b, int score_nc,
+                      float* logits, float* scores, int32_t* labels, cudaStream_t st);
 
 }  // namespace moyolo
 
@@ -189,8 +190,28 @@ extern "C" int moyolo_linear_add_layernorm(const void* x, int64_t ldx, const voi
                      (out_lp == nullptr || aligned16(out_lp)) && (pos == nullptr || aligned16(pos)) &&
                      (out_pos_lp == nullptr || aligned16(out_pos_lp)),
                  MOYOLO_ERR_ALIGNMENT, "moyolo_linear_add_layernorm: row buffers must be 16-byte aligned");
-  return linear_ln_tcgen05(x, ldx, w, bias, residual, gamma, beta, eps, M, K, out_f32, out_lp, pos, out_pos_lp,
-                           static_cast<cudaStream_t>(stream));
+  return linear_ln_tcgen05(x, ldx, w, bias, residual, gamma, beta, eps, M, K, out_f32, out_lp, pos, out_pos_lp, nullptr,
+                           nullptr, 0, nullptr, nullptr, nullptr, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int moyolo_linear_add_layernorm_scores(const void* x, int64_t ldx, const void* w, const float* bias,
+                                                  const float* residual, const float* gamma, const float* beta,
+                                                  float eps, int64_t M, int N, int K, float* out_f32, void* out_lp,
+                                                  const float* score_w, const float* score_b, int nc, float* logits,
+                                                  float* scores, int32_t* labels, moyolo_stream_t stream) {
+  using namespace moyolo;
+  MOYOLO_REQUIRE(x && w && gamma && beta && score_w && score_b, MOYOLO_ERR_BAD_ARG,
+                 "moyolo_linear_add_layernorm_scores: null pointer");
+  MOYOLO_REQUIRE(M >= 0 && K > 0 && ldx >= K && nc > 0 && nc <= 8, MOYOLO_ERR_BAD_SHAPE,
+                 "moyolo_linear_add_layernorm_scores: bad sizes (1 <= nc <= 8)");
+  if (M == 0) return MOYOLO_OK;
+  MOYOLO_REQUIRE(linear_ln_tcgen05_supported(x, ldx, w, M, N, K), MOYOLO_ERR_UNSUPPORTED,
+                 "moyolo_linear_add_layernorm_scores: needs N == 256, K %% 64 == 0 and 16B-aligned bf16 operands");
+  MOYOLO_REQUIRE((residual == nullptr || aligned16(residual)) && (out_f32 == nullptr || aligned16(out_f32)) &&
+                     (out_lp == nullptr || aligned16(out_lp)),
+                 MOYOLO_ERR_ALIGNMENT, "moyolo_linear_add_layernorm_scores: row buffers must be 16-byte aligned");
+  return linear_ln_tcgen05(x, ldx, w, bias, residual, gamma, beta, eps, M, K, out_f32, out_lp, nullptr, nullptr, score_w,
+                           score_b, nc, logits, scores, labels, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int moyolo_ffn_add_layernorm(const void* x, int64_t ldx, const void* w1, const float* b1, const void* w2,

@@ -237,7 +237,7 @@ def qkv_proj(xq_lp, x_lp, w, b, out, C: int, eng) -> None:
 
 
 def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offsets, row_offsets_host, pos_cur,
-                 pos_next, dt, before_gather=None) -> None:
+                 pos_next, dt, before_gather=None, score=None) -> None:
     """One post-norm decoder layer on workspace buffers. In: ws.x (fp32 residual), ws.x_lp, ws.xq_lp
     (= x + pos operand). Out: the same three for the next layer (xq only when pos_next is given)."""
     C = pk.C
@@ -276,6 +276,11 @@ def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offset
                                   out_pos=ws.xq_lp if pos_next is not None else None)
             return
         ops.linear(ws.x2_lp, pk.ffn1.w, pk.ffn1.b, relu=True, out=ws.h, engine=eng)
+        if score is not None and pos_next is None:   # last layer: class-score head fused behind the LayerNorm
+            sw, sb, logits, scores, labels = score
+            ops.linear_add_layernorm_scores(ws.h, pk.ffn2.w, pk.ffn2.b, ws.x2, g, b_, e, sw, sb, out_f32=ws.x,
+                                            out_lp=ws.x_lp, logits=logits, scores=scores, labels=labels)
+            return
         ops.linear_add_layernorm(ws.h, pk.ffn2.w, pk.ffn2.b, ws.x2, g, b_, e, out_f32=ws.x, out_lp=ws.x_lp,
                                  pos=pos_next, out_pos=ws.xq_lp if pos_next is not None else None)
         return

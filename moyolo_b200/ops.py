@@ -311,6 +311,27 @@ def ffn_add_layernorm(x: torch.Tensor, w1: torch.Tensor, b1, w2: torch.Tensor, b
         _stream()))
 
 
+SCORE_FUSED = _os.environ.get("MOYOLO_SCORE_FUSED", "1") != "0"
+
+
+def linear_add_layernorm_scores(x: torch.Tensor, w: torch.Tensor, b, residual, gamma, beta, eps: float,
+                                score_w: torch.Tensor, score_b: torch.Tensor, out_f32=None, out_lp=None, logits=None,
+                                scores=None, labels=None) -> None:
+    """linear_add_layernorm + the class-score head (logits, sigmoid(max), argmax) of the normalised rows in ONE
+    launch; score_w fp32 [nc, 256], nc <= 8."""
+    _cuda(x, w, b, residual, gamma, beta, score_w, score_b, out_f32, out_lp, logits, scores, labels)
+    M, K = x.shape
+    N = w.shape[0]
+    nc = score_w.shape[0]
+    if x.stride(1) != 1 or not w.is_contiguous() or not score_w.is_contiguous() or score_w.shape[1] != N:
+        raise ValueError("linear_add_layernorm_scores: x columns / w / score_w must be contiguous, score_w [nc, N]")
+    _count(1)
+    _lib.check(_lib.lib().moyolo_linear_add_layernorm_scores(
+        x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), _ptr(residual), gamma.data_ptr(), beta.data_ptr(), float(eps),
+        M, N, K, _ptr(out_f32), _ptr(out_lp), score_w.data_ptr(), score_b.data_ptr(), nc, _ptr(logits), _ptr(scores),
+        _ptr(labels), _stream()))
+
+
 def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, row_offsets: torch.Tensor,
                    row_offsets_host: Sequence[int], n_heads: int, attn_mask: Optional[torch.Tensor] = None,
                    out: Optional[torch.Tensor] = None, seg_len: Optional[torch.Tensor] = None) -> torch.Tensor:

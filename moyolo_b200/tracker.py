@@ -360,6 +360,9 @@ class TrackEngine:
                            x_lp=None if dt == torch.float32 else ws.x_lp, xq_lp=ws.xq_lp)
         # host-side bound of the device offsets, used for grid sizing only: sum_s ceil(N_s/16) <= R/16 + S
         ro_host = [16 * i for i in range(S)] + [16 * S + R]
+        # class-score head inside the last layer's FFN2 GEMM+LayerNorm launch (bf16 fused-epilogue path, nc <= 8)
+        score_fused = ops.SCORE_FUSED and ex.fused_epilogues(dt, C) and spec.nc <= 8 and \
+            not ops.ffn_fused_supported(dt, C, W.layers[-1].ffn1.w.shape[0])
         for i, pk in enumerate(W.layers):
             last = i + 1 == n_l
             value_view = values[:, :, i * C:(i + 1) * C]
@@ -380,7 +383,8 @@ class TrackEngine:
             if self._vp_ahead and i == self._vp_gate_layer:   # experiment knob: release the next projection earlier
                 _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
             ex.run_layer_ws(pk, ws, ws.refer[i].view(R, 1, 4), value_view, self.shapes, S, ws.ro, ro_host,
-                            ws.pos, None if last else ws.pos, dt, before_gather)
+                            ws.pos, None if last else ws.pos, dt, before_gather,
+                            score=(W.score_w, W.score_b, ws.logits, ws.scores, ws.labels) if (last and score_fused) else None)
             # box refinement of this layer (transformer.py:709): only the NEXT layer's gather needs it
             # (the last layer's box head runs next to the score head, which only needs the layer output)
             if fork:
@@ -392,7 +396,8 @@ class TrackEngine:
         if self._vp_ahead and self._vp_gate_layer >= n_l:  # the next frame's value projection may start now: only the tail is left
             _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
         boxes = ws.refer[n_l]
-        ops.score_head(ws.x_lp, W.score_w, W.score_b, out=(ws.logits, ws.scores, ws.labels))
+        if not score_fused:
+            ops.score_head(ws.x_lp, W.score_w, W.score_b, out=(ws.logits, ws.scores, ws.labels))
         st, ft, mt, it = self.thr
         # ID assignment (head.py:1232-1243) + active-track selection/compaction (qim.py:184-187) in one launch. With
         # side branches it does not touch the refined boxes (frame_writeback gathers them through the selection), so

@@ -200,3 +200,37 @@ def test_ffn_add_layernorm_fused(dev, M, F, with_pos):
     t = hid @ w2.double().T + b2.double() + res.double()
     ref = torch.nn.functional.layer_norm(t, (C,), gam.double(), bet.double(), 1e-5)
     assert rel_rms(f32.cpu().double().numpy(), ref.numpy()) < 5e-3  # bf16 rounding of the hidden layer dominates
+
+
+@pytest.mark.parametrize("M,K,nc", [(382, 1024, 1), (77, 256, 5), (300, 1024, 8)])
+def test_linear_add_layernorm_scores(dev, M, K, nc):
+    """GEMM + residual + LayerNorm with the class-score head fused behind it (partials sent to cluster rank 0 with
+    st.async) against the two launches it replaces: rows bit-identical, logits equal up to fp32 summation order,
+    same labels, and an fp64 reference of the score head on the bf16-rounded rows."""
+    from moyolo_b200 import ops
+    C = 256
+    g = torch.Generator().manual_seed(M + K + nc)
+    x = torch.randn(M, K, generator=g).bfloat16().to(dev)
+    w = (torch.randn(C, K, generator=g) / K ** 0.5).bfloat16().to(dev)
+    b = (torch.randn(C, generator=g) * 0.1).to(dev)
+    res = torch.randn(M, C, generator=g).to(dev)
+    gam, bet = (torch.rand(C, generator=g) + 0.5).to(dev), (torch.randn(C, generator=g) * 0.1).to(dev)
+    sw, sb = (torch.randn(nc, C, generator=g) * 0.3).to(dev), torch.randn(nc, generator=g).to(dev)
+    a32, alp = torch.zeros(M, C, device=dev), torch.zeros(M, C, dtype=torch.bfloat16, device=dev)
+    ops.linear_add_layernorm(x, w, b, res, gam, bet, 1e-5, out_f32=a32, out_lp=alp)
+    lg_a, sc_a, lb_a = ops.score_head(alp, sw, sb)
+    f32, flp = torch.zeros(M, C, device=dev), torch.zeros(M, C, dtype=torch.bfloat16, device=dev)
+    lg = torch.zeros(M, nc, device=dev)
+    sc = torch.zeros(M, device=dev)
+    lb = torch.full((M,), -1, dtype=torch.int32, device=dev)
+    ops.linear_add_layernorm_scores(x, w, b, res, gam, bet, 1e-5, sw, sb, out_f32=f32, out_lp=flp, logits=lg, scores=sc,
+                                    labels=lb)
+    torch.cuda.synchronize()
+    assert torch.equal(f32, a32) and torch.equal(flp, alp)
+    ref = flp.double().cpu() @ sw.double().cpu().T + sb.double().cpu()
+    assert rel_rms(lg.cpu().double().numpy(), ref.numpy()) < 2e-5
+    assert rel_rms(lg.cpu().numpy(), lg_a.cpu().numpy()) < 2e-5
+    assert rel_rms(sc.cpu().numpy(), sc_a.cpu().numpy()) < 2e-5
+    top2 = ref.topk(min(2, nc), dim=1).values
+    clear = torch.ones(M, dtype=torch.bool) if nc == 1 else (top2[:, 0] - top2[:, 1]) > 1e-4
+    assert torch.equal(lb.cpu()[clear].long(), ref.argmax(1)[clear]) and torch.equal(lb.cpu()[clear], lb_a.cpu()[clear])
