@@ -402,7 +402,7 @@ int moyolo_mask_rows(const float* x, const uint8_t* zero_rows, int64_t period, f
 
 /* ---------------------------------------------------------------------------------------------
  * Host-side frame submission: the stream operations around one captured frame graph as ONE call
- * (the frame itself takes ~0.35 ms on the device; issuing these from an interpreter costs more).
+ * (the frame itself takes ~0.26 ms on the device; issuing these one by one from an interpreter costs more).
  *   on copy_stream: [wait ev_slot_free] [wait for main_stream if sync_inputs] n_inputs x memcpyAsync
  *                   (host-pinned or device sources, UVA) -> record ev_copy
  *   on main_stream: wait ev_copy -> launch graph_exec -> n_outputs x memcpyAsync -> record ev_done
