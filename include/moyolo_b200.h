@@ -328,7 +328,10 @@ int moyolo_track_compact(const int64_t* obj_idxes, int64_t n, int32_t* n_active,
  *   lock-step slot to the global sequence index.
  *
  * ctrl: device int32 [8] control block = {abort, frame counter, table cursor, table overflow, rows wanted
- *   by the aborting frame, ...}. The host may launch a frame speculatively with a rows_pad derived from an
+ *   by the aborting frame, track overflow, ...}. ctrl[5] (track overflow) is set, sticky, by frame_compact /
+ *   frame_assign_compact when a sequence has more active tracks than the carried state holds (`cap`): the surplus
+ *   tracks are dropped from the state (the reference's Instances has no such limit), so the host must treat the
+ *   flag as an error (moyolo_b200.TrackEngine raises) and re-run with a larger capacity. The host may launch a frame speculatively with a rows_pad derived from an
  *   OLDER frame's track counts: if the real row count does not fit, frame_assemble sets the sticky abort
  *   flag, builds an in-bounds detect-only frame, and every state-writing call (track_assign_batched,
  *   frame_compact, frame_writeback, frame_emit) of this and later frames is a no-op until the host clears
@@ -345,7 +348,7 @@ int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* row_offsets, 
                          const int64_t* dis, const int32_t* labels, const float* refer_logit,
                          const float* pos, const float* hs, const float* boxes, int32_t* n_active,
                          int32_t* active_index, float* c_ref, float* c_pos, float* c_hs, float* c_box,
-                         int32_t* t_label, int64_t* t_ids, int64_t* t_dis, const int32_t* ctrl,
+                         int32_t* t_label, int64_t* t_ids, int64_t* t_dis, int32_t* ctrl,
                          void* q_qk_lp, void* q_tgt_lp, int lp_dtype, int num_pos_feats, float temperature,
                          moyolo_stream_t stream);
 int moyolo_frame_assign_compact(int n_seq, int C, int cap, int64_t rows_pad, const int32_t* row_offsets,
@@ -354,7 +357,7 @@ int moyolo_frame_assign_compact(int n_seq, int C, int cap, int64_t rows_pad, con
                                 int miss_tolerance, int64_t* ids_out, int64_t* dis_out, const int32_t* labels,
                                 const float* refer_logit, const float* pos, const float* hs, const float* boxes,
                                 int32_t* n_active, int32_t* active_index, float* c_ref, float* c_pos, float* c_hs,
-                                float* c_box, int32_t* t_label, int64_t* t_ids, int64_t* t_dis, const int32_t* ctrl,
+                                float* c_box, int32_t* t_label, int64_t* t_ids, int64_t* t_dis, int32_t* ctrl,
                                 void* q_qk_lp, void* q_tgt_lp, int lp_dtype, int num_pos_feats, float temperature,
                                 moyolo_stream_t stream);
 int moyolo_frame_writeback(int n_seq, int C, int cap, const int32_t* row_offsets, const int32_t* n_active,

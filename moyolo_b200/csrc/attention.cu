@@ -519,12 +519,13 @@ extern "C" int moyolo_self_attention(const void* q, int64_t ldq, const void* k, 
     const __nv_bfloat16 *qq = static_cast<const __nv_bfloat16*>(q), *kk = static_cast<const __nv_bfloat16*>(k),
                         *vv = static_cast<const __nv_bfloat16*>(v);
     if (splitk) {
-      static std::atomic<bool> configured{false};  // benign if two host threads race: the attribute is idempotent
-      if (!configured.load(std::memory_order_acquire)) {
+      static DeviceOnce once;
+      const int dev_ = DeviceOnce::current();
+      if (!once.done(dev_)) {
         cudaError_t e = cudaFuncSetAttribute(self_attention_splitk32_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSplitkSmem));
         if (e != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
-        configured.store(true, std::memory_order_release);
+        once.set(dev_);
       }
       launch_k(self_attention_splitk32_kernel, dim3(mgrid), dim3(128), kSplitkSmem, st, qq, ldq, kk, ldk, vv, ldv,
                static_cast<__nv_bfloat16*>(out), ldo, batch, row_offsets, seg_len);

@@ -5,6 +5,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/moyolo_b200.h"
 
 namespace moyolo {
@@ -20,6 +22,24 @@ int check_launch(const char* what);
   } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Once-per-DEVICE flag: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count are properties of a
+// device, not of the process, so launchers key their one-time setup by the current device (bit d of the mask).
+// Benign if two host threads race: the attribute is idempotent.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  int n_sm[64] = {};
+  static int current() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d < 0 || d > 63 ? 63 : d;
+  }
+  bool done(int dev) const { return (mask.load(std::memory_order_acquire) >> dev) & 1ull; }
+  void set(int dev) {
+    cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev);
+    mask.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------
 // Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization so

@@ -14,7 +14,8 @@
 namespace moyolo {
 
 // control block shared by the frame kernels (device int32[8])
-enum { kCtrlAbort = 0, kCtrlFrame = 1, kCtrlCursor = 2, kCtrlTableOverflow = 3, kCtrlAbortRows = 4 };
+enum { kCtrlAbort = 0, kCtrlFrame = 1, kCtrlCursor = 2, kCtrlTableOverflow = 3, kCtrlAbortRows = 4,
+       kCtrlTrackOverflow = 5 };  // sticky: a sequence had more active tracks than the state capacity `cap`
 
 __device__ __forceinline__ float inv_sigmoid_(float x) {
   x = fminf(fmaxf(x, 0.0f), 1.0f);
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
     const float* __restrict__ pos, const float* __restrict__ hs, const float* __restrict__ boxes,
     int32_t* __restrict__ n_active, int32_t* __restrict__ active_index, float* __restrict__ c_ref,
     float* __restrict__ c_pos, float* __restrict__ c_hs, float* __restrict__ c_box, int32_t* __restrict__ t_label,
-    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis, const int32_t* __restrict__ ctrl,
+    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis, int32_t* __restrict__ ctrl,
     void* __restrict__ q_qk_lp, void* __restrict__ q_tgt_lp, int lp_bf16, int num_pos_feats, float temperature) {
   pdl_trigger();
   pdl_wait();
@@ -178,6 +179,9 @@ __global__ void __launch_bounds__(1024) frame_compact_kernel(
   for (int i = begin; i < end; ++i) local += ids[off + i] >= 0 ? 1 : 0;
   int total;
   int rank = block_exclusive_scan_f(local, &total, s_warp);
+  // more active tracks than the carried state holds: the surplus would silently lose its identity (the reference
+  // has no such limit) -> sticky flag, the host raises (TrackEngine.collect / track_table)
+  if (total > cap && first && threadIdx.x == 0 && ctrl != nullptr) ctrl[kCtrlTrackOverflow] = 1;
   total = min(total, cap);
   for (int i = begin; i < end; ++i)
     if (ids[off + i] >= 0) {
@@ -244,7 +248,7 @@ __global__ void __launch_bounds__(kAssignThreads) frame_assign_compact_kernel(
     const float* __restrict__ pos, const float* __restrict__ hs, const float* __restrict__ boxes,
     int32_t* __restrict__ n_active, int32_t* __restrict__ active_index, float* __restrict__ c_ref,
     float* __restrict__ c_pos, float* __restrict__ c_hs, float* __restrict__ c_box, int32_t* __restrict__ t_label,
-    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis, const int32_t* __restrict__ ctrl,
+    int64_t* __restrict__ t_ids, int64_t* __restrict__ t_dis, int32_t* __restrict__ ctrl,
     void* __restrict__ q_qk_lp, void* __restrict__ q_tgt_lp, int lp_bf16, int num_pos_feats, float temperature) {
   pdl_trigger();
   __shared__ int s_warp[33];
@@ -275,6 +279,7 @@ __global__ void __launch_bounds__(kAssignThreads) frame_assign_compact_kernel(
   int total;
   const int rank = block_exclusive_scan_f(local, &total, s_warp);
   int new_rank = rank & 0xffff, act_rank = rank >> 16;
+  if ((total >> 16) > cap && first && threadIdx.x == 0 && ctrl != nullptr) ctrl[kCtrlTrackOverflow] = 1;  // see frame_compact
   const int n_act = min(total >> 16, cap);
   for (int i = begin; i < end; ++i) {
     int64_t id = ids_in[off + i];
@@ -475,7 +480,7 @@ extern "C" int moyolo_frame_compact(int n_seq, int C, int cap, const int32_t* ro
                                     const int64_t* dis, const int32_t* labels, const float* refer_logit,
                                     const float* pos, const float* hs, const float* boxes, int32_t* n_active,
                                     int32_t* active_index, float* c_ref, float* c_pos, float* c_hs, float* c_box,
-                                    int32_t* t_label, int64_t* t_ids, int64_t* t_dis, const int32_t* ctrl,
+                                    int32_t* t_label, int64_t* t_ids, int64_t* t_dis, int32_t* ctrl,
                                     void* q_qk_lp, void* q_tgt_lp, int lp_dtype, int num_pos_feats,
                                     float temperature, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(row_offsets && ids && dis && labels && refer_logit && pos && hs && boxes && n_active &&
@@ -499,7 +504,7 @@ extern "C" int moyolo_frame_assign_compact(int n_seq, int C, int cap, int64_t ro
                                            const float* hs, const float* boxes, int32_t* n_active,
                                            int32_t* active_index, float* c_ref, float* c_pos, float* c_hs,
                                            float* c_box, int32_t* t_label, int64_t* t_ids, int64_t* t_dis,
-                                           const int32_t* ctrl, void* q_qk_lp, void* q_tgt_lp, int lp_dtype,
+                                           int32_t* ctrl, void* q_qk_lp, void* q_tgt_lp, int lp_dtype,
                                            int num_pos_feats, float temperature, moyolo_stream_t stream) {
   MOYOLO_REQUIRE(row_offsets && scores && ids_in && dis_in && counters && ids_out && dis_out && labels &&
                      refer_logit && pos && hs && n_active && active_index && c_ref && c_pos && c_hs &&

@@ -1245,13 +1245,14 @@ static int launch_gemm(const CUtensorMap& tx, const CUtensorMap& tx2, const CUte
   constexpr size_t smem_base = kStages * (kBM * kBK * 2 + BN * kBK * 2) + sizeof(GemmCtl<BN, LN>) + 1024;
   constexpr size_t smem_max = smem_base + (LN ? kMaxScoreNc * (kLnCols / BN) * kBM * 4 : 0);
   const size_t smem = smem_base + (LN ? static_cast<size_t>(e.score_nc) * (kLnCols / BN) * kBM * 4 : 0);
-  static std::atomic<bool> configured{false};  // benign if two host threads race: the attribute is idempotent  // per template instantiation
-  if (!configured.load(std::memory_order_acquire)) {
+  static DeviceOnce once;  // per template instantiation and device
+  const int dev_ = DeviceOnce::current();
+  if (!once.done(dev_)) {
     cudaError_t err = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, TO, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem_max));
     if (err != cudaSuccess)
       return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", smem, cudaGetErrorString(err));
-    configured.store(true, std::memory_order_release);
+    once.set(dev_);
   }
   dim3 grid((e.N + BN - 1) / BN, static_cast<unsigned>((e.M + kBM - 1) / kBM));
   if constexpr (LN)
@@ -1268,18 +1269,16 @@ static int launch_stream_bn(const void* x, int64_t ldx, const void* w, const flo
                           kStreamEpiWarps * StreamCfg<BN>::kSlabs * kSlabBytes +
                           sizeof(StreamCtl<BN>) + 1024;
   static_assert(smem <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt in to");
-  static std::atomic<bool> configured{false};  // benign if two host threads race: the attribute is idempotent
-  static int n_sm = 0;
-  if (!configured.load(std::memory_order_acquire)) {
+  static DeviceOnce once;
+  const int dev_ = DeviceOnce::current();
+  if (!once.done(dev_)) {
     cudaError_t err = cudaFuncSetAttribute(gemm_stream_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem));
     if (err != cudaSuccess)
       return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(stream smem=%zu): %s", smem, cudaGetErrorString(err));
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    configured.store(true, std::memory_order_release);
+    once.set(dev_);
   }
+  const int n_sm = once.n_sm[dev_];
   CUtensorMap tx, tw, ty;
   int rc = make_tmap(&tx, x, M, kSK, ldx, kBM);
   if (rc != MOYOLO_OK) return rc;
@@ -1405,13 +1404,14 @@ static int launch_ffn_ln(const CUtensorMap& tx, const CUtensorMap& tw1, const CU
                          const FfnArgs& e, cudaStream_t st) {
   const size_t smem = kStages * (kBM * kBK * 2 + BN1 * kBK * 2) + static_cast<size_t>(e.F / kBK) * 32 * kBK * 2 +
                       sizeof(FfnCtl<BN1>) + 1024;
-  static std::atomic<bool> configured{false};  // benign if two host threads race: the attribute is idempotent
-  if (!configured.load(std::memory_order_acquire)) {
+  static DeviceOnce once;
+  const int dev_ = DeviceOnce::current();
+  if (!once.done(dev_)) {
     cudaError_t err = cudaFuncSetAttribute(gemm_ffn_ln_kernel<BN1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem));
     if (err != cudaSuccess)
       return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(ffn smem=%zu): %s", smem, cudaGetErrorString(err));
-    configured.store(true, std::memory_order_release);
+    once.set(dev_);
   }
   dim3 grid(kLnCols / 32, static_cast<unsigned>((e.M + kBM - 1) / kBM));
   launch_cluster(gemm_ffn_ln_kernel<BN1>, grid, dim3(kGemmThreads), smem, st, kLnCols / 32, tx, tw1, th, tw2, e);
@@ -1442,13 +1442,14 @@ int ffn_ln_tcgen05(const void* x, int64_t ldx, const void* w1, const float* b1, 
 // Tall Linear(256->256) + LayerNorm (+ class scores): see gemm_rowln_kernel.
 int linear_rowln_tcgen05(const void* x, int64_t ldx, const void* w, const RowLnArgs& a, cudaStream_t st) {
   constexpr size_t smem = 4 * (kBM * kBK * 2 + kLnCols * kBK * 2) + sizeof(RowLnCtl) + 1024;
-  static std::atomic<bool> configured{false};  // benign if two host threads race: the attribute is idempotent
-  if (!configured.load(std::memory_order_acquire)) {
+  static DeviceOnce once;
+  const int dev_ = DeviceOnce::current();
+  if (!once.done(dev_)) {
     cudaError_t err = cudaFuncSetAttribute(gemm_rowln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(smem));
     if (err != cudaSuccess)
       return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(rowln smem=%zu): %s", smem, cudaGetErrorString(err));
-    configured.store(true, std::memory_order_release);
+    once.set(dev_);
   }
   CUtensorMap tx, tw;
   int rc = make_tmap(&tx, x, a.M, kLnCols, ldx, kBM);

@@ -207,13 +207,21 @@ class _DecoderLayerBase(nn.Module):
     def with_pos_embed(tensor, pos):
         return tensor if pos is None else tensor + pos
 
-    def _check_mode(self):
+    def _check_mode(self, *inputs):
         if self.training and self._p_drop > 0:
             raise NotImplementedError("moyolo_b200 decoder layers are inference kernels: dropout>0 in "
                                       "training mode is not implemented")
+        # The decoder-layer kernels build no autograd graph (packed, detached weights): refuse what looks like a
+        # training step instead of silently returning outputs that give the parameters no gradient.
+        if torch.is_grad_enabled() and (any(torch.is_tensor(t) and t.requires_grad for t in inputs) or
+                                        (self.training and any(p.requires_grad for p in self.parameters()))):
+            raise RuntimeError("moyolo_b200 decoder layers run inference kernels that build no autograd graph, but "
+                               "gradients were requested (an input requires grad, or the layer is in training mode "
+                               "with trainable parameters): call under torch.no_grad() / .eval(), or train through "
+                               "MSDeformAttn(differentiable=True)")
 
     def _forward_impl(self, embed, refer_bbox, feats, shapes, padding_mask, attn_mask, query_pos):
-        self._check_mode()
+        self._check_mode(embed, refer_bbox, feats, query_pos)
         dt = ex.lp_dtype(self.precision or ex.get_default_precision())
         pk = ex.cached_pack(self, "layer", ex.LayerPack, dt)
         bs, Q, C = embed.shape
@@ -295,7 +303,7 @@ class _DecoderBase(nn.Module):
         otherwise the same positional embedding is used by every layer (:705-707).
         """
         for l in self.layers:
-            l._check_mode()
+            l._check_mode(embed, refer_bbox, feats, fixed_pos)
         prec = self.precision or ex.get_default_precision()
         dt = ex.lp_dtype(prec)
         bs, Q, C = embed.shape

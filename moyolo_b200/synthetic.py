@@ -287,3 +287,107 @@ def calibrate_score_bias(sd: Dict[str, torch.Tensor], frame0_logits: torch.Tenso
     key = f"dec_score_head.{spec.n_layers - 1}.bias"
     out[key] = sd[key] + (target - q)
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Planted-margin tracking workload (VERDICT r1 task 1a): births and deaths are planted, every score sits far
+# from the 0.4 / 0.5 thresholds of RuntimeTrackerBase (head.py:1146), so free-running ID parity can be checked
+# on every frame in fp32 AND bf16.
+#
+# Mechanism. The first P = 1 + nc channels of the residual stream are "protected": no sub-layer writes to them
+# (rows [:P] of out_proj / output_proj / linear2 and their biases are zero), every LayerNorm scales them by one
+# common gain and no shift, so their SIGNS and RATIOS survive all 18 post-norm steps of the decoder while the
+# other 256 - P channels stay fully random. Channel 0 carries "objectness" (+A: an object, -A: none), channel
+# 1 + c the class one-hot. The last score head reads logit_c = k_obj * x[0] + k_cls * x[1 + c] + small random
+# terms, so sign(x[0]) decides score >> 0.5 or << 0.4 and argmax_c is the planted class.
+#   * births: each frame a random subset of the detect queries carries +A in channel 0 (head.py:1232-1236);
+#   * carried tracks restart from denoising_class_embed[label] (head.py:888-900): classes in `persistent` hold
+#     +A there (the track keeps scoring high), the others -A (the track scores low on every later frame, its
+#     disappear_time runs up and it dies after `miss_tolerance` frames, head.py:1238-1243).
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class PlantSpec:
+    births_per_frame: float = 8.0
+    persistent: Tuple[int, ...] = ()      # class ids whose tracks never die
+    amp: float = 4.0                      # |planted value| in the input embeddings
+    ln_gain: float = 1.4                  # LayerNorm weight of the protected channels
+    k_obj: float = 0.4
+    k_cls: float = 0.25
+    bias: float = -2.0
+    w_noise: float = 0.012                # std of the random part of the score head
+
+
+def make_tracking_state(spec: DecoderSpec, seed: int = 0, plant: PlantSpec = PlantSpec()) -> Dict[str, torch.Tensor]:
+    """make_decoder_state with the protected objectness / class channels described above."""
+    sd = dict(make_decoder_state(spec, seed))
+    P, nc, A = 1 + spec.nc, spec.nc, plant.amp
+    for i in range(spec.n_layers):
+        p = f"layers.{i}."
+        for name in ("self_attn.out_proj", "cross_attn.output_proj", "linear2"):
+            w, b = sd[p + name + ".weight"].clone(), sd[p + name + ".bias"].clone()
+            w[:P] = 0
+            b[:P] = 0
+            sd[p + name + ".weight"], sd[p + name + ".bias"] = w, b
+        for name in ("norm1", "norm2", "norm3"):
+            w, b = sd[p + name + ".weight"].clone(), sd[p + name + ".bias"].clone()
+            w[:P] = plant.ln_gain
+            b[:P] = 0
+            sd[p + name + ".weight"], sd[p + name + ".bias"] = w, b
+    g = _gen(104729 + seed)
+    last = spec.n_layers - 1
+    w = torch.randn(nc, spec.d_model, generator=g) * plant.w_noise
+    w[:, :P] = 0
+    w[:, 0] = plant.k_obj
+    for c in range(nc):
+        w[c, 1 + c] = plant.k_cls
+    sd[f"dec_score_head.{last}.weight"] = w
+    sd[f"dec_score_head.{last}.bias"] = torch.full((nc,), plant.bias)
+    ce = sd["denoising_class_embed.weight"].clone()
+    ce[:, :P] = -A
+    for c in range(nc):
+        ce[c, 0] = A if c in plant.persistent else -A
+        ce[c, 1 + c] = A
+    sd["denoising_class_embed.weight"] = ce
+    return sd
+
+
+class PlantedSequenceGenerator(SequenceGenerator):
+    """SequenceGenerator whose detect embeddings carry the planted objectness / class channels."""
+
+    def __init__(self, spec: SequenceSpec, dspec: DecoderSpec, plant: PlantSpec = PlantSpec(), device="cpu",
+                 dtype=torch.float32):
+        super().__init__(spec, dspec.d_model, device, dtype)
+        self.plant, self.nc = plant, dspec.nc
+
+    def next_frame(self):
+        feats, de, dr = super().next_frame()
+        nd, A, nc = de.shape[0], self.plant.amp, self.nc
+        fire = torch.rand(nd, generator=self.g, device=self.device) < self.plant.births_per_frame / nd
+        cls = torch.randint(0, nc, (nd,), generator=self.g, device=self.device)
+        de = de.clone()
+        de[:, 0] = torch.where(fire, A, -A)
+        de[:, 1:1 + nc] = -A
+        de[torch.arange(nd, device=self.device), 1 + cls] = A
+        return feats, de, dr
+
+
+# named tracking workloads (BASELINE.json configs[1..3]): pyramid, classes, planted dynamics
+TRACKING_WORKLOADS: Dict[str, dict] = {
+    # MOT17: one class, every track dies miss_tolerance frames after its birth -> constant churn, ~40 carried tracks
+    "MOT17": dict(pyramid="MOT17", nc=1, plant=PlantSpec(births_per_frame=8.0, persistent=())),
+    # DanceTrack: one class, tracks persist -> the query count grows towards 500 (configs[2])
+    "DanceTrack": dict(pyramid="DanceTrack", nc=1, plant=PlantSpec(births_per_frame=5.0, persistent=(0,))),
+    # KITTI: KITTI.yaml's 5 classes, classes 0-2 persist, 3-4 die (configs[3])
+    "KITTI": dict(pyramid="KITTI", nc=5, plant=PlantSpec(births_per_frame=6.0, persistent=(0, 1, 2))),
+    "C1": dict(pyramid="C1", nc=1, plant=PlantSpec(births_per_frame=8.0, persistent=())),
+    "tiny": dict(pyramid="tiny", nc=1, plant=PlantSpec(births_per_frame=4.0, persistent=())),
+    "tiny5": dict(pyramid="tiny", nc=5, plant=PlantSpec(births_per_frame=4.0, persistent=(0, 1, 2))),
+}
+
+
+def tracking_workload(name: str, seed: int = 0):
+    """(DecoderSpec, shapes, state_dict, PlantSpec) of a named planted tracking workload."""
+    w = TRACKING_WORKLOADS[name]
+    spec = DecoderSpec(nc=w["nc"])
+    shapes = [list(s) for s in PYRAMIDS[w["pyramid"]]]
+    return spec, shapes, make_tracking_state(spec, seed, w["plant"]), w["plant"]

@@ -40,7 +40,7 @@ from . import executor as ex
 from . import ops
 from .synthetic import DecoderSpec, level_sizes
 
-CTRL_ABORT, CTRL_FRAME, CTRL_CURSOR, CTRL_TABLE_OVERFLOW, CTRL_ABORT_ROWS = 0, 1, 2, 3, 4
+CTRL_ABORT, CTRL_FRAME, CTRL_CURSOR, CTRL_TABLE_OVERFLOW, CTRL_ABORT_ROWS, CTRL_TRACK_OVERFLOW = 0, 1, 2, 3, 4, 5
 
 
 class DecoderWeights:
@@ -142,6 +142,66 @@ class FrameWorkspace:
         self.q_tgt_lp3 = z(R, C, **lp)
         self.q_h = z(R, d_qim, **lp)
         self.q_new = z(R, C, **f32)
+
+
+def qim_update_ws(W: DecoderWeights, spec: DecoderSpec, ws: "FrameWorkspace", ro_host) -> None:
+    """QueryInteractionModule._update_track_embedding (MOTR/models/qim.py:251-301) for the active
+    tracks of every sequence at once: rows of sequence s are [ro[s], ro[s] + n_active[s]) of the
+    compact buffers (the rest is padding). ref_pts <- inverse_sigmoid(pred_boxes) (qim.py:299) is
+    fused into frame_writeback."""
+    C = spec.d_model
+    dt, q, H = W.dt, W.qim, 8  # nn.MultiheadAttention(dim_in, 8, ...) qim.py:88
+    eng = ex._GEMM_ENGINE
+    # q = k = tgt + pos2posemb(ref_pts), v = tgt (qim.py:255, 271): operands written by frame_compact
+    ex.qkv_proj(ws.q_qk_lp, ws.q_tgt_lp, q["qkv_w"], q["qkv_b"], ws.qkv, C, eng)
+    ops.self_attention(ws.qkv[:, :C], ws.qkv[:, C:2 * C], ws.qkv[:, 2 * C:], ws.ro, ro_host, H, out=ws.att,
+                       seg_len=ws.n_active)
+    if ex.fused_epilogues(dt, C) and q["l1_w"].shape[0] % 64 == 0:
+        ops.linear_add_layernorm(ws.att, q["o_w"], q["o_b"], ws.c_hs, *q["norm1"], 1e-5, out_f32=ws.q_tgt,   # :277-278
+                                 out_lp=ws.q_tgt_lp2)
+        if ops.ffn_fused_supported(dt, C, q["l1_w"].shape[0]):   # each FFN block of the QIM in one launch
+            ops.ffn_add_layernorm(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], q["l2_w"], q["l2_b"], ws.q_h, ws.q_tgt,
+                                  *q["norm2"], 1e-5, out_lp=ws.q_tgt_lp3)                                    # :280-282
+            ops.ffn_add_layernorm(ws.q_tgt_lp3, q["f1_w"], q["f1_b"], q["f2_w"], q["f2_b"], ws.q_h, ws.c_pos,
+                                  *q["norm_feat"], 1e-5, out_f32=ws.q_new)                                   # :290-298
+            return
+        ops.linear(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], relu=True, out=ws.q_h, engine=eng)
+        ops.linear_add_layernorm(ws.q_h, q["l2_w"], q["l2_b"], ws.q_tgt, *q["norm2"], 1e-5,                  # :280-282
+                                 out_lp=ws.q_tgt_lp3)
+        ops.linear(ws.q_tgt_lp3, q["f1_w"], q["f1_b"], relu=True, out=ws.q_h, engine=eng)
+        ops.linear_add_layernorm(ws.q_h, q["f2_w"], q["f2_b"], ws.c_pos, *q["norm_feat"], 1e-5,              # :290-298
+                                 out_f32=ws.q_new)
+        return
+    ops.linear(ws.att, q["o_w"], q["o_b"], out=ws.t, engine=eng)
+    ops.add_layernorm(ws.t, ws.c_hs, *q["norm1"], 1e-5, out_f32=ws.q_tgt,                       # :277-278
+                      out_lp=None if dt == torch.float32 else ws.q_tgt_lp2)
+    ops.linear(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], relu=True, out=ws.q_h, engine=eng)
+    ops.linear(ws.q_h, q["l2_w"], q["l2_b"], out=ws.t, engine=eng)                               # :280
+    ops.add_layernorm(ws.t, ws.q_tgt, *q["norm2"], 1e-5, want_f32=False, out_lp=ws.q_tgt_lp3)   # :281-282
+    ops.linear(ws.q_tgt_lp3, q["f1_w"], q["f1_b"], relu=True, out=ws.q_h, engine=eng)
+    ops.linear(ws.q_h, q["f2_w"], q["f2_b"], out=ws.t, engine=eng)                               # :290
+    ops.add_layernorm(ws.t, ws.c_pos, *q["norm_feat"], 1e-5, out_f32=ws.q_new)                  # :294-298
+
+
+def qim_update(weights: DecoderWeights, ref_pts: torch.Tensor, query_pos: torch.Tensor, out_embed: torch.Tensor,
+               pred_boxes: torch.Tensor):
+    """QueryInteractionModule._update_track_embedding (MOTR/models/qim.py:251-301) for one set of T tracks through
+    the kernels the frame uses (`qim_update_ws`): ref_pts [T,4] logits, query_pos / out_embed [T,C] fp32,
+    pred_boxes [T,4] -> (new query_pos [T,C] fp32, new ref_pts [T,4] = inverse_sigmoid(pred_boxes), qim.py:299)."""
+    spec, dt, dev = weights.spec, weights.dt, ref_pts.device
+    T, C = out_embed.shape
+    R = max(16, (T + 15) // 16 * 16)
+    ws = FrameWorkspace(R, 1, spec, dt, dev, weights.qim["l1_w"].shape[0])
+    ws.c_hs[:T].copy_(out_embed)
+    ws.c_pos[:T].copy_(query_pos)
+    ops.pos2posemb(ref_pts.float().contiguous(), out=ws.q_pos[:T])                  # qim.py:255
+    ops.add_cast(ws.c_hs[:T], ws.q_pos[:T], dt, out=ws.q_qk_lp[:T])                 # q = k = tgt + query_pos (:271)
+    if dt != torch.float32:
+        ops.add_cast(ws.c_hs[:T], None, dt, out=ws.q_tgt_lp[:T])
+    ws.ro.copy_(torch.tensor([0, T], dtype=torch.int32))
+    ws.n_active.fill_(T)
+    qim_update_ws(weights, spec, ws, [0, 16 + R])
+    return ws.q_new[:T].clone(), ops.inverse_sigmoid(pred_boxes.float().contiguous())
 
 
 class _FramePlan:
@@ -283,6 +343,8 @@ class TrackEngine:
             self.n_tracks[seq] = 0
             self.counters[seq].zero_()
             self._T[seq] = 0
+            # collect() of the next frame slices its packed rows with the counts that frame STARTED with
+            self._T_before[self._next] = list(self._T)
 
     def set_seq_ids(self, ids) -> None:
         """Global sequence index of every lock-step slot (the `seq` column of the emitted rows)."""
@@ -431,43 +493,7 @@ class TrackEngine:
                             active_index=ws.active_index if fork else None)
 
     def _qim_update(self, ws: FrameWorkspace, ro_host) -> None:
-        """QueryInteractionModule._update_track_embedding (MOTR/models/qim.py:251-301) for the active
-        tracks of every sequence at once: rows of sequence s are [ro[s], ro[s] + n_active[s]) of the
-        compact buffers (the rest is padding). ref_pts <- inverse_sigmoid(pred_boxes) (qim.py:299) is
-        fused into frame_writeback."""
-        W = self.W
-        C = self.spec.d_model
-        dt, q, H = W.dt, W.qim, 8  # nn.MultiheadAttention(dim_in, 8, ...) qim.py:88
-        eng = ex._GEMM_ENGINE
-        # q = k = tgt + pos2posemb(ref_pts), v = tgt (qim.py:255, 271): operands written by frame_compact
-        ex.qkv_proj(ws.q_qk_lp, ws.q_tgt_lp, q["qkv_w"], q["qkv_b"], ws.qkv, C, eng)
-        ops.self_attention(ws.qkv[:, :C], ws.qkv[:, C:2 * C], ws.qkv[:, 2 * C:], ws.ro, ro_host, H, out=ws.att,
-                           seg_len=ws.n_active)
-        if ex.fused_epilogues(dt, C) and q["l1_w"].shape[0] % 64 == 0:
-            ops.linear_add_layernorm(ws.att, q["o_w"], q["o_b"], ws.c_hs, *q["norm1"], 1e-5, out_f32=ws.q_tgt,   # :277-278
-                                     out_lp=ws.q_tgt_lp2)
-            if ops.ffn_fused_supported(dt, C, q["l1_w"].shape[0]):   # each FFN block of the QIM in one launch
-                ops.ffn_add_layernorm(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], q["l2_w"], q["l2_b"], ws.q_h, ws.q_tgt,
-                                      *q["norm2"], 1e-5, out_lp=ws.q_tgt_lp3)                                    # :280-282
-                ops.ffn_add_layernorm(ws.q_tgt_lp3, q["f1_w"], q["f1_b"], q["f2_w"], q["f2_b"], ws.q_h, ws.c_pos,
-                                      *q["norm_feat"], 1e-5, out_f32=ws.q_new)                                   # :290-298
-                return
-            ops.linear(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], relu=True, out=ws.q_h, engine=eng)
-            ops.linear_add_layernorm(ws.q_h, q["l2_w"], q["l2_b"], ws.q_tgt, *q["norm2"], 1e-5,                  # :280-282
-                                     out_lp=ws.q_tgt_lp3)
-            ops.linear(ws.q_tgt_lp3, q["f1_w"], q["f1_b"], relu=True, out=ws.q_h, engine=eng)
-            ops.linear_add_layernorm(ws.q_h, q["f2_w"], q["f2_b"], ws.c_pos, *q["norm_feat"], 1e-5,              # :290-298
-                                     out_f32=ws.q_new)
-            return
-        ops.linear(ws.att, q["o_w"], q["o_b"], out=ws.t, engine=eng)
-        ops.add_layernorm(ws.t, ws.c_hs, *q["norm1"], 1e-5, out_f32=ws.q_tgt,                       # :277-278
-                          out_lp=None if dt == torch.float32 else ws.q_tgt_lp2)
-        ops.linear(ws.q_tgt_lp2, q["l1_w"], q["l1_b"], relu=True, out=ws.q_h, engine=eng)
-        ops.linear(ws.q_h, q["l2_w"], q["l2_b"], out=ws.t, engine=eng)                               # :280
-        ops.add_layernorm(ws.t, ws.q_tgt, *q["norm2"], 1e-5, want_f32=False, out_lp=ws.q_tgt_lp3)   # :281-282
-        ops.linear(ws.q_tgt_lp3, q["f1_w"], q["f1_b"], relu=True, out=ws.q_h, engine=eng)
-        ops.linear(ws.q_h, q["f2_w"], q["f2_b"], out=ws.t, engine=eng)                               # :290
-        ops.add_layernorm(ws.t, ws.c_pos, *q["norm_feat"], 1e-5, out_f32=ws.q_new)                  # :294-298
+        qim_update_ws(self.W, self.spec, ws, ro_host)
 
     # ---- plans ------------------------------------------------------------------------------------
     def _state_snapshot(self):
@@ -706,6 +732,10 @@ class TrackEngine:
             if int(info[self.n_seq + CTRL_ABORT]) != 0:
                 self._recover()
                 continue
+            if int(info[self.n_seq + CTRL_TRACK_OVERFLOW]) != 0:
+                raise RuntimeError(f"moyolo_b200: a sequence carried more than cap={self.cap} active tracks in frame "
+                                   f"{rec['frame']}; the surplus tracks lost their identity. Construct TrackEngine with "
+                                   "a larger cap and re-run the sequence")
             self._inflight.pop(0)
             self._T = info[:self.n_seq].tolist()
             self._known = rec["frame"]

@@ -87,9 +87,13 @@ def msda_core_gather(value: Tensor, shapes: Sequence[Sequence[int]], loc: Tensor
 
 def msdeform_attn_forward(p: Dict[str, Tensor], query: Tensor, refer_bbox: Tensor, value: Tensor,
                           shapes: Sequence[Sequence[int]], n_heads: int, n_levels: int, n_points: int,
-                          value_mask: Optional[Tensor] = None, core=msda_core_gridsample) -> Tensor:
+                          value_mask: Optional[Tensor] = None, core=msda_core_gridsample,
+                          my_softmax: bool = False) -> Tensor:
     """MSDeformAttn.forward, ultralytics/nn/modules/transformer.py:246-287.
-    p keys: sampling_offsets/attention_weights/value_proj/output_proj .weight/.bias (:214-217)."""
+    p keys: sampling_offsets/attention_weights/value_proj/output_proj .weight/.bias (:214-217).
+    my_softmax: MOTRMSDeformAttn's optional normalisation exp(x) / (1 + sum exp(x)) (`_custom_softmax`,
+    transformer.py:239-244, selected at :369-371). UNPINNED: the reference method lacks `self`, so the reference
+    itself raises when the flag is set; this restates the arithmetic of :241-244."""
     B, Q, C = query.shape
     Lv = value.shape[1]
     assert sum(h * w for h, w in shapes) == Lv                                # :262
@@ -100,7 +104,12 @@ def msdeform_attn_forward(p: Dict[str, Tensor], query: Tensor, refer_bbox: Tenso
     off = F.linear(query, p["sampling_offsets.weight"], p["sampling_offsets.bias"])
     off = off.view(B, Q, n_heads, n_levels, n_points, 2)                       # :268
     att = F.linear(query, p["attention_weights.weight"], p["attention_weights.bias"])
-    att = F.softmax(att.view(B, Q, n_heads, n_levels * n_points), -1)          # :269-271
+    att = att.view(B, Q, n_heads, n_levels * n_points)
+    if my_softmax:
+        e = torch.exp(att)                                                     # :241
+        att = e / (1 + e.sum(-1, keepdim=True))                                # :242-244
+    else:
+        att = F.softmax(att, -1)                                               # :269-271
     att = att.view(B, Q, n_heads, n_levels, n_points)
     d = refer_bbox.shape[-1]
     if d == 2:                                                                 # :276-279

@@ -747,3 +747,57 @@ def test_msdeform_attn_module_training_path(dev, ref_dim, with_mask):
     with torch.no_grad():
         out_inf = attn(qd.detach(), rd.detach(), vd.detach(), shapes, None if mask is None else mask.to(dev))
     assert rel_rms(out_inf.cpu().numpy(), out64.detach().numpy()) < FP32_TOL
+
+
+# ------------------------------------------------------------------ a9: QIM against the reference goldens, directly
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_MODULE_TOL)])
+@pytest.mark.parametrize("name", ["qim_a", "qim_one"])
+def test_qim_update_vs_reference_golden(dev, name, precision, tol):
+    """QueryInteractionModule._update_track_embedding (MOTR/models/qim.py:251-301): the frame's QIM kernels
+    (tracker.qim_update -> qim_update_ws) against outputs of the reference module itself (oracle/make_golden.py
+    gen_qim), T = 23 tracks and the single-track edge case."""
+    m, ops, syn, mg, tp = _mods()
+    from moyolo_b200.tracker import DecoderWeights, qim_update
+    meta, g = load_golden(name)
+    spec = syn.DecoderSpec()
+    sd = syn.make_decoder_state(spec, meta["weight_seed"])
+    W = DecoderWeights(sd, spec, dev, precision)
+    t = {k: torch.from_numpy(v).to(dev) for k, v in g.items()}
+    qp, rp = qim_update(W, t["ref_pts"], t["query_pos"], t["out_embed"], t["pred_boxes"])
+    assert qp.shape == g["new_query_pos"].shape
+    assert rel_rms(qp.cpu().numpy(), g["new_query_pos"]) < tol
+    assert np.allclose(rp.cpu().numpy(), g["new_ref_pts"], rtol=2e-6, atol=2e-6)   # logf rounding only
+
+
+# ------------------------------------------------------------------ a3: MOTRMSDeformAttn(my_softmax=True)
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_MODULE_TOL)])
+def test_motr_msdeform_attn_my_softmax(dev, precision, tol):
+    """transformer.py:239-244, 369-371: attention weights exp(x) / (1 + sum exp(x)) instead of softmax. The
+    reference method lacks `self` and raises when enabled, so the check is against the oracle's restatement of
+    :241-244 (documented there as unpinned). Also checks that the flag changes the result and that the plain
+    MSDeformAttn class ignores it (it never reads my_softmax, transformer.py:271)."""
+    m, ops, syn, mg, tp = _mods()
+    spec = syn.DecoderSpec()
+    sd = syn.make_decoder_state(spec, 5)
+    p = syn.sub_state(sd, "layers.0.cross_attn.")
+    for B, Q, pyr, ref_dim, ref_levels in ((2, 77, "tiny", 4, 1), (1, 300, "C1", 4, 1), (1, 9, "tiny", 2, 3)):
+        shapes = [list(s) for s in syn.PYRAMIDS[pyr]]
+        q, refer, feats, _ = syn.make_module_inputs(31 + Q, B, Q, spec.d_model, shapes, ref_dim, ref_levels)
+        with torch.no_grad():
+            ref = tp.msdeform_attn_forward(p, q, refer, feats, shapes, spec.n_heads, spec.n_levels, spec.n_points,
+                                           my_softmax=True).numpy()
+            ref_plain = tp.msdeform_attn_forward(p, q, refer, feats, shapes, spec.n_heads, spec.n_levels,
+                                                 spec.n_points).numpy()
+        mod = m.MOTRMSDeformAttn(spec.d_model, spec.n_levels, spec.n_heads, spec.n_points, my_softmax=True)
+        mod.load_state_dict(p)
+        mod = mod.to(dev).eval()
+        mod.precision = precision
+        out = mod(q.to(dev), refer.to(dev), feats.to(dev), shapes).cpu().numpy()
+        assert rel_rms(out, ref) < tol, (B, Q, pyr)
+        assert rel_rms(ref, ref_plain) > 0.05, "the flag must matter for this check to mean anything"
+        plain = m.MSDeformAttn(spec.d_model, spec.n_levels, spec.n_heads, spec.n_points, my_softmax=True)
+        plain.load_state_dict(p)
+        plain = plain.to(dev).eval()
+        plain.precision = precision
+        out2 = plain(q.to(dev), refer.to(dev), feats.to(dev), shapes).cpu().numpy()
+        assert rel_rms(out2, ref_plain) < tol, (B, Q, pyr, "MSDeformAttn ignores my_softmax")

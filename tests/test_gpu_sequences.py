@@ -1,0 +1,137 @@
+"""Free-running track-ID parity on the benchmarked configurations (VERDICT r1 tasks 1a-1c).
+
+The planted-margin workloads of moyolo_b200.synthetic (TRACKING_WORKLOADS) keep every score far from the 0.4 / 0.5
+thresholds of RuntimeTrackerBase (ultralytics/nn/modules/head.py:1146), so the GPU engine and the CPU oracle "O3"
+(oracle/tracker_port.py) must assign IDENTICAL track IDs on EVERY frame, in fp32 and in bf16, at the shapes
+bench.py runs: MOT17 (300 detect queries, Lv = 13 566), DanceTrack (Q -> 500) and KITTI (nc = 5, which exercises
+the label -> denoising_class_embed[argmax] path of head.py:888-900), with 1 and 4 lock-step sequences.
+
+Tolerances: IDs, labels, disappear counters, ID counters bit-exact; boxes fp32 <= 1e-4 * rms(ref), bf16 <= 5e-3
+absolute (normalised coordinates); scores fp32 <= 1e-4, bf16 <= 2e-2 absolute.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+N_FRAMES = 32
+_ORACLE = {}   # (workload, seq seed) -> (frames, oracle records): shared by the precision / S parametrisation
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from moyolo_b200 import _lib
+    assert _lib.lib().moyolo_device_supported() == 1, "libmoyolo_b200 targets sm_100a (B200) only"
+    return torch.device("cuda:0")
+
+
+def _oracle_sequence(name, seq_seed, n_frames=N_FRAMES, nd=300):
+    from moyolo_b200 import synthetic as syn
+    from oracle.tracker_port import track_sequence_port
+    key = (name, seq_seed, n_frames, nd)
+    if key not in _ORACLE:
+        spec, shapes, sd, plant = syn.tracking_workload(name, 7)
+        g = syn.PlantedSequenceGenerator(syn.SequenceSpec(name, n_frames, nd, seq_seed, shapes=shapes), spec, plant)
+        frames = [tuple(t.clone() for t in g.next_frame()) for _ in range(n_frames)]
+        torch.set_num_threads(max(torch.get_num_threads(), 8))
+        recs = track_sequence_port(sd, frames, shapes, spec.n_heads, spec.n_levels, spec.n_points, spec.n_layers, spec.nc)
+        _ORACLE[key] = (frames, recs)
+    return _ORACLE[key]
+
+
+def _margin(rec):
+    s = rec["scores"]
+    return float(np.minimum(np.abs(s - 0.4), np.abs(s - 0.5)).min())
+
+
+CASES = [("MOT17", 1), ("MOT17", 4), ("DanceTrack", 1), ("KITTI", 1), ("KITTI", 4)]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("name,S", CASES)
+def test_free_running_ids_on_bench_configs(dev, name, S, precision):
+    from moyolo_b200 import synthetic as syn
+    from moyolo_b200.tracker import TrackEngine
+    from oracle.tracker_port import TrackerPort
+    if precision == "fp32" and S > 1:
+        pytest.skip("fp32 is covered at S=1 (same kernels per row)")
+    spec, shapes, sd, plant = syn.tracking_workload(name, 7)
+    nd = 300
+    seqs = [_oracle_sequence(name, 1 + s) for s in range(S)]
+    margin_need = 2e-2 if precision == "bf16" else 2e-5
+    score_tol = 2e-2 if precision == "bf16" else 1e-4
+    eng = TrackEngine(sd, spec, shapes, dev, precision, nd, S)
+    forced = [TrackerPort() for _ in range(S)]
+    prev = [(np.zeros(0, np.int64), np.zeros(0, np.int64)) for _ in range(S)]
+    alive = [True] * S
+    compared, excluded, max_box, max_score, max_T = 0, 0, 0.0, 0.0, 0
+    for t in range(N_FRAMES):
+        batch = [torch.stack([seqs[s][0][t][k] for s in range(S)]).to(dev) for k in range(3)]
+        outs = eng.step(*batch)
+        for s in range(S):
+            r = seqs[s][1][t]
+            o = {k: v.cpu().numpy() for k, v in outs[s].items()}
+            # teacher-forced integer logic on the GPU's own scores (bit-exact, every frame)
+            ids = np.concatenate([prev[s][0], np.full(nd, -1, np.int64)])
+            dis = np.concatenate([prev[s][1], np.zeros(nd, np.int64)])
+            forced[s].update(o["scores"], o["boxes"], ids, dis)
+            assert np.array_equal(o["ids"], ids), (name, s, t, "teacher-forced ids")
+            assert eng.counters[s].tolist() == [forced[s].max_obj_id, forced[s].max_obj_id_pre], (name, s, t)
+            act = ids >= 0
+            prev[s] = (ids[act], dis[act])
+            # free-running against the oracle
+            if not alive[s]:
+                continue
+            if _margin(r) < margin_need:
+                alive[s] = False
+                excluded += N_FRAMES - t
+                continue
+            assert o["ids"].shape == r["ids"].shape, (name, s, t, "row count")
+            assert np.array_equal(o["ids"], r["ids"]), (name, s, t, "free-running ids")
+            assert np.array_equal(o["labels"], r["labels"]), (name, s, t, "labels")
+            assert eng.counters[s].tolist() == list(r["counters"]), (name, s, t, "id counters")
+            scale = 1.0 if precision == "bf16" else float(np.sqrt((r["boxes"] ** 2).mean()))
+            box_tol = 5e-3 if precision == "bf16" else 1e-4 * scale
+            eb = float(np.abs(o["boxes"] - r["boxes"]).max())
+            es = float(np.abs(o["scores"] - r["scores"]).max())
+            assert eb < box_tol, (name, s, t, "boxes", eb)
+            assert es < score_tol, (name, s, t, "scores", es)
+            max_box, max_score, max_T = max(max_box, eb), max(max_score, es), max(max_T, r["n_tracks_in"])
+            compared += 1
+    print(f"[{name} S={S} {precision}] frames compared {compared}/{S * N_FRAMES}, excluded by margin {excluded}, "
+          f"max carried tracks {max_T}, max box err {max_box:.2e}, max score err {max_score:.2e}")
+    assert compared >= 0.8 * S * N_FRAMES, f"only {compared} of {S * N_FRAMES} frames compared"
+    assert max_T > 20, "sequence never carried more than 20 tracks"
+    deaths = sum(int((seqs[0][1][t]["ids"][:seqs[0][1][t]["n_tracks_in"]] < 0).sum()) for t in range(N_FRAMES))
+    if name != "DanceTrack":
+        assert deaths > 0, "no planted death happened"
+
+
+def test_free_running_pipelined_bf16(dev):
+    """The same comparison through the pipelined submit()/collect() path bench.py times (host buffers, speculative
+    padded sizes, CUDA graphs): MOT17, one sequence, bf16, pinned host inputs."""
+    from moyolo_b200 import synthetic as syn
+    from moyolo_b200.tracker import TrackEngine
+    name, nd = "MOT17", 300
+    spec, shapes, sd, plant = syn.tracking_workload(name, 7)
+    frames, recs = _oracle_sequence(name, 1)
+    eng = TrackEngine(sd, spec, shapes, dev, "bf16", nd, 1)
+    eng.prepare(96)
+    host = [tuple(x[None].to(torch.bfloat16 if k == 0 else torch.float32).contiguous().pin_memory()
+                  for k, x in enumerate(f)) for f in frames]
+    got = {}
+    for t in range(N_FRAMES):
+        eng.submit(*host[t], want_rows=True)
+        if t > 0:
+            got[t - 1] = {k: v.clone() for k, v in eng.collect(t - 1)[0].items()}
+    got[N_FRAMES - 1] = {k: v.clone() for k, v in eng.collect(N_FRAMES - 1)[0].items()}
+    for t in range(N_FRAMES):
+        r = recs[t]
+        assert np.array_equal(got[t]["ids"].numpy(), r["ids"]), (t, "ids")
+        assert float(np.abs(got[t]["boxes"].numpy() - r["boxes"]).max()) < 5e-3, t
+    table = eng.track_table().cpu().numpy()
+    want = sum(int((r["ids"] >= 0).sum()) for r in recs)
+    assert table.shape[0] == want
