@@ -315,6 +315,7 @@ class PlantSpec:
     k_cls: float = 0.25
     bias: float = -2.0
     w_noise: float = 0.012                # std of the random part of the score head
+    box_gain: float = 0.25                # scale of the last box-head layer
 
 
 def make_tracking_state(spec: DecoderSpec, seed: int = 0, plant: PlantSpec = PlantSpec()) -> Dict[str, torch.Tensor]:
@@ -333,6 +334,8 @@ def make_tracking_state(spec: DecoderSpec, seed: int = 0, plant: PlantSpec = Pla
             w[:P] = plant.ln_gain
             b[:P] = 0
             sd[p + name + ".weight"], sd[p + name + ".bias"] = w, b
+    for i in range(spec.n_layers):   # small refinement steps: errors of carried boxes must not compound across frames
+        sd[f"dec_bbox_head.{i}.layers.2.weight"] = sd[f"dec_bbox_head.{i}.layers.2.weight"] * plant.box_gain
     g = _gen(104729 + seed)
     last = spec.n_layers - 1
     w = torch.randn(nc, spec.d_model, generator=g) * plant.w_noise
@@ -352,15 +355,41 @@ def make_tracking_state(spec: DecoderSpec, seed: int = 0, plant: PlantSpec = Pla
 
 
 class PlantedSequenceGenerator(SequenceGenerator):
-    """SequenceGenerator whose detect embeddings carry the planted objectness / class channels."""
+    """SequenceGenerator whose detect embeddings carry the planted objectness / class channels and whose feature
+    maps are SPATIALLY smooth (coarse noise, bilinearly upsampled 8x per level, unit variance): a white-noise map
+    makes bilinear sampling ill-conditioned in the sampling location (d value / d loc grows with the map width), so
+    rounding noise in the offsets would be amplified ~W-fold per layer -- no real backbone produces such maps."""
+
+    SMOOTH = 8  # upsampling factor of the coarse noise
 
     def __init__(self, spec: SequenceSpec, dspec: DecoderSpec, plant: PlantSpec = PlantSpec(), device="cpu",
                  dtype=torch.float32):
         super().__init__(spec, dspec.d_model, device, dtype)
         self.plant, self.nc = plant, dspec.nc
+        self.feats = self._smooth_noise()
+
+    def _smooth_noise(self) -> torch.Tensor:
+        import torch.nn.functional as F
+        out = []
+        for h, w in self.spec.shapes:
+            ch, cw = -(-int(h) // self.SMOOTH) + 1, -(-int(w) // self.SMOOTH) + 1
+            coarse = torch.randn(1, self.d, ch, cw, generator=self.g, device=self.device)
+            m = F.interpolate(coarse, size=(int(h), int(w)), mode="bilinear", align_corners=True)
+            out.append(m[0].flatten(1).t())
+        x = torch.cat(out, 0)
+        return x / x.std()
 
     def next_frame(self):
-        feats, de, dr = super().next_frame()
+        if self.t > 0:
+            s = self.spec.drift
+            self.feats = self.feats + s * self._smooth_noise()
+            self.det_embed = self.det_embed + s * torch.randn(self.det_embed.shape, generator=self.g,
+                                                              device=self.device)
+            jitter = 0.01 * torch.randn(self.det_box.shape, generator=self.g, device=self.device)
+            self.det_box = (self.det_box + jitter).clamp(0.02, 0.98)
+        self.t += 1
+        b = self.det_box
+        feats, de, dr = self.feats.to(self.dtype), self.det_embed, torch.log(b / (1 - b))
         nd, A, nc = de.shape[0], self.plant.amp, self.nc
         fire = torch.rand(nd, generator=self.g, device=self.device) < self.plant.births_per_frame / nd
         cls = torch.randint(0, nc, (nd,), generator=self.g, device=self.device)

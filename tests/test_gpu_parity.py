@@ -770,7 +770,7 @@ def test_qim_update_vs_reference_golden(dev, name, precision, tol):
 
 
 # ------------------------------------------------------------------ a3: MOTRMSDeformAttn(my_softmax=True)
-@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_MODULE_TOL)])
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", 4e-2)])   # max-norm over up to 76 800 outputs
 def test_motr_msdeform_attn_my_softmax(dev, precision, tol):
     """transformer.py:239-244, 369-371: attention weights exp(x) / (1 + sum exp(x)) instead of softmax. The
     reference method lacks `self` and raises when enabled, so the check is against the oracle's restatement of
