@@ -75,6 +75,10 @@ int moyolo_version(void);
 const char* moyolo_last_error(void);
 /* 1 if the current device is compute capability 10.x (the only supported target), else 0. */
 int moyolo_device_supported(void);
+/* Number of kernels this library has launched (or recorded into a graph being captured) from the CALLING host
+ * thread since it first called the library. Monotonic, thread-local, never reset: callers take differences
+ * (bench.py's `gpu_launches`, the per-graph launch count of moyolo_b200.TrackEngine). */
+uint64_t moyolo_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Multi-scale deformable attention gather.

@@ -38,6 +38,7 @@ SIGNATURES = {
     "moyolo_version": (_i, []),
     "moyolo_last_error": (C.c_char_p, []),
     "moyolo_device_supported": (_i, []),
+    "moyolo_launch_count": (C.c_uint64, []),
     "moyolo_msda_sampled_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _p, _i, _l, _p, _p, _l, _p]),
     "moyolo_msda_sampled_backward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _p, _i, _p, _l, _l, _p, _p,
                                           _p, _p, _p]),

@@ -8,6 +8,10 @@
 namespace moyolo {
 
 static thread_local char g_last_error[512] = "";
+static thread_local unsigned long long g_launches = 0;
+
+void note_launch() { ++g_launches; }
+unsigned long long launches() { return g_launches; }
 
 char* last_error_buf() { return g_last_error; }
 
@@ -55,7 +59,9 @@ int make_levels(const int32_t* shapes_hw_host, int n_levels, int64_t len_v, Leve
 
 }  // namespace moyolo
 
+namespace moyolo { unsigned long long launches(); }
 extern "C" int moyolo_version(void) { return MOYOLO_VERSION; }
+extern "C" uint64_t moyolo_launch_count(void) { return moyolo::launches(); }
 extern "C" const char* moyolo_last_error(void) { return moyolo::last_error_buf(); }
 extern "C" int moyolo_device_supported(void) {
   int dev = 0;

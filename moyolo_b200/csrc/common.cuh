@@ -51,6 +51,7 @@ struct DeviceOnce {
 //     (weights, biases and LayerNorm parameters are immutable; activations, masks and state are not).
 // MOYOLO_PDL=0 in the environment disables the attribute (the device instructions are then no-ops).
 bool pdl_enabled();
+void note_launch();  // per-thread count of kernels launched through launch_k (moyolo_launch_count)
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
@@ -68,6 +69,7 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  note_launch();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

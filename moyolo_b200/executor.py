@@ -237,7 +237,7 @@ def qkv_proj(xq_lp, x_lp, w, b, out, C: int, eng) -> None:
 
 
 def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offsets, row_offsets_host, pos_cur,
-                 pos_next, dt, before_gather=None, score=None) -> None:
+                 pos_next, dt, before_gather=None, score=None, gather_probe=None) -> None:
     """One post-norm decoder layer on workspace buffers. In: ws.x (fp32 residual), ws.x_lp, ws.xq_lp
     (= x + pos operand). Out: the same three for the next layer (xq only when pos_next is given)."""
     C = pk.C
@@ -260,13 +260,13 @@ def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offset
             if before_gather is not None:
                 before_gather()
             ops.msda_proj_fused(value_view, shapes, ws.x1q_lp, pkm.offlog.w, pkm.offlog.b, refer, pkm.n_heads,
-                                pkm.n_points, batch, pkm.softmax_mode, row_offsets, out=ws.g)
+                                pkm.n_points, batch, pkm.softmax_mode, row_offsets, out=ws.g, probe=gather_probe)
         else:
             ops.linear(ws.x1q_lp, pkm.offlog.w, pkm.offlog.b, out=ws.ol, engine=eng)
             if before_gather is not None:
                 before_gather()
             ops.msda_fused(value_view, shapes, ws.ol[:, :pkm.n_off], ws.ol[:, pkm.n_off:], refer, pkm.n_heads,
-                           pkm.n_points, batch, pkm.softmax_mode, row_offsets, out=ws.g)
+                           pkm.n_points, batch, pkm.softmax_mode, row_offsets, out=ws.g, probe=gather_probe)
         g, b_, e = pk.norms[1]
         ops.linear_add_layernorm(ws.g, pkm.out.w, pkm.out.b, ws.x1, g, b_, e, out_f32=ws.x2, out_lp=ws.x2_lp)
         g, b_, e = pk.norms[2]
@@ -295,7 +295,7 @@ def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offset
     if before_gather is not None:
         before_gather()
     ops.msda_fused(value_view, shapes, ws.ol[:, :pkm.n_off], ws.ol[:, pkm.n_off:], refer, pkm.n_heads, pkm.n_points,
-                   batch, pkm.softmax_mode, row_offsets, out=ws.g)
+                   batch, pkm.softmax_mode, row_offsets, out=ws.g, probe=gather_probe)
     ops.linear(ws.g, pkm.out.w, pkm.out.b, out=ws.t, engine=eng)
     g, b_, e = pk.norms[1]
     ops.add_layernorm(ws.t, ws.x1, g, b_, e, out_f32=ws.x2, out_lp=None if f32 else ws.x2_lp)

@@ -38,22 +38,26 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-# number of kernels launched through the C ABI since the last reset (bench.py `gpu_launches`)
-LAUNCHES = 0
-# optional (pre, post) callables invoked around every deformable-gather launch (bench.py roofline leg)
-GATHER_HOOK = None
-# the roofline leg repeats each (idempotent) gather launch this many times between one event pair so the
-# event-node overhead (~5 us per pair inside a graph) is amortised; 1 everywhere else
-GATHER_REPEAT = 1
 # offsets|logits projection inside the gather kernel (MOYOLO_PROJ_FUSED=0 disables; row bound see proj_fused_supported)
 import os as _os  # noqa: E402
 PROJ_FUSED = _os.environ.get("MOYOLO_PROJ_FUSED", "1") != "0"
 PROJ_FUSED_MAX_ROWS = int(_os.environ.get("MOYOLO_PROJ_FUSED_MAX_ROWS", "1024"))
 
 
-def _count(n: int = 1) -> None:
-    global LAUNCHES
-    LAUNCHES += n
+def launch_count() -> int:
+    """Kernels launched (or recorded into a graph being captured) through the C ABI by this host thread so far:
+    a monotonic thread-local counter kept by the library (moyolo_launch_count); callers take differences."""
+    return int(_lib.lib().moyolo_launch_count())
+
+
+class GatherProbe:
+    """Instrumentation handed to a gather call by its caller (bench.py's roofline leg): `pre(B, Lv, C, R, H, L, P,
+    value_bytes)` / `post()` run around the launch and the (idempotent) launch is repeated `repeat` times between
+    them, so the ~5 us of a CUDA-event node pair inside a graph is amortised."""
+    __slots__ = ("pre", "post", "repeat")
+
+    def __init__(self, pre, post, repeat: int = 1):
+        self.pre, self.post, self.repeat = pre, post, repeat
 
 
 def _shapes_arr(shapes: Sequence[Sequence[int]]):
@@ -80,7 +84,6 @@ def msda_sampled(value: torch.Tensor, shapes, loc: torch.Tensor, weights: torch.
     out = torch.empty(B, Q, H * Dh, dtype=value.dtype, device=value.device)
     if B * Q == 0:
         return out
-    _count(1)
     _lib.check(_lib.lib().moyolo_msda_sampled_forward(
         value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, H, Dh, P,
         loc.data_ptr(), weights.data_ptr(), _dt(loc), B * Q, _ptr(row_offsets), out.data_ptr(), H * Dh,
@@ -112,7 +115,6 @@ def msda_sampled_backward(value: torch.Tensor, shapes, loc: torch.Tensor, weight
     grad_w = torch.zeros_like(weights)
     if B * Q == 0:
         return grad_value, grad_loc, grad_w
-    _count(1)
     _lib.check(_lib.lib().moyolo_msda_sampled_backward(
         value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, H, Dh, P, loc.data_ptr(),
         weights.data_ptr(), _dt(loc), grad_out.data_ptr(), grad_out.stride(0), B * Q, _ptr(row_offsets),
@@ -122,7 +124,8 @@ def msda_sampled_backward(value: torch.Tensor, shapes, loc: torch.Tensor, weight
 
 def msda_fused(value: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch.Tensor, refer: torch.Tensor,
                n_heads: int, n_points: int, batch: int, softmax_mode: int = _lib.SOFTMAX,
-               row_offsets: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               row_offsets: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+               probe: Optional[GatherProbe] = None) -> torch.Tensor:
     """Fused softmax + location + bilinear gather (transformer.py:268-285).
 
     value  [B, Lv, C] view (last dim contiguous; arbitrary batch/position strides)
@@ -147,25 +150,23 @@ def msda_fused(value: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch
         out = torch.empty(R, Cc, dtype=value.dtype, device=value.device)
     if R == 0:
         return out
-    _count(1)
-    hook = GATHER_HOOK
-    if hook is not None:
-        hook[0](B, Lv, Cc, R, n_heads, L, n_points, value.element_size())
-    for _ in range(GATHER_REPEAT if hook is not None else 1):
+    if probe is not None:
+        probe.pre(B, Lv, Cc, R, n_heads, L, n_points, value.element_size())
+    for _ in range(probe.repeat if probe is not None else 1):
         _lib.check(_lib.lib().moyolo_msda_fused_forward(
             value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, n_heads, Dh, n_points,
             offsets.data_ptr(), offsets.stride(0), logits.data_ptr(), logits.stride(0), refer.data_ptr(),
             refer.shape[1], refer.shape[2], softmax_mode, R, _ptr(row_offsets), out.data_ptr(), out.stride(0),
             _stream()))
-    if hook is not None:
-        hook[1]()
+    if probe is not None:
+        probe.post()
     return out
 
 
 def msda_proj_fused(value: torch.Tensor, shapes, xq: torch.Tensor, w_offlog: torch.Tensor, b_offlog: torch.Tensor,
                     refer: torch.Tensor, n_heads: int, n_points: int, batch: int,
                     softmax_mode: int = _lib.SOFTMAX, row_offsets: Optional[torch.Tensor] = None,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    out: Optional[torch.Tensor] = None, probe: Optional[GatherProbe] = None) -> torch.Tensor:
     """msda_fused with the offsets|logits projection (xq . w_offlog^T + b_offlog) inside the gather kernel:
     transformer.py:268-285 in one launch. bf16, 8 heads x 32, 3 levels x 4 points."""
     _cuda(value, xq, w_offlog, b_offlog, refer)
@@ -181,18 +182,16 @@ def msda_proj_fused(value: torch.Tensor, shapes, xq: torch.Tensor, w_offlog: tor
         out = torch.empty(R, Cc, dtype=value.dtype, device=value.device)
     if R == 0:
         return out
-    _count(1)
-    hook = GATHER_HOOK
-    if hook is not None:
-        hook[0](B, Lv, Cc, R, n_heads, L, n_points, value.element_size())
-    for _ in range(GATHER_REPEAT if hook is not None else 1):
+    if probe is not None:
+        probe.pre(B, Lv, Cc, R, n_heads, L, n_points, value.element_size())
+    for _ in range(probe.repeat if probe is not None else 1):
         _lib.check(_lib.lib().moyolo_msda_proj_fused_forward(
             value.data_ptr(), _dt(value), value.stride(0), value.stride(1), arr, L, B, Lv, n_heads, Cc // n_heads,
             n_points, xq.data_ptr(), xq.stride(0), w_offlog.data_ptr(), b_offlog.data_ptr(), refer.data_ptr(),
             refer.shape[1], refer.shape[2], softmax_mode, R, _ptr(row_offsets), out.data_ptr(), out.stride(0),
             _stream()))
-    if hook is not None:
-        hook[1]()
+    if probe is not None:
+        probe.post()
     return out
 
 
@@ -219,7 +218,6 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out_dtyp
     out_dtype = out_dtype or x.dtype
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=x.device)
-    _count(1)
     _lib.check(_lib.lib().moyolo_linear(
         x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), out.data_ptr(), out.stride(0), M, N, K, _dt(x),
         _dt(out), _lib.EPI_RELU if relu else _lib.EPI_NONE, _ptr(zero_rows), engine, _stream()))
@@ -236,7 +234,6 @@ def linear_tall(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out
     if x.stride(1) != 1 or out.stride(1) != 1 or not w.is_contiguous() or x.dtype != torch.bfloat16 or \
             out.dtype != torch.bfloat16:
         raise ValueError("linear_tall: bf16 x / w / out with contiguous columns")
-    _count(1)
     _lib.check(_lib.lib().moyolo_linear_tall(x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), out.data_ptr(),
                                              out.stride(0), M, N, K, _ptr(zero_rows), int(max_ctas), _stream()))
     return out
@@ -251,7 +248,6 @@ def linear_dual(x1: torch.Tensor, x2: torch.Tensor, n_split: int, w: torch.Tenso
     N = w.shape[0]
     if x1.stride(1) != 1 or x2.stride(1) != 1 or not w.is_contiguous() or x2.shape != x1.shape:
         raise ValueError("linear_dual: x1/x2 must be [M, K] with contiguous columns, w contiguous [N, K]")
-    _count(1)
     _lib.check(_lib.lib().moyolo_linear_dual(
         x1.data_ptr(), x1.stride(0), x2.data_ptr(), x2.stride(0), int(n_split), w.data_ptr(), _ptr(b), out.data_ptr(),
         out.stride(0), M, N, K, _dt(out), _stream()))
@@ -272,7 +268,6 @@ def linear_add_layernorm(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Ten
     for t in (residual, out_f32, out_lp, pos, out_pos):
         if t is not None and (not t.is_contiguous() or t.shape != (M, N)):
             raise ValueError("linear_add_layernorm: row buffers must be contiguous [M, N]")
-    _count(1)
     _lib.check(_lib.lib().moyolo_linear_add_layernorm(
         x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), _ptr(residual), gamma.data_ptr(), beta.data_ptr(),
         float(eps), M, N, K, _ptr(out_f32), _ptr(out_lp), _ptr(pos), _ptr(out_pos), _stream()))
@@ -304,7 +299,6 @@ def ffn_add_layernorm(x: torch.Tensor, w1: torch.Tensor, b1, w2: torch.Tensor, b
     for t in (residual, out_f32, out_lp, pos, out_pos):
         if t is not None and (not t.is_contiguous() or t.shape != (M, Cc)):
             raise ValueError("ffn_add_layernorm: row buffers must be contiguous [M, C]")
-    _count(1)
     _lib.check(_lib.lib().moyolo_ffn_add_layernorm(
         x.data_ptr(), x.stride(0), w1.data_ptr(), _ptr(b1), w2.data_ptr(), _ptr(b2), h.data_ptr(), F, _ptr(residual),
         gamma.data_ptr(), beta.data_ptr(), float(eps), M, Cc, _ptr(out_f32), _ptr(out_lp), _ptr(pos), _ptr(out_pos),
@@ -325,7 +319,6 @@ def linear_add_layernorm_scores(x: torch.Tensor, w: torch.Tensor, b, residual, g
     nc = score_w.shape[0]
     if x.stride(1) != 1 or not w.is_contiguous() or not score_w.is_contiguous() or score_w.shape[1] != N:
         raise ValueError("linear_add_layernorm_scores: x columns / w / score_w must be contiguous, score_w [nc, N]")
-    _count(1)
     _lib.check(_lib.lib().moyolo_linear_add_layernorm_scores(
         x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), _ptr(residual), gamma.data_ptr(), beta.data_ptr(), float(eps),
         M, N, K, _ptr(out_f32), _ptr(out_lp), score_w.data_ptr(), score_b.data_ptr(), nc, _ptr(logits), _ptr(scores),
@@ -341,7 +334,6 @@ def self_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, row_offset
     if out is None:
         out = torch.empty(R, Cc, dtype=q.dtype, device=q.device)
     host = (C.c_int32 * len(row_offsets_host))(*[int(x) for x in row_offsets_host])
-    _count(1)
     _lib.check(_lib.lib().moyolo_self_attention(
         q.data_ptr(), q.stride(0), k.data_ptr(), k.stride(0), v.data_ptr(), v.stride(0), out.data_ptr(),
         out.stride(0), _dt(q), len(row_offsets_host) - 1, row_offsets.data_ptr(), host, _ptr(seg_len), n_heads,
@@ -366,7 +358,6 @@ def add_layernorm(x: torch.Tensor, residual: Optional[torch.Tensor], gamma: torc
         out_lp = torch.empty(R, Cc, dtype=lp_dtype, device=x.device)
     if out_pos is None and pos is not None:
         out_pos = torch.empty(R, Cc, dtype=lp_dtype, device=x.device)
-    _count(1)
     _lib.check(_lib.lib().moyolo_add_layernorm(
         x.data_ptr(), _ptr(residual), gamma.data_ptr(), beta.data_ptr(), float(eps), R, Cc, _ptr(out_f32),
         _ptr(out_lp), _ptr(pos), _ptr(out_pos), _DT[lp_dtype], _stream()))
@@ -378,7 +369,6 @@ def add_cast(a: torch.Tensor, b: Optional[torch.Tensor], dtype: torch.dtype,
     _cuda(a, b)
     if out is None:
         out = torch.empty(a.shape, dtype=dtype, device=a.device)
-    _count(1)
     _lib.check(_lib.lib().moyolo_add_cast(a.data_ptr(), _ptr(b), out.data_ptr(), _DT[dtype], a.numel(), _stream()))
     return out
 
@@ -391,7 +381,6 @@ def box_refine(h: torch.Tensor, w3: torch.Tensor, b3: torch.Tensor, ref: torch.T
         out = torch.empty(R, 4, dtype=torch.float32, device=h.device)
     elif not out.is_contiguous() or out.dtype != torch.float32 or out.numel() != R * 4:
         raise ValueError("box_refine: out must be contiguous fp32 with R*4 elements")
-    _count(1)
     _lib.check(_lib.lib().moyolo_box_refine(h.data_ptr(), h.stride(0), _dt(h), w3.data_ptr(), b3.data_ptr(),
                                             ref.data_ptr(), out.data_ptr(), R, K, _stream()))
     return out
@@ -409,7 +398,6 @@ def score_head(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, want_scores: b
         logits = torch.empty(R, nc, dtype=torch.float32, device=x.device)
         scores = torch.empty(R, dtype=torch.float32, device=x.device) if want_scores else None
         labels = torch.empty(R, dtype=torch.int32, device=x.device) if want_scores else None
-    _count(1)
     _lib.check(_lib.lib().moyolo_score_head(x.data_ptr(), x.stride(0), _dt(x), w.data_ptr(), b.data_ptr(),
                                             logits.data_ptr(), _ptr(scores), _ptr(labels), R, K, nc, _ptr(max_logit),
                                             _stream()))
@@ -420,7 +408,6 @@ def sigmoid(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor
     _cuda(x)
     x = x.contiguous()
     y = torch.empty_like(x) if out is None else out
-    _count(1)
     _lib.check(_lib.lib().moyolo_sigmoid(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
     return y
 
@@ -429,7 +416,6 @@ def inverse_sigmoid(x: torch.Tensor) -> torch.Tensor:
     _cuda(x)
     x = x.contiguous()
     y = torch.empty_like(x)
-    _count(1)
     _lib.check(_lib.lib().moyolo_inverse_sigmoid(x.data_ptr(), y.data_ptr(), x.numel(), _stream()))
     return y
 
@@ -442,7 +428,6 @@ def pos2posemb(pos: torch.Tensor, num_pos_feats: int = 64, temperature: float = 
     rows = pos.numel() // n_coord
     emb = out if out is not None else torch.empty(*pos.shape[:-1], n_coord * num_pos_feats, dtype=torch.float32,
                                                   device=pos.device)
-    _count(1)
     _lib.check(_lib.lib().moyolo_pos2posemb(pos.data_ptr(), emb.data_ptr(), rows, n_coord, num_pos_feats,
                                             float(temperature), _stream()))
     return emb
@@ -453,7 +438,6 @@ def linear_k4_relu(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, out_dtype:
     R = x.shape[0]
     N = w.shape[0]
     y = torch.empty(R, N, dtype=out_dtype, device=x.device)
-    _count(1)
     _lib.check(_lib.lib().moyolo_linear_k4_relu(x.data_ptr(), w.data_ptr(), _ptr(b), y.data_ptr(), _DT[out_dtype],
                                                 R, N, _stream()))
     return y
@@ -471,7 +455,6 @@ def track_assign(scores: torch.Tensor, boxes: torch.Tensor, obj_idxes: torch.Ten
     n = scores.shape[0]
     assert obj_idxes.dtype == torch.int64 and disappear_time.dtype == torch.int64 and counters.dtype == torch.int64
     assert workspace.numel() * workspace.element_size() >= track_workspace_bytes(n)
-    _count(1)
     _lib.check(_lib.lib().moyolo_track_assign(
         scores.data_ptr(), boxes.data_ptr(), obj_idxes.data_ptr(), disappear_time.data_ptr(), counters.data_ptr(), n,
         float(score_thresh), float(filter_thresh), int(miss_tolerance), float(iou_thresh), workspace.data_ptr(),
@@ -487,7 +470,6 @@ def track_compact(obj_idxes: torch.Tensor, fields: Sequence[torch.Tensor], outs:
     src = (C.c_void_p * nf)(*[f.data_ptr() for f in fields])
     dst = (C.c_void_p * nf)(*[o.data_ptr() for o in outs])
     rb = (C.c_int64 * nf)(*[f.stride(0) * f.element_size() if f.dim() > 1 else f.element_size() for f in fields])
-    _count(1 + nf)
     _lib.check(_lib.lib().moyolo_track_compact(obj_idxes.data_ptr(), n, n_active.data_ptr(), active_index.data_ptr(),
                                                src, dst, rb, nf, _stream()))
 
@@ -498,7 +480,6 @@ def track_assign_batched(scores, boxes, ids, dis, counters, row_offsets, n_seq: 
     """RuntimeTrackerBase.update for every lock-step sequence in one launch (one CTA per sequence)."""
     _cuda(scores, boxes, ids, dis, counters, row_offsets, workspace)
     assert workspace.numel() * workspace.element_size() >= n_seq * track_workspace_bytes(max_rows_per_seq)
-    _count(1)
     _lib.check(_lib.lib().moyolo_track_assign_batched(
         scores.data_ptr(), boxes.data_ptr(), ids.data_ptr(), dis.data_ptr(), counters.data_ptr(),
         row_offsets.data_ptr(), n_seq, max_rows_per_seq, float(score_thresh), float(filter_thresh),
@@ -510,7 +491,6 @@ def frame_assemble(n_seq, n_detect, C, cap, n_tracks, t_ref, t_qpos, t_label, t_
                    temperature=10000.0, ctrl=None, refer_sig=None, x_lp=None, xq_lp=None) -> None:
     """Optional fused outputs: refer_sig = sigmoid(refer_logit), x_lp = x and xq_lp = x + pos as GEMM operands."""
     lp = x_lp if x_lp is not None else xq_lp
-    _count(1)
     _lib.check(_lib.lib().moyolo_frame_assemble(
         n_seq, n_detect, C, cap, n_tracks.data_ptr(), t_ref.data_ptr(), t_qpos.data_ptr(), t_label.data_ptr(),
         t_ids.data_ptr(), t_dis.data_ptr(), class_embed.data_ptr(), det_embed.data_ptr(), det_refer.data_ptr(),
@@ -524,7 +504,6 @@ def frame_compact(n_seq, C, cap, row_offsets, ids, dis, labels, refer_logit, pos
                   num_pos_feats=64, temperature=10000.0) -> None:
     """Optional fused QIM operands: q_qk_lp = c_hs + pos2posemb(c_ref), q_tgt_lp = c_hs (qim.py:255,271)."""
     lp = q_qk_lp if q_qk_lp is not None else q_tgt_lp
-    _count(1)
     _lib.check(_lib.lib().moyolo_frame_compact(
         n_seq, C, cap, row_offsets.data_ptr(), ids.data_ptr(), dis.data_ptr(), labels.data_ptr(),
         refer_logit.data_ptr(), pos.data_ptr(), hs.data_ptr(), boxes.data_ptr(), n_active.data_ptr(),
@@ -540,7 +519,6 @@ def frame_assign_compact(n_seq, C, cap, rows_pad, row_offsets, scores, ids_in, d
     """ID assignment (head.py:1232-1243) + active-track compaction in one launch; `counters` is only read
     (follow with track_suppress_batched)."""
     lp = q_qk_lp if q_qk_lp is not None else q_tgt_lp
-    _count(1)
     _lib.check(_lib.lib().moyolo_frame_assign_compact(
         n_seq, C, cap, rows_pad, row_offsets.data_ptr(), scores.data_ptr(), ids_in.data_ptr(), dis_in.data_ptr(),
         counters.data_ptr(), float(score_thresh), float(filter_thresh), int(miss_tolerance), ids_out.data_ptr(),
@@ -556,7 +534,6 @@ def track_suppress_batched(boxes, ids, counters, row_offsets, n_seq: int, max_ro
     frame_assign_compact already updated."""
     _cuda(boxes, ids, counters, row_offsets, workspace)
     assert workspace.numel() * workspace.element_size() >= n_seq * track_workspace_bytes(max_rows_per_seq)
-    _count(1)
     _lib.check(_lib.lib().moyolo_track_suppress_batched(
         boxes.data_ptr(), ids.data_ptr(), counters.data_ptr(), row_offsets.data_ptr(), n_seq, max_rows_per_seq,
         float(iou_thresh), workspace.data_ptr(), _ptr(ctrl), _stream()))
@@ -565,7 +542,6 @@ def track_suppress_batched(boxes, ids, counters, row_offsets, n_seq: int, max_ro
 def frame_writeback(n_seq, C, cap, row_offsets, n_active, new_qpos, c_box, t_qpos, t_ref, n_tracks, ctrl=None,
                     info=None, boxes=None, active_index=None) -> None:
     """c_box None: the boxes of the active rows are gathered from `boxes` through `active_index`."""
-    _count(1)
     _lib.check(_lib.lib().moyolo_frame_writeback(
         n_seq, C, cap, row_offsets.data_ptr(), n_active.data_ptr(), new_qpos.data_ptr(), _ptr(c_box),
         t_qpos.data_ptr(), t_ref.data_ptr(), n_tracks.data_ptr(), _ptr(ctrl), _ptr(info), _ptr(boxes),
@@ -575,7 +551,6 @@ def frame_writeback(n_seq, C, cap, row_offsets, n_active, new_qpos, c_box, t_qpo
 def frame_emit(n_seq, rows_pad, row_offsets, ids, boxes, scores, labels, n_active, active_index, seq_ids, frame_rows,
                table, ctrl) -> None:
     """Per-frame packed result rows + append of the tracked objects to the device track table."""
-    _count(1)
     _lib.check(_lib.lib().moyolo_frame_emit(
         n_seq, rows_pad, row_offsets.data_ptr(), ids.data_ptr(), boxes.data_ptr(), scores.data_ptr(),
         labels.data_ptr(), n_active.data_ptr(), active_index.data_ptr(), seq_ids.data_ptr(), frame_rows.data_ptr(),
@@ -589,7 +564,6 @@ def enc_output_scores(x: torch.Tensor, w: torch.Tensor, b, gamma, beta, eps: flo
     _cuda(x, w, b, gamma, beta, zero_in_rows, score_w, score_b, out_f32, out_lp, logits, max_logit)
     M = x.shape[0]
     nc = 0 if score_w is None else score_w.shape[0]
-    _count(1)
     _lib.check(_lib.lib().moyolo_enc_output_scores(
         x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), gamma.data_ptr(), beta.data_ptr(), float(eps),
         _ptr(zero_in_rows), _ptr(score_w), _ptr(score_b), nc, M, _ptr(out_f32), _ptr(out_lp), _ptr(logits),
@@ -605,7 +579,6 @@ def topk(scores: torch.Tensor, k: int, out: Optional[torch.Tensor] = None, vals:
         raise ValueError("topk: scores must be fp32 with contiguous columns")
     if out is None:
         out = torch.empty(B, k, dtype=torch.int32, device=scores.device)
-    _count(1)
     _lib.check(_lib.lib().moyolo_topk(scores.data_ptr(), scores.stride(0), n, B, int(k), out.data_ptr(), _ptr(vals),
                                       _stream()))
     return out
@@ -617,7 +590,6 @@ def select_gather(features: torch.Tensor, logits, idx: torch.Tensor, embed: torc
     B, Lv, Cc = features.shape
     k = idx.shape[1]
     nc = 0 if logits is None else logits.shape[-1]
-    _count(1)
     _lib.check(_lib.lib().moyolo_select_gather(
         features.data_ptr(), _ptr(logits), idx.data_ptr(), B, k, Lv, Cc, nc, embed.data_ptr(), _ptr(embed_lp),
         _dt(embed_lp) if embed_lp is not None else F32, _ptr(enc_scores), _stream()))
@@ -628,7 +600,6 @@ def anchor_box(h: torch.Tensor, w3: torch.Tensor, b3: torch.Tensor, idx: torch.T
     _cuda(h, w3, b3, idx, out)
     R, K = h.shape
     arr, L = _shapes_arr(shapes)
-    _count(1)
     _lib.check(_lib.lib().moyolo_anchor_box(h.data_ptr(), h.stride(0), _dt(h), w3.data_ptr(), b3.data_ptr(),
                                             idx.data_ptr(), arr, L, len_v, float(grid_size), float(eps), out.data_ptr(),
                                             R, K, _stream()))
@@ -639,7 +610,6 @@ def anchor_invalid(shapes, len_v: int, device, grid_size: float = 0.05, eps: flo
     """uint8 [len_v]: 1 where the anchor of a pyramid position is masked out (head.py:1006)."""
     arr, L = _shapes_arr(shapes)
     out = torch.empty(len_v, dtype=torch.uint8, device=device)
-    _count(1)
     _lib.check(_lib.lib().moyolo_anchor_invalid(arr, L, len_v, float(grid_size), float(eps), out.data_ptr(), _stream()))
     return out
 
@@ -650,7 +620,6 @@ def mask_rows(x: torch.Tensor, zero_rows: torch.Tensor, out: Optional[torch.Tens
     R, Cc = x.shape
     if out is None:
         out = torch.empty_like(x)
-    _count(1)
     _lib.check(_lib.lib().moyolo_mask_rows(x.data_ptr(), zero_rows.data_ptr(), zero_rows.numel(), out.data_ptr(), R, Cc,
                                            _stream()))
     return out

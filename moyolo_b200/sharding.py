@@ -4,7 +4,7 @@ Tracking is sequential within a video and independent across videos (the referen
 video, ultralytics/models/MOTRtrack/val.py:288-291, and upstream loops videos serially,
 MOTR/submit_dance.py:499-504), so videos are assigned to ranks up front (longest-processing-time
 first), each rank runs its videos in lock-step on its own GPU with NO collective inside the frame
-loop, and one two-phase all_gather at the end collects the fixed-width track rows
+loop, and ONE all_gather_into_tensor of fixed-capacity buffers at the end collects the fixed-width track rows
     [seq, frame, id, cx, cy, w, h, score, cls]   (float32)
 on every rank (NCCL over NVLink on the GPU box, gloo in the CPU tests).
 """
@@ -61,23 +61,67 @@ def finalize_rows(frame_rows: List[torch.Tensor], device) -> torch.Tensor:
     return allr[allr[:, 2] >= 0].contiguous()
 
 
-def gather_track_rows(local_rows: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
-    """Two-phase all_gather: row counts, then rows padded to the per-rank maximum. Every rank returns
-    the full table sorted by (seq, frame, original order). Single process: returns the input."""
+class GatheredTable:
+    """Result of `gather_track_rows`: the track rows of every rank, merged on the device by rank offset. Nothing
+    here synchronises the host until `rows()` / `count()` is called."""
+
+    def __init__(self, merged: torch.Tensor, total: Optional[torch.Tensor], n_host: Optional[int] = None,
+                 overflow: Optional[torch.Tensor] = None):
+        self._merged, self._total, self._n, self._overflow = merged, total, n_host, overflow
+
+    def count(self) -> int:
+        if self._n is None:
+            if self._overflow is not None:
+                info = torch.stack([self._total.reshape(()), self._overflow.reshape(())]).cpu()   # ONE host sync
+                if int(info[1]) != 0:
+                    raise RuntimeError("gather_track_rows: a rank produced more rows than the fixed gather capacity")
+                self._n = int(info[0])
+            else:
+                self._n = int(self._total.cpu())
+        return self._n
+
+    def rows(self, sort: bool = False) -> torch.Tensor:
+        """[n, 9] rows ordered by rank, then as each rank emitted them (frame, lock-step slot, query order). Ranks
+        own disjoint sequences, so this is already grouped per sequence and frame-ordered within one;
+        sort=True gives the canonical (seq, frame, original order) ordering, identical for every world size."""
+        r = self._merged[:self.count()]
+        return _sort_rows(r) if sort else r
+
+
+def gather_track_rows(local_rows: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
+                      capacity: Optional[int] = None) -> GatheredTable:
+    """All ranks' track rows on every rank with ONE collective and no host synchronisation: each rank contributes
+    a fixed-capacity buffer [capacity + 1, 9] whose row 0 is a header (row count, overflow flag),
+    `all_gather_into_tensor` moves it, and the ranks' segments are merged by offset on the device (exclusive
+    prefix sum of the header counts + one index_copy; fixed shapes, nothing is read back).
+    capacity: rows per rank, known to every rank without communication (e.g. frames x sequences x a bound on
+    tracked objects per frame). None: a count exchange picks the exact capacity first (one extra small collective
+    and one host read). Single process: returns the input."""
+    n_local = int(local_rows.shape[0])
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return _sort_rows(local_rows)
+        return GatheredTable(local_rows, None, n_local)
     world = dist.get_world_size(group)
     dev = local_rows.device
-    count = torch.tensor([local_rows.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, count, group=group)
-    counts = [int(c.item()) for c in counts]
-    mx = max(max(counts), 1)
-    padded = torch.zeros(mx, ROW_WIDTH, dtype=torch.float32, device=dev)
-    padded[:local_rows.shape[0]] = local_rows
-    bufs = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(bufs, padded, group=group)
-    return _sort_rows(torch.cat([b[:c] for b, c in zip(bufs, counts)], 0))
+    if capacity is None:
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, torch.tensor([n_local], dtype=torch.int64, device=dev), group=group)
+        capacity = max(int(counts.max().cpu()), 1)
+    cap = int(capacity)
+    send = torch.zeros(cap + 1, ROW_WIDTH, dtype=torch.float32, device=dev)
+    n_send = min(n_local, cap)
+    send[0, 0] = float(n_send)
+    send[0, 1] = 1.0 if n_local > cap else 0.0
+    send[1:1 + n_send] = local_rows[:n_send]
+    recv = torch.empty(world * (cap + 1), ROW_WIDTH, dtype=torch.float32, device=dev)   # concatenated along dim 0
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, cap + 1, ROW_WIDTH)
+    counts = recv[:, 0, 0].round().long()                                  # [world], on the device
+    offsets = torch.cumsum(counts, 0) - counts                             # exclusive prefix sum
+    i = torch.arange(cap, device=dev)
+    dst = torch.where(i[None, :] < counts[:, None], offsets[:, None] + i[None, :], world * cap)   # invalid -> dump row
+    merged = torch.zeros(world * cap + 1, ROW_WIDTH, dtype=torch.float32, device=dev)
+    merged.index_copy_(0, dst.reshape(-1), recv[:, 1:].reshape(world * cap, ROW_WIDTH))
+    return GatheredTable(merged, counts.sum(), None, recv[:, 0, 1].sum())
 
 
 def _sort_rows(rows: torch.Tensor) -> torch.Tensor:
@@ -89,8 +133,16 @@ def _sort_rows(rows: torch.Tensor) -> torch.Tensor:
 
 
 def run_sharded(make_engine, sequences: Sequence[Dict], rank: int, world_size: int, max_in_flight: int = 4,
-                group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
-    """Track every sequence; return the gathered table on all ranks.
+                group: Optional[dist.ProcessGroup] = None, batch_fn=None, rows_per_frame: Optional[int] = None,
+                sort: bool = True, sync_inputs: bool = True, before_gather=None):
+    """Track every sequence; return the gathered table on all ranks (a tensor in canonical (seq, frame) order, or
+    with sort=False the lazy `GatheredTable`, which costs no host synchronisation).
+
+    batch_fn(group_seq_ids, t) -> (feats, det_embed, det_refer) already stacked for the lock-step group (avoids
+    the per-frame torch.stack); rows_per_frame: bound on tracked objects per frame and sequence -> fixed gather
+    capacity, one collective, no count exchange. sync_inputs=False: the frame tensors are complete when they are
+    handed over (resident inputs), so their copy need not wait for the caller's stream. before_gather(local_table)
+    is called once this rank's table is complete (bench.py puts its timing mark there).
 
     sequences[i] = {"n_frames": int, "frames": callable t -> (feats, det_embed, det_refer)}.
     make_engine(n_seq) -> moyolo_b200.tracker.TrackEngine (or an object with the same reset /
@@ -103,22 +155,37 @@ def run_sharded(make_engine, sequences: Sequence[Dict], rank: int, world_size: i
     mine = lpt_assign(counts, world_size)[rank]
     tables: List[torch.Tensor] = []
     device = None
-    for grp in lockstep_groups(mine, counts, max_in_flight):
+    groups = lockstep_groups(mine, counts, max_in_flight)
+    for grp in groups:
         eng = make_engine(len(grp))
         eng.reset()
         eng.set_seq_ids(grp)
         for t in range(max(counts[i] for i in grp)):
-            batch = [sequences[i]["frames"](min(t, counts[i] - 1)) for i in grp]
-            feats = torch.stack([b[0] for b in batch])
-            de = torch.stack([b[1] for b in batch])
-            dr = torch.stack([b[2] for b in batch])
+            if batch_fn is not None:
+                feats, de, dr = batch_fn(grp, t)
+            else:
+                batch = [sequences[i]["frames"](min(t, counts[i] - 1)) for i in grp]
+                feats = torch.stack([b[0] for b in batch])
+                de = torch.stack([b[1] for b in batch])
+                dr = torch.stack([b[2] for b in batch])
             device = feats.device
-            eng.submit(feats, de, dr, want_rows=False, sync_inputs=True)
+            eng.submit(feats, de, dr, want_rows=False, sync_inputs=sync_inputs)
         tab = eng.track_table()
-        n_frames = torch.as_tensor(counts, dtype=torch.float32, device=tab.device)
-        if tab.shape[0]:
+        g_max = max(counts[i] for i in grp)
+        if tab.shape[0] and any(counts[i] != g_max for i in grp):   # drop the surplus frames of early-ending sequences
+            n_frames = torch.as_tensor(counts, dtype=torch.float32, device=tab.device)
             tab = tab[tab[:, 1] < n_frames[tab[:, 0].long()]]
-        tables.append(tab.clone())
-    local = torch.cat(tables, 0) if tables else torch.zeros(0, ROW_WIDTH, dtype=torch.float32,
-                                                            device=device or torch.device("cpu"))
-    return gather_track_rows(local, group)
+        tables.append(tab if len(groups) == 1 else tab.clone())   # (make_engine may hand out one engine repeatedly)
+    if len(tables) == 1:
+        local = tables[0]     # (a view of the engine's table: consumed by the gather before the engine runs again)
+    else:
+        local = torch.cat(tables, 0) if tables else torch.zeros(0, ROW_WIDTH, dtype=torch.float32,
+                                                                device=device or torch.device("cpu"))
+    capacity = None
+    if rows_per_frame is not None:   # the same number on every rank: the most loaded rank's frames x the bound
+        assign = lpt_assign(counts, world_size)
+        capacity = max(1, max(sum(counts[i] for i in a) for a in assign) * int(rows_per_frame))
+    if before_gather is not None:
+        before_gather(local)
+    table = gather_track_rows(local, group, capacity)
+    return table.rows(sort=True) if sort else table

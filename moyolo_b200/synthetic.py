@@ -315,7 +315,8 @@ class PlantSpec:
     k_cls: float = 0.25
     bias: float = -2.0
     w_noise: float = 0.012                # std of the random part of the score head
-    box_gain: float = 0.25                # scale of the last box-head layer
+    box_gain: float = 0.25
+    persistent_until: int = 32            # persistent classes are only born in frames < this (bounds the track count)                # scale of the last box-head layer
 
 
 def make_tracking_state(spec: DecoderSpec, seed: int = 0, plant: PlantSpec = PlantSpec()) -> Dict[str, torch.Tensor]:
@@ -393,6 +394,11 @@ class PlantedSequenceGenerator(SequenceGenerator):
         nd, A, nc = de.shape[0], self.plant.amp, self.nc
         fire = torch.rand(nd, generator=self.g, device=self.device) < self.plant.births_per_frame / nd
         cls = torch.randint(0, nc, (nd,), generator=self.g, device=self.device)
+        if self.t > self.plant.persistent_until and self.plant.persistent:   # (self.t is already this frame's index + 1)
+            is_p = torch.zeros(nd, dtype=torch.bool, device=self.device)
+            for c in self.plant.persistent:
+                is_p |= cls == c
+            fire &= ~is_p
         de = de.clone()
         de[:, 0] = torch.where(fire, A, -A)
         de[:, 1:1 + nc] = -A

@@ -218,8 +218,10 @@ class TrackEngine:
                  n_seq: int = 1, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, iou_thresh=0.8,
                  weights: Optional[DecoderWeights] = None, cap: int = 512, bucket: int = 64, margin: int = 32,
                  use_graphs: bool = True, table_rows: int = 1 << 18, branches: bool = True, selector=None,
-                 value_ahead: Optional[bool] = None):
+                 value_ahead: Optional[bool] = None, gather_probe: Optional[ops.GatherProbe] = None):
         self.dev = torch.device(device)
+        self.gather_probe = gather_probe   # instrumentation of every gather launch (bench.py roofline leg)
+        self.launches = 0                  # kernels launched by this engine's frames (graph replays included)
         self.spec, self.shapes, self.n_detect, self.n_seq = spec, [list(s) for s in shapes], n_detect, n_seq
         self.Lv = level_sizes(shapes)
         self.W = weights or DecoderWeights(sd, spec, self.dev, precision)
@@ -446,7 +448,8 @@ class TrackEngine:
                 _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
             ex.run_layer_ws(pk, ws, ws.refer[i].view(R, 1, 4), value_view, self.shapes, S, ws.ro, ro_host,
                             ws.pos, None if last else ws.pos, dt, before_gather,
-                            score=(W.score_w, W.score_b, ws.logits, ws.scores, ws.labels) if (last and score_fused) else None)
+                            score=(W.score_w, W.score_b, ws.logits, ws.scores, ws.labels) if (last and score_fused) else None,
+                            gather_probe=self.gather_probe)
             # box refinement of this layer (transformer.py:709): only the NEXT layer's gather needs it
             # (the last layer's box head runs next to the score head, which only needs the layer output)
             if fork:
@@ -530,13 +533,12 @@ class TrackEngine:
             torch.cuda.synchronize(self.dev)
             self._state_restore(snap)
             g = torch.cuda.CUDAGraph()
-            before = ops.LAUNCHES
+            before = ops.launch_count()
             with torch.cuda.graph(g):
                 self._body(p)
             p.graph = g
             p.desc = self._make_desc(p)
-            p.n_launch = ops.LAUNCHES - before  # kernels replayed by every graph launch
-            ops.LAUNCHES = before
+            p.n_launch = ops.launch_count() - before  # kernel nodes replayed by every graph launch
             self._state_restore(snap)  # capture does not execute, but keep the invariant explicit
             torch.cuda.synchronize(self.dev)
         self._plans[(rows_pad, slot)] = p
@@ -586,7 +588,7 @@ class TrackEngine:
         d.n_outputs = 2 if want_rows else 1
         self._keep[slot] = (feats, det_embed, det_refer)
         _lib.check(_lib.lib().moyolo_frame_submit(ctypes.byref(d)))
-        ops.LAUNCHES += p.n_launch + (1 if self._vp_ahead else 0) + (self._pre_launches if self._sel_ahead else 0)
+        self.launches += p.n_launch + (1 if self._vp_ahead else 0) + (self._pre_launches if self._sel_ahead else 0)
         self._last_plan = p
         return {"frame": t, "plan": p, "rows_pad": rows_pad, "want_rows": want_rows}
 
@@ -662,11 +664,10 @@ class TrackEngine:
         torch.cuda.current_stream(self.dev).wait_stream(side)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
-        before = ops.LAUNCHES
+        before = ops.launch_count()
         with torch.cuda.graph(g):
             run()
-        self._pre_launches = ops.LAUNCHES - before
-        ops.LAUNCHES = before
+        self._pre_launches = ops.launch_count() - before
         torch.cuda.synchronize(self.dev)
         self._pre_graphs[slot] = g
         return g
@@ -682,7 +683,7 @@ class TrackEngine:
             with torch.cuda.stream(vs):
                 g.replay()
                 self._ev_vp[slot].record(vs)
-            ops.LAUNCHES += self._pre_launches
+            self.launches += self._pre_launches
             self._main.wait_event(self._ev_vp[slot])
             return
         if not self._vp_ahead:
@@ -696,6 +697,7 @@ class TrackEngine:
             ops.linear_tall(self.feats_in[slot].view(S * self.Lv, C), self.W.value_proj.w, self.W.value_proj.b,
                             self.values_buf[slot].view(S * self.Lv, n_l * C), max_ctas=self._vp_ctas)
             self._ev_vp[slot].record(vs)
+        self.launches += 1
         self._main.wait_event(self._ev_vp[slot])
 
     def _launch(self, frame: int, rows_pad: int, want_rows: bool) -> dict:
@@ -707,9 +709,11 @@ class TrackEngine:
             main.wait_event(self._ev_copy[slot])
             if self.use_graphs:
                 p.graph.replay()
-                ops.LAUNCHES += p.n_launch
+                self.launches += p.n_launch
             else:
+                before = ops.launch_count()
                 self._body(p)
+                self.launches += ops.launch_count() - before
             # the frame's host-visible results: [active-track counts | control block] and, optionally, the
             # packed rows -- one small device->host copy each
             self._h_info[h].copy_(p.info, non_blocking=True)

@@ -98,8 +98,11 @@ class TrackerPort:
 
 
 def track_sequence_port(sd: Dict[str, torch.Tensor], frames, shapes, n_heads: int, n_levels: int, n_points: int,
-                        n_layers: int, nc: int, core=tp.msda_core_gridsample, record_embed: bool = False):
-    """O3 frame loop on the CPU (see module docstring).
+                        n_layers: int, nc: int, core=tp.msda_core_gridsample, record_embed: bool = False,
+                        device="cpu", autocast_dtype=None):
+    """O3 frame loop on the CPU (see module docstring). With device="cuda" the same PyTorch ops run eagerly on the
+    GPU (bench.py's `gpu_eager_baseline`: what the reference's modules do after `.cuda()`, optionally under
+    torch.autocast(autocast_dtype)); the ID assigner stays the host loop it is in the reference (head.py:1232-1243).
 
     frames: iterable of (feats [Lv, C], detect_embed [nd, C], detect_refer_logit [nd, 4]) fp32 CPU tensors.
     Query assembly follows head.py:1056-1064,1108-1109 (tracks first): embed = cat(class_embed[argmax
@@ -107,37 +110,46 @@ def track_sequence_port(sd: Dict[str, torch.Tensor], frames, shapes, n_heads: in
     query_pos, pos2posemb(detect refer)).
     Returns a list of per-frame dicts {ids, boxes, scores, labels, n_tracks_in, counters}.
     """
+    import contextlib
+    dev = torch.device(device)
+    if dev.type != "cpu":
+        sd = {k: v.to(dev) for k, v in sd.items()}
     C = sd["denoising_class_embed.weight"].shape[1]
     trk = TrackerPort()
-    t_ref = torch.zeros(0, 4)
-    t_qpos = torch.zeros(0, C)
-    t_logits = torch.zeros(0, nc)
+    t_ref = torch.zeros(0, 4, device=dev)
+    t_qpos = torch.zeros(0, C, device=dev)
+    t_logits = torch.zeros(0, nc, device=dev)
     t_ids = np.zeros(0, dtype=np.int64)
     t_dis = np.zeros(0, dtype=np.int64)
     out = []
-    with torch.no_grad():
+    amp = torch.autocast(dev.type, dtype=autocast_dtype) if autocast_dtype is not None else contextlib.nullcontext()
+    with torch.no_grad(), amp:
         for feats, det_embed, det_refer in frames:
+            if dev.type != "cpu":
+                feats, det_embed, det_refer = feats.to(dev), det_embed.to(dev), det_refer.to(dev)
             T = t_ref.shape[0]
             nd = det_embed.shape[0]
-            cls_embed = sd["denoising_class_embed.weight"][t_logits.argmax(-1)] if T else torch.zeros(0, C)
+            cls_embed = sd["denoising_class_embed.weight"][t_logits.argmax(-1)] if T else torch.zeros(0, C, device=dev)
             embed = torch.cat([cls_embed, det_embed], 0)[None]
             refer = torch.cat([t_ref, det_refer], 0)[None]
             qpos = torch.cat([t_qpos, tp.pos2posemb(det_refer)], 0)[None]
             boxes, logits, hs = tp.decoder_forward(sd, embed, refer, feats[None], shapes, n_heads, n_levels,
                                                    n_points, n_layers, "motr", qpos, core=core)
-            boxes, logits, hs = boxes[0, 0], logits[0, 0], hs[0]
+            boxes, logits, hs = boxes[0, 0].float(), logits[0, 0].float(), hs[0].float()
             scores = logits.sigmoid().max(-1).values                          # head.py:310
             ids = np.concatenate([t_ids, np.full(nd, -1, dtype=np.int64)])    # R2
             dis = np.concatenate([t_dis, np.zeros(nd, dtype=np.int64)])
-            trk.update(scores.numpy(), boxes.numpy(), ids, dis)
-            act = torch.from_numpy(np.nonzero(ids >= 0)[0])                   # R3 (qim.py:184-187)
-            rec = {"ids": ids.copy(), "boxes": boxes.numpy().copy(), "scores": scores.numpy().copy(),
-                   "labels": logits.argmax(-1).numpy().copy(), "n_tracks_in": T,
+            boxes_h, scores_h = boxes.cpu().numpy(), scores.cpu().numpy()     # (host copy, as head.py:1157 does)
+            trk.update(scores_h, boxes_h, ids, dis)
+            act_np = np.nonzero(ids >= 0)[0]
+            act = torch.from_numpy(act_np).to(dev)                            # R3 (qim.py:184-187)
+            rec = {"ids": ids.copy(), "boxes": boxes_h.copy(), "scores": scores_h.copy(),
+                   "labels": logits.argmax(-1).cpu().numpy().copy(), "n_tracks_in": T,
                    "counters": (trk.max_obj_id, trk.max_obj_id_pre)}
             if record_embed:
-                rec["hs"] = hs.numpy().copy()
+                rec["hs"] = hs.cpu().numpy().copy()
             out.append(rec)
             new_qpos, new_ref = tp.qim_update(sd, refer[0][act], qpos[0][act], hs[act], boxes[act], n_heads)
-            t_ref, t_qpos, t_logits = new_ref, new_qpos, logits[act]
-            t_ids, t_dis = ids[act.numpy()], dis[act.numpy()]
+            t_ref, t_qpos, t_logits = new_ref.float(), new_qpos.float(), logits[act]
+            t_ids, t_dis = ids[act_np], dis[act_np]
     return out

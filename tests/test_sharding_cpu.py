@@ -80,6 +80,18 @@ def _worker(rank, world, port, out_dir):
     try:
         table = sharding.run_sharded(_FakeEngine, _sequences(), rank, world, max_in_flight=2)
         torch.save(table, os.path.join(out_dir, f"t{rank}.pt"))
+        # fixed-capacity single-collective variant (no count exchange): same table
+        fixed = sharding.run_sharded(_FakeEngine, _sequences(), rank, world, max_in_flight=2, rows_per_frame=6)
+        assert torch.equal(fixed, table)
+        lazy = sharding.run_sharded(_FakeEngine, _sequences(), rank, world, max_in_flight=2, rows_per_frame=6, sort=False)
+        assert lazy.count() == table.shape[0] and torch.equal(lazy.rows(sort=True), table)
+        # a capacity that is too small is reported, not silently truncated
+        small = sharding.gather_track_rows(torch.ones(5, sharding.ROW_WIDTH), capacity=3)
+        try:
+            small.count()
+            raise AssertionError("overflow not detected")
+        except RuntimeError as e:
+            assert "capacity" in str(e)
     finally:
         dist.destroy_process_group()
 
@@ -102,4 +114,5 @@ def test_gather_single_process_sorts_rows():
     rows = torch.tensor([[1, 2, 0, 0, 0, 0, 0, 0, 0], [0, 5, 1, 0, 0, 0, 0, 0, 0], [0, 1, 2, 0, 0, 0, 0, 0, 0]],
                         dtype=torch.float32)
     out = sharding.gather_track_rows(rows)
-    assert out[:, :2].tolist() == [[0, 1], [0, 5], [1, 2]]
+    assert out.count() == 3 and torch.equal(out.rows(), rows)          # single process: untouched, no sort
+    assert out.rows(sort=True)[:, :2].tolist() == [[0, 1], [0, 5], [1, 2]]
