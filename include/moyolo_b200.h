@@ -465,6 +465,65 @@ typedef struct {
 } moyolo_frame_submit_t;
 int moyolo_frame_submit(const moyolo_frame_submit_t* d);
 
+/* ---------------------------------------------------------------------------------------------
+ * Whole decoder in ONE launch (moyolo_b200/csrc/decoder_cluster.cu). Replaces MOTRTransformerDecoder.forward
+ * (ultralytics/nn/modules/transformer.py:676-728): for every layer the self-attention (nn.MultiheadAttention,
+ * :637-641), MSDeformAttn (:246-287; value_proj excepted -- `values` holds all layers' projections, one GEMM ahead
+ * of the frame), the FFN (:576-580), the three LayerNorms, the box refinement sigmoid(bbox_head[i](x) +
+ * inverse_sigmoid(refer)) (:709) and, after the last layer, the class-score head (:717-721).
+ * Ragged lock-step batch: rows [row_offsets[s], row_offsets[s+1]) belong to sequence s (device array, int32).
+ * A cluster of 8 CTAs owns `rows_per_tile` (32 or 64) query rows through all layers; the clusters meet at one
+ * grid-wide barrier per layer (self-attention keys), so ALL clusters must be co-resident: the call fails with
+ * MOYOLO_ERR_UNSUPPORTED when ceil(rows_pad / rows_per_tile) + n_seq - 1 exceeds moyolo_decoder_cluster_limits'
+ * max_clusters; sequences longer than kv_cap rows are reported through *status (device int, set to 1).
+ * bf16 weights [out, in] row-major as in the checkpoint; fp32 biases / LayerNorm parameters; built for d_model 256,
+ * 8 heads, d_ffn 1024, 3 levels x 4 points, nc <= 8.
+ * -------------------------------------------------------------------------------------------*/
+typedef struct {
+  const void *wqkv, *wo;        /* self_attn.in_proj_weight [768,256], self_attn.out_proj.weight [256,256]          */
+  const void *woff;             /* [sampling_offsets.weight (192) ; attention_weights.weight (96)] x 256            */
+  const void *wout;             /* cross_attn.output_proj.weight [256,256]                                          */
+  const void *w1, *w2;          /* linear1.weight [1024,256], linear2.weight [256,1024]                             */
+  const void *wb1, *wb2;        /* dec_bbox_head[i].layers.{0,1}.weight [256,256]                                   */
+  const float *bqkv, *bo, *boff, *bout, *b1, *b2, *bb1, *bb2;
+  const float *wb3, *bb3;       /* dec_bbox_head[i].layers.2 weight [4,256] / bias [4], fp32                        */
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
+} moyolo_decoder_layer_weights_t;
+
+typedef struct {
+  int n_layers, d_model, n_heads, d_ffn, n_levels, n_points;
+  moyolo_decoder_layer_weights_t layers[8];
+  const float* x_in;            /* [rows_pad, 256] content embeddings (residual stream)                             */
+  const float* pos;             /* [rows_pad, 256] track_query_embed / query_pos, the same in every layer (:705-707) */
+  const float* refer0;          /* [rows_pad, 4] sigmoid(refer_bbox) (:690)                                         */
+  float* x_out;                 /* [rows_pad, 256] output embedding of the last layer                               */
+  void* x_lp_out;               /* optional bf16 copy of x_out                                                      */
+  float* refer_out[8];          /* refer_out[i]: [rows_pad, 4] refined boxes after layer i (entries may be NULL)    */
+  void* kv;                     /* scratch, bf16 [2, rows_pad, 512]                                                 */
+  const void* values;           /* bf16 [B, Lv, n_layers*256]: layer i reads columns [256 i, 256 i + 256)           */
+  int64_t value_batch_stride, value_pos_stride;   /* elements                                                      */
+  int32_t value_shapes[2 * MOYOLO_MAX_LEVELS];    /* (H, W) per level, host                                        */
+  int softmax_mode;
+  const int32_t* row_offsets;   /* device int32 [n_seq + 1]                                                         */
+  int n_seq;
+  int64_t rows_pad;
+  int rows_per_tile;            /* 32 or 64                                                                         */
+  void* grid_barrier;           /* device uint32, must be 0 when the kernel starts                                  */
+  int reset_barrier;            /* 1: the call enqueues a memset of grid_barrier first                              */
+  int* status;                  /* optional device int                                                              */
+  const float *score_w, *score_b;   /* dec_score_head[last]: fp32 [nc, 256], [nc]; NULL = no score head            */
+  int nc;
+  float* logits;                /* [rows_pad, nc]                                                                   */
+  float* scores;                /* [rows_pad] sigmoid(max logit)                                                    */
+  int32_t* labels;              /* [rows_pad] argmax                                                                */
+  float eps;                    /* LayerNorm eps                                                                    */
+  void* profile;                /* optional device int64 [n_layers, 16]: %globaltimer stamps of the stages of cluster
+                                 * 0 / rank 0 (benchmarks/dc_stages.py); NULL in production                          */
+} moyolo_decoder_cluster_t;
+int moyolo_decoder_cluster_forward(const moyolo_decoder_cluster_t* a, moyolo_stream_t stream);
+/* Co-resident clusters of the current device and the longest sequence (rows) the key/value staging holds. */
+int moyolo_decoder_cluster_limits(int rows_per_tile, int* max_clusters, int* kv_cap);
+
 /* Raw CUDA events that may be recorded inside a captured graph and waited on from outside it (ev_tail_prev above):
  * moyolo_event_record uses cudaEventRecordExternal while `stream` is capturing, a plain record otherwise. */
 void* moyolo_event_create(void);

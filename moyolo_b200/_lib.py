@@ -33,12 +33,33 @@ class FrameSubmit(C.Structure):
                 ("vp_M", _l), ("vp_N", _i), ("vp_max_ctas", _i), ("pre_graph_exec", _p)]
 
 
+class DecoderLayerWeights(C.Structure):
+    """moyolo_decoder_layer_weights_t (include/moyolo_b200.h)."""
+    _fields_ = [(n, _p) for n in ("wqkv", "wo", "woff", "wout", "w1", "w2", "wb1", "wb2", "bqkv", "bo", "boff", "bout",
+                                  "b1", "b2", "bb1", "bb2", "wb3", "bb3", "ln1_w", "ln1_b", "ln2_w", "ln2_b", "ln3_w",
+                                  "ln3_b")]
+
+
+class DecoderCluster(C.Structure):
+    """moyolo_decoder_cluster_t (include/moyolo_b200.h)."""
+    _fields_ = [("n_layers", _i), ("d_model", _i), ("n_heads", _i), ("d_ffn", _i), ("n_levels", _i), ("n_points", _i),
+                ("layers", DecoderLayerWeights * 8),
+                ("x_in", _p), ("pos", _p), ("refer0", _p), ("x_out", _p), ("x_lp_out", _p), ("refer_out", _p * 8),
+                ("kv", _p), ("values", _p), ("value_batch_stride", _l), ("value_pos_stride", _l),
+                ("value_shapes", C.c_int32 * 16), ("softmax_mode", _i), ("row_offsets", _p), ("n_seq", _i),
+                ("rows_pad", _l), ("rows_per_tile", _i), ("grid_barrier", _p), ("reset_barrier", _i), ("status", _p),
+                ("score_w", _p), ("score_b", _p), ("nc", _i), ("logits", _p), ("scores", _p), ("labels", _p),
+                ("eps", _f), ("profile", _p)]
+
+
 # name -> (restype, argtypes); must list every symbol include/moyolo_b200.h declares
 SIGNATURES = {
     "moyolo_version": (_i, []),
     "moyolo_last_error": (C.c_char_p, []),
     "moyolo_device_supported": (_i, []),
     "moyolo_launch_count": (C.c_uint64, []),
+    "moyolo_decoder_cluster_forward": (_i, [_p, _p]),
+    "moyolo_decoder_cluster_limits": (_i, [_i, _p, _p]),
     "moyolo_msda_sampled_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _p, _i, _l, _p, _p, _l, _p]),
     "moyolo_msda_sampled_backward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _p, _i, _p, _l, _l, _p, _p,
                                           _p, _p, _p]),

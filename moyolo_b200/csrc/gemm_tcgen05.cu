@@ -1236,6 +1236,7 @@ static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
+  note_launch();
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -17,7 +17,7 @@ stay fp32).
 from __future__ import annotations
 
 import os
-from typing import Sequence
+from typing import Optional, Sequence
 
 import torch
 
@@ -311,3 +311,101 @@ def bbox_head_ws(mp: MlpPack, ws, refer_in, refer_out) -> None:
     ops.linear(ws.x_lp, mp.hidden[0].w, mp.hidden[0].b, relu=True, out=ws.bh1, engine=_GEMM_ENGINE)
     ops.linear(ws.bh1, mp.hidden[1].w, mp.hidden[1].b, relu=True, out=ws.bh2, engine=_GEMM_ENGINE)
     ops.box_refine(ws.bh2, mp.last_w, mp.last_b, refer_in, out=refer_out)
+
+
+# ------------------------------------------------------------------------------------------------
+# Whole decoder in one launch (csrc/decoder_cluster.cu): the row-tile-persistent cluster kernel.
+# ------------------------------------------------------------------------------------------------
+CLUSTER_DECODER = os.environ.get("MOYOLO_CLUSTER_DECODER", "1") != "0"
+
+
+class ClusterDecoder:
+    """Descriptor of moyolo_decoder_cluster_forward for one set of decoder weights: all layers of
+    MOTRTransformerDecoder.forward (transformer.py:676-728) incl. box refinement and the last layer's score head in
+    ONE kernel. bf16, d_model 256, 8 heads, d_ffn 1024, 3 levels x 4 points, ReLU, nc <= 8."""
+
+    def __init__(self, layer_packs: Sequence[LayerPack], bbox_packs: Sequence[MlpPack], shapes, score_w=None,
+                 score_b=None):
+        import ctypes as C
+        self._C = C
+        self.n_layers = len(layer_packs)
+        self.shapes = [[int(h), int(w)] for h, w in shapes]
+        d = _lib.DecoderCluster()
+        pk0 = layer_packs[0]
+        d.n_layers, d.d_model, d.n_heads = self.n_layers, pk0.C, pk0.n_heads
+        d.d_ffn, d.n_levels, d.n_points = pk0.ffn1.w.shape[0], pk0.msda.n_levels, pk0.msda.n_points
+        self._keep = []
+        for i, (pk, bp) in enumerate(zip(layer_packs, bbox_packs)):
+            L = d.layers[i]
+            pairs = dict(wqkv=pk.qkv.w, wo=pk.o.w, woff=pk.msda.offlog.w, wout=pk.msda.out.w, w1=pk.ffn1.w, w2=pk.ffn2.w,
+                         wb1=bp.hidden[0].w, wb2=bp.hidden[1].w, bqkv=pk.qkv.b, bo=pk.o.b, boff=pk.msda.offlog.b,
+                         bout=pk.msda.out.b, b1=pk.ffn1.b, b2=pk.ffn2.b, bb1=bp.hidden[0].b, bb2=bp.hidden[1].b,
+                         wb3=bp.last_w, bb3=bp.last_b, ln1_w=pk.norms[0][0], ln1_b=pk.norms[0][1], ln2_w=pk.norms[1][0],
+                         ln2_b=pk.norms[1][1], ln3_w=pk.norms[2][0], ln3_b=pk.norms[2][1])
+            for name, t in pairs.items():
+                if not t.is_contiguous():
+                    raise ValueError(f"ClusterDecoder: {name} must be contiguous")
+                setattr(L, name, t.data_ptr())
+                self._keep.append(t)
+        self.eps = float(layer_packs[0].norms[0][2])
+        self.softmax_mode = layer_packs[0].msda.softmax_mode
+        flat = [v for hw in self.shapes for v in hw]
+        for k, v in enumerate(flat):
+            d.value_shapes[k] = v
+        d.softmax_mode, d.eps = self.softmax_mode, self.eps
+        if score_w is not None:
+            d.score_w, d.score_b, d.nc = score_w.data_ptr(), score_b.data_ptr(), score_w.shape[0]
+            self._keep += [score_w, score_b]
+        self.desc = d
+        self._limits = {}
+
+    @staticmethod
+    def supports(dt, spec_like) -> bool:
+        """Static configuration check (d_model 256, 8 heads, d_ffn 1024, 3 levels x 4 points, bf16, nc <= 8)."""
+        return (CLUSTER_DECODER and dt == torch.bfloat16 and spec_like.d_model == 256 and spec_like.n_heads == 8 and
+                spec_like.d_ffn == 1024 and spec_like.n_levels == 3 and spec_like.n_points == 4 and
+                getattr(spec_like, "nc", 1) <= 8 and _GEMM_ENGINE != _lib.GEMM_SIMT)
+
+    def limits(self, rows_per_tile: int):
+        """(co-resident clusters, longest sequence in rows) for a tile height of 32 or 64 rows."""
+        if rows_per_tile not in self._limits:
+            C = self._C
+            mc, kc = C.c_int(0), C.c_int(0)
+            _lib.check(_lib.lib().moyolo_decoder_cluster_limits(rows_per_tile, C.byref(mc), C.byref(kc)))
+            self._limits[rows_per_tile] = (mc.value, kc.value)
+        return self._limits[rows_per_tile]
+
+    def tile_rows(self, rows_pad: int, n_seq: int, max_seq_rows: int) -> int:
+        """Tile height (32 or 64 rows) that fits the device for this frame size, 0 if neither does."""
+        for m in (32, 64):
+            max_clusters, kv_cap = self.limits(m)
+            if (rows_pad + m - 1) // m + n_seq - 1 <= max_clusters and max_seq_rows <= kv_cap:
+                return m
+        return 0
+
+    def run(self, x_in, pos, refer0, values, row_offsets, n_seq: int, rows_pad: int, rows_per_tile: int, x_out,
+            kv, grid_barrier, refer_out: Sequence[Optional[torch.Tensor]], x_lp_out=None, logits=None, scores=None,
+            labels=None, status=None, reset_barrier: bool = True, profile=None) -> None:
+        """values: bf16 [B, Lv, n_layers*256] (all layers' value projections); kv: bf16 scratch [2, rows_pad, 512];
+        grid_barrier: uint32/int32 [1]; refer_out[i]: fp32 [rows_pad, 4] or None."""
+        d = self.desc
+        for t in (x_in, pos, refer0, x_out):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("ClusterDecoder.run: x_in / pos / refer0 / x_out must be contiguous fp32")
+        if values.dtype != torch.bfloat16 or values.stride(2) != 1 or kv.numel() < 2 * rows_pad * 512:
+            raise ValueError("ClusterDecoder.run: values must be bf16 [B, Lv, n_layers*256], kv bf16 [2, rows_pad, 512]")
+        d.x_in, d.pos, d.refer0, d.x_out = x_in.data_ptr(), pos.data_ptr(), refer0.data_ptr(), x_out.data_ptr()
+        d.x_lp_out = None if x_lp_out is None else x_lp_out.data_ptr()
+        for i in range(8):
+            t = refer_out[i] if i < len(refer_out) else None
+            d.refer_out[i] = None if t is None else t.data_ptr()
+        d.kv, d.values = kv.data_ptr(), values.data_ptr()
+        d.value_batch_stride, d.value_pos_stride = values.stride(0), values.stride(1)
+        d.row_offsets, d.n_seq, d.rows_pad, d.rows_per_tile = row_offsets.data_ptr(), n_seq, rows_pad, rows_per_tile
+        d.grid_barrier, d.reset_barrier = grid_barrier.data_ptr(), 1 if reset_barrier else 0
+        d.status = None if status is None else status.data_ptr()
+        d.logits = None if logits is None else logits.data_ptr()
+        d.scores = None if scores is None else scores.data_ptr()
+        d.labels = None if labels is None else labels.data_ptr()
+        d.profile = None if profile is None else profile.data_ptr()
+        _lib.check(_lib.lib().moyolo_decoder_cluster_forward(self._C.byref(d), torch.cuda.current_stream().cuda_stream))

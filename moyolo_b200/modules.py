@@ -286,6 +286,14 @@ class MOTRDecoderLayer(_DecoderLayerBase):
         return self._forward_impl(embed, refer_bbox, feats, shapes, padding_mask, attn_mask, track_query_pos)
 
 
+class _Dims:
+    """d_model / n_heads / d_ffn / n_levels / n_points / nc of a decoder, as ClusterDecoder.supports reads them."""
+
+    def __init__(self, d_model, n_heads, d_ffn, n_levels, n_points, nc):
+        self.d_model, self.n_heads, self.d_ffn, self.n_levels, self.n_points, self.nc = d_model, n_heads, d_ffn, \
+            n_levels, n_points, nc
+
+
 class _DecoderBase(nn.Module):
     def __init__(self, hidden_dim, decoder_layer, num_layers, eval_idx=-1):
         super().__init__()
@@ -338,6 +346,28 @@ class _DecoderBase(nn.Module):
         n_out = n_l if self.training else 1
         dec_bboxes = torch.empty(n_out, bs, Q, 4, dtype=torch.float32, device=dev)
         dec_cls = []
+        # Eval, one fixed positional embedding (the MOTR decoder), no masks: every layer up to eval_idx, the box
+        # refinements and the score head run as ONE cluster kernel (csrc/decoder_cluster.cu) when the frame fits.
+        if (not self.training and fixed_pos is not None and mask is None and zero_rows is None and refer.shape[-1] == 4 and
+                ex.ClusterDecoder.supports(dt, _Dims(C, packs[0].n_heads, packs[0].ffn1.w.shape[0], packs[0].msda.n_levels,
+                                                     packs[0].msda.n_points, score_head[self.eval_idx].weight.shape[0]))):
+            n_run = self.eval_idx + 1
+            head = score_head[self.eval_idx]
+            sw, sb = head.weight.detach().float().contiguous(), head.bias.detach().float().contiguous()
+            cd = ex.ClusterDecoder(packs[:n_run], bpacks[:n_run], shapes, sw, sb)
+            m_rows = cd.tile_rows(R, bs, Q)
+            if m_rows:
+                nc = sw.shape[0]
+                x_out = torch.empty(R, C, dtype=torch.float32, device=dev)
+                logits = torch.empty(R, nc, dtype=torch.float32, device=dev)
+                kv = torch.empty(2, R, 2 * C, dtype=dt, device=dev)
+                bar = torch.zeros(1, dtype=torch.int32, device=dev)
+                status = torch.zeros(1, dtype=torch.int32, device=dev)
+                refer_out = [None] * (n_run - 1) + [dec_bboxes[0].view(R, 4)]
+                cd.run(x_f32, pos, refer.view(R, 4).contiguous(), values, ro, bs, R, m_rows, x_out, kv, bar, refer_out,
+                       logits=logits, status=status)
+                out_dt = embed.dtype
+                return dec_bboxes.to(out_dt), logits.view(1, bs, Q, nc).to(out_dt), x_out.view(bs, Q, C).to(out_dt)
         for i, pk in enumerate(packs):
             pos_next = pos if (fixed_pos is not None and i + 1 < n_l) else None
             x_f32, x_lp, xq_next = ex.run_layer(pk, x_f32, x_lp, xq_lp, refer.view(R, 1, -1),

@@ -142,6 +142,11 @@ class FrameWorkspace:
         self.q_tgt_lp3 = z(R, C, **lp)
         self.q_h = z(R, d_qim, **lp)
         self.q_new = z(R, C, **f32)
+        # cluster decoder (csrc/decoder_cluster.cu): self-attention K|V scratch (double-buffered by layer parity),
+        # grid barrier counter, status flag
+        self.kv = z(2, R, 2 * C, **lp) if dt == torch.bfloat16 else None
+        self.grid_bar = z(1, dtype=torch.int32, device=dev)
+        self.dc_status = z(1, dtype=torch.int32, device=dev)
 
 
 def qim_update_ws(W: DecoderWeights, spec: DecoderSpec, ws: "FrameWorkspace", ro_host) -> None:
@@ -218,7 +223,8 @@ class TrackEngine:
                  n_seq: int = 1, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, iou_thresh=0.8,
                  weights: Optional[DecoderWeights] = None, cap: int = 512, bucket: int = 64, margin: int = 32,
                  use_graphs: bool = True, table_rows: int = 1 << 18, branches: bool = True, selector=None,
-                 value_ahead: Optional[bool] = None, gather_probe: Optional[ops.GatherProbe] = None):
+                 value_ahead: Optional[bool] = None, gather_probe: Optional[ops.GatherProbe] = None,
+                 cluster_decoder: Optional[bool] = None):
         self.dev = torch.device(device)
         self.gather_probe = gather_probe   # instrumentation of every gather launch (bench.py roofline leg)
         self.launches = 0                  # kernels launched by this engine's frames (graph replays included)
@@ -226,6 +232,12 @@ class TrackEngine:
         self.Lv = level_sizes(shapes)
         self.W = weights or DecoderWeights(sd, spec, self.dev, precision)
         self.thr = (score_thresh, filter_thresh, miss_tolerance, iou_thresh)
+        # whole decoder as one cluster kernel where the frame fits the device (see _cluster_rows)
+        self._cd = None
+        if ex.ClusterDecoder.supports(self.W.dt, spec) and cluster_decoder is not False:
+            self._cd = ex.ClusterDecoder(self.W.layers, self.W.bbox, self.shapes, self.W.score_w, self.W.score_b)
+        elif cluster_decoder:
+            raise ValueError("cluster_decoder=True needs bf16, d_model 256, 8 heads, d_ffn 1024, 3 levels x 4 points")
         self.cap, self.bucket, self.margin, self.use_graphs = cap, bucket, margin, use_graphs
         self.branches = branches
         # split value projection (see _body): bf16 tcgen05 path with the persistent kernel's shape constraints
@@ -427,38 +439,20 @@ class TrackEngine:
         # class-score head inside the last layer's FFN2 GEMM+LayerNorm launch (bf16 fused-epilogue path, nc <= 8)
         score_fused = ops.SCORE_FUSED and ex.fused_epilogues(dt, C) and spec.nc <= 8 and \
             not ops.ffn_fused_supported(dt, C, W.layers[-1].ffn1.w.shape[0])
-        for i, pk in enumerate(W.layers):
-            last = i + 1 == n_l
-            value_view = values[:, :, i * C:(i + 1) * C]
-
-            def before_gather(i=i):
-                if not fork:
-                    return
-                if i == 0:
-                    if self._ev_v0 is not None:
-                        cur.wait_event(self._ev_v0)   # layer 0's value slice only
-                    else:
-                        cur.wait_stream(self._s_val)
-                else:
-                    if i == 1 and self._ev_v0 is not None:
-                        cur.wait_stream(self._s_val)  # the other layers' slices
-                    cur.wait_stream(self._s_box)   # refer[i] comes from the box head of layer i-1
-
-            if self._vp_ahead and i == self._vp_gate_layer:   # experiment knob: release the next projection earlier
-                _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
-            ex.run_layer_ws(pk, ws, ws.refer[i].view(R, 1, 4), value_view, self.shapes, S, ws.ro, ro_host,
-                            ws.pos, None if last else ws.pos, dt, before_gather,
-                            score=(W.score_w, W.score_b, ws.logits, ws.scores, ws.labels) if (last and score_fused) else None,
-                            gather_probe=self.gather_probe)
-            # box refinement of this layer (transformer.py:709): only the NEXT layer's gather needs it
-            # (the last layer's box head runs next to the score head, which only needs the layer output)
-            if fork:
-                self._s_box.wait_stream(cur)
-                with torch.cuda.stream(self._s_box):
-                    ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
-            else:
-                ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
-        if self._vp_ahead and self._vp_gate_layer >= n_l:  # the next frame's value projection may start now: only the tail is left
+        m_rows = self._cluster_rows(R)
+        if m_rows:
+            # ONE launch for all layers (self-attention, deformable attention, FFN, LayerNorms, box refinement) and the
+            # score head: csrc/decoder_cluster.cu. The residual stream is updated in place (a cluster reads and writes
+            # only its own rows of ws.x).
+            if fork and not (self._vp_ahead or self._sel_ahead):
+                cur.wait_stream(self._s_val)   # all layers' value slices
+            self._cd.run(ws.x, ws.pos, ws.refer[0], values, ws.ro, S, R, m_rows, ws.x, ws.kv, ws.grid_bar,
+                         ws.refer[1:], x_lp_out=ws.x_lp, logits=ws.logits, scores=ws.scores, labels=ws.labels,
+                         status=ws.dc_status)
+            score_fused = True   # (scores, labels and logits are already there)
+        else:
+            self._layer_chain(p, values, ro_host, score_fused, fork, cur)
+        if self._vp_ahead and (m_rows or self._vp_gate_layer >= n_l):  # the next frame's value projection may start now: only the tail is left
             _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
         boxes = ws.refer[n_l]
         if not score_fused:
@@ -494,6 +488,50 @@ class TrackEngine:
         ops.frame_writeback(S, C, self.cap, ws.ro, ws.n_active, ws.q_new, None if fork else ws.c_box, self.t_qpos,
                             self.t_ref, self.n_tracks, ctrl=self.ctrl, info=p.info, boxes=boxes if fork else None,
                             active_index=ws.active_index if fork else None)
+
+    def _cluster_rows(self, rows_pad: int) -> int:
+        """Tile height (32 / 64 rows) of the one-launch cluster decoder for a frame of rows_pad rows, 0 = the frame
+        does not fit the co-resident clusters / key staging of this device (launch-chained schedule then)."""
+        if self._cd is None or self.gather_probe is not None:
+            return 0
+        return self._cd.tile_rows(rows_pad, self.n_seq, rows_pad - (self.n_seq - 1) * self.n_detect)
+
+    def _layer_chain(self, p: "_FramePlan", values, ro_host, score_fused: bool, fork: bool, cur) -> None:
+        """Launch-chained schedule of the decoder layers (7 launches per layer on the main chain + a 3-launch box
+        head side branch): frames that do not fit the cluster decoder, fp32, and the instrumented roofline leg."""
+        W, S, C, ws, R = self.W, self.n_seq, self.spec.d_model, p.ws, p.rows_pad
+        dt, n_l = W.dt, self.spec.n_layers
+        for i, pk in enumerate(W.layers):
+            last = i + 1 == n_l
+            value_view = values[:, :, i * C:(i + 1) * C]
+
+            def before_gather(i=i):
+                if not fork:
+                    return
+                if i == 0:
+                    if self._ev_v0 is not None:
+                        cur.wait_event(self._ev_v0)   # layer 0's value slice only
+                    else:
+                        cur.wait_stream(self._s_val)
+                else:
+                    if i == 1 and self._ev_v0 is not None:
+                        cur.wait_stream(self._s_val)  # the other layers' slices
+                    cur.wait_stream(self._s_box)   # refer[i] comes from the box head of layer i-1
+
+            if self._vp_ahead and i == self._vp_gate_layer:   # experiment knob: release the next projection earlier
+                _lib.check(_lib.lib().moyolo_event_record(self._ev_tail[p.slot], cur.cuda_stream))
+            ex.run_layer_ws(pk, ws, ws.refer[i].view(R, 1, 4), value_view, self.shapes, S, ws.ro, ro_host,
+                            ws.pos, None if last else ws.pos, dt, before_gather,
+                            score=(W.score_w, W.score_b, ws.logits, ws.scores, ws.labels) if (last and score_fused) else None,
+                            gather_probe=self.gather_probe)
+            # box refinement of this layer (transformer.py:709): only the NEXT layer's gather needs it
+            # (the last layer's box head runs next to the score head, which only needs the layer output)
+            if fork:
+                self._s_box.wait_stream(cur)
+                with torch.cuda.stream(self._s_box):
+                    ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
+            else:
+                ex.bbox_head_ws(W.bbox[i], ws, ws.refer[i], ws.refer[i + 1])
 
     def _qim_update(self, ws: FrameWorkspace, ro_host) -> None:
         qim_update_ws(self.W, self.spec, ws, ro_host)
