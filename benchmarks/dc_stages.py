@@ -26,7 +26,7 @@ bar = torch.zeros(1, dtype=torch.int32, device=dev)
 refs = [torch.zeros(R, 4, device=dev) for _ in range(6)]
 prof = torch.zeros(6, 16, dtype=torch.int64, device=dev)
 m = cd.tile_rows(R, 1, R)
-print("tile rows", m, "limits", cd.limits(32), cd.limits(64))
+print("tile rows", m, "limits", cd.limits(32))
 logits, scores, labels = torch.zeros(R, spec.nc, device=dev), torch.zeros(R, device=dev), torch.zeros(R, dtype=torch.int32, device=dev)
 acc = None
 N = 20
@@ -43,9 +43,9 @@ for _ in range(N):
 b.record()
 torch.cuda.synchronize()
 acc = acc / N
-names = ["grid barrier wait", "K/V staging", "attention", "att exchange", "out_proj GEMM", "LayerNorm1", "x1 exchange",
-         "offsets|logits GEMM", "gather", "gather exchange", "output_proj+LN2+exch", "FFN1", "FFN2+reduce-scatter",
-         "LN3+exchange", "next qkv + arrive / outputs"]
+names = ["grid barrier wait", "K/V staging", "attention", "att exchange", "out_proj GEMM + send", "LN1 exchange + LayerNorm1",
+         "offsets|logits GEMM", "gather", "gather exchange", "output_proj + exchange + LN2", "FFN1", "FFN2 + send",
+         "reduce-scatter wait + sum + send", "LN3 exchange + LayerNorm3", "next qkv + box1 + arrive / outputs"]
 d = (acc[:, 1:] - acc[:, :-1]) / 1e3
 res = {n: round(float(d[:, i].mean()), 2) for i, n in enumerate(names)}
 nxt = (acc[1:, 0] - acc[:-1, 15]) / 1e3

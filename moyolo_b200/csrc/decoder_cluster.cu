@@ -7,22 +7,29 @@
 // schedule (executor.run_layer_ws) become one kernel for the whole decoder; the value projection stays a separate
 // tcgen05 GEMM (it depends on the frame's feature maps only and runs ahead of the frame).
 //
-// Decomposition. A thread-block CLUSTER of 8 CTAs owns a tile of M = 32 (or 64) query rows through every row-local
+// Decomposition. A thread-block CLUSTER of 8 CTAs owns a tile of M = 32 query rows through every row-local
 // operation of every layer; CTA rank r of the cluster owns
 //   * attention head r (self-attention and deformable gather are per head), and
 //   * the 32-column slab r of every 256-wide GEMM output (128-column slab of the FFN hidden layer).
-// The activation tile [M, 256] (bf16 GEMM operand) is REPLICATED in the shared memory of all 8 CTAs; every stage
-// computes its slab and writes it into the 8 replicas through distributed shared memory (st.shared::cluster),
-// followed by one cluster barrier. LayerNorm statistics (mean, centred sum of squares per slab) are exchanged the
-// same way and merged with the parallel-variance formula. The FFN's second GEMM is split along K (each CTA
-// multiplies its own 128 hidden columns: no exchange of the hidden activations) and reduce-scattered through
-// DSMEM. Weights are never staged in shared memory: each warp loads its mma.sync B fragments straight from
-// global memory / L2 with 128-bit read-only loads (8 consecutive k per lane, a k-permutation that the A
-// fragments mirror), each weight byte is read once per cluster from L2.
-// The only data another cluster needs are the keys / values of the self-attention: they go through global
-// memory and a grid-wide barrier per layer (release/acquire on a global counter; all clusters are co-resident,
-// the host checks the occupancy). Tensor work is mma.sync m16n8k16 (bf16 in, fp32 accumulate): the tiles are
-// 32 rows x 8..32 columns per warp task, far below a 128-row tcgen05 tile, and the kernel is latency-bound.
+// GEMM operands (activation tiles [32, 256] bf16) are REPLICATED in the shared memory of the 8 CTAs. A stage
+// computes its slab and sends it to all 8 replicas with asynchronous distributed-shared-memory stores that
+// complete a transaction barrier in the RECEIVING CTA (st.async ... mbarrier::complete_tx): a receiver waits on
+// its own mbarrier for the expected byte count, there is no cluster-wide barrier in the layer loop. Buffers are
+// re-used only along the dependency chain of the exchanges themselves (a peer can send exchange k + 1 only after
+// it received this CTA's part of exchange k), which is what makes the re-use race-free without extra handshakes.
+//   * LayerNorm: the pre-norm fp32 slab is sent to all peers, every CTA then normalises the full rows locally
+//     (two-pass mean / variance in registers) and writes the bf16 operand tile(s) of the next GEMM itself.
+//   * FFN: linear1 produces this CTA's 128 hidden columns, linear2 is split along K (no exchange of the hidden
+//     activations) and the partial sums are reduce-scattered to the slab owners.
+//   * Weights are never staged in shared memory: each warp loads its mma.sync B fragments straight from global
+//     memory / L2 with 128-bit read-only loads (8 consecutive k per lane, a k-permutation mirrored by the A
+//     fragments) and ISSUES them one stage ahead, so their latency hides behind the preceding exchange.
+//   * Biases and LayerNorm parameters of a layer are staged in shared memory one layer ahead (cp.async).
+// The only data another cluster needs are the keys / values of the self-attention: they go through global memory
+// (double-buffered by layer parity) and a grid-wide barrier per layer (release/acquire on a global counter; all
+// clusters are co-resident, the host checks the occupancy). Tensor work is mma.sync m16n8k16 (bf16 in, fp32
+// accumulate): the tiles are 32 rows x 8..32 columns per warp task, far below a 128-row tcgen05 tile, and the
+// kernel is latency-bound (benchmarks/dc_stages.py prints the stage timeline).
 //
 // Numerics follow the launch-chained bf16 path: bf16 GEMM operands and value tensor; fp32 residual stream,
 // LayerNorm, softmax, sampling locations, accumulation; class scores from the bf16-rounded output row.
@@ -37,12 +44,13 @@ namespace moyolo {
 namespace dc {
 
 constexpr int kThreads = 256, kWarps = 8, kCluster = 8;
+constexpr int M = 32;     // query rows per cluster tile
 constexpr int kC = 256, kDh = 32;
 constexpr int kFs = 128;  // FFN hidden columns per CTA (d_ffn 1024 / 8)
 constexpr int kPA = 288;  // bf16 pitch of the activation tiles: 576 B = 64 (mod 128) -> conflict-free 128-bit A loads
 constexpr int kPH = 160;  // bf16 pitch of the FFN hidden slab [M][128]: 320 B = 64 (mod 128)
 constexpr int kPQ = 40;   // bf16 pitch of Q / K / V head rows (ldmatrix layout of attention.cu)
-constexpr int kPY = 33;   // fp32 pitch of the pre-LayerNorm slab
+constexpr int kPY = 260;  // fp32 pitch of the pre-LayerNorm tile [M][256]
 constexpr int kPO = 40;   // fp32 pitch of one row's offsets | logits (36 used)
 constexpr int kNP = 4, kNL = 3, kLP = kNP * kNL;  // sampling points x levels (the model's configuration)
 constexpr int kNU = kLP * 4;                       // bilinear corners per (row, head)
@@ -80,12 +88,56 @@ struct Params {
   float* scores;
   int32_t* labels;
   float eps;
-  int kv_cap;             // keys (rounded to 32) that fit the K/V staging area
   long long* profile;     // optional [n_layers][16] globaltimer stamps of cluster 0 / rank 0 (benchmarks/dc_stages.py)
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// cluster / DSMEM / grid-barrier primitives
+// Shared-memory plan of one CTA (bytes). The tail [TB, TC, TD, H, PART] doubles as the key / value staging of the
+// self-attention (none of those buffers is live between the grid barrier and the end of the attention).
+// ---------------------------------------------------------------------------------------------------------
+namespace sm {
+constexpr size_t kTile = size_t(M) * kPA * 2;             // one bf16 activation tile
+constexpr size_t oTA = 0;                                 // attention output / gathered tile (received)
+constexpr size_t oYF = oTA + kTile;                       // pre-LayerNorm fp32 tile (received); attention partial O
+constexpr size_t oRes = oYF + size_t(M) * kPY * 4;        // residual stream, own 32 columns, fp32
+constexpr size_t oPos = oRes + size_t(M) * 32 * 4;        // query_pos, full rows, fp32
+constexpr size_t oOL = oPos + size_t(M) * kC * 4;         // offsets | logits of this head
+constexpr size_t oQ = oOL + size_t(M) * kPO * 4;          // q of this head
+constexpr size_t oRef = oQ + size_t(M) * kPQ * 2;         // reference boxes of the tile
+constexpr size_t oStage = oRef + size_t(M) * 16;          // gather staging: per warp 4 items x 48 corners x (off, w)
+constexpr size_t oMl = oStage + size_t(kWarps) * 4 * kNU * 8;   // attention partial (max, sum)
+constexpr size_t oSlab = oMl + size_t(kWarps) * 16 * 2 * 4;     // bf16 slab staging [M][32]
+constexpr int kParamFloats = 1968;                        // see PF:: below
+constexpr size_t oParam = oSlab + size_t(M) * 32 * 2;     // 2 x per-layer parameter block (layer parity)
+constexpr size_t oBq0 = oParam + 2 * size_t(kParamFloats) * 4;  // in-projection bias of layer 0 (this head)
+constexpr size_t oBars = oBq0 + 96 * 4;                   // 8 mbarriers
+constexpr size_t oTB = (oBars + 8 * 8 + 127) / 128 * 128; // x + pos operand tiles (written locally by the LayerNorms)
+constexpr size_t oTC = oTB + kTile;                       // x3 tile (local) / box-head hidden 2 (received)
+constexpr size_t oTD = oTC + kTile;                       // box-head hidden 1 (received)
+constexpr size_t oH = oTD + kTile;                        // FFN hidden slab
+constexpr size_t oPart = oH + size_t(M) * kPH * 2;        // split-K partial sums [8 sources][M][32] fp32 (received)
+constexpr size_t kTotal = 232448 - 512;                   // everything a CTA can opt in to, minus alignment slack
+constexpr size_t kPartBytes = size_t(kCluster) * M * 32 * 4;
+static_assert(oPart + kPartBytes <= kTotal, "shared-memory plan exceeds 227 KiB");
+constexpr int kKvCap = static_cast<int>((kTotal - oTB) / (2 * kPQ * 2)) / 32 * 32;   // keys the tail can stage
+constexpr size_t kPoBytes = size_t(kWarps) * 16 * 32 * 4;
+static_assert(kPoBytes <= size_t(M) * kPY * 4, "attention partials must fit the pre-LayerNorm tile they alias");
+}  // namespace sm
+
+// per-layer parameter block (float offsets)
+namespace PF {
+constexpr int bo = 0, bout = 32, b2 = 64, bb1 = 96, bb2 = 128, boff = 160 /* 24 offsets + 12 logits, pad to 40 */,
+              b1 = 200, bqkv = 328 /* q | k | v of the NEXT layer's in-projection */, bb3 = 424,
+              g1 = 432, be1 = 688, g2 = 944, be2 = 1200, g3 = 1456, be3 = 1712;
+static_assert(be3 + 256 == sm::kParamFloats, "parameter block layout");
+}  // namespace PF
+
+enum { E_ATT = 0, E_LN1, E_G, E_LN2, E_RS, E_LN3, E_H1, E_H2, kNumBars };
+constexpr uint32_t kBf16TileBytes = kCluster * M * 32 * 2;   // 8 senders x [32][32] bf16
+constexpr uint32_t kF32TileBytes = kCluster * M * 32 * 4;    // 8 senders x [32][32] fp32
+
+// ---------------------------------------------------------------------------------------------------------
+// cluster / DSMEM / mbarrier / grid-barrier primitives
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
@@ -100,12 +152,32 @@ __device__ __forceinline__ uint32_t map_peer(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_peer_v4(uint32_t addr, const uint4& v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
-               : "memory");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void st_peer_v2f(uint32_t addr, float a, float b) {
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+__device__ __forceinline__ void mbar_arm(uint32_t bar, uint32_t bytes) {  // one arrival + the bytes this phase expects
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// 16-byte asynchronous store into a CTA of the cluster; completes 16 bytes on that CTA's mbarrier when it lands.
+__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t remote_bar, uint32_t x, uint32_t y, uint32_t z,
+                                            uint32_t w) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                   remote_addr),
+               "r"(x), "r"(y), "r"(z), "r"(w), "r"(remote_bar)
+               : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
@@ -115,22 +187,25 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
 __device__ __forceinline__ void red_release_gpu_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-
-// Every CTA of the cluster has finished its global writes of this phase (cluster_sync), then ONE thread of the
-// cluster publishes them at gpu scope and counts the cluster in.
-__device__ __forceinline__ void grid_arrive(unsigned* bar, uint32_t rank) {
-  cluster_sync();
-  if (rank == 0 && threadIdx.x == 0) {
+// Grid barrier: every CTA counts itself in once all its threads' global writes of the phase are done.
+__device__ __forceinline__ void grid_arrive(unsigned* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
     __threadfence();
     red_release_gpu_add(bar, 1u);
   }
 }
-__device__ __forceinline__ void grid_wait(const unsigned* bar, unsigned target, uint32_t rank) {
-  if (rank == 0 && threadIdx.x == 0) {
-    while (ld_acquire_gpu(bar) < target) __nanosleep(32);
+__device__ __forceinline__ void grid_wait(const unsigned* bar, unsigned target) {
+  if (threadIdx.x == 0) {
+    while (ld_acquire_gpu(bar) < target) __nanosleep(20);
     __threadfence();
   }
-  cluster_sync();
+  __syncthreads();
+}
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -165,10 +240,16 @@ __device__ __forceinline__ void mma_tiles(float (&acc)[NM][4], const __nv_bfloat
   }
 }
 
-__device__ __forceinline__ long long globaltimer_ns() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
+// C-fragment transpose inside lane pairs (t, t^1): afterwards an even-t lane holds row g, columns [2t, 2t+4) of the
+// n8-tile and an odd-t lane holds row g + 8, columns [2(t-1), 2(t-1)+4): one 16-byte vector per lane.
+__device__ __forceinline__ float4 pair_rows(const float (&c)[4], int lane, int* row_in_tile, int* col_in_tile) {
+  const bool even = (lane & 1) == 0;
+  const float x = __shfl_xor_sync(0xffffffffu, even ? c[2] : c[0], 1);
+  const float y = __shfl_xor_sync(0xffffffffu, even ? c[3] : c[1], 1);
+  const int g = lane >> 2, t = lane & 3;
+  *row_in_tile = even ? g : g + 8;
+  *col_in_tile = even ? 2 * t : 2 * (t - 1);
+  return even ? make_float4(c[0], c[1], x, y) : make_float4(x, y, c[2], c[3]);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -177,47 +258,11 @@ __device__ __forceinline__ float inverse_sigmoidf_(float x) {  // utils.py:34-38
   return logf(fmaxf(x, 1e-5f) / fmaxf(1.0f - x, 1e-5f));
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Shared-memory plan of one CTA
-// ---------------------------------------------------------------------------------------------------------
-template <int MT>
-struct Smem {
-  static constexpr int M = 16 * MT;
-  static constexpr size_t oA0 = 0;
-  static constexpr size_t oA1 = oA0 + size_t(M) * kPA * 2;
-  static constexpr size_t oH = oA1 + size_t(M) * kPA * 2;
-  static constexpr size_t oY = oH + size_t(M) * kPH * 2;
-  static constexpr size_t oRes = oY + size_t(M) * kPY * 4;
-  static constexpr size_t oPos = oRes + size_t(M) * 32 * 4;
-  static constexpr size_t oSlab0 = oPos + size_t(M) * 32 * 4;
-  static constexpr size_t oSlab1 = oSlab0 + size_t(M) * 32 * 2;
-  static constexpr size_t oStat = oSlab1 + size_t(M) * 32 * 2;
-  static constexpr size_t oRef = oStat + size_t(kCluster) * M * 8;
-  static constexpr size_t oOL = oRef + size_t(M) * 16;
-  static constexpr size_t oQ = oOL + size_t(M) * kPO * 4;
-  static constexpr size_t oStage = oQ + size_t(M) * kPQ * 2;
-  static constexpr size_t oMl = oStage + size_t(kWarps) * 2 * kNU * 8;
-  static constexpr size_t oScratch = ((oMl + size_t(kWarps) * 16 * 2 * 4) + 127) / 128 * 128;
-  // scratch: attention = partial O [8 warps][16][32] fp32, then K [kv_cap][kPQ], V [kv_cap][kPQ];
-  //          FFN2      = split-K partial sums [8 sources][M][32] fp32 (aliases the attention area)
-  static constexpr size_t kPoBytes = size_t(kWarps) * 16 * 32 * 4;
-  static constexpr size_t kPartBytes = size_t(kCluster) * M * 32 * 4;
-  static constexpr size_t kTotalMax = 232448 - 1024;  // 227 KiB minus alignment slack
-  static constexpr int kv_cap() {
-    return static_cast<int>((kTotalMax - oScratch - kPoBytes) / (2 * kPQ * 2)) / 32 * 32;
-  }
-  static constexpr size_t total() {
-    const size_t att = kPoBytes + size_t(kv_cap()) * 2 * kPQ * 2;
-    return oScratch + (att > kPartBytes ? att : kPartBytes);
-  }
-};
-
 struct Tile {
   int seq, row0, n, seq_start, seq_len;
 };
 
 // tile `idx` of the frame: tiles are enumerated per sequence (a tile never spans two sequences).
-template <int M>
 __device__ __forceinline__ bool find_tile(const Params& p, int idx, Tile* t, int* total_tiles, int* max_len) {
   int acc = 0, ml = 0;
   bool found = false;
@@ -241,135 +286,106 @@ __device__ __forceinline__ bool find_tile(const Params& p, int idx, Tile* t, int
   return found;
 }
 
-// Write this CTA's bf16 slab [M][32] into columns [col0, col0 + 32) of tile `dst` in ALL 8 CTAs of the cluster
-// (warp w -> peer w, 16-byte chunks).
-template <int M>
-__device__ __forceinline__ void broadcast_slab(const __nv_bfloat16* slab, __nv_bfloat16* dst, int col0, int warp, int lane) {
-  const uint32_t base = map_peer(smem_addr(dst), static_cast<uint32_t>(warp));
-  for (int c = lane; c < M * 4; c += 32) {
-    const int row = c >> 2, part = c & 3;
-    const uint4 v = *reinterpret_cast<const uint4*>(slab + row * 32 + part * 8);
-    st_peer_v4(base + static_cast<uint32_t>((row * kPA + col0 + part * 8) * 2), v);
-  }
-}
-
-// LayerNorm of rows whose 256 columns are spread over the 8 CTAs (32 each). In: sY[row][lane] = pre-norm value of
-// this CTA's slab (all M rows written, block-synchronised). Exchanges (mean, centred sum of squares) of the slab
-// with all peers, merges the eight slabs (parallel-variance formula), and calls emit(row, lane, normalised value).
-template <int MT, typename Emit>
-__device__ __forceinline__ void cluster_layernorm(const float* sY, float* sStat, const float* __restrict__ gamma,
-                                                  const float* __restrict__ beta, float eps, uint32_t rank, int warp,
-                                                  int lane, Emit emit) {
-  constexpr int M = 16 * MT, RPW = M / kWarps;
-  float v[RPW];
-  const uint32_t stat_peer = map_peer(smem_addr(sStat), static_cast<uint32_t>(lane & 7));
-#pragma unroll
-  for (int i = 0; i < RPW; ++i) {
-    const int row = warp + i * kWarps;
-    v[i] = sY[row * kPY + lane];
-    const float mean = warp_sum(v[i]) * (1.0f / 32.0f);
-    const float d = v[i] - mean;
-    const float m2 = warp_sum(d * d);
-    if (lane < kCluster) st_peer_v2f(stat_peer + static_cast<uint32_t>((rank * M + row) * 8), mean, m2);
-  }
-  const float g = __ldg(gamma + lane), b = __ldg(beta + lane);
-  cluster_sync();
-#pragma unroll
-  for (int i = 0; i < RPW; ++i) {
-    const int row = warp + i * kWarps;
-    const float2 st = *reinterpret_cast<const float2*>(sStat + ((lane & 7) * M + row) * 2);
-    float ms = st.x;
-    ms += __shfl_xor_sync(0xffffffffu, ms, 1);
-    ms += __shfl_xor_sync(0xffffffffu, ms, 2);
-    ms += __shfl_xor_sync(0xffffffffu, ms, 4);
-    const float mean = ms * (1.0f / kCluster);
-    const float dm = st.x - mean;
-    float m2 = st.y + 32.0f * dm * dm;
-    m2 += __shfl_xor_sync(0xffffffffu, m2, 1);
-    m2 += __shfl_xor_sync(0xffffffffu, m2, 2);
-    m2 += __shfl_xor_sync(0xffffffffu, m2, 4);
-    const float rstd = rsqrtf(m2 * (1.0f / kC) + eps);
-    emit(row, lane, (v[i] - mean) * rstd * g + b);
-  }
-}
-
-// One 32-column-slab GEMM over K = 256: y[row][col] = A[row] . W[n0 + col] + bias[n0 + col] (+ residual) -> sY.
-// Warp task = (n8-tile w & 3, m-group w >> 2) with MT / 2 m-tiles per group.
-template <int MT, bool RELU_TO_SLAB>
-__device__ __forceinline__ void gemm_slab32(const __nv_bfloat16* sA, const __nv_bfloat16* __restrict__ w, int n0,
-                                            const float* __restrict__ bias, const float* sRes, float* sY,
-                                            __nv_bfloat16* slab, int warp, int lane) {
-  constexpr int NM = MT / 2;
-  const int j = warp & 3, mg = warp >> 2;
-  const int g = lane >> 2, t = lane & 3;
-  uint4 b[8];
-  load_b<8>(b, w + static_cast<int64_t>(n0 + j * 8 + g) * kC + t * 8, true);
-  float acc[NM][4];
-#pragma unroll
-  for (int i = 0; i < NM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
-  mma_tiles<8, NM>(acc, sA + (mg * NM * 16) * kPA, kPA, b, lane);
-  const int col = j * 8 + 2 * t;
-  const float b0 = __ldg(bias + n0 + col), b1 = __ldg(bias + n0 + col + 1);
-#pragma unroll
-  for (int i = 0; i < NM; ++i) {
-    const int r0 = (mg * NM + i) * 16 + g, r1 = r0 + 8;
-    if (RELU_TO_SLAB) {
-      *reinterpret_cast<uint32_t*>(slab + r0 * 32 + col) = float2_to_bf16x2(fmaxf(acc[i][0] + b0, 0.0f), fmaxf(acc[i][1] + b1, 0.0f));
-      *reinterpret_cast<uint32_t*>(slab + r1 * 32 + col) = float2_to_bf16x2(fmaxf(acc[i][2] + b0, 0.0f), fmaxf(acc[i][3] + b1, 0.0f));
-    } else {
-      sY[r0 * kPY + col] = acc[i][0] + b0 + sRes[r0 * 32 + col];
-      sY[r0 * kPY + col + 1] = acc[i][1] + b1 + sRes[r0 * 32 + col + 1];
-      sY[r1 * kPY + col] = acc[i][2] + b0 + sRes[r1 * 32 + col];
-      sY[r1 * kPY + col + 1] = acc[i][3] + b1 + sRes[r1 * 32 + col + 1];
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // The kernel
 // ---------------------------------------------------------------------------------------------------------
-template <int MT>
 __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     decoder_cluster_kernel(const __grid_constant__ Params p) {
-  using S = Smem<MT>;
-  constexpr int M = S::M;
   extern __shared__ __align__(128) uint8_t dc_smem[];
-  __nv_bfloat16* sA0 = reinterpret_cast<__nv_bfloat16*>(dc_smem + S::oA0);
-  __nv_bfloat16* sA1 = reinterpret_cast<__nv_bfloat16*>(dc_smem + S::oA1);
-  __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(dc_smem + S::oH);
-  float* sY = reinterpret_cast<float*>(dc_smem + S::oY);
-  float* sRes = reinterpret_cast<float*>(dc_smem + S::oRes);
-  float* sPos = reinterpret_cast<float*>(dc_smem + S::oPos);
-  __nv_bfloat16* sSlab0 = reinterpret_cast<__nv_bfloat16*>(dc_smem + S::oSlab0);
-  __nv_bfloat16* sSlab1 = reinterpret_cast<__nv_bfloat16*>(dc_smem + S::oSlab1);
-  float* sStat = reinterpret_cast<float*>(dc_smem + S::oStat);
-  float* sRef = reinterpret_cast<float*>(dc_smem + S::oRef);
-  float* sOL = reinterpret_cast<float*>(dc_smem + S::oOL);
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(dc_smem + S::oQ);
-  int* sStage = reinterpret_cast<int*>(dc_smem + S::oStage);
-  float* sMl = reinterpret_cast<float*>(dc_smem + S::oMl);
-  float* sPO = reinterpret_cast<float*>(dc_smem + S::oScratch);
-  __nv_bfloat16* sK = reinterpret_cast<__nv_bfloat16*>(dc_smem + S::oScratch + S::kPoBytes);
-  float* sPart = reinterpret_cast<float*>(dc_smem + S::oScratch);
+  __nv_bfloat16* sTA = reinterpret_cast<__nv_bfloat16*>(dc_smem + sm::oTA);
+  float* sYF = reinterpret_cast<float*>(dc_smem + sm::oYF);
+  float* sPO = sYF;  // attention partial O aliases the pre-LayerNorm tile
+  float* sRes = reinterpret_cast<float*>(dc_smem + sm::oRes);
+  float* sPos = reinterpret_cast<float*>(dc_smem + sm::oPos);
+  float* sOL = reinterpret_cast<float*>(dc_smem + sm::oOL);
+  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(dc_smem + sm::oQ);
+  float* sRef = reinterpret_cast<float*>(dc_smem + sm::oRef);
+  int* sStage = reinterpret_cast<int*>(dc_smem + sm::oStage);
+  float* sMl = reinterpret_cast<float*>(dc_smem + sm::oMl);
+  __nv_bfloat16* sSlab = reinterpret_cast<__nv_bfloat16*>(dc_smem + sm::oSlab);
+  float* sParam = reinterpret_cast<float*>(dc_smem + sm::oParam);
+  float* sBq0 = reinterpret_cast<float*>(dc_smem + sm::oBq0);
+  __nv_bfloat16* sTB = reinterpret_cast<__nv_bfloat16*>(dc_smem + sm::oTB);
+  __nv_bfloat16* sTC = reinterpret_cast<__nv_bfloat16*>(dc_smem + sm::oTC);
+  __nv_bfloat16* sTD = reinterpret_cast<__nv_bfloat16*>(dc_smem + sm::oTD);
+  __nv_bfloat16* sH = reinterpret_cast<__nv_bfloat16*>(dc_smem + sm::oH);
+  float* sPart = reinterpret_cast<float*>(dc_smem + sm::oPart);
+  __nv_bfloat16* sK = sTB;  // key / value staging aliases [TB, TC, TD, H, PART]
+  __nv_bfloat16* sV = sK + static_cast<size_t>(sm::kKvCap) * kPQ;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const uint32_t rank = cluster_rank();
   const int cl = static_cast<int>(blockIdx.x) / kCluster;
   const int n0 = static_cast<int>(rank) * 32;  // this CTA's column slab / head
+  const uint32_t smem_base = smem_addr(dc_smem);
   pdl_wait();
 
   Tile tile;
   int total_tiles, max_len;
-  const bool have = find_tile<M>(p, cl, &tile, &total_tiles, &max_len);
+  const bool have = find_tile(p, cl, &tile, &total_tiles, &max_len);
   const int n_clusters = static_cast<int>(gridDim.x) / kCluster;
-  if (total_tiles > n_clusters || max_len > p.kv_cap) {  // cannot run: the host sized the launch wrongly
+  if (total_tiles > n_clusters || max_len > sm::kKvCap) {  // cannot run: the host sized the launch wrongly
     if (p.status != nullptr && blockIdx.x == 0 && tid == 0) *p.status = 1;
     return;
   }
   if (!have) return;  // whole cluster idle (uniform over its 8 CTAs)
-  __nv_bfloat16* sV = sK + static_cast<size_t>(p.kv_cap) * kPQ;
-  const unsigned n_tiles_u = static_cast<unsigned>(total_tiles);
+  const unsigned n_cta_u = static_cast<unsigned>(total_tiles) * kCluster;
+
+  // peer w of this warp (bf16 slab sends, FFN reduce-scatter) and all peers (fp32 slab sends from registers)
+  const uint32_t peer_w = map_peer(smem_base, static_cast<uint32_t>(warp));
+  auto peer_all = [&](int q) { return map_peer(smem_base, static_cast<uint32_t>(q)); };
+  auto bar_local = [&](int e) { return smem_base + static_cast<uint32_t>(sm::oBars + e * 8); };
+
+  if (tid == 0) {
+    for (int e = 0; e < kNumBars; ++e) mbar_init(bar_local(e), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto arm_all = [&]() {  // expected bytes of one layer's exchanges (thread 0)
+    mbar_arm(bar_local(E_ATT), kBf16TileBytes);
+    mbar_arm(bar_local(E_LN1), kF32TileBytes);
+    mbar_arm(bar_local(E_G), kBf16TileBytes);
+    mbar_arm(bar_local(E_LN2), kF32TileBytes);
+    mbar_arm(bar_local(E_RS), kF32TileBytes);
+    mbar_arm(bar_local(E_LN3), kF32TileBytes);
+    mbar_arm(bar_local(E_H1), kBf16TileBytes);
+    mbar_arm(bar_local(E_H2), kBf16TileBytes);
+  };
+  if (tid == 0) arm_all();
+  cluster_sync();  // every CTA's barriers are initialised and armed before any peer may send
+
+  // ---- per-layer parameter block -> shared memory (cp.async; issued one layer ahead) ----
+  auto stage_params = [&](int layer) {
+    float* dst = sParam + (layer & 1) * sm::kParamFloats;
+    const LayerW& W = p.L[layer];
+    auto cp = [&](int off, const float* src, int n) {  // n floats, multiple of 4, 16-byte aligned source
+      for (int i = tid; i < n / 4; i += kThreads) cp_async16(smem_addr(dst + off + i * 4), src + i * 4, true);
+    };
+    cp(PF::bo, W.bo + n0, 32);
+    cp(PF::bout, W.bout + n0, 32);
+    cp(PF::b2, W.b2 + n0, 32);
+    cp(PF::bb1, W.bb1 + n0, 32);
+    cp(PF::bb2, W.bb2 + n0, 32);
+    cp(PF::boff, W.boff + static_cast<int>(rank) * 2 * kLP, 2 * kLP);
+    cp(PF::boff + 2 * kLP, W.boff + kCluster * 2 * kLP + static_cast<int>(rank) * kLP, kLP);
+    cp(PF::b1, W.b1 + static_cast<int>(rank) * kFs, kFs);
+    if (layer + 1 < p.n_layers) {
+      const float* bq = p.L[layer + 1].bqkv;
+      cp(PF::bqkv, bq + n0, 32);
+      cp(PF::bqkv + 32, bq + kC + n0, 32);
+      cp(PF::bqkv + 64, bq + 2 * kC + n0, 32);
+    }
+    cp(PF::bb3, W.bb3, 4);
+    cp(PF::g1, W.g1, kC);
+    cp(PF::be1, W.be1, kC);
+    cp(PF::g2, W.g2, kC);
+    cp(PF::be2, W.be2, kC);
+    cp(PF::g3, W.g3, kC);
+    cp(PF::be3, W.be3, kC);
+    cp_async_commit();
+  };
+  stage_params(0);
 
   // ---------------- prologue: tile of x / pos / refer, operands of the first in-projection ----------------
   for (int i = tid; i < M * (kC / 4); i += kThreads) {
@@ -384,33 +400,41 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     a.y = float2_to_bf16x2(xv.z, xv.w);
     b.x = float2_to_bf16x2(xv.x + pv.x, xv.y + pv.y);
     b.y = float2_to_bf16x2(xv.z + pv.z, xv.w + pv.w);
-    *reinterpret_cast<uint2*>(sA0 + row * kPA + c4) = a;
-    *reinterpret_cast<uint2*>(sA1 + row * kPA + c4) = b;
-    if (c4 >= n0 && c4 < n0 + 32) {
-      *reinterpret_cast<float4*>(sRes + row * 32 + (c4 - n0)) = xv;
-      *reinterpret_cast<float4*>(sPos + row * 32 + (c4 - n0)) = pv;
-    }
+    *reinterpret_cast<uint2*>(sTC + row * kPA + c4) = a;   // x       (operand of v)
+    *reinterpret_cast<uint2*>(sTB + row * kPA + c4) = b;   // x + pos (operand of q, k)
+    *reinterpret_cast<float4*>(sPos + row * kC + c4) = pv;
+    if (c4 >= n0 && c4 < n0 + 32) *reinterpret_cast<float4*>(sRes + row * 32 + (c4 - n0)) = xv;
   }
   for (int i = tid; i < M * 4; i += kThreads) {
     const int row = i >> 2;
     sRef[i] = row < tile.n ? p.refer0[static_cast<int64_t>(tile.row0 + row) * 4 + (i & 3)] : 0.5f;
   }
+  // (the parameter block holds the NEXT layer's in-projection bias; layer 0's is read directly)
+  if (tid < 96) sBq0[tid] = __ldg(p.L[0].bqkv + (tid >> 5) * kC + n0 + (tid & 31));
   __syncthreads();
 
-  // q, k (from x + pos) and v (from x) of THIS head for the tile's rows (transformer.py:637-638): q stays in
-  // shared memory, k / v go to global memory for the other clusters.
-  auto qkv_proj = [&](const LayerW& W, int for_layer) {
+  // In-projection of the next self-attention for the tile's rows (transformer.py:637-638): q, k from x + pos (TB),
+  // v from x (TC), this head only; q stays in shared memory, k / v go to global memory for the other clusters.
+  // 12 n8-tiles x 2 m-tiles = 24 warp tasks, three per warp.
+  uint4 bq[3][8];
+  auto qkv_load = [&](const LayerW& W) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int task = warp + kWarps * i, nt = task % 12;
+      const int wrow = (nt >> 2) * kC + n0 + (nt & 3) * 8;
+      load_b<8>(bq[i], W.wqkv + static_cast<int64_t>(wrow + g) * kC + t * 8, true);
+    }
+  };
+  auto qkv_compute = [&](const float* bias /* q|k|v of this head, 96 floats */, int for_layer) {
     __nv_bfloat16* kv_w = p.kv + static_cast<size_t>(for_layer & 1) * p.rows_pad * (2 * kC);
-    for (int task = warp; task < 12 * MT; task += kWarps) {
-      const int nt = task % 12, mt = task / 12;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const int task = warp + kWarps * i, nt = task % 12, mt = task / 12;
       const int sec = nt >> 2, j = nt & 3;  // section 0 = q, 1 = k, 2 = v
-      const int wrow = sec * kC + n0 + j * 8;
-      uint4 b[8];
-      load_b<8>(b, W.wqkv + static_cast<int64_t>(wrow + g) * kC + t * 8, true);
       float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
-      mma_tiles<8, 1>(acc, (sec == 2 ? sA0 : sA1) + (mt * 16) * kPA, kPA, b, lane);
+      mma_tiles<8, 1>(acc, (sec == 2 ? sTC : sTB) + (mt * 16) * kPA, kPA, bq[i], lane);
       const int col = j * 8 + 2 * t;
-      const float b0 = __ldg(W.bqkv + wrow + 2 * t), b1 = __ldg(W.bqkv + wrow + 2 * t + 1);
+      const float b0 = bias[sec * 32 + col], b1 = bias[sec * 32 + col + 1];
       const int r0 = mt * 16 + g, r1 = r0 + 8;
       const uint32_t v0 = float2_to_bf16x2(acc[0][0] + b0, acc[0][1] + b1);
       const uint32_t v1 = float2_to_bf16x2(acc[0][2] + b0, acc[0][3] + b1);
@@ -424,24 +448,100 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
       }
     }
   };
-  qkv_proj(p.L[0], 0);
-  grid_arrive(p.grid_bar, rank);
+  // one 32-column bf16 slab GEMM with ReLU (box-head hidden layers): warp task = (n8-tile w & 3, m-tile w >> 2)
+  auto relu_slab = [&](const __nv_bfloat16* sA, const uint4 (&b)[8], const float* bias32) {
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    mma_tiles<8, 1>(acc, sA + ((warp >> 2) * 16) * kPA, kPA, b, lane);
+    const int col = (warp & 3) * 8 + 2 * t, r0 = (warp >> 2) * 16 + g;
+    const float b0 = bias32[col], b1 = bias32[col + 1];
+    *reinterpret_cast<uint32_t*>(sSlab + r0 * 32 + col) = float2_to_bf16x2(fmaxf(acc[0][0] + b0, 0.f), fmaxf(acc[0][1] + b1, 0.f));
+    *reinterpret_cast<uint32_t*>(sSlab + (r0 + 8) * 32 + col) = float2_to_bf16x2(fmaxf(acc[0][2] + b0, 0.f), fmaxf(acc[0][3] + b1, 0.f));
+  };
+  // send this CTA's bf16 slab (sSlab [M][32]) into columns [n0, n0+32) of tile `tile_off` of every CTA: warp w ->
+  // peer w, 16-byte chunks; completes bytes on exchange barrier e of the receiver
+  auto send_slab = [&](size_t tile_off, int e) {
+    const uint32_t dst = peer_w + static_cast<uint32_t>(tile_off), rbar = peer_w + static_cast<uint32_t>(sm::oBars + e * 8);
+    for (int c = lane; c < M * 4; c += 32) {
+      const int row = c >> 2, part = c & 3;
+      const uint4 v = *reinterpret_cast<const uint4*>(sSlab + row * 32 + part * 8);
+      st_async_v4(dst + static_cast<uint32_t>((row * kPA + n0 + part * 8) * 2), rbar, v.x, v.y, v.z, v.w);
+    }
+  };
+  // 32-column fp32 slab GEMM over K = 256 whose pre-LayerNorm result (+ bias + residual) goes STRAIGHT from the
+  // accumulator registers to the pre-LN tile of all 8 CTAs (one 16-byte st.async per peer and lane)
+  auto preln_slab = [&](const __nv_bfloat16* sA, const uint4 (&b)[8], const float* bias32, int e) {
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    mma_tiles<8, 1>(acc, sA + ((warp >> 2) * 16) * kPA, kPA, b, lane);
+    const int col = (warp & 3) * 8 + 2 * t, r0 = (warp >> 2) * 16 + g;
+    const float b0 = bias32[col], b1 = bias32[col + 1];
+    const float c[4] = {acc[0][0] + b0 + sRes[r0 * 32 + col], acc[0][1] + b1 + sRes[r0 * 32 + col + 1],
+                        acc[0][2] + b0 + sRes[(r0 + 8) * 32 + col], acc[0][3] + b1 + sRes[(r0 + 8) * 32 + col + 1]};
+    int rr, cc;
+    const float4 v = pair_rows(c, lane, &rr, &cc);
+    const uint32_t off = static_cast<uint32_t>(sm::oYF + (((warp >> 2) * 16 + rr) * kPY + n0 + (warp & 3) * 8 + cc) * 4);
+#pragma unroll
+    for (int q = 0; q < kCluster; ++q)
+      st_async_v4(peer_all(q) + off, peer_all(q) + static_cast<uint32_t>(sm::oBars + e * 8), __float_as_uint(v.x),
+                  __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+  };
+  // LayerNorm of the full rows of the received pre-LN tile (two-pass, fp32): warp w normalises rows w, w+8, ...;
+  // lane l owns columns [8 l, 8 l + 8). emit(row, col0, values[8]).
+  auto layernorm_rows = [&](const float* gamma, const float* beta, auto emit) {
+#pragma unroll
+    for (int i = 0; i < M / kWarps; ++i) {
+      const int row = warp + i * kWarps;
+      const float4 a = *reinterpret_cast<const float4*>(sYF + row * kPY + lane * 8);
+      const float4 b = *reinterpret_cast<const float4*>(sYF + row * kPY + lane * 8 + 4);
+      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+      const float mean = warp_sum(s) * (1.0f / kC);
+      float q2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v[k] -= mean;
+        q2 = fmaf(v[k], v[k], q2);
+      }
+      const float rstd = rsqrtf(warp_sum(q2) * (1.0f / kC) + p.eps);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = v[k] * rstd * gamma[lane * 8 + k] + beta[lane * 8 + k];
+      if ((lane >> 2) == static_cast<int>(rank)) {  // the four lanes that hold this CTA's residual slab
+        *reinterpret_cast<float4*>(sRes + row * 32 + (lane & 3) * 8) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(sRes + row * 32 + (lane & 3) * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+      emit(row, lane * 8, v);
+    }
+  };
+  auto pack8 = [](const float (&v)[8]) {
+    return make_uint4(float2_to_bf16x2(v[0], v[1]), float2_to_bf16x2(v[2], v[3]), float2_to_bf16x2(v[4], v[5]),
+                      float2_to_bf16x2(v[6], v[7]));
+  };
+
+  qkv_load(p.L[0]);
+  qkv_compute(sBq0, 0);
+  grid_arrive(p.grid_bar);
 
   const float sl2 = rsqrtf(static_cast<float>(kDh)) * 1.4426950408889634f;  // softmax in base 2 (attention.cu)
   const int ps = static_cast<int>(p.v_pos_stride);
-
   const bool prof = p.profile != nullptr && blockIdx.x == 0 && tid == 0;
   int mark_i = 0;
   auto mark = [&](int layer) {
     if (prof && mark_i < 16) p.profile[layer * 16 + mark_i] = globaltimer_ns();
     ++mark_i;
   };
+
   for (int layer = 0; layer < p.n_layers; ++layer) {
     const LayerW& W = p.L[layer];
     const bool last = layer + 1 == p.n_layers;
+    const uint32_t par = static_cast<uint32_t>(layer & 1);
+    const float* P = sParam + (layer & 1) * sm::kParamFloats;
     mark_i = 0;
-    mark(layer);   // 0: layer start (before the grid barrier)
-    grid_wait(p.grid_bar, n_tiles_u * static_cast<unsigned>(layer + 1), rank);
+    mark(layer);   // 0: layer start
+    if (!last) stage_params(layer + 1);   // (this layer's block was requested one layer ago)
+    uint4 bo[8];   // out_proj fragments: requested before the grid barrier
+    load_b<8>(bo, W.wo + static_cast<int64_t>(n0 + (warp & 3) * 8 + g) * kC + t * 8, true);
+    grid_wait(p.grid_bar, n_cta_u * static_cast<unsigned>(layer + 1));
     if (last) pdl_trigger();
     mark(layer);   // 1: grid barrier passed
 
@@ -458,11 +558,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         cp_async16(smem_addr(sV + key * kPQ + c * 8), src + kC, ok);
       }
       cp_async_commit();
-      cp_async_wait<0>();
+      cp_async_wait<0>();   // (also this layer's parameter block, and the next one's if it is already there)
       __syncthreads();
       mark(layer);   // 2: K/V staged
-      constexpr int NS = kWarps / MT;  // key splits
-      const int mt = warp % MT, split = warp / MT;
+      constexpr int NS = 4;  // key splits: warp = split * 2 + m-tile
+      const int mt = warp & 1, split = warp >> 1;
       uint32_t qa[2][4];
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks)
@@ -527,7 +627,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       }
-      // merge the NS key-range partials of every m-tile
+      // merge the four key-range partials of each m-tile
       l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
       l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
       l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
@@ -545,16 +645,16 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         *reinterpret_cast<float2*>(po + (g + 8) * 32 + n * 8 + 2 * t) = make_float2(o[n][2], o[n][3]);
       }
       __syncthreads();
-      for (int idx = tid; idx < M * 8; idx += kThreads) {
-        const int row = idx >> 3, c4 = (idx & 7) * 4;
+      {
+        const int row = tid >> 3, c4 = (tid & 7) * 4;   // 256 threads = 32 rows x 8 column quads
         const int mtr = row >> 4, r16 = row & 15;
         float Mx = -INFINITY;
 #pragma unroll
-        for (int s2 = 0; s2 < NS; ++s2) Mx = fmaxf(Mx, sMl[((s2 * MT + mtr) * 16 + r16) * 2]);
+        for (int s2 = 0; s2 < NS; ++s2) Mx = fmaxf(Mx, sMl[((s2 * 2 + mtr) * 16 + r16) * 2]);
         float Lsum = 0.0f, acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
         for (int s2 = 0; s2 < NS; ++s2) {
-          const int w2 = s2 * MT + mtr;
+          const int w2 = s2 * 2 + mtr;
           const float mw = sMl[(w2 * 16 + r16) * 2];
           const float a = mw == -INFINITY ? 0.0f : exp2f((mw - Mx) * sl2);
           Lsum = fmaf(a, sMl[(w2 * 16 + r16) * 2 + 1], Lsum);
@@ -568,68 +668,72 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         uint2 pk;
         pk.x = float2_to_bf16x2(acc[0] * inv, acc[1] * inv);
         pk.y = float2_to_bf16x2(acc[2] * inv, acc[3] * inv);
-        *reinterpret_cast<uint2*>(sSlab0 + row * 32 + c4) = pk;
+        *reinterpret_cast<uint2*>(sSlab + row * 32 + c4) = pk;
       }
       __syncthreads();
       mark(layer);   // 3: attention computed
-      broadcast_slab<M>(sSlab0, sA0, n0, warp, lane);
-      cluster_sync();
-      mark(layer);   // 4: attention tile exchanged
+      send_slab(sm::oTA, E_ATT);
+      mbar_wait(bar_local(E_ATT), par);
+      mark(layer);   // 4: attention tile received
     }
 
-    // ======================= out_proj + residual + LayerNorm1 (transformer.py:638-641) =======================
-    gemm_slab32<MT, false>(sA0, W.wo, n0, W.bo, sRes, sY, nullptr, warp, lane);
-    __syncthreads();
-    mark(layer);   // 5: out_proj GEMM
-    cluster_layernorm<MT>(sY, sStat, W.g1 + n0, W.be1 + n0, p.eps, rank, warp, lane, [&](int row, int c, float v) {
-      sRes[row * 32 + c] = v;
-      sSlab0[row * 32 + c] = __float2bfloat16_rn(v + sPos[row * 32 + c]);  // cross-attention query = x + pos (:644)
-    });
-    __syncthreads();
-    mark(layer);   // 6: LayerNorm1 (stats exchange + normalise)
-    broadcast_slab<M>(sSlab0, sA1, n0, warp, lane);
-    cluster_sync();
-    mark(layer);   // 7: x1 + pos exchanged
-
-    // ======================= MSDeformAttn of head `rank` (transformer.py:268-285) =======================
-    // offsets | logits of this head: 24 + 12 = 36 projection rows -> 5 n8-tiles x 2 m-groups = 10 warp tasks
-    {
-      constexpr int NM = MT / 2;
-      for (int task = warp; task < 10; task += kWarps) {
-        const int j = task % 5, mg = task / 5;
-        const int n = j * 8 + g;  // projection row of this head owned by the lane
+    // ======================= out_proj + residual -> LayerNorm1 (transformer.py:638-641) =======================
+    preln_slab(sTA, bo, P + PF::bo, E_LN1);
+    mark(layer);   // 5: out_proj GEMM sent
+    // offsets | logits fragments of this head (24 + 12 = 36 projection rows -> 5 n8-tiles x 2 m-tiles = 10 warp
+    // tasks: warps 0, 1 take a second one), requested before the LayerNorm exchange completes
+    uint4 bf[2][8];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int task = warp + kWarps * i;
+      if (task < 10) {
+        const int n = (task % 5) * 8 + g;  // projection row of this head owned by the lane
         const bool ok = n < 3 * kLP;
         const int src = n < 2 * kLP ? static_cast<int>(rank) * 2 * kLP + n : kCluster * 2 * kLP + static_cast<int>(rank) * kLP + (n - 2 * kLP);
-        uint4 b[8];
-        load_b<8>(b, W.woff + static_cast<int64_t>(ok ? src : 0) * kC + t * 8, ok);
-        float acc[NM][4];
+        load_b<8>(bf[i], W.woff + static_cast<int64_t>(ok ? src : 0) * kC + t * 8, ok);
+      }
+    }
+    mbar_wait(bar_local(E_LN1), par);
+    layernorm_rows(P + PF::g1, P + PF::be1, [&](int row, int c0, float (&v)[8]) {
+      const float4 pa = *reinterpret_cast<const float4*>(sPos + row * kC + c0);
+      const float4 pb = *reinterpret_cast<const float4*>(sPos + row * kC + c0 + 4);
+      const float q[8] = {v[0] + pa.x, v[1] + pa.y, v[2] + pa.z, v[3] + pa.w, v[4] + pb.x, v[5] + pb.y, v[6] + pb.z, v[7] + pb.w};
+      *reinterpret_cast<uint4*>(sTB + row * kPA + c0) = pack8(q);   // cross-attention query = x + pos (:644)
+    });
+    __syncthreads();
+    mark(layer);   // 6: LayerNorm1
+
+    // ======================= MSDeformAttn of head `rank` (transformer.py:268-285) =======================
+    uint4 bout[8];   // output_proj fragments: in flight during the gather
+    {
 #pragma unroll
-        for (int i = 0; i < NM; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
-        mma_tiles<8, NM>(acc, sA1 + (mg * NM * 16) * kPA, kPA, b, lane);
-        const int c0 = j * 8 + 2 * t;  // output column pair; bias of columns c0, c0 + 1
-        auto bias_of = [&](int c) {
-          if (c >= 3 * kLP) return 0.0f;
-          const int s2 = c < 2 * kLP ? static_cast<int>(rank) * 2 * kLP + c : kCluster * 2 * kLP + static_cast<int>(rank) * kLP + (c - 2 * kLP);
-          return __ldg(W.boff + s2);
-        };
-        const float b0 = bias_of(c0), b1 = bias_of(c0 + 1);
-#pragma unroll
-        for (int i = 0; i < NM; ++i) {
-          const int r0 = (mg * NM + i) * 16 + g, r1 = r0 + 8;
-          *reinterpret_cast<float2*>(sOL + r0 * kPO + c0) = make_float2(acc[i][0] + b0, acc[i][1] + b1);
-          *reinterpret_cast<float2*>(sOL + r1 * kPO + c0) = make_float2(acc[i][2] + b0, acc[i][3] + b1);
+      for (int i = 0; i < 2; ++i) {
+        const int task = warp + kWarps * i;
+        if (task < 10) {
+          const int j = task % 5, mg = task / 5;
+          float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+          mma_tiles<8, 1>(acc, sTB + (mg * 16) * kPA, kPA, bf[i], lane);
+          const int c0 = j * 8 + 2 * t;
+          // (columns 36..39 read the neighbouring parameters: they are never consumed)
+          const float b0 = P[PF::boff + c0], b1 = P[PF::boff + c0 + 1];
+          const int r0 = mg * 16 + g;
+          *reinterpret_cast<float2*>(sOL + r0 * kPO + c0) = make_float2(acc[0][0] + b0, acc[0][1] + b1);
+          *reinterpret_cast<float2*>(sOL + (r0 + 8) * kPO + c0) = make_float2(acc[0][2] + b0, acc[0][3] + b1);
         }
       }
+      load_b<8>(bout, W.wout + static_cast<int64_t>(n0 + (warp & 3) * 8 + g) * kC + t * 8, true);
       __syncthreads();
-      mark(layer);   // 8: offsets | logits projection
-      // gather: every warp takes M/8 rows, two at a time (lanes 0..15 / 16..31 own the 12 sampling points of the
-      // two rows; then 8 sub-groups of 4 lanes fetch 6 corner rows each per item: 12 128-bit loads in flight)
+      mark(layer);   // 7: offsets | logits projection
+      // gather: warp w owns rows w, w+8, w+16, w+24. Phase 1 (softmax, locations, corners) runs twice with lanes
+      // 0..15 / 16..31 on two rows each; phase 2 keeps all 4 x 6 corner rows of a lane in flight at once.
       const __nv_bfloat16* vbase = p.values + static_cast<int64_t>(tile.seq) * p.v_batch_stride + layer * kC + n0;
-      int* st_off = sStage + warp * (2 * kNU * 2);
-      float* st_w = reinterpret_cast<float*>(st_off + 2 * kNU);
-      for (int pr = 0; pr < MT; ++pr) {
+      int* st_off = sStage + warp * (4 * kNU * 2);
+      float* st_w = reinterpret_cast<float*>(st_off + 4 * kNU);
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
         const int half = lane >> 4, pl = lane & 15;
-        const int row = warp + kWarps * (2 * pr + half);
+        const int item = 2 * pr + half;
+        const int row = warp + kWarps * item;
         const bool okp = pl < kLP;
         const float* ol = sOL + row * kPO;
         const float lg = okp ? ol[2 * kLP + pl] : -INFINITY;
@@ -650,152 +754,159 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         if (okp) {
           const int level = pl / kNP;
           const Corners c = make_corners(lx, ly, p.lv.h[level], p.lv.w[level], p.lv.start[level], aw);
-          *reinterpret_cast<int4*>(st_off + half * kNU + pl * 4) =
+          *reinterpret_cast<int4*>(st_off + item * kNU + pl * 4) =
               make_int4(c.pos[0] < 0 ? -1 : c.pos[0] * ps, c.pos[1] < 0 ? -1 : c.pos[1] * ps,
                         c.pos[2] < 0 ? -1 : c.pos[2] * ps, c.pos[3] < 0 ? -1 : c.pos[3] * ps);
-          *reinterpret_cast<float4*>(st_w + half * kNU + pl * 4) = make_float4(c.w[0], c.w[1], c.w[2], c.w[3]);
+          *reinterpret_cast<float4*>(st_w + item * kNU + pl * 4) = make_float4(c.w[0], c.w[1], c.w[2], c.w[3]);
         }
-        __syncwarp();
-        const int sg = lane >> 2, sub = lane & 3;
-        uint4 v[2][6];
-        float wv[2][6];
+      }
+      __syncwarp();
+      const int sg = lane >> 2, sub = lane & 3;
+      uint4 v[4][6];
+      float wv[4][6];
 #pragma unroll
-        for (int it = 0; it < 2; ++it)
+      for (int it = 0; it < 4; ++it)
 #pragma unroll
-          for (int u = 0; u < 6; ++u) {
-            const int eo = st_off[it * kNU + sg + 8 * u];
-            wv[it][u] = st_w[it * kNU + sg + 8 * u];
-            v[it][u] = ldg128_if(vbase + eo + sub * 8, eo >= 0);
-          }
-        float acc[2][8];
-#pragma unroll
-        for (int it = 0; it < 2; ++it) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[it][k] = 0.0f;
-#pragma unroll
-          for (int u = 0; u < 6; ++u) fma_bf16x8(acc[it], v[it][u], wv[it][u]);
+        for (int u = 0; u < 6; ++u) {
+          const int eo = st_off[it * kNU + sg + 8 * u];
+          wv[it][u] = st_w[it * kNU + sg + 8 * u];
+          v[it][u] = ldg128_if(vbase + eo + sub * 8, eo >= 0);
         }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        float acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 6; ++u) fma_bf16x8(acc, v[it][u], wv[it][u]);
         // recursive halving across the 8 sub-groups (msda.cu phase 3): 8 -> 4 -> 2 -> 1 channels per lane
+        int ch = 0, n = 8;
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          int ch = 0, n = 8;
+        for (int o2 = 16; o2 >= 4; o2 >>= 1) {
+          n >>= 1;
+          const bool up = (lane & o2) != 0;
 #pragma unroll
-          for (int o2 = 16; o2 >= 4; o2 >>= 1) {
-            n >>= 1;
-            const bool up = (lane & o2) != 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (i < n) {
-                const float send = up ? acc[it][i] : acc[it][i + n];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, o2);
-                acc[it][i] = (up ? acc[it][i + n] : acc[it][i]) + recv;
-              }
+          for (int i = 0; i < 4; ++i) {
+            if (i < n) {
+              const float send = up ? acc[i] : acc[i + n];
+              const float recv = __shfl_xor_sync(0xffffffffu, send, o2);
+              acc[i] = (up ? acc[i + n] : acc[i]) + recv;
             }
-            ch += up ? n : 0;
           }
-          const float hi = __shfl_xor_sync(0xffffffffu, acc[it][0], 4);  // odd-channel partner
-          const int orow = warp + kWarps * (2 * pr + it);
-          if ((lane & 4) == 0)
-            *reinterpret_cast<uint32_t*>(sSlab0 + orow * 32 + sub * 8 + ch) = float2_to_bf16x2(acc[it][0], hi);
+          ch += up ? n : 0;
         }
-        __syncwarp();
+        const float hi = __shfl_xor_sync(0xffffffffu, acc[0], 4);  // odd-channel partner
+        const int orow = warp + kWarps * it;
+        if ((lane & 4) == 0) *reinterpret_cast<uint32_t*>(sSlab + orow * 32 + sub * 8 + ch) = float2_to_bf16x2(acc[0], hi);
       }
       __syncthreads();
-      mark(layer);   // 9: gather
-      broadcast_slab<M>(sSlab0, sA0, n0, warp, lane);
-      cluster_sync();
-      mark(layer);   // 10: gathered tile exchanged
+      mark(layer);   // 8: gather
+      send_slab(sm::oTA, E_G);
+      mbar_wait(bar_local(E_G), par);
+      mark(layer);   // 9: gathered tile received
     }
 
-    // ======================= output_proj + residual + LayerNorm2 (transformer.py:286, 646-647) =======================
-    gemm_slab32<MT, false>(sA0, W.wout, n0, W.bout, sRes, sY, nullptr, warp, lane);
-    __syncthreads();
-    cluster_layernorm<MT>(sY, sStat, W.g2 + n0, W.be2 + n0, p.eps, rank, warp, lane, [&](int row, int c, float v) {
-      sRes[row * 32 + c] = v;
-      sSlab0[row * 32 + c] = __float2bfloat16_rn(v);
+    // ======================= output_proj + residual -> LayerNorm2 (transformer.py:286, 646-647) =======================
+    preln_slab(sTA, bout, P + PF::bout, E_LN2);
+    // FFN fragments: linear1 = this CTA's 128 hidden columns (16 n8-tiles, two per warp); linear2 = the K slice of
+    // those 128 columns for the output columns [32 w, 32 w + 32) of cluster rank w (4 n8-tiles x 4 k-blocks)
+    uint4 b1f[2][8], b2f[4][4];
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+      load_b<8>(b1f[jj], W.w1 + static_cast<int64_t>(static_cast<int>(rank) * kFs + (warp * 2 + jj) * 8 + g) * kC + t * 8, true);
+    mbar_wait(bar_local(E_LN2), par);
+    layernorm_rows(P + PF::g2, P + PF::be2, [&](int row, int c0, float (&v)[8]) {
+      *reinterpret_cast<uint4*>(sTB + row * kPA + c0) = pack8(v);
     });
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+      load_b<4>(b2f[jj], W.w2 + static_cast<int64_t>(warp * 32 + jj * 8 + g) * (kFs * kCluster) + static_cast<int>(rank) * kFs + t * 8, true);
     __syncthreads();
-    broadcast_slab<M>(sSlab0, sA1, n0, warp, lane);
-    cluster_sync();
-    mark(layer);   // 11: output_proj + LayerNorm2 + exchange
+    mark(layer);   // 10: output_proj + LayerNorm2
 
     // ======================= FFN (transformer.py:576-580) =======================
-    // linear1: this CTA's 128 hidden columns (16 n8-tiles, two per warp), ReLU, kept in shared memory
-    {
 #pragma unroll
-      for (int jj = 0; jj < 2; ++jj) {
-        const int nt = warp * 2 + jj;
-        const int hrow = static_cast<int>(rank) * kFs + nt * 8;
-        uint4 b[8];
-        load_b<8>(b, W.w1 + static_cast<int64_t>(hrow + g) * kC + t * 8, true);
-        float acc[MT][4];
+    for (int jj = 0; jj < 2; ++jj) {
+      const int nt = warp * 2 + jj;
+      float acc[2][4];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
-        mma_tiles<8, MT>(acc, sA1, kPA, b, lane);
-        const float b0 = __ldg(W.b1 + hrow + 2 * t), b1 = __ldg(W.b1 + hrow + 2 * t + 1);
-        const int col = nt * 8 + 2 * t;
+      for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+      mma_tiles<8, 2>(acc, sTB, kPA, b1f[jj], lane);
+      const int col = nt * 8 + 2 * t;
+      const float b0 = P[PF::b1 + col], b1 = P[PF::b1 + col + 1];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) {
-          *reinterpret_cast<uint32_t*>(sH + (i * 16 + g) * kPH + col) =
-              float2_to_bf16x2(fmaxf(acc[i][0] + b0, 0.0f), fmaxf(acc[i][1] + b1, 0.0f));
-          *reinterpret_cast<uint32_t*>(sH + (i * 16 + g + 8) * kPH + col) =
-              float2_to_bf16x2(fmaxf(acc[i][2] + b0, 0.0f), fmaxf(acc[i][3] + b1, 0.0f));
-        }
+      for (int i = 0; i < 2; ++i) {
+        *reinterpret_cast<uint32_t*>(sH + (i * 16 + g) * kPH + col) =
+            float2_to_bf16x2(fmaxf(acc[i][0] + b0, 0.0f), fmaxf(acc[i][1] + b1, 0.0f));
+        *reinterpret_cast<uint32_t*>(sH + (i * 16 + g + 8) * kPH + col) =
+            float2_to_bf16x2(fmaxf(acc[i][2] + b0, 0.0f), fmaxf(acc[i][3] + b1, 0.0f));
       }
-      __syncthreads();
-      mark(layer);   // 12: FFN linear1
-      // linear2, split along K: partial[M, 256] = h[:, own 128] . W2[:, own 128]^T; warp w computes output columns
-      // [32 w, 32 w + 32) = the slab of cluster rank w and sends them there (reduce-scatter through DSMEM)
-      const uint32_t part_peer = map_peer(smem_addr(sPart), static_cast<uint32_t>(warp));
+    }
+    __syncthreads();
+    mark(layer);   // 11: FFN linear1
+    // linear2, split along K: partial[M, 256] = h[:, own 128] . W2[:, own 128]^T; warp w's 32 output columns go to
+    // cluster rank w (reduce-scatter through DSMEM, 16 bytes per store)
+    {
+      const uint32_t rbar = peer_w + static_cast<uint32_t>(sm::oBars + E_RS * 8);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
-        const int ncol = warp * 32 + jj * 8;
-        uint4 b[4];
-        load_b<4>(b, W.w2 + static_cast<int64_t>(ncol + g) * (kFs * kCluster) + static_cast<int>(rank) * kFs + t * 8, true);
-        float acc[MT][4];
+        float acc[2][4];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
-        mma_tiles<4, MT>(acc, sH, kPH, b, lane);
+        for (int i = 0; i < 2; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+        mma_tiles<4, 2>(acc, sH, kPH, b2f[jj], lane);
 #pragma unroll
-        for (int i = 0; i < MT; ++i) {
-          const int r0 = i * 16 + g, r1 = r0 + 8;
-          const int c = jj * 8 + 2 * t;
-          st_peer_v2f(part_peer + static_cast<uint32_t>(((rank * M + r0) * 32 + c) * 4), acc[i][0], acc[i][1]);
-          st_peer_v2f(part_peer + static_cast<uint32_t>(((rank * M + r1) * 32 + c) * 4), acc[i][2], acc[i][3]);
+        for (int i = 0; i < 2; ++i) {
+          int rr, cc;
+          const float4 v = pair_rows(acc[i], lane, &rr, &cc);
+          const uint32_t off = static_cast<uint32_t>(sm::oPart + ((rank * M + i * 16 + rr) * 32 + jj * 8 + cc) * 4);
+          st_async_v4(peer_w + off, rbar, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
         }
       }
-      cluster_sync();
-      mark(layer);   // 13: FFN linear2 (split-K) + reduce-scatter
-      for (int i = tid; i < M * 32; i += kThreads) {
-        const int row = i >> 5, c = i & 31;
-        float s2 = __ldg(W.b2 + n0 + c) + sRes[row * 32 + c];
-#pragma unroll
-        for (int src = 0; src < kCluster; ++src) s2 += sPart[(src * M + row) * 32 + c];  // fixed order: deterministic
-        sY[row * kPY + c] = s2;
-      }
-      __syncthreads();
-      cluster_layernorm<MT>(sY, sStat, W.g3 + n0, W.be3 + n0, p.eps, rank, warp, lane, [&](int row, int c, float v) {
-        sRes[row * 32 + c] = v;
-        sSlab0[row * 32 + c] = __float2bfloat16_rn(v);
-        sSlab1[row * 32 + c] = __float2bfloat16_rn(v + sPos[row * 32 + c]);
-      });
-      __syncthreads();
-      broadcast_slab<M>(sSlab0, sA0, n0, warp, lane);
-      if (!last) broadcast_slab<M>(sSlab1, sA1, n0, warp, lane);
-      cluster_sync();
-      mark(layer);   // 14: LayerNorm3 + exchange
     }
+    mark(layer);   // 12: FFN linear2 partials sent
+    mbar_wait(bar_local(E_RS), par);
+    {
+      // sum of the 8 partial slabs (fixed order: deterministic) + bias + residual -> pre-LN slab, sent to all CTAs
+      const int row = tid >> 3, c4 = (tid & 7) * 4;
+      float4 s4 = *reinterpret_cast<const float4*>(P + PF::b2 + c4);
+      const float4 r4 = *reinterpret_cast<const float4*>(sRes + row * 32 + c4);
+      s4.x += r4.x; s4.y += r4.y; s4.z += r4.z; s4.w += r4.w;
+#pragma unroll
+      for (int src = 0; src < kCluster; ++src) {
+        const float4 q4 = *reinterpret_cast<const float4*>(sPart + (src * M + row) * 32 + c4);
+        s4.x += q4.x; s4.y += q4.y; s4.z += q4.z; s4.w += q4.w;
+      }
+      const uint32_t off = static_cast<uint32_t>(sm::oYF + (row * kPY + n0 + c4) * 4);
+#pragma unroll
+      for (int q = 0; q < kCluster; ++q)
+        st_async_v4(peer_all(q) + off, peer_all(q) + static_cast<uint32_t>(sm::oBars + E_LN3 * 8), __float_as_uint(s4.x),
+                    __float_as_uint(s4.y), __float_as_uint(s4.z), __float_as_uint(s4.w));
+    }
+    mark(layer);   // 13: reduce-scatter received, pre-LN slab sent
+    uint4 bh1[8];
+    load_b<8>(bh1, W.wb1 + static_cast<int64_t>(n0 + (warp & 3) * 8 + g) * kC + t * 8, true);
+    if (!last) qkv_load(p.L[layer + 1]);   // next in-projection fragments: in flight across the LayerNorm exchange
+    mbar_wait(bar_local(E_LN3), par);
+    layernorm_rows(P + PF::g3, P + PF::be3, [&](int row, int c0, float (&v)[8]) {
+      *reinterpret_cast<uint4*>(sTC + row * kPA + c0) = pack8(v);             // x3: operand of v, box head, scores
+      const float4 pa = *reinterpret_cast<const float4*>(sPos + row * kC + c0);
+      const float4 pb = *reinterpret_cast<const float4*>(sPos + row * kC + c0 + 4);
+      const float q[8] = {v[0] + pa.x, v[1] + pa.y, v[2] + pa.z, v[3] + pa.w, v[4] + pb.x, v[5] + pb.y, v[6] + pb.z, v[7] + pb.w};
+      *reinterpret_cast<uint4*>(sTB + row * kPA + c0) = pack8(q);             // x3 + pos: operand of q, k
+    });
+    __syncthreads();
+    mark(layer);   // 14: LayerNorm3
 
     if (last) {
       // output embedding (fp32 + optional bf16) and the class-score head on the bf16-rounded row
       for (int row = warp; row < tile.n; row += kWarps) {
         const int64_t gr = static_cast<int64_t>(tile.row0 + row) * kC + n0 + lane;
         p.x_out[gr] = sRes[row * 32 + lane];
-        if (p.x_lp_out != nullptr) p.x_lp_out[gr] = sSlab0[row * 32 + lane];
+        if (p.x_lp_out != nullptr) p.x_lp_out[gr] = sTC[row * kPA + n0 + lane];
       }
       if (p.nc > 0) {
         for (int row = static_cast<int>(rank) + kCluster * warp; row < tile.n; row += kCluster * kWarps) {
-          const uint4 xv = *reinterpret_cast<const uint4*>(sA0 + row * kPA + lane * 8);
+          const uint4 xv = *reinterpret_cast<const uint4*>(sTC + row * kPA + lane * 8);
           const float2 x01 = bf16x2_to_float2(xv.x), x23 = bf16x2_to_float2(xv.y), x45 = bf16x2_to_float2(xv.z),
                        x67 = bf16x2_to_float2(xv.w);
           float best = -INFINITY;
@@ -822,33 +933,43 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         }
       }
     } else {
-      qkv_proj(p.L[layer + 1], layer + 1);
-      grid_arrive(p.grid_bar, rank);  // (its cluster barrier also frees sA1 for the box head below)
+      qkv_compute(P + PF::bqkv, layer + 1);
     }
-
-    mark(layer);   // 15: next in-projection + grid arrive (or outputs + scores)
     // ======================= box head + refinement (transformer.py:709) =======================
-    gemm_slab32<MT, true>(sA0, W.wb1, n0, W.bb1, nullptr, nullptr, sSlab0, warp, lane);
+    relu_slab(sTC, bh1, P + PF::bb1);
+    if (!last) grid_arrive(p.grid_bar); else __syncthreads();   // (the barrier's __syncthreads also completes sSlab)
+    mark(layer);   // 15: next in-projection + box-head layer 1 (+ grid arrive)
+    if (tid == 0 && !last) {   // next layer's expectations for the six exchanges that have completed in this layer
+      mbar_arm(bar_local(E_ATT), kBf16TileBytes);
+      mbar_arm(bar_local(E_LN1), kF32TileBytes);
+      mbar_arm(bar_local(E_G), kBf16TileBytes);
+      mbar_arm(bar_local(E_LN2), kF32TileBytes);
+      mbar_arm(bar_local(E_RS), kF32TileBytes);
+      mbar_arm(bar_local(E_LN3), kF32TileBytes);
+    }
+    send_slab(sm::oTD, E_H1);
+    uint4 bh2[8];
+    load_b<8>(bh2, W.wb2 + static_cast<int64_t>(n0 + (warp & 3) * 8 + g) * kC + t * 8, true);
+    mbar_wait(bar_local(E_H1), par);
+    __syncthreads();   // every warp has sent its part of sSlab before it is overwritten
+    if (tid == 0 && !last) mbar_arm(bar_local(E_H1), kBf16TileBytes);
+    relu_slab(sTD, bh2, P + PF::bb2);
     __syncthreads();
-    broadcast_slab<M>(sSlab0, sA1, n0, warp, lane);
-    cluster_sync();
-    gemm_slab32<MT, true>(sA1, W.wb2, n0, W.bb2, nullptr, nullptr, sSlab0, warp, lane);
-    __syncthreads();
-    broadcast_slab<M>(sSlab0, sA0, n0, warp, lane);
-    cluster_sync();
-    {
-      float w3[4][8];
+    send_slab(sm::oTC, E_H2);
+    float w3[4][8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(W.wb3 + j * kC + lane * 8));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(W.wb3 + j * kC + lane * 8 + 4));
-        w3[j][0] = a.x; w3[j][1] = a.y; w3[j][2] = a.z; w3[j][3] = a.w;
-        w3[j][4] = b.x; w3[j][5] = b.y; w3[j][6] = b.z; w3[j][7] = b.w;
-      }
-      const float bias = lane < 4 ? __ldg(W.bb3 + lane) : 0.0f;
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(W.wb3 + j * kC + lane * 8));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(W.wb3 + j * kC + lane * 8 + 4));
+      w3[j][0] = a.x; w3[j][1] = a.y; w3[j][2] = a.z; w3[j][3] = a.w;
+      w3[j][4] = b.x; w3[j][5] = b.y; w3[j][6] = b.z; w3[j][7] = b.w;
+    }
+    mbar_wait(bar_local(E_H2), par);
+    {
+      const float bias = lane < 4 ? P[PF::bb3 + lane] : 0.0f;
       float* rout = p.refer_out[layer];
       for (int row = warp; row < M; row += kWarps) {
-        const uint4 hv = *reinterpret_cast<const uint4*>(sA0 + row * kPA + lane * 8);
+        const uint4 hv = *reinterpret_cast<const uint4*>(sTC + row * kPA + lane * 8);
         const float2 h01 = bf16x2_to_float2(hv.x), h23 = bf16x2_to_float2(hv.y), h45 = bf16x2_to_float2(hv.z),
                      h67 = bf16x2_to_float2(hv.w);
         float d[4];
@@ -873,8 +994,10 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         }
       }
       __syncthreads();
+      if (tid == 0 && !last) mbar_arm(bar_local(E_H2), kBf16TileBytes);
     }
   }
+  cluster_sync();  // no CTA may exit while a peer can still address its shared memory
 }
 
 }  // namespace dc
@@ -887,14 +1010,13 @@ using namespace moyolo;
 // ---------------------------------------------------------------------------------------------------------
 namespace {
 
-template <int MT>
 int dc_configure(int* max_clusters, size_t* smem_out) {
   static DeviceOnce once;
   static int max_cl[64];
   const int dev = DeviceOnce::current();
-  const size_t smem = dc::Smem<MT>::total();
+  const size_t smem = dc::sm::kTotal;
   if (!once.done(dev)) {
-    cudaError_t e = cudaFuncSetAttribute(dc::decoder_cluster_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(dc::decoder_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "cudaFuncSetAttribute(decoder_cluster smem=%zu): %s", smem, cudaGetErrorString(e));
     cudaLaunchConfig_t cfg = {};
@@ -902,7 +1024,7 @@ int dc_configure(int* max_clusters, size_t* smem_out) {
     cfg.blockDim = dim3(dc::kThreads);
     cfg.dynamicSmemBytes = smem;
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, dc::decoder_cluster_kernel<MT>, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&n, dc::decoder_cluster_kernel, &cfg);
     if (e != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "cudaOccupancyMaxActiveClusters(decoder_cluster): %s", cudaGetErrorString(e));
     max_cl[dev] = n;
     once.set(dev);
@@ -915,13 +1037,13 @@ int dc_configure(int* max_clusters, size_t* smem_out) {
 }  // namespace
 
 extern "C" int moyolo_decoder_cluster_limits(int rows_per_tile, int* max_clusters, int* kv_cap) {
-  MOYOLO_REQUIRE(rows_per_tile == 32 || rows_per_tile == 64, MOYOLO_ERR_BAD_ARG, "decoder_cluster: rows_per_tile must be 32 or 64");
+  MOYOLO_REQUIRE(rows_per_tile == dc::M, MOYOLO_ERR_BAD_ARG, "decoder_cluster: rows_per_tile must be %d", dc::M);
   size_t smem = 0;
   int mc = 0;
-  const int rc = rows_per_tile == 32 ? dc_configure<2>(&mc, &smem) : dc_configure<4>(&mc, &smem);
+  const int rc = dc_configure(&mc, &smem);
   if (rc != MOYOLO_OK) return rc;
   if (max_clusters) *max_clusters = mc;
-  if (kv_cap) *kv_cap = rows_per_tile == 32 ? dc::Smem<2>::kv_cap() : dc::Smem<4>::kv_cap();
+  if (kv_cap) *kv_cap = dc::sm::kKvCap;
   return MOYOLO_OK;
 }
 
@@ -934,7 +1056,7 @@ extern "C" int moyolo_decoder_cluster_forward(const moyolo_decoder_cluster_t* a,
                  MOYOLO_ERR_BAD_ARG, "decoder_cluster: null pointer");
   MOYOLO_REQUIRE(a->nc >= 0 && a->nc <= dc::kMaxScoreNc, MOYOLO_ERR_UNSUPPORTED, "decoder_cluster: nc must be <= %d", dc::kMaxScoreNc);
   MOYOLO_REQUIRE(a->n_seq >= 1 && a->rows_pad >= 1, MOYOLO_ERR_BAD_SHAPE, "decoder_cluster: bad n_seq / rows_pad");
-  MOYOLO_REQUIRE(a->rows_per_tile == 32 || a->rows_per_tile == 64, MOYOLO_ERR_BAD_ARG, "decoder_cluster: rows_per_tile must be 32 or 64");
+  MOYOLO_REQUIRE(a->rows_per_tile == dc::M, MOYOLO_ERR_BAD_ARG, "decoder_cluster: rows_per_tile must be %d", dc::M);
   dc::Params p = {};
   for (int l = 0; l < a->n_layers; ++l) {
     const moyolo_decoder_layer_weights_t& s = a->layers[l];
@@ -970,12 +1092,10 @@ extern "C" int moyolo_decoder_cluster_forward(const moyolo_decoder_cluster_t* a,
   p.profile = static_cast<long long*>(a->profile);
   size_t smem = 0;
   int max_clusters = 0;
-  const bool small = a->rows_per_tile == 32;
-  rc = small ? dc_configure<2>(&max_clusters, &smem) : dc_configure<4>(&max_clusters, &smem);
+  rc = dc_configure(&max_clusters, &smem);
   if (rc != MOYOLO_OK) return rc;
-  p.kv_cap = small ? dc::Smem<2>::kv_cap() : dc::Smem<4>::kv_cap();
-  // tiles <= rows_pad / M + n_seq (every sequence may end with a partial tile)
-  const int64_t tiles_bound = (a->rows_pad + a->rows_per_tile - 1) / a->rows_per_tile + (a->n_seq - 1);
+  // tiles <= rows_pad / M + n_seq - 1 (every sequence may end with a partial tile)
+  const int64_t tiles_bound = (a->rows_pad + dc::M - 1) / dc::M + (a->n_seq - 1);
   MOYOLO_REQUIRE(tiles_bound <= max_clusters, MOYOLO_ERR_UNSUPPORTED,
                  "decoder_cluster: %lld row tiles need more than the %d co-resident clusters of this device",
                  (long long)tiles_bound, max_clusters);
@@ -985,9 +1105,6 @@ extern "C" int moyolo_decoder_cluster_forward(const moyolo_decoder_cluster_t* a,
     if (e != cudaSuccess) return fail(MOYOLO_ERR_CUDA, "decoder_cluster: memset of the grid barrier: %s", cudaGetErrorString(e));
   }
   const dim3 grid(static_cast<unsigned>(tiles_bound) * dc::kCluster);
-  if (small)
-    launch_k(dc::decoder_cluster_kernel<2>, grid, dim3(dc::kThreads), smem, st, p);
-  else
-    launch_k(dc::decoder_cluster_kernel<4>, grid, dim3(dc::kThreads), smem, st, p);
+  launch_k(dc::decoder_cluster_kernel, grid, dim3(dc::kThreads), smem, st, p);
   return check_launch("decoder_cluster_kernel");
 }

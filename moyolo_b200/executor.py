@@ -367,7 +367,7 @@ class ClusterDecoder:
                 getattr(spec_like, "nc", 1) <= 8 and _GEMM_ENGINE != _lib.GEMM_SIMT)
 
     def limits(self, rows_per_tile: int):
-        """(co-resident clusters, longest sequence in rows) for a tile height of 32 or 64 rows."""
+        """(co-resident clusters, longest sequence in rows) for the kernel's tile height of 32 rows."""
         if rows_per_tile not in self._limits:
             C = self._C
             mc, kc = C.c_int(0), C.c_int(0)
@@ -376,11 +376,12 @@ class ClusterDecoder:
         return self._limits[rows_per_tile]
 
     def tile_rows(self, rows_pad: int, n_seq: int, max_seq_rows: int) -> int:
-        """Tile height (32 or 64 rows) that fits the device for this frame size, 0 if neither does."""
-        for m in (32, 64):
-            max_clusters, kv_cap = self.limits(m)
-            if (rows_pad + m - 1) // m + n_seq - 1 <= max_clusters and max_seq_rows <= kv_cap:
-                return m
+        """Tile height (32 rows) if the frame fits the device (every row tile needs its own co-resident cluster and
+        a sequence's keys must fit the key / value staging), else 0."""
+        m = 32
+        max_clusters, kv_cap = self.limits(m)
+        if (rows_pad + m - 1) // m + n_seq - 1 <= max_clusters and max_seq_rows <= kv_cap:
+            return m
         return 0
 
     def run(self, x_in, pos, refer0, values, row_offsets, n_seq: int, rows_pad: int, rows_per_tile: int, x_out,
