@@ -472,10 +472,12 @@ int moyolo_frame_submit(const moyolo_frame_submit_t* d);
  * of the frame), the FFN (:576-580), the three LayerNorms, the box refinement sigmoid(bbox_head[i](x) +
  * inverse_sigmoid(refer)) (:709) and, after the last layer, the class-score head (:717-721).
  * Ragged lock-step batch: rows [row_offsets[s], row_offsets[s+1]) belong to sequence s (device array, int32).
- * A cluster of 8 CTAs owns `rows_per_tile` (32 or 64) query rows through all layers; the clusters meet at one
+ * A cluster of 8 CTAs owns `rows_per_tile` (= 32) query rows through all layers; the clusters meet at one
  * grid-wide barrier per layer (self-attention keys), so ALL clusters must be co-resident: the call fails with
  * MOYOLO_ERR_UNSUPPORTED when ceil(rows_pad / rows_per_tile) + n_seq - 1 exceeds moyolo_decoder_cluster_limits'
  * max_clusters; sequences longer than kv_cap rows are reported through *status (device int, set to 1).
+ * Measured on B200 this one-launch schedule is NOT faster than the launch-chained layers, so
+ * moyolo_b200.TrackEngine uses it only on request.
  * bf16 weights [out, in] row-major as in the checkpoint; fp32 biases / LayerNorm parameters; built for d_model 256,
  * 8 heads, d_ffn 1024, 3 levels x 4 points, nc <= 8.
  * -------------------------------------------------------------------------------------------*/
@@ -507,7 +509,7 @@ typedef struct {
   const int32_t* row_offsets;   /* device int32 [n_seq + 1]                                                         */
   int n_seq;
   int64_t rows_pad;
-  int rows_per_tile;            /* 32 or 64                                                                         */
+  int rows_per_tile;            /* 32                                                                               */
   void* grid_barrier;           /* device uint32, must be 0 when the kernel starts                                  */
   int reset_barrier;            /* 1: the call enqueues a memset of grid_barrier first                              */
   int* status;                  /* optional device int                                                              */

@@ -12,9 +12,10 @@
 //   * attention head r (self-attention and deformable gather are per head), and
 //   * the 32-column slab r of every 256-wide GEMM output (128-column slab of the FFN hidden layer).
 // GEMM operands (activation tiles [32, 256] bf16) are REPLICATED in the shared memory of the 8 CTAs. A stage
-// computes its slab and sends it to all 8 replicas with asynchronous distributed-shared-memory stores that
-// complete a transaction barrier in the RECEIVING CTA (st.async ... mbarrier::complete_tx): a receiver waits on
-// its own mbarrier for the expected byte count, there is no cluster-wide barrier in the layer loop. Buffers are
+// computes its slab, stages it in its own shared memory and sends it to all 8 replicas with bulk asynchronous
+// distributed-shared-memory copies (cp.async.bulk.shared::cluster.shared::cta, one row per thread) that complete a
+// transaction barrier in the RECEIVING CTA (mbarrier::complete_tx): a receiver waits on its own mbarrier for the
+// expected byte count, there is no cluster-wide barrier in the layer loop. Buffers are
 // re-used only along the dependency chain of the exchanges themselves (a peer can send exchange k + 1 only after
 // it received this CTA's part of exchange k), which is what makes the re-use race-free without extra handshakes.
 //   * LayerNorm: the pre-norm fp32 slab is sent to all peers, every CTA then normalises the full rows locally
@@ -110,7 +111,8 @@ constexpr size_t oSlab = oMl + size_t(kWarps) * 16 * 2 * 4;     // bf16 slab sta
 constexpr int kParamFloats = 1968;                        // see PF:: below
 constexpr size_t oParam = oSlab + size_t(M) * 32 * 2;     // 2 x per-layer parameter block (layer parity)
 constexpr size_t oBq0 = oParam + 2 * size_t(kParamFloats) * 4;  // in-projection bias of layer 0 (this head)
-constexpr size_t oBars = oBq0 + 96 * 4;                   // 8 mbarriers
+constexpr size_t oYs = oBq0 + 96 * 4;                     // fp32 slab staging [M][32] (source of the pre-LN bulk copies)
+constexpr size_t oBars = oYs + size_t(M) * 32 * 4;        // 8 mbarriers
 constexpr size_t oTB = (oBars + 8 * 8 + 127) / 128 * 128; // x + pos operand tiles (written locally by the LayerNorms)
 constexpr size_t oTC = oTB + kTile;                       // x3 tile (local) / box-head hidden 2 (received)
 constexpr size_t oTD = oTC + kTile;                       // box-head hidden 1 (received)
@@ -171,14 +173,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
-// 16-byte asynchronous store into a CTA of the cluster; completes 16 bytes on that CTA's mbarrier when it lands.
-__device__ __forceinline__ void st_async_v4(uint32_t remote_addr, uint32_t remote_bar, uint32_t x, uint32_t y, uint32_t z,
-                                            uint32_t w) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
-                   remote_addr),
-               "r"(x), "r"(y), "r"(z), "r"(w), "r"(remote_bar)
+// Bulk asynchronous copy (async proxy / TMA engine) of `bytes` (multiple of 16) from this CTA's shared memory into a
+// CTA of the cluster; completes the bytes on that CTA's mbarrier. Generic-proxy writes of the source must be made
+// visible to the async proxy first (fence_proxy_async by the writers, then a block barrier).
+__device__ __forceinline__ void bulk_to_peer(uint32_t remote_addr, uint32_t local_src, uint32_t bytes, uint32_t remote_bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(remote_addr),
+               "r"(local_src), "r"(bytes), "r"(remote_bar)
                : "memory");
 }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -238,18 +241,6 @@ __device__ __forceinline__ void mma_tiles(float (&acc)[NM][4], const __nv_bfloat
       mma_bf16_16816(acc[i], a1, b[kb].z, b[kb].w);
     }
   }
-}
-
-// C-fragment transpose inside lane pairs (t, t^1): afterwards an even-t lane holds row g, columns [2t, 2t+4) of the
-// n8-tile and an odd-t lane holds row g + 8, columns [2(t-1), 2(t-1)+4): one 16-byte vector per lane.
-__device__ __forceinline__ float4 pair_rows(const float (&c)[4], int lane, int* row_in_tile, int* col_in_tile) {
-  const bool even = (lane & 1) == 0;
-  const float x = __shfl_xor_sync(0xffffffffu, even ? c[2] : c[0], 1);
-  const float y = __shfl_xor_sync(0xffffffffu, even ? c[3] : c[1], 1);
-  const int g = lane >> 2, t = lane & 3;
-  *row_in_tile = even ? g : g + 8;
-  *col_in_tile = even ? 2 * t : 2 * (t - 1);
-  return even ? make_float4(c[0], c[1], x, y) : make_float4(x, y, c[2], c[3]);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
@@ -332,9 +323,6 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   if (!have) return;  // whole cluster idle (uniform over its 8 CTAs)
   const unsigned n_cta_u = static_cast<unsigned>(total_tiles) * kCluster;
 
-  // peer w of this warp (bf16 slab sends, FFN reduce-scatter) and all peers (fp32 slab sends from registers)
-  const uint32_t peer_w = map_peer(smem_base, static_cast<uint32_t>(warp));
-  auto peer_all = [&](int q) { return map_peer(smem_base, static_cast<uint32_t>(q)); };
   auto bar_local = [&](int e) { return smem_base + static_cast<uint32_t>(sm::oBars + e * 8); };
 
   if (tid == 0) {
@@ -459,13 +447,19 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
   };
   // send this CTA's bf16 slab (sSlab [M][32]) into columns [n0, n0+32) of tile `tile_off` of every CTA: warp w ->
   // peer w, 16-byte chunks; completes bytes on exchange barrier e of the receiver
-  auto send_slab = [&](size_t tile_off, int e) {
-    const uint32_t dst = peer_w + static_cast<uint32_t>(tile_off), rbar = peer_w + static_cast<uint32_t>(sm::oBars + e * 8);
-    for (int c = lane; c < M * 4; c += 32) {
-      const int row = c >> 2, part = c & 3;
-      const uint4 v = *reinterpret_cast<const uint4*>(sSlab + row * 32 + part * 8);
-      st_async_v4(dst + static_cast<uint32_t>((row * kPA + n0 + part * 8) * 2), rbar, v.x, v.y, v.z, v.w);
-    }
+  auto send_slab = [&](size_t tile_off, int e) {   // (callers: fence_proxy_async() + __syncthreads() after writing sSlab)
+    const int row = tid >> 3;
+    const uint32_t pb = map_peer(smem_base, static_cast<uint32_t>(tid & 7));
+    bulk_to_peer(pb + static_cast<uint32_t>(tile_off + (row * kPA + n0) * 2), smem_addr(sSlab + row * 32), 64u,
+                 pb + static_cast<uint32_t>(sm::oBars + e * 8));
+  };
+  // send this CTA's fp32 pre-LayerNorm slab (sYs [M][32], staged in shared memory) to the pre-LN tile of every CTA
+  float* sYs = reinterpret_cast<float*>(dc_smem + sm::oYs);
+  auto send_preln = [&](int e) {                  // (callers: fence_proxy_async() + __syncthreads() after writing sYs)
+    const int row = tid >> 3;
+    const uint32_t pb = map_peer(smem_base, static_cast<uint32_t>(tid & 7));
+    bulk_to_peer(pb + static_cast<uint32_t>(sm::oYF + (row * kPY + n0) * 4), smem_addr(sYs + row * 32), 128u,
+                 pb + static_cast<uint32_t>(sm::oBars + e * 8));
   };
   // 32-column fp32 slab GEMM over K = 256 whose pre-LayerNorm result (+ bias + residual) goes STRAIGHT from the
   // accumulator registers to the pre-LN tile of all 8 CTAs (one 16-byte st.async per peer and lane)
@@ -476,13 +470,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     const float b0 = bias32[col], b1 = bias32[col + 1];
     const float c[4] = {acc[0][0] + b0 + sRes[r0 * 32 + col], acc[0][1] + b1 + sRes[r0 * 32 + col + 1],
                         acc[0][2] + b0 + sRes[(r0 + 8) * 32 + col], acc[0][3] + b1 + sRes[(r0 + 8) * 32 + col + 1]};
-    int rr, cc;
-    const float4 v = pair_rows(c, lane, &rr, &cc);
-    const uint32_t off = static_cast<uint32_t>(sm::oYF + (((warp >> 2) * 16 + rr) * kPY + n0 + (warp & 3) * 8 + cc) * 4);
-#pragma unroll
-    for (int q = 0; q < kCluster; ++q)
-      st_async_v4(peer_all(q) + off, peer_all(q) + static_cast<uint32_t>(sm::oBars + e * 8), __float_as_uint(v.x),
-                  __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+    *reinterpret_cast<float2*>(sYs + r0 * 32 + col) = make_float2(c[0], c[1]);
+    *reinterpret_cast<float2*>(sYs + (r0 + 8) * 32 + col) = make_float2(c[2], c[3]);
+    fence_proxy_async();
+    __syncthreads();
+    send_preln(e);
   };
   // LayerNorm of the full rows of the received pre-LN tile (two-pass, fp32): warp w normalises rows w, w+8, ...;
   // lane l owns columns [8 l, 8 l + 8). emit(row, col0, values[8]).
@@ -670,6 +662,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         pk.y = float2_to_bf16x2(acc[2] * inv, acc[3] * inv);
         *reinterpret_cast<uint2*>(sSlab + row * 32 + c4) = pk;
       }
+      fence_proxy_async();
       __syncthreads();
       mark(layer);   // 3: attention computed
       send_slab(sm::oTA, E_ATT);
@@ -799,6 +792,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         const int orow = warp + kWarps * it;
         if ((lane & 4) == 0) *reinterpret_cast<uint32_t*>(sSlab + orow * 32 + sub * 8 + ch) = float2_to_bf16x2(acc[0], hi);
       }
+      fence_proxy_async();
       __syncthreads();
       mark(layer);   // 8: gather
       send_slab(sm::oTA, E_G);
@@ -847,7 +841,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     // linear2, split along K: partial[M, 256] = h[:, own 128] . W2[:, own 128]^T; warp w's 32 output columns go to
     // cluster rank w (reduce-scatter through DSMEM, 16 bytes per store)
     {
-      const uint32_t rbar = peer_w + static_cast<uint32_t>(sm::oBars + E_RS * 8);
+      float* sRs = reinterpret_cast<float*>(sTB);   // [8 destinations][M][32] fp32 staging (TB, TC are dead here)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         float acc[2][4];
@@ -856,12 +850,17 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         mma_tiles<4, 2>(acc, sH, kPH, b2f[jj], lane);
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          int rr, cc;
-          const float4 v = pair_rows(acc[i], lane, &rr, &cc);
-          const uint32_t off = static_cast<uint32_t>(sm::oPart + ((rank * M + i * 16 + rr) * 32 + jj * 8 + cc) * 4);
-          st_async_v4(peer_w + off, rbar, __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+          const int c = jj * 8 + 2 * t;
+          *reinterpret_cast<float2*>(sRs + (warp * M + i * 16 + g) * 32 + c) = make_float2(acc[i][0], acc[i][1]);
+          *reinterpret_cast<float2*>(sRs + (warp * M + i * 16 + g + 8) * 32 + c) = make_float2(acc[i][2], acc[i][3]);
         }
       }
+      fence_proxy_async();
+      __syncthreads();
+      const int row = tid >> 3, dst = tid & 7;
+      const uint32_t pb = map_peer(smem_base, static_cast<uint32_t>(dst));
+      bulk_to_peer(pb + static_cast<uint32_t>(sm::oPart + ((rank * M + row) * 32) * 4), smem_addr(sRs + (dst * M + row) * 32), 128u,
+                   pb + static_cast<uint32_t>(sm::oBars + E_RS * 8));
     }
     mark(layer);   // 12: FFN linear2 partials sent
     mbar_wait(bar_local(E_RS), par);
@@ -876,12 +875,11 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
         const float4 q4 = *reinterpret_cast<const float4*>(sPart + (src * M + row) * 32 + c4);
         s4.x += q4.x; s4.y += q4.y; s4.z += q4.z; s4.w += q4.w;
       }
-      const uint32_t off = static_cast<uint32_t>(sm::oYF + (row * kPY + n0 + c4) * 4);
-#pragma unroll
-      for (int q = 0; q < kCluster; ++q)
-        st_async_v4(peer_all(q) + off, peer_all(q) + static_cast<uint32_t>(sm::oBars + E_LN3 * 8), __float_as_uint(s4.x),
-                    __float_as_uint(s4.y), __float_as_uint(s4.z), __float_as_uint(s4.w));
+      *reinterpret_cast<float4*>(sYs + row * 32 + c4) = s4;
     }
+    fence_proxy_async();
+    __syncthreads();
+    send_preln(E_LN3);
     mark(layer);   // 13: reduce-scatter received, pre-LN slab sent
     uint4 bh1[8];
     load_b<8>(bh1, W.wb1 + static_cast<int64_t>(n0 + (warp & 3) * 8 + g) * kC + t * 8, true);
@@ -937,6 +935,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     }
     // ======================= box head + refinement (transformer.py:709) =======================
     relu_slab(sTC, bh1, P + PF::bb1);
+    fence_proxy_async();
     if (!last) grid_arrive(p.grid_bar); else __syncthreads();   // (the barrier's __syncthreads also completes sSlab)
     mark(layer);   // 15: next in-projection + box-head layer 1 (+ grid arrive)
     if (tid == 0 && !last) {   // next layer's expectations for the six exchanges that have completed in this layer
@@ -954,6 +953,7 @@ __global__ void __cluster_dims__(kCluster, 1, 1) __launch_bounds__(kThreads, 1)
     __syncthreads();   // every warp has sent its part of sSlab before it is overwritten
     if (tid == 0 && !last) mbar_arm(bar_local(E_H1), kBf16TileBytes);
     relu_slab(sTD, bh2, P + PF::bb2);
+    fence_proxy_async();
     __syncthreads();
     send_slab(sm::oTC, E_H2);
     float w3[4][8];

@@ -316,7 +316,10 @@ def bbox_head_ws(mp: MlpPack, ws, refer_in, refer_out) -> None:
 # ------------------------------------------------------------------------------------------------
 # Whole decoder in one launch (csrc/decoder_cluster.cu): the row-tile-persistent cluster kernel.
 # ------------------------------------------------------------------------------------------------
-CLUSTER_DECODER = os.environ.get("MOYOLO_CLUSTER_DECODER", "1") != "0"
+# Opt-in (MOYOLO_CLUSTER_DECODER=1 or TrackEngine(cluster_decoder=True)): measured on B200 the one-launch decoder
+# takes 237 us per MOT17 frame against ~200 us for the launch-chained layers it replaces (profiles/README.md,
+# "cluster decoder"), so the chain stays the default schedule.
+CLUSTER_DECODER = os.environ.get("MOYOLO_CLUSTER_DECODER", "0") == "1"
 
 
 class ClusterDecoder:
@@ -362,7 +365,7 @@ class ClusterDecoder:
     @staticmethod
     def supports(dt, spec_like) -> bool:
         """Static configuration check (d_model 256, 8 heads, d_ffn 1024, 3 levels x 4 points, bf16, nc <= 8)."""
-        return (CLUSTER_DECODER and dt == torch.bfloat16 and spec_like.d_model == 256 and spec_like.n_heads == 8 and
+        return (dt == torch.bfloat16 and spec_like.d_model == 256 and spec_like.n_heads == 8 and
                 spec_like.d_ffn == 1024 and spec_like.n_levels == 3 and spec_like.n_points == 4 and
                 getattr(spec_like, "nc", 1) <= 8 and _GEMM_ENGINE != _lib.GEMM_SIMT)
 

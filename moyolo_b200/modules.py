@@ -348,7 +348,8 @@ class _DecoderBase(nn.Module):
         dec_cls = []
         # Eval, one fixed positional embedding (the MOTR decoder), no masks: every layer up to eval_idx, the box
         # refinements and the score head run as ONE cluster kernel (csrc/decoder_cluster.cu) when the frame fits.
-        if (not self.training and fixed_pos is not None and mask is None and zero_rows is None and refer.shape[-1] == 4 and
+        if (ex.CLUSTER_DECODER and not self.training and fixed_pos is not None and mask is None and zero_rows is None and
+                refer.shape[-1] == 4 and
                 ex.ClusterDecoder.supports(dt, _Dims(C, packs[0].n_heads, packs[0].ffn1.w.shape[0], packs[0].msda.n_levels,
                                                      packs[0].msda.n_points, score_head[self.eval_idx].weight.shape[0]))):
             n_run = self.eval_idx + 1

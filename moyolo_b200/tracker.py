@@ -234,7 +234,8 @@ class TrackEngine:
         self.thr = (score_thresh, filter_thresh, miss_tolerance, iou_thresh)
         # whole decoder as one cluster kernel where the frame fits the device (see _cluster_rows)
         self._cd = None
-        if ex.ClusterDecoder.supports(self.W.dt, spec) and cluster_decoder is not False:
+        want_cd = ex.CLUSTER_DECODER if cluster_decoder is None else bool(cluster_decoder)
+        if want_cd and ex.ClusterDecoder.supports(self.W.dt, spec):
             self._cd = ex.ClusterDecoder(self.W.layers, self.W.bbox, self.shapes, self.W.score_w, self.W.score_b)
         elif cluster_decoder:
             raise ValueError("cluster_decoder=True needs bf16, d_model 256, 8 heads, d_ffn 1024, 3 levels x 4 points")
