@@ -216,6 +216,22 @@ def make_decoder_inputs(seed: int, B: int, Q: int, d_model: int, shapes):
     return embed, refer_logit, feats, query_pos
 
 
+def make_denoising_masks(seed: int, B: int, Q: int, Lv: int, n_groups: int = 2, group_size: int = 6, pad_frac: float = 0.2):
+    """Masks in the shapes the reference's training path produces: the [Q, Q] bool self-attention mask of the
+    denoising groups (ultralytics/models/utils/ops.py:363-375: matching queries cannot see the reconstruction
+    queries, the groups cannot see each other; True = masked) and a [B, Lv] bool value padding mask (True rows of
+    the value tensor are zeroed, transformer.py:265-266)."""
+    num_dn = n_groups * group_size
+    assert num_dn < Q
+    attn = torch.zeros(Q, Q, dtype=torch.bool)
+    attn[num_dn:, :num_dn] = True
+    for i in range(n_groups):
+        attn[group_size * i:group_size * (i + 1), group_size * (i + 1):num_dn] = True
+        attn[group_size * i:group_size * (i + 1), :group_size * i] = True
+    pad = torch.rand(B, Lv, generator=_gen(seed)) < pad_frac
+    return attn, pad
+
+
 def checksum(*tensors: torch.Tensor) -> float:
     """Order-sensitive float64 checksum used to verify regenerated inputs against a golden file."""
     acc = 0.0

@@ -157,6 +157,50 @@ def gen_layers(T):
                              checksum=syn.checksum(q, refer, feats, qpos)), out=o)
 
 
+MASKED_CASES = [   # attn_mask / padding_mask at layer and decoder level (transformer.py:637-645, models/utils/ops.py:363-375)
+    dict(name="layer_motr_masked", kind="layer", cls="MOTRDecoderLayer", seed=71, B=2, Q=50, shapes=syn.PYRAMIDS["tiny"], float_mask=False),
+    dict(name="layer_deformable_masked_f", kind="layer", cls="DeformableTransformerDecoderLayer", seed=72, B=1, Q=37,
+         shapes=syn.PYRAMIDS["tiny"], float_mask=True),
+    dict(name="decoder_motr_masked", kind="decoder", mode="motr", seed=73, B=2, Q=48, shapes=syn.PYRAMIDS["tiny"], nc=1),
+    dict(name="decoder_deformable_masked", kind="decoder", mode="deformable", seed=74, B=1, Q=40, shapes=syn.PYRAMIDS["tiny"], nc=1),
+]
+
+
+def masks_for(c):
+    attn, pad = syn.make_denoising_masks(c["seed"], c["B"], c["Q"], syn.level_sizes(c["shapes"]))
+    if c.get("float_mask"):   # additive float mask: nn.MultiheadAttention adds it to the scores
+        attn = torch.zeros(attn.shape).masked_fill(attn, float("-inf"))
+    return attn, pad
+
+
+def gen_masked(T):
+    for c in MASKED_CASES:
+        spec = syn.DecoderSpec(nc=c.get("nc", 1))
+        sd = syn.make_decoder_state(spec, WEIGHT_SEED)
+        shapes = [list(s) for s in c["shapes"]]
+        attn, pad = masks_for(c)
+        if c["kind"] == "layer":
+            m = getattr(T, c["cls"])(spec.d_model, spec.n_heads, spec.d_ffn, 0.0, torch.nn.ReLU(), spec.n_levels,
+                                     spec.n_points).eval()
+            m.load_state_dict(syn.sub_state(sd, "layers.1."))
+            q, refer, feats, qpos = syn.make_module_inputs(c["seed"], c["B"], c["Q"], spec.d_model, c["shapes"], 4, 1)
+            with torch.no_grad():
+                o = m(q, refer[:, :, 0], feats, shapes, pad, attn, qpos)
+            save(c["name"], dict(c, shapes=shapes, weight_seed=WEIGHT_SEED, checksum=syn.checksum(q, refer, feats, qpos)), out=o)
+        else:
+            dec, bbox, score, pos = build_ref_decoder(T, spec, sd, c["mode"])
+            embed, refer, feats, qpos = syn.make_decoder_inputs(c["seed"], c["B"], c["Q"], spec.d_model, c["shapes"])
+            with torch.no_grad():
+                if c["mode"] == "motr":
+                    b, s_, o = dec(embed, refer, feats, shapes, bbox, score, pos, attn_mask=attn, padding_mask=pad,
+                                   track_query_embed=qpos)
+                else:
+                    b, s_ = dec(embed, refer, feats, shapes, bbox, score, pos, attn_mask=attn, padding_mask=pad)
+                    o = torch.zeros(0)
+            save(c["name"], dict(c, shapes=shapes, weight_seed=WEIGHT_SEED,
+                                 checksum=syn.checksum(embed, refer, feats, qpos)), boxes=b, scores=s_, hs=o)
+
+
 def build_ref_decoder(T, spec, sd, mode):
     layer_cls = T.MOTRDecoderLayer if mode == "motr" else T.DeformableTransformerDecoderLayer
     layer = layer_cls(spec.d_model, spec.n_heads, spec.d_ffn, 0.0, torch.nn.ReLU(), spec.n_levels, spec.n_points)
@@ -335,6 +379,7 @@ def main():
     gen_msda(T)
     gen_layers(T)
     gen_decoders(T)
+    gen_masked(T)
     print("head-side goldens (full reference import with stubs)")
     head, qim, structures = ref_loader.load_full_reference()
     gen_kat0()

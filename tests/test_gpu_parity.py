@@ -801,3 +801,45 @@ def test_motr_msdeform_attn_my_softmax(dev, precision, tol):
         plain.precision = precision
         out2 = plain(q.to(dev), refer.to(dev), feats.to(dev), shapes).cpu().numpy()
         assert rel_rms(out2, ref_plain) < tol, (B, Q, pyr, "MSDeformAttn ignores my_softmax")
+
+
+# ------------------------------------------------------------------ a4 / a5 with attn_mask and padding_mask
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_masked_layers_and_decoders_vs_reference_golden(dev, precision):
+    """Self-attention mask (bool [Q, Q] as ultralytics/models/utils/ops.py:363-375 builds it, and the additive float
+    form nn.MultiheadAttention also takes) and value padding mask through the drop-in layer and decoder classes
+    (transformer.py:637-645, 265-266) against goldens minted from the unmodified reference."""
+    m, ops, syn, mg, tp = _mods()
+    for case in mg.MASKED_CASES:
+        meta, g = load_golden(case["name"])
+        spec = syn.DecoderSpec(nc=case.get("nc", 1))
+        sd = syn.make_decoder_state(spec, meta["weight_seed"])
+        attn, pad = mg.masks_for(case)
+        attn, pad = attn.to(dev), pad.to(dev)
+        if case["kind"] == "layer":
+            layer = getattr(m, case["cls"])(spec.d_model, spec.n_heads, spec.d_ffn, 0.0, torch.nn.ReLU(), spec.n_levels,
+                                            spec.n_points)
+            layer = _load_layer(m, syn, sd, "layers.1.", layer).to(dev)
+            layer.precision = precision
+            q, refer, feats, qpos = syn.make_module_inputs(case["seed"], case["B"], case["Q"], spec.d_model, case["shapes"], 4, 1)
+            out = layer(q.to(dev), refer[:, :, 0].to(dev), feats.to(dev), meta["shapes"], pad, attn, qpos.to(dev))
+            assert rel_rms(out.cpu().numpy(), g["out"]) < (FP32_TOL if precision == "fp32" else BF16_MODULE_TOL), case["name"]
+        else:
+            dec, bbox, score, pos = _build_decoder(m, syn, spec, sd, case["mode"], dev, precision)
+            embed, refer, feats, qpos = syn.make_decoder_inputs(case["seed"], case["B"], case["Q"], spec.d_model, case["shapes"])
+            args = (embed.to(dev), refer.to(dev), feats.to(dev), meta["shapes"], bbox, score, pos)
+            if case["mode"] == "motr":
+                b, s, _ = dec(*args, attn_mask=attn, padding_mask=pad, track_query_embed=qpos.to(dev))
+            else:
+                b, s = dec(*args, attn_mask=attn, padding_mask=pad)
+            if precision == "fp32":
+                assert rel_rms(b.cpu().numpy(), g["boxes"]) < FP32_TOL and rel_rms(s.cpu().numpy(), g["scores"]) < FP32_TOL, case["name"]
+            else:
+                assert float(np.abs(b.cpu().numpy() - g["boxes"]).max()) < 5e-3, case["name"]
+                assert rel_rms(s.cpu().numpy(), g["scores"]) < 5e-2, case["name"]
+    # masks the kernels do not implement are refused, not ignored
+    layer = m.MOTRDecoderLayer(256, 8, 1024, 0.0, torch.nn.ReLU(), 3, 4).to(dev).eval()
+    q, refer, feats, qpos = syn.make_module_inputs(1, 1, 8, 256, syn.PYRAMIDS["tiny"], 4, 1)
+    with pytest.raises(NotImplementedError):
+        layer(q.to(dev), refer[:, :, 0].to(dev), feats.to(dev), [list(x) for x in syn.PYRAMIDS["tiny"]], None,
+              torch.zeros(8, 8, 8, dtype=torch.bool, device=dev), qpos.to(dev))

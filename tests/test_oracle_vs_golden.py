@@ -162,3 +162,26 @@ def test_query_selection_restatement(name):
     assert rel_rms(got[fin], ref[fin]) < 1e-6
     assert rel_rms(tp.pos2posemb(sel["refer"]).nan_to_num(0.0, 0.0, 0.0).numpy(),
                    np.nan_to_num(g["query_pos"], nan=0.0, posinf=0.0, neginf=0.0)) < 1e-5
+
+
+@pytest.mark.parametrize("case", mg.MASKED_CASES, ids=lambda c: c["name"])
+def test_masked_layers_and_decoders_port(case):
+    """attn_mask (bool [Q, Q] of the denoising groups, or additive float) and padding_mask at layer and decoder level
+    (transformer.py:637-645; models/utils/ops.py:363-375) against goldens minted from the unmodified reference."""
+    meta, g = load_golden(case["name"])
+    spec = syn.DecoderSpec(nc=case.get("nc", 1))
+    sd = syn.make_decoder_state(spec, meta["weight_seed"])
+    attn, pad = mg.masks_for(case)
+    with torch.no_grad():
+        if case["kind"] == "layer":
+            q, refer, feats, qpos = syn.make_module_inputs(case["seed"], case["B"], case["Q"], spec.d_model, case["shapes"], 4, 1)
+            out = tp.decoder_layer_forward(syn.sub_state(sd, "layers.1."), q, refer[:, :, 0], feats, meta["shapes"],
+                                           spec.n_heads, spec.n_levels, spec.n_points, pad, attn, qpos)
+            assert rel_rms(out.numpy(), g["out"]) < FP32_TOL
+        else:
+            embed, refer, feats, qpos = syn.make_decoder_inputs(case["seed"], case["B"], case["Q"], spec.d_model, case["shapes"])
+            b, s, hs = tp.decoder_forward(sd, embed, refer, feats, meta["shapes"], spec.n_heads, spec.n_levels,
+                                          spec.n_points, spec.n_layers, case["mode"], qpos, attn_mask=attn, padding_mask=pad)
+            assert rel_rms(b.numpy(), g["boxes"]) < FP32_TOL and rel_rms(s.numpy(), g["scores"]) < FP32_TOL
+            if case["mode"] == "motr":
+                assert rel_rms(hs.numpy(), g["hs"]) < FP32_TOL
