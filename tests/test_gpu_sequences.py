@@ -140,6 +140,16 @@ def test_free_running_pipelined_bf16(dev):
         r = recs[t]
         assert np.array_equal(got[t]["ids"].numpy(), r["ids"]), (t, "ids")
         assert float(np.abs(got[t]["boxes"].numpy() - r["boxes"]).max()) < 1e-2, t
-    table = eng.track_table().cpu().numpy()
+    table_dev = eng.track_table()
+    table = table_dev.cpu().numpy()
     want = sum(int((r["ids"] >= 0).sum()) for r in recs)
     assert table.shape[0] == want
+    # HOTA of the device-resident table (moyolo_b200.hota) with the ORACLE's tracks as ground truth:
+    # identical ids and boxes within 1e-2 -> perfect detection and association up to alpha = 0.75
+    from moyolo_b200 import hota as H
+    gt = np.concatenate([np.concatenate([np.zeros((int((r["ids"] >= 0).sum()), 1)), np.full((int((r["ids"] >= 0).sum()), 1), t),
+                                         r["ids"][r["ids"] >= 0][:, None], r["boxes"][r["ids"] >= 0]], 1)
+                         for t, r in enumerate(recs)])
+    res = H.hota_from_tables(table_dev, torch.from_numpy(gt).float().to(table_dev.device))["combined"]
+    assert res["HOTA_TP"][0] == want and res["HOTA_FP"][0] == 0 and res["HOTA_FN"][0] == 0
+    assert np.allclose(res["AssA"][:15], 1.0) and np.allclose(res["DetA"][:15], 1.0) and res["LocA"][0] > 0.97
