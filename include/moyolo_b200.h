@@ -526,6 +526,23 @@ int moyolo_decoder_cluster_forward(const moyolo_decoder_cluster_t* a, moyolo_str
 /* Co-resident clusters of the current device and the longest sequence (rows) the key/value staging holds. */
 int moyolo_decoder_cluster_limits(int rows_per_tile, int* max_clusters, int* kv_cap);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fixed-Size Query Memory, one `FSQM.online_update` (MOTR/models/fsqm.py:155-180): (1) update_confidence of the
+ * tracked slots (:117-132), (2) inject_new_queries into the free slots in index order (:46-100; score >
+ * in_threshold; "memory full -> not injected", :78-81), (3) remove_inactive_queries (:102-115). State (device,
+ * caller-owned, N = max_num_queries): query_memory fp32 [N, d], confidence fp32 [N], ids int64 [N] (-1 = free),
+ * bounding_boxes fp32 [N, 4], consecutive_low_frames int32 [N], id_pool int64 [2N] ring buffer of the FIFO
+ * `global_id_pool` with id_pool_header int32 {head, count} (initially pool = 0..N-1, header = {0, N}).
+ * Semantics: the repaired specification F1-F3 stated in oracle/fsqm_port.py (identical to the shipped class
+ * wherever that class is self-consistent). One single-CTA launch, no host synchronisation.
+ * -------------------------------------------------------------------------------------------*/
+int moyolo_fsqm_update(int max_num_queries, int feature_dim, float in_threshold, float out_threshold,
+                       int consecutive_frames, float* query_memory, float* confidence, int64_t* ids,
+                       float* bounding_boxes, int32_t* consecutive_low_frames, int64_t* id_pool,
+                       int32_t* id_pool_header, int n_track, const int64_t* track_ids, const float* track_scores,
+                       const float* track_boxes, int n_detect, const float* detect_embedding,
+                       const float* detect_scores, const float* detect_boxes, moyolo_stream_t stream);
+
 /* Raw CUDA events that may be recorded inside a captured graph and waited on from outside it (ev_tail_prev above):
  * moyolo_event_record uses cudaEventRecordExternal while `stream` is capturing, a plain record otherwise. */
 void* moyolo_event_create(void);

@@ -19,7 +19,7 @@ CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 LIB = PKG / "libmoyolo_b200.so"
 SOURCES = ["common.cu", "msda.cu", "msda_backward.cu", "linear_simt.cu", "gemm_tcgen05.cu", "elementwise.cu", "attention.cu",
-           "tracker.cu", "frame.cu", "runtime.cu", "selector.cu", "decoder_cluster.cu"]
+           "tracker.cu", "frame.cu", "runtime.cu", "selector.cu", "decoder_cluster.cu", "fsqm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -224,7 +224,20 @@ class TrackEngine:
                  weights: Optional[DecoderWeights] = None, cap: int = 512, bucket: int = 64, margin: int = 32,
                  use_graphs: bool = True, table_rows: int = 1 << 18, branches: bool = True, selector=None,
                  value_ahead: Optional[bool] = None, gather_probe: Optional[ops.GatherProbe] = None,
-                 cluster_decoder: Optional[bool] = None):
+                 cluster_decoder: Optional[bool] = None, static_tracks: Optional[int] = None, on_full: str = "raise"):
+        # Fixed-size query memory (the stated purpose of MOTR/models/fsqm.py:8-10): with
+        # `static_tracks=N` every sequence owns N track slots and EVERY frame runs with the same N + n_detect rows per
+        # sequence -- one CUDA graph serves all frames, the host never needs the track counts to size a launch (no
+        # speculative size, no abort / re-launch path). Unused slots are padding rows that no real row ever reads
+        # (row counts live in device memory), so results are bit-identical to the dynamic engine while the tracks fit.
+        # When more than N objects are alive: on_full="raise" (default) reports it, on_full="drop" applies FSQM's rule
+        # "memory full -> the new query is not injected" (fsqm.py:78-81): surplus newborn objects are reported in the
+        # frame they appear in but not carried.
+        if on_full not in ("raise", "drop"):
+            raise ValueError("on_full must be 'raise' or 'drop'")
+        self.static_tracks, self.on_full = static_tracks, on_full
+        if static_tracks is not None:
+            cap = int(static_tracks)
         self.dev = torch.device(device)
         self.gather_probe = gather_probe   # instrumentation of every gather launch (bench.py roofline leg)
         self.launches = 0                  # kernels launched by this engine's frames (graph replays included)
@@ -312,6 +325,7 @@ class TrackEngine:
         self._ev_tail = [_lib.lib().moyolo_event_create() for _ in range(2)]
         # pinned host rings: [n_active (S) | ctrl (8)] and the packed frame rows
         self._max_rows = self._round(S * (n_detect + cap))
+        self._static_rows = self._max_rows if static_tracks is not None else None
         self._h_info = torch.zeros(self.DEPTH, S + 8, dtype=torch.int32).pin_memory()
         self._h_rows = torch.zeros(self.DEPTH, self._max_rows, 8).pin_memory()
         self._plans: Dict[tuple, _FramePlan] = {}
@@ -642,6 +656,10 @@ class TrackEngine:
         if not self.use_graphs:
             return 0
         self.drain()
+        if self._static_rows is not None:
+            self._plan(self._static_rows, 0)
+            self._plan(self._static_rows, 1)
+            return len(self._plans)
         lo = self.n_seq * self.n_detect
         hi = self.n_seq * (self.n_detect + max_tracks_per_seq) + self.margin
         r = self._round(lo)
@@ -775,7 +793,7 @@ class TrackEngine:
             if int(info[self.n_seq + CTRL_ABORT]) != 0:
                 self._recover()
                 continue
-            if int(info[self.n_seq + CTRL_TRACK_OVERFLOW]) != 0:
+            if int(info[self.n_seq + CTRL_TRACK_OVERFLOW]) != 0 and self.on_full == "raise":
                 raise RuntimeError(f"moyolo_b200: a sequence carried more than cap={self.cap} active tracks in frame "
                                    f"{rec['frame']}; the surplus tracks lost their identity. Construct TrackEngine with "
                                    "a larger cap and re-run the sequence")
@@ -811,10 +829,13 @@ class TrackEngine:
         t = self._next
         self._harvest(t - 2, block=True)    # at most two frames in flight
         self._harvest(t - 1, block=False)   # use the newest counts if they are already here
-        rows = sum(self._T) + self.n_seq * self.n_detect
-        exact = self._known == t - 1
-        rows_pad = self._round(rows if exact else rows + self.margin)
-        rows_pad = min(rows_pad, self._max_rows)
+        if self._static_rows is not None:   # fixed-size query memory: the same launch for every frame
+            rows_pad = self._static_rows
+        else:
+            rows = sum(self._T) + self.n_seq * self.n_detect
+            exact = self._known == t - 1
+            rows_pad = self._round(rows if exact else rows + self.margin)
+            rows_pad = min(rows_pad, self._max_rows)
         if self._native_ok(feats, det_embed, det_refer):
             self._inflight.append(self._submit_native(t, rows_pad, feats, det_embed, det_refer, want_rows, sync_inputs))
         else:

@@ -302,6 +302,59 @@ def gen_qim(qim, structures):
              pred_boxes=boxes, new_query_pos=o.query_pos, new_ref_pts=o.ref_pts)
 
 
+def fsqm_inputs(seed, n_frames, N, d, n_det, clean):
+    """Seeded per-frame inputs of FSQM.online_update (MOTR/models/fsqm.py:155-180): detect queries (embedding, score,
+    box) and track queries (obj id, score, box). clean=True stays inside the domain where the reference class is
+    self-consistent: every track id names a live slot whose id equals its index, a slot that received a score
+    below out_threshold is not tracked again (it is freed consecutive_frames later and its slot re-used), and the id
+    pool is never drained down to the -1 entries the reference appends to it; clean=False exercises everything else (recycled
+    ids, ids >= N, id -1, low tracked scores)."""
+    g = torch.Generator().manual_seed(seed)
+    frames = []
+    for t in range(n_frames):
+        emb = torch.randn(n_det, d, generator=g)
+        sc = torch.rand(n_det, generator=g)
+        if clean:
+            sc = torch.where(torch.rand(n_det, generator=g) < 0.15, 0.75 + 0.2 * sc, 0.6 * sc)
+            if t == 0:
+                sc[:3] = 0.9                                   # slots 0..2 are live from the first frame on
+        box = torch.rand(n_det, 4, generator=g)
+        k = int(torch.randint(2, 7, (1,), generator=g))
+        if clean:
+            k = 0 if t == 0 else k
+            tid = torch.randint(0, 3 if t < 4 else 2, (k,), generator=g)   # only slots that are certainly live
+            tsc = 0.3 + 0.7 * torch.rand(k, generator=g)
+            if t == 4:                                         # slot 2 fades out: one low score, never tracked again
+                tid = torch.cat([tid, torch.tensor([2])])
+                tsc = torch.cat([tsc, torch.tensor([0.1])])
+        else:
+            tid = torch.randint(-1, N + 3, (k,), generator=g)
+            tsc = torch.rand(k, generator=g)
+        tbox = torch.rand(tid.shape[0], 4, generator=g)
+        frames.append(dict(emb=emb, sc=sc, box=box, tid=tid, tsc=tsc, tbox=tbox))
+    return frames
+
+
+def gen_fsqm(structures):
+    """The reference FSQM class itself (MOTR/models/fsqm.py:7-189) driven over seeded frames; its complete state after
+    every online_update is the golden."""
+    import importlib
+    F = importlib.import_module("MOTR.models.fsqm")
+    Instances = structures.Instances
+    for name, seed, N, d, n_det, n_frames, clean in (("fsqm_clean", 91, 24, 8, 6, 10, True), ("fsqm_quirks", 92, 8, 8, 6, 16, False)):
+        m = F.FSQM(N, d)
+        rec = {}
+        for t, fr in enumerate(fsqm_inputs(seed, n_frames, N, d, n_det, clean)):
+            det = Instances((0, 0), output_embedding=fr["emb"], scores=fr["sc"], pred_boxes=fr["box"])
+            trk = Instances((0, 0), obj_idxes=fr["tid"].view(-1, 1), scores=fr["tsc"], pred_boxes=fr["tbox"])
+            out = m.online_update(det, trk)
+            assert out is trk                                      # fsqm.py:180: the input comes back unchanged
+            rec.update({f"ids_{t}": m.ids.clone(), f"conf_{t}": m.confidence.clone(), f"low_{t}": m.consecutive_low_frames.clone(),
+                        f"boxes_{t}": m.bounding_boxes.clone(), f"mem_{t}": m.query_memory.clone(),
+                        f"pool_{t}": torch.tensor(m.global_id_pool, dtype=torch.long)})
+        save(name, dict(seed=seed, N=N, d=d, n_det=n_det, n_frames=n_frames, clean=clean, source="MOTR/models/fsqm.py:7-189"), **rec)
+
+
 def gen_selection(head):
     """Encoder-side query selection of the reference MYDecoder (head.py:1012-1029, 993-1010, 1031-1113), eval mode,
     first-frame path (no carried tracks): feats, detect embeddings, logit-space boxes, encoder scores."""
@@ -385,6 +438,7 @@ def main():
     gen_kat0()
     gen_tracker(head, structures)
     gen_qim(qim, structures)
+    gen_fsqm(structures)
     gen_selection(head)
     gen_formats()
 
