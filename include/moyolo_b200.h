@@ -543,6 +543,13 @@ int moyolo_fsqm_update(int max_num_queries, int feature_dim, float in_threshold,
                        const float* track_boxes, int n_detect, const float* detect_embedding,
                        const float* detect_scores, const float* detect_boxes, moyolo_stream_t stream);
 
+/* fp32 operands on the bf16 tensor cores: three-term bf16 expansion of an fp32 matrix [M, K] laid out as six column
+ * blocks [M, 6K] (role 0 = activation order, 1 = weight order) such that ONE bf16 GEMM over K' = 6K (moyolo_linear,
+ * fp32 accumulate) equals the fp32 product to ~3e-8 relative to rms. The fp32 precision mode of the drop-in modules
+ * uses it for every nn.Linear with K % 64 == 0, N % 32 == 0 (moyolo_b200.ops.linear). */
+int moyolo_split_bf16x3(const float* x, int64_t ldx, void* out, int64_t ldo, int64_t M, int K, int role,
+                        moyolo_stream_t stream);
+
 /* Raw CUDA events that may be recorded inside a captured graph and waited on from outside it (ev_tail_prev above):
  * moyolo_event_record uses cudaEventRecordExternal while `stream` is capturing, a plain record otherwise. */
 void* moyolo_event_create(void);

@@ -232,8 +232,14 @@ def qkv_proj(xq_lp, x_lp, w, b, out, C: int, eng) -> None:
     if fused_epilogues(xq_lp.dtype, C):
         ops.linear_dual(xq_lp, x_lp, 2 * C, w, b, out=out)
         return
-    ops.linear(xq_lp, w[:2 * C], b[:2 * C], out=out[:, :2 * C], engine=eng)
-    ops.linear(x_lp, w[2 * C:], b[2 * C:], out=out[:, 2 * C:], engine=eng)
+    # (the row-block views are made once per weight and kept on it: ops.linear caches per-weight data on the tensor
+    # OBJECT it is handed, so the same objects must come back every call)
+    parts = getattr(w, "_moyolo_qkv_parts", None)
+    if parts is None:
+        parts = (w[:2 * C], b[:2 * C], w[2 * C:], b[2 * C:])
+        w._moyolo_qkv_parts = parts
+    ops.linear(xq_lp, parts[0], parts[1], out=out[:, :2 * C], engine=eng)
+    ops.linear(x_lp, parts[2], parts[3], out=out[:, 2 * C:], engine=eng)
 
 
 def run_layer_ws(pk: LayerPack, ws, refer, value_view, shapes, batch, row_offsets, row_offsets_host, pos_cur,

@@ -202,6 +202,26 @@ def proj_fused_supported(value_dtype, n_heads: int, head_dim: int, n_levels: int
             and n_points == 4 and rows <= PROJ_FUSED_MAX_ROWS)
 
 
+# fp32 Linear layers on the tensor cores (MOYOLO_FP32_TENSOR=0: the CUDA-core kernel linear_simt instead): both
+# operands are expanded into three bf16 terms laid out along K (moyolo_split_bf16x3) and ONE bf16 tcgen05 GEMM over
+# K' = 6K with fp32 accumulation gives the fp32 product to ~3e-8 relative to rms.
+FP32_TENSOR = _os.environ.get("MOYOLO_FP32_TENSOR", "1") != "0"
+
+
+def split_bf16x3(x: torch.Tensor, role: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[M, K] fp32 -> [M, 6K] bf16 three-term expansion in activation (role 0) or weight (role 1) block order."""
+    M, K = x.shape
+    if out is None:
+        out = torch.empty(M, 6 * K, dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().moyolo_split_bf16x3(x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), M, K, role, _stream()))
+    return out
+
+
+def _fp32_tensor_ok(x, w, M, N, K, engine) -> bool:
+    return (FP32_TENSOR and x.dtype == torch.float32 and engine != _lib.GEMM_SIMT and M > 0 and K % 64 == 0 and
+            N % 32 == 0 and x.stride(0) % 4 == 0)
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out_dtype: torch.dtype = None,
            relu: bool = False, zero_rows: Optional[torch.Tensor] = None, engine: int = _lib.GEMM_AUTO,
            out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -218,6 +238,26 @@ def linear(x: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], out_dtyp
     out_dtype = out_dtype or x.dtype
     if out is None:
         out = torch.empty(M, N, dtype=out_dtype, device=x.device)
+    if _fp32_tensor_ok(x, w, M, N, K, engine):
+        # the weight's expansion is cached ON the tensor object (it lives and dies with it; re-made after an in-place
+        # update): packed weights (executor.LinearPack) are persistent objects, so this runs once per weight
+        cached = getattr(w, "_moyolo_split", None)
+        if cached is None or cached[0] != w._version:
+            # The GEMM kernels fetch WEIGHTS before their programmatic-dependency wait (weights are immutable while
+            # frames run, common.cuh), so a freshly written expansion must be complete before the first GEMM that
+            # reads it is even launched: one host synchronisation per weight, at first use (never in steady state).
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("moyolo_b200: an fp32 weight expansion would be created inside a CUDA graph capture; "
+                                   "run the captured code once eagerly first")
+            cached = (w._version, split_bf16x3(w, 1))
+            torch.cuda.current_stream().synchronize()
+            w._moyolo_split = cached
+        w6 = cached[1]
+        x6 = split_bf16x3(x, 0)
+        _lib.check(_lib.lib().moyolo_linear(
+            x6.data_ptr(), x6.stride(0), w6.data_ptr(), _ptr(b), out.data_ptr(), out.stride(0), M, N, 6 * K, BF16,
+            _dt(out), _lib.EPI_RELU if relu else _lib.EPI_NONE, _ptr(zero_rows), _lib.GEMM_TCGEN05, _stream()))
+        return out
     _lib.check(_lib.lib().moyolo_linear(
         x.data_ptr(), x.stride(0), w.data_ptr(), _ptr(b), out.data_ptr(), out.stride(0), M, N, K, _dt(x),
         _dt(out), _lib.EPI_RELU if relu else _lib.EPI_NONE, _ptr(zero_rows), engine, _stream()))
