@@ -448,6 +448,44 @@ __global__ void __launch_bounds__(256) frame_emit_kernel(
   }
 }
 
+// ---- final track-row gather (moyolo_b200/sharding.py): fixed-capacity buffers, merged by rank offset ----
+// send = [header | rows]: header row = {count, overflow flag, 0...}; one launch.
+__global__ void table_pack_kernel(const float* __restrict__ rows, int64_t n_rows, int64_t cap, float* __restrict__ send) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t n = n_rows < cap ? n_rows : cap;
+  const int64_t total = (n + 1) * 9;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    if (i < 9) send[i] = i == 0 ? static_cast<float>(n) : (i == 1 ? (n_rows > cap ? 1.0f : 0.0f) : 0.0f);
+    else send[i] = rows[i - 9];
+  }
+}
+// recv = [world][cap + 1][9] -> out rows ordered by rank (exclusive prefix sum of the header counts); info = {total
+// rows, number of ranks whose buffer overflowed}. One launch, nothing is read back.
+__global__ void table_merge_kernel(const float* __restrict__ recv, int world, int64_t cap, float* __restrict__ out,
+                                   int32_t* __restrict__ info) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = blockIdx.y;
+  int64_t off = 0;
+  int over = 0;
+  for (int q = 0; q < world; ++q) {
+    const float* h = recv + static_cast<int64_t>(q) * (cap + 1) * 9;
+    if (q < r) off += static_cast<int64_t>(h[0] + 0.5f);
+    over += h[1] > 0.5f ? 1 : 0;
+  }
+  const float* src = recv + (static_cast<int64_t>(r) * (cap + 1) + 1) * 9;
+  const int64_t n = static_cast<int64_t>(recv[static_cast<int64_t>(r) * (cap + 1) * 9] + 0.5f);
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n * 9;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    out[off * 9 + i] = src[i];
+  if (r == world - 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+    info[0] = static_cast<int32_t>(off + n);
+    info[1] = over;
+  }
+}
+
 }  // namespace moyolo
 
 using namespace moyolo;
@@ -557,4 +595,21 @@ extern "C" int moyolo_frame_emit(int n_seq, int64_t rows_pad, const int32_t* row
       n_seq, static_cast<int>(rows_pad), row_offsets, ids, boxes, scores, labels, n_active, active_index, seq_ids,
       frame_rows, table, static_cast<int>(table_cap), ctrl);
   return check_launch("frame_emit_kernel");
+}
+
+extern "C" int moyolo_table_pack(const float* rows, int64_t n_rows, int64_t capacity, float* send, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(send && (rows || n_rows == 0) && n_rows >= 0 && capacity > 0, MOYOLO_ERR_BAD_ARG, "table_pack: bad arguments");
+  const int64_t n = n_rows < capacity ? n_rows : capacity;
+  const unsigned blocks = static_cast<unsigned>(((n + 1) * 9 + 255) / 256 > 592 ? 592 : ((n + 1) * 9 + 255) / 256);
+  launch_k(table_pack_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, n_rows, capacity, send);
+  return check_launch("table_pack_kernel");
+}
+
+extern "C" int moyolo_table_merge(const float* recv, int world, int64_t capacity, float* out, int32_t* info,
+                                  moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(recv && out && info && world > 0 && capacity > 0, MOYOLO_ERR_BAD_ARG, "table_merge: bad arguments");
+  const unsigned bx = static_cast<unsigned>((capacity * 9 + 255) / 256 > 64 ? 64 : (capacity * 9 + 255) / 256);
+  launch_k(table_merge_kernel, dim3(bx, static_cast<unsigned>(world)), dim3(256), 0, static_cast<cudaStream_t>(stream), recv,
+           world, capacity, out, info);
+  return check_launch("table_merge_kernel");
 }

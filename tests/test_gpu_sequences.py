@@ -155,3 +155,28 @@ def test_free_running_pipelined_bf16(dev):
     # (objects planted on the same detect box in consecutive frames are exact duplicates: the Hungarian matching may
     # pair them crosswise, which costs association, not detection)
     assert np.all(res["AssA"][:15] > 0.99) and np.allclose(res["DetA"][:15], 1.0) and res["LocA"][0] > 0.97
+
+
+def test_table_pack_merge_kernels(dev):
+    """moyolo_table_pack / moyolo_table_merge (the two launches around the final all_gather, sharding.py) against the
+    host-logic merge the gloo tests run: ragged counts, an empty rank, an overflowing rank."""
+    from moyolo_b200 import _lib
+    L = _lib.lib()
+    st = torch.cuda.current_stream(dev).cuda_stream
+    cap, world = 37, 4
+    g = torch.Generator().manual_seed(3)
+    tabs = [torch.randn(n, 9, generator=g).to(dev) for n in (11, 0, 37, 52)]
+    recv = torch.empty(world, cap + 1, 9, device=dev)
+    for r, t in enumerate(tabs):
+        send = torch.full((cap + 1, 9), -7.0, device=dev)
+        _lib.check(L.moyolo_table_pack(t.data_ptr() if t.shape[0] else None, t.shape[0], cap, send.data_ptr(), st))
+        n = min(t.shape[0], cap)
+        assert send[0, 0].item() == n and send[0, 1].item() == float(t.shape[0] > cap)
+        assert torch.equal(send[1:1 + n], t[:n])
+        recv[r] = send
+    out = torch.zeros(world * cap, 9, device=dev)
+    info = torch.zeros(2, dtype=torch.int32, device=dev)
+    _lib.check(L.moyolo_table_merge(recv.data_ptr(), world, cap, out.data_ptr(), info.data_ptr(), st))
+    want = torch.cat([t[:cap] for t in tabs])
+    assert info.tolist() == [want.shape[0], 1]
+    assert torch.equal(out[:want.shape[0]], want)
