@@ -319,7 +319,7 @@ def run_moyolo(args):
     table = gathered.rows(sort=True)
     n_rows_table = int(table.shape[0])
     aborts_value = eng.aborts
-    local_table = mid["local"]
+    local_table = mid["local"]()
     per_frame = torch.bincount(local_table[:, 1].long(), minlength=K).float() if local_table.shape[0] else torch.zeros(K)
     tracks_seen = [float(v) for v in per_frame.cpu().tolist()]
 

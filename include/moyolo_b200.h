@@ -552,10 +552,13 @@ int moyolo_split_bf16x3(const float* x, int64_t ldx, void* out, int64_t ldo, int
 
 /* Final gather of the per-rank track tables (moyolo_b200/sharding.py; the reference evaluates its videos one after
  * the other on one GPU, MOTR/submit_dance.py:499-504): table_pack builds the fixed-capacity send buffer
- * [capacity + 1, 9] = header row {row count, overflow flag} + rows; after ONE all_gather table_merge compacts the
+ * [capacity + 1, 9] = header row {row count, overflow flag} + rows (n_rows_dev, when not NULL, is a device int32
+ * holding the row count -- the engine's table cursor -- and overrides n_rows; overflow_dev, when not NULL, is a device
+ * int32 that also raises the overflow flag when non-zero); after ONE all_gather table_merge compacts the
  * [world, capacity + 1, 9] receive buffer into `out` [world * capacity, 9] ordered by rank and writes
  * info = {total rows, overflowed ranks}. Two launches around the collective, no host synchronisation. */
-int moyolo_table_pack(const float* rows, int64_t n_rows, int64_t capacity, float* send, moyolo_stream_t stream);
+int moyolo_table_pack(const float* rows, int64_t n_rows, const int32_t* n_rows_dev, const int32_t* overflow_dev,
+                      int64_t capacity, float* send, moyolo_stream_t stream);
 int moyolo_table_merge(const float* recv, int world, int64_t capacity, float* out, int32_t* info, moyolo_stream_t stream);
 
 /* Raw CUDA events that may be recorded inside a captured graph and waited on from outside it (ev_tail_prev above):

@@ -60,7 +60,7 @@ SIGNATURES = {
     "moyolo_launch_count": (C.c_uint64, []),
     "moyolo_decoder_cluster_forward": (_i, [_p, _p]),
     "moyolo_decoder_cluster_limits": (_i, [_i, _p, _p]),
-    "moyolo_table_pack": (_i, [_p, _l, _l, _p, _p]),
+    "moyolo_table_pack": (_i, [_p, _l, _p, _p, _l, _p, _p]),
     "moyolo_table_merge": (_i, [_p, _i, _l, _p, _p, _p]),
     "moyolo_split_bf16x3": (_i, [_p, _l, _p, _l, _l, _i, _i, _p]),
     "moyolo_fsqm_update": (_i, [_i, _i, _f, _f, _i, _p, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p, _i, _p, _p, _p, _p]),

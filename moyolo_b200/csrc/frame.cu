@@ -450,14 +450,17 @@ __global__ void __launch_bounds__(256) frame_emit_kernel(
 
 // ---- final track-row gather (moyolo_b200/sharding.py): fixed-capacity buffers, merged by rank offset ----
 // send = [header | rows]: header row = {count, overflow flag, 0...}; one launch.
-__global__ void table_pack_kernel(const float* __restrict__ rows, int64_t n_rows, int64_t cap, float* __restrict__ send) {
+__global__ void table_pack_kernel(const float* __restrict__ rows, int64_t n_rows, const int32_t* __restrict__ n_rows_dev,
+                                  const int32_t* __restrict__ overflow_dev, int64_t cap, float* __restrict__ send) {
   pdl_trigger();
   pdl_wait();
+  if (n_rows_dev != nullptr) n_rows = *n_rows_dev;   // the engine's table cursor: no host read before the gather
+  const bool over = n_rows > cap || (overflow_dev != nullptr && *overflow_dev != 0);
   const int64_t n = n_rows < cap ? n_rows : cap;
   const int64_t total = (n + 1) * 9;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    if (i < 9) send[i] = i == 0 ? static_cast<float>(n) : (i == 1 ? (n_rows > cap ? 1.0f : 0.0f) : 0.0f);
+    if (i < 9) send[i] = i == 0 ? static_cast<float>(n) : (i == 1 && over ? 1.0f : 0.0f);
     else send[i] = rows[i - 9];
   }
 }
@@ -597,11 +600,14 @@ extern "C" int moyolo_frame_emit(int n_seq, int64_t rows_pad, const int32_t* row
   return check_launch("frame_emit_kernel");
 }
 
-extern "C" int moyolo_table_pack(const float* rows, int64_t n_rows, int64_t capacity, float* send, moyolo_stream_t stream) {
-  MOYOLO_REQUIRE(send && (rows || n_rows == 0) && n_rows >= 0 && capacity > 0, MOYOLO_ERR_BAD_ARG, "table_pack: bad arguments");
-  const int64_t n = n_rows < capacity ? n_rows : capacity;
+extern "C" int moyolo_table_pack(const float* rows, int64_t n_rows, const int32_t* n_rows_dev, const int32_t* overflow_dev,
+                                 int64_t capacity, float* send, moyolo_stream_t stream) {
+  MOYOLO_REQUIRE(send && (rows || (n_rows == 0 && !n_rows_dev)) && n_rows >= 0 && capacity > 0, MOYOLO_ERR_BAD_ARG,
+                 "table_pack: bad arguments");
+  const int64_t n = n_rows_dev ? capacity : (n_rows < capacity ? n_rows : capacity);
   const unsigned blocks = static_cast<unsigned>(((n + 1) * 9 + 255) / 256 > 592 ? 592 : ((n + 1) * 9 + 255) / 256);
-  launch_k(table_pack_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, n_rows, capacity, send);
+  launch_k(table_pack_kernel, dim3(blocks), dim3(256), 0, static_cast<cudaStream_t>(stream), rows, n_rows, n_rows_dev,
+           overflow_dev, capacity, send);
   return check_launch("table_pack_kernel");
 }
 

@@ -89,19 +89,27 @@ class GatheredTable:
 
 
 def gather_track_rows(local_rows: torch.Tensor, group: Optional[dist.ProcessGroup] = None,
-                      capacity: Optional[int] = None) -> GatheredTable:
+                      capacity: Optional[int] = None, count_dev: Optional[torch.Tensor] = None,
+                      overflow_dev: Optional[torch.Tensor] = None) -> GatheredTable:
     """All ranks' track rows on every rank with ONE collective and no host synchronisation: each rank contributes
     a fixed-capacity buffer [capacity + 1, 9] whose row 0 is a header (row count, overflow flag),
     `all_gather_into_tensor` moves it, and the ranks' segments are merged by offset on the device (exclusive
     prefix sum of the header counts + one index_copy; fixed shapes, nothing is read back).
     capacity: rows per rank, known to every rank without communication (e.g. frames x sequences x a bound on
     tracked objects per frame). None: a count exchange picks the exact capacity first (one extra small collective
-    and one host read). Single process: returns the input."""
-    n_local = int(local_rows.shape[0])
+    and one host read). Single process: returns the input.
+    count_dev (CUDA, needs `capacity`): device int32 holding this rank's row count -- `local_rows` is then the whole
+    table buffer and the host never learns the count before the collective (TrackEngine.track_table_device);
+    overflow_dev: device int32, non-zero = this rank's table is incomplete."""
+    n_local = int(local_rows.shape[0]) if count_dev is None else 0
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        if count_dev is not None:
+            return GatheredTable(local_rows, count_dev.reshape(()), None, None if overflow_dev is None else overflow_dev.reshape(()))
         return GatheredTable(local_rows, None, n_local)
     world = dist.get_world_size(group)
     dev = local_rows.device
+    if count_dev is not None and (capacity is None or dev.type != "cuda"):
+        raise ValueError("gather_track_rows: count_dev needs a CUDA table and a fixed capacity")
     if capacity is None:
         counts = torch.zeros(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(counts, torch.tensor([n_local], dtype=torch.int64, device=dev), group=group)
@@ -115,7 +123,10 @@ def gather_track_rows(local_rows: torch.Tensor, group: Optional[dist.ProcessGrou
         send, recv, merged, info = bufs
         st = torch.cuda.current_stream(dev).cuda_stream
         rows = local_rows if local_rows.is_contiguous() else local_rows.contiguous()
-        _lib.check(_lib.lib().moyolo_table_pack(rows.data_ptr() if n_local else None, n_local, cap, send.data_ptr(), st))
+        _lib.check(_lib.lib().moyolo_table_pack(
+            rows.data_ptr() if (n_local or count_dev is not None) else None, n_local,
+            None if count_dev is None else count_dev.data_ptr(), None if overflow_dev is None else overflow_dev.data_ptr(),
+            cap, send.data_ptr(), st))
         dist.all_gather_into_tensor(recv, send, group=group)
         _lib.check(_lib.lib().moyolo_table_merge(recv.data_ptr(), world, cap, merged.data_ptr(), info.data_ptr(), st))
         return GatheredTable(merged, info[0], None, info[1])
@@ -161,6 +172,11 @@ def _sort_rows(rows: torch.Tensor) -> torch.Tensor:
     return rows[order]
 
 
+def _stack_frames(sequences, counts, grp, t):
+    batch = [sequences[i]["frames"](min(t, counts[i] - 1)) for i in grp]
+    return tuple(torch.stack([b[k] for b in batch]) for k in range(3))
+
+
 def run_sharded(make_engine, sequences: Sequence[Dict], rank: int, world_size: int, max_in_flight: int = 4,
                 group: Optional[dist.ProcessGroup] = None, batch_fn=None, rows_per_frame: Optional[int] = None,
                 sort: bool = True, sync_inputs: bool = True, before_gather=None):
@@ -170,8 +186,9 @@ def run_sharded(make_engine, sequences: Sequence[Dict], rank: int, world_size: i
     batch_fn(group_seq_ids, t) -> (feats, det_embed, det_refer) already stacked for the lock-step group (avoids
     the per-frame torch.stack); rows_per_frame: bound on tracked objects per frame and sequence -> fixed gather
     capacity, one collective, no count exchange. sync_inputs=False: the frame tensors are complete when they are
-    handed over (resident inputs), so their copy need not wait for the caller's stream. before_gather(local_table)
-    is called once this rank's table is complete (bench.py puts its timing mark there).
+    handed over (resident inputs), so their copy need not wait for the caller's stream. before_gather(get_local)
+    is called once this rank's table is complete on the stream (bench.py puts its timing mark there); get_local()
+    returns this rank's rows (it may synchronise: call it after the run).
 
     sequences[i] = {"n_frames": int, "frames": callable t -> (feats, det_embed, det_refer)}.
     make_engine(n_seq) -> moyolo_b200.tracker.TrackEngine (or an object with the same reset /
@@ -185,18 +202,37 @@ def run_sharded(make_engine, sequences: Sequence[Dict], rank: int, world_size: i
     tables: List[torch.Tensor] = []
     device = None
     groups = lockstep_groups(mine, counts, max_in_flight)
+    capacity = None
+    if rows_per_frame is not None:   # the same number on every rank: the most loaded rank's frames x the bound
+        assign = lpt_assign(counts, world_size)
+        capacity = max(1, max(sum(counts[i] for i in a) for a in assign) * int(rows_per_frame))
+    # fully asynchronous tail: one lock-step group of equally long sequences on a CUDA engine with a fixed gather
+    # capacity -> the gather is enqueued behind the last frame without the host ever reading the row count
+    if (world_size > 1 and capacity is not None and len(groups) == 1 and len({counts[i] for i in groups[0]}) == 1):
+        grp = groups[0]
+        eng = make_engine(len(grp))
+        if hasattr(eng, "track_table_device"):
+            eng.reset()
+            eng.set_seq_ids(grp)
+            for t in range(counts[grp[0]]):
+                feats, de, dr = batch_fn(grp, t) if batch_fn is not None else _stack_frames(sequences, counts, grp, t)
+                eng.submit(feats, de, dr, want_rows=False, sync_inputs=sync_inputs)
+            while True:
+                aborts = eng.aborts
+                buf, n_dev, over_dev = eng.track_table_device()
+                if before_gather is not None:
+                    before_gather(lambda: eng.track_table())
+                table = gather_track_rows(buf, group, capacity, n_dev, over_dev)
+                eng.drain()
+                if eng.aborts == aborts:     # no speculative frame was re-run after the gather was enqueued
+                    break
+            return table.rows(sort=True) if sort else table
     for grp in groups:
         eng = make_engine(len(grp))
         eng.reset()
         eng.set_seq_ids(grp)
         for t in range(max(counts[i] for i in grp)):
-            if batch_fn is not None:
-                feats, de, dr = batch_fn(grp, t)
-            else:
-                batch = [sequences[i]["frames"](min(t, counts[i] - 1)) for i in grp]
-                feats = torch.stack([b[0] for b in batch])
-                de = torch.stack([b[1] for b in batch])
-                dr = torch.stack([b[2] for b in batch])
+            feats, de, dr = batch_fn(grp, t) if batch_fn is not None else _stack_frames(sequences, counts, grp, t)
             device = feats.device
             eng.submit(feats, de, dr, want_rows=False, sync_inputs=sync_inputs)
         tab = eng.track_table()
@@ -210,11 +246,7 @@ def run_sharded(make_engine, sequences: Sequence[Dict], rank: int, world_size: i
     else:
         local = torch.cat(tables, 0) if tables else torch.zeros(0, ROW_WIDTH, dtype=torch.float32,
                                                                 device=device or torch.device("cpu"))
-    capacity = None
-    if rows_per_frame is not None:   # the same number on every rank: the most loaded rank's frames x the bound
-        assign = lpt_assign(counts, world_size)
-        capacity = max(1, max(sum(counts[i] for i in a) for a in assign) * int(rows_per_frame))
     if before_gather is not None:
-        before_gather(local)
+        before_gather(lambda: local)
     table = gather_track_rows(local, group, capacity)
     return table.rows(sort=True) if sort else table

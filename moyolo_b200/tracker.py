@@ -404,6 +404,14 @@ class TrackEngine:
                                "construct TrackEngine with a larger table_rows")
         return self.table[:int(info[CTRL_CURSOR])]
 
+    def track_table_device(self):
+        """(table buffer [table_rows, 9], device int32 row count, device int32 overflow flag) WITHOUT waiting for the
+        in-flight frames: work enqueued on the current stream after this call sees the table as of the last
+        submitted frame (sharding.run_sharded packs it for the final gather with no host read). The caller must
+        drain() afterwards and repeat if `aborts` changed (a speculative frame was re-run)."""
+        torch.cuda.current_stream(self.dev).wait_event(self._ev_done[(self._next - 1) % self.DEPTH])
+        return (self.table, self.ctrl[CTRL_CURSOR:CTRL_CURSOR + 1], self.ctrl[CTRL_TABLE_OVERFLOW:CTRL_TABLE_OVERFLOW + 1])
+
     # ---- one frame: every launch ----------------------------------------------------------------
     def _body(self, p: _FramePlan) -> None:
         """All launches of one frame for plan `p` (graph-capturable: no host sync, no allocation, shapes

@@ -169,11 +169,18 @@ def test_table_pack_merge_kernels(dev):
     recv = torch.empty(world, cap + 1, 9, device=dev)
     for r, t in enumerate(tabs):
         send = torch.full((cap + 1, 9), -7.0, device=dev)
-        _lib.check(L.moyolo_table_pack(t.data_ptr() if t.shape[0] else None, t.shape[0], cap, send.data_ptr(), st))
+        _lib.check(L.moyolo_table_pack(t.data_ptr() if t.shape[0] else None, t.shape[0], None, None, cap, send.data_ptr(), st))
         n = min(t.shape[0], cap)
         assert send[0, 0].item() == n and send[0, 1].item() == float(t.shape[0] > cap)
         assert torch.equal(send[1:1 + n], t[:n])
         recv[r] = send
+    # count and overflow flag read on the device (the engine's table cursor / overflow word)
+    big = torch.randn(64, 9, generator=g).to(dev)
+    ctrl = torch.tensor([20, 0, 50, 1], dtype=torch.int32, device=dev)
+    for ci, oi, n_want, over in ((0, 1, 20, 0.0), (2, 1, cap, 1.0), (0, 3, 20, 1.0)):
+        send = torch.full((cap + 1, 9), -7.0, device=dev)
+        _lib.check(L.moyolo_table_pack(big.data_ptr(), 0, ctrl[ci:].data_ptr(), ctrl[oi:].data_ptr(), cap, send.data_ptr(), st))
+        assert send[0, :2].tolist() == [float(n_want), over] and torch.equal(send[1:1 + n_want], big[:n_want])
     out = torch.zeros(world * cap, 9, device=dev)
     info = torch.zeros(2, dtype=torch.int32, device=dev)
     _lib.check(L.moyolo_table_merge(recv.data_ptr(), world, cap, out.data_ptr(), info.data_ptr(), st))
