@@ -229,6 +229,7 @@ def run_moyolo(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    host_binding = sharding.bind_host_to_gpu(local_rank) if world > 1 else None   # pinned buffers local to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     assert _lib.lib().moyolo_device_supported() == 1, "libmoyolo_b200 targets sm_100a (B200) only"
@@ -240,9 +241,12 @@ def run_moyolo(args):
     eng = TrackEngine(sd, spec, shapes, device, args.precision, args.n_detect, S, weights=weights)
     n_graphs = eng.prepare(args.max_tracks)  # frame graphs captured up front, none inside the timed region
 
-    # frames resident in HBM before the timed region: K distinct frames per sequence slot; global sequence ids are
-    # rank-major, every sequence has K frames (LPT then gives rank r the sequences [r*S, (r+1)*S))
-    seqs = [make_frames(args, syn, spec, plant, shapes, device, 1 + rank * S + s, K, lp) for s in range(S)]
+    # frames resident in HBM before the timed region: K distinct frames per sequence slot. Every sequence has K
+    # frames, so the launcher's LPT assignment deals them round-robin (rank r tracks r, r + world, ...); sequence q is
+    # generated from seed 1 + q on whichever rank owns it.
+    assign = sharding.lpt_assign([K] * (world * S), world)
+    mine = sorted(assign[rank])           # = the order of the launcher's lock-step group
+    seqs = [make_frames(args, syn, spec, plant, shapes, device, 1 + q, K, lp) for q in mine]
     warm = make_frames(args, syn, spec, plant, shapes, device, 9999, max(Wm, 1), lp)
 
     def batch(t, src):
@@ -258,8 +262,7 @@ def run_moyolo(args):
     in_bytes = sum(x.numel() * x.element_size() for x in dev_batches[0])
     gather_cap = K * S * args.table_rows_per_frame   # fixed gather capacity: one collective, no count exchange
     job = [{"n_frames": K} for _ in range(world * S)]
-    assign = sharding.lpt_assign([K] * (world * S), world)
-    assert sorted(assign[rank]) == list(range(rank * S, (rank + 1) * S)), "rank-major sequence assignment expected"
+    assert len(mine) == S
 
     def barrier():
         if world > 1:
@@ -329,13 +332,14 @@ def run_moyolo(args):
         ok = 0
         chk = TrackEngine(sd, spec, shapes, device, args.precision, args.n_detect, S, weights=weights)
         for r in range(world):
-            fr = [make_frames(args, syn, spec, plant, shapes, device, 1 + r * S + s, K, lp) for s in range(S)]
+            theirs = sorted(assign[r])
+            fr = [make_frames(args, syn, spec, plant, shapes, device, 1 + q, K, lp) for q in theirs]
             chk.reset()
-            chk.set_seq_ids(list(range(r * S, (r + 1) * S)))
+            chk.set_seq_ids(theirs)
             for t in range(K):
                 chk.submit(*batch(t, fr), want_rows=False, sync_inputs=True)
             ref_tab = sharding._sort_rows(chk.track_table().clone())
-            for q in range(r * S, (r + 1) * S):
+            for q in theirs:
                 a, b = ref_tab[ref_tab[:, 0] == q], table[table[:, 0] == q]
                 ok += int(a.shape == b.shape and torch.equal(a, b))
         table_check = {"sequences": world * S, "bit_equal_to_single_gpu_run": ok}
@@ -419,7 +423,7 @@ def run_moyolo(args):
     # the same pinned-host path. With fewer than 100 steps the K-step sequence is repeated (reset in between) and
     # the MEDIAN repeat is reported together with the spread.
     reps = 1 if K >= 100 else min(9, max(3, -(-100 // K)))
-    e2e_ms, host_checksum, d2h_bytes = [], 0.0, 0
+    e2e_ms, e2e_local, host_checksum, d2h_bytes = [], [], 0.0, 0
     gpu_rows = []   # host copies of the first cpu_frames frames' result rows (sequence 0) for the parity check
     for rep in range(-1, reps):   # pass -1 is untimed: it keeps host copies of the result rows for the parity check
         warmup(warm_host, True)
@@ -449,7 +453,14 @@ def run_moyolo(args):
             dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
         if rep >= 0:
             e2e_ms.append(float(ms2.item()))
+            e2e_local.append(e0.elapsed_time(e1))
     e2e_sorted = sorted(e2e_ms)
+    by_rank = torch.tensor([sorted(e2e_local)[len(e2e_local) // 2]], device=device)
+    if world > 1:
+        allr = torch.zeros(world, device=device)
+        dist.all_gather_into_tensor(allr, by_rank)
+        by_rank = allr
+    e2e_by_rank = [round(float(v), 3) for v in by_rank.cpu().tolist()]
     ms_e2e = e2e_sorted[len(e2e_sorted) // 2]
 
     clocks = sampler.stop() if rank == 0 else None
@@ -466,6 +477,7 @@ def run_moyolo(args):
             "run_info": {"sequences_per_gpu": S, "frames_per_sequence": K, "sequences_total": world * S,
                          "queries_per_frame_mean": round(rows_mean, 1),
                          "tracks_carried_max": max(tracks_seen) if tracks_seen else 0, "track_rows_gathered": n_rows_table,
+                         "host_binding": host_binding, "e2e_median_ms_by_rank": e2e_by_rank,
                          "final_gather_ms": round(ms_gather, 3), "gather": "one all_gather_into_tensor, fixed capacity "
                          f"{gather_cap} rows per rank, merged by offset on the device, no host sync",
                          "launcher": "moyolo_b200.sharding.run_sharded (LPT assignment, lock-step groups)",

@@ -19,7 +19,7 @@ except Exception as e:
     print("${tag} n=$n FAILED", e)
 PY
 }
-for n in 1 2 4 8; do run $n mot17; done
-run 1 dancetrack --workload DanceTrack --seqs-per-gpu 4
-run 8 dancetrack --workload DanceTrack --seqs-per-gpu 4
-for n in 1 2 4 8; do run $n kitti --workload KITTI --seqs-per-gpu 4; done
+NS="${NS:-1 2 4 8}"
+for n in $NS; do run $n mot17; done
+for n in 1 8; do case " $NS " in *" $n "*) run $n dancetrack --workload DanceTrack --seqs-per-gpu 4;; esac; done
+for n in $NS; do run $n kitti --workload KITTI --seqs-per-gpu 4; done

@@ -18,6 +18,33 @@ import torch.distributed as dist
 ROW_WIDTH = 9
 
 
+def bind_host_to_gpu(local_rank: int) -> Optional[str]:
+    """Pin this process to the CPU cores of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node), so
+    that the pinned host buffers it allocates afterwards are local to the GPU's PCIe root: with 8 ranks streaming
+    frames from host memory, buffers on the wrong socket cross the inter-socket link and the copies slow down.
+    Best effort: returns a description, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node}, {len(cpus)} cpus"
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def lpt_assign(frame_counts: Sequence[int], world_size: int) -> List[List[int]]:
     """Longest-processing-time-first assignment of sequence indices to ranks (ties: lower index,
     lower rank), deterministic on every rank."""
