@@ -318,6 +318,12 @@ def run_moyolo(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     ms_gather = e_mid.elapsed_time(e1)
+    frames_by_rank = torch.tensor([e0.elapsed_time(e_mid)], device=device)   # this rank's frame loop alone
+    if world > 1:
+        allr = torch.zeros(world, device=device)
+        dist.all_gather_into_tensor(allr, frames_by_rank)
+        frames_by_rank = allr
+    frames_ms_by_rank = [round(float(v), 3) for v in frames_by_rank.cpu().tolist()]
     launches = eng.launches - launches0
     table = gathered.rows(sort=True)
     n_rows_table = int(table.shape[0])
@@ -478,6 +484,7 @@ def run_moyolo(args):
                          "queries_per_frame_mean": round(rows_mean, 1),
                          "tracks_carried_max": max(tracks_seen) if tracks_seen else 0, "track_rows_gathered": n_rows_table,
                          "host_binding": host_binding, "e2e_median_ms_by_rank": e2e_by_rank,
+                         "frame_loop_ms_by_rank": frames_ms_by_rank,
                          "final_gather_ms": round(ms_gather, 3), "gather": "one all_gather_into_tensor, fixed capacity "
                          f"{gather_cap} rows per rank, merged by offset on the device, no host sync",
                          "launcher": "moyolo_b200.sharding.run_sharded (LPT assignment, lock-step groups)",
