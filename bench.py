@@ -14,6 +14,7 @@ the end, inside the timed region).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -229,7 +230,8 @@ def run_moyolo(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    host_binding = sharding.bind_host_to_gpu(local_rank) if world > 1 else None   # pinned buffers local to the GPU
+    host_binding = (sharding.bind_host_to_gpu(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+                    if world > 1 else None)   # own cores per rank, pinned buffers local to the GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     assert _lib.lib().moyolo_device_supported() == 1, "libmoyolo_b200 targets sm_100a (B200) only"
@@ -283,6 +285,12 @@ def run_moyolo(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    # the enqueue loop runs ~10 us ahead of the device per launch: a generation-2 garbage collection in the middle of
+    # a 20-frame region is a millisecond stall on one rank (seen as 10-20 % outliers at N=8). Freeze what exists and
+    # keep the collector off while timing, as a serving loop would.
+    gc.collect()
+    gc.freeze()
+    gc.disable()
 
     # ---------------- leg 1: `value` -- inputs resident in HBM, through the sharding launcher ----------------
     # sharding.run_sharded drives the real TrackEngine: the host only enqueues (frame t+1 is submitted while frame t
@@ -469,6 +477,7 @@ def run_moyolo(args):
     e2e_by_rank = [round(float(v), 3) for v in by_rank.cpu().tolist()]
     ms_e2e = e2e_sorted[len(e2e_sorted) // 2]
 
+    gc.enable()
     clocks = sampler.stop() if rank == 0 else None
     frames_total = K * S * world
     line = None

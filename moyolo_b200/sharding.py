@@ -18,31 +18,46 @@ import torch.distributed as dist
 ROW_WIDTH = 9
 
 
-def bind_host_to_gpu(local_rank: int) -> Optional[str]:
-    """Pin this process to the CPU cores of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node), so
-    that the pinned host buffers it allocates afterwards are local to the GPU's PCIe root: with 8 ranks streaming
-    frames from host memory, buffers on the wrong socket cross the inter-socket link and the copies slow down.
-    Best effort: returns a description, or None when the topology cannot be read (nothing is changed then)."""
+def bind_host_to_gpu(local_rank: int, local_world: int = 1) -> Optional[str]:
+    """Pin this process (and the threads it starts later: NCCL proxy, copy helpers) to its own CPU cores: first the
+    cores of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node), so pinned host buffers allocated
+    afterwards are local to the GPU's PCIe root, then an equal slice of those cores per local rank, so the
+    latency-critical enqueue threads of the ranks never share or migrate between cores. Best effort: returns a
+    description, or None when nothing could be changed."""
     import os
     try:
-        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
-        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
-        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
-        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
-        node = int(open(path).read().strip())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return f"numa node {node}, {len(cpus)} cpus"
-    except (OSError, ValueError, AttributeError, RuntimeError):
+        cpus = set(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
         return None
+    what = []
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        path = f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node >= 0:
+            local = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                local.update(range(int(lo), int(hi or lo) + 1))
+            n_nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+            if local & cpus and n_nodes > 1:
+                cpus &= local
+                what.append(f"numa node {node}")
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        pass
+    if local_world > 1:
+        order = sorted(cpus)
+        per = len(order) // local_world
+        if per >= 2:
+            cpus = set(order[(local_rank % local_world) * per:(local_rank % local_world + 1) * per])
+            what.append(f"cpus {min(cpus)}-{max(cpus)}")
+    if not what:
+        return None
+    try:
+        os.sched_setaffinity(0, cpus)
+    except OSError:
+        return None
+    return ", ".join(what)
 
 
 def lpt_assign(frame_counts: Sequence[int], world_size: int) -> List[List[int]]:
