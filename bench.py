@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=12, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-tracks", type=int, default=160, help="pre-capture frame graphs up to this many tracks/seq")
+    ap.add_argument("--host-lag", type=int, default=6, help="frames the enqueueing host may run ahead (TrackEngine host_lag)")
     ap.add_argument("--no-selection", action="store_true", help="skip the query-selection (f1) leg")
     ap.add_argument("--check-table", action="store_true",
                     help="rank 0 re-runs every sequence of the job on one GPU and compares it with the gathered table")
@@ -240,7 +241,7 @@ def run_moyolo(args):
     lp = torch.bfloat16 if args.precision == "bf16" else torch.float32
     S, K, Wm = args.seqs_per_gpu, args.steps, args.warmup
     weights = DecoderWeights(sd, spec, device, args.precision)
-    eng = TrackEngine(sd, spec, shapes, device, args.precision, args.n_detect, S, weights=weights)
+    eng = TrackEngine(sd, spec, shapes, device, args.precision, args.n_detect, S, weights=weights, host_lag=args.host_lag)
     n_graphs = eng.prepare(args.max_tracks)  # frame graphs captured up front, none inside the timed region
 
     # frames resident in HBM before the timed region: K distinct frames per sequence slot. Every sequence has K
@@ -296,46 +297,59 @@ def run_moyolo(args):
     # sharding.run_sharded drives the real TrackEngine: the host only enqueues (frame t+1 is submitted while frame t
     # runs), tracked objects are appended to a device-resident table by the frame graph itself and gathered with ONE
     # NCCL all_gather_into_tensor at the end, inside the timed region.
-    warmup(warm_dev, False)
-    launches0 = eng.launches
-    barrier()
-    e0, e_mid, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    # With fewer than 100 steps the K-step region is run several times (reset + warm-up in between, like the e2e
+    # leg) and the MEDIAN repeat is reported with the spread and every repeat's time: on a shared 8-GPU box one rank
+    # in eight sees a 0.5-2 ms stall in roughly every other 5 ms region (profiles/r02_scaling.md).
+    value_reps = 1 if K >= 100 else 5
     mid = {}
 
     def engine_for(n):
         assert n == S
         return eng
 
-    def mark(local):   # this rank's table is complete here: everything after it is the gather
-        e_mid.record()
-        mid["local"] = local
+    def value_pass():
+        warmup(warm_dev, False)
+        launches0 = eng.launches
+        barrier()
+        e0, e_mid, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
 
-    if args.profiler_range:
-        torch.cuda.cudart().cudaProfilerStart()
-    e0.record()
-    gathered = sharding.run_sharded(engine_for, job, rank, world, max_in_flight=S,
-                                    batch_fn=lambda grp, t: dev_batches[t], rows_per_frame=args.table_rows_per_frame,
-                                    sort=False, sync_inputs=False, before_gather=mark)
-    e1.record()
-    if args.profiler_range:
-        torch.cuda.synchronize()
-        torch.cuda.cudart().cudaProfilerStop()
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=device)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
-    ms_gather = e_mid.elapsed_time(e1)
-    frames_by_rank = torch.tensor([e0.elapsed_time(e_mid)], device=device)   # this rank's frame loop alone
-    if world > 1:
-        allr = torch.zeros(world, device=device)
-        dist.all_gather_into_tensor(allr, frames_by_rank)
-        frames_by_rank = allr
-    frames_ms_by_rank = [round(float(v), 3) for v in frames_by_rank.cpu().tolist()]
-    launches = eng.launches - launches0
+        def mark(local):   # this rank's table is complete here: everything after it is the gather
+            e_mid.record()
+            mid["local"] = local
+
+        if args.profiler_range:
+            torch.cuda.cudart().cudaProfilerStart()
+        e0.record()
+        gathered = sharding.run_sharded(engine_for, job, rank, world, max_in_flight=S,
+                                        batch_fn=lambda grp, t: dev_batches[t], rows_per_frame=args.table_rows_per_frame,
+                                        sort=False, sync_inputs=False, before_gather=mark)
+        e1.record()
+        if args.profiler_range:
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStop()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1), e0.elapsed_time(e_mid)], device=device)
+        if world > 1:
+            allr = torch.zeros(world, 2, device=device)
+            dist.all_gather_into_tensor(allr.view(-1), t)
+            t = allr
+        t = t.view(-1, 2).cpu()
+        return {"ms": float(t[:, 0].max()), "gather_ms": e_mid.elapsed_time(e1), "gathered": gathered,
+                "launches": eng.launches - launches0, "frame_loop_ms_by_rank": [round(float(v), 3) for v in t[:, 1]]}
+
+    passes = [value_pass() for _ in range(value_reps)]
+    order = sorted(range(value_reps), key=lambda i: passes[i]["ms"])
+    best = passes[order[value_reps // 2]]          # the median repeat
+    value_ms_all = [round(p["ms"], 3) for p in passes]
+    ms_total, ms_gather, frames_ms_by_rank = best["ms"], best["gather_ms"], best["frame_loop_ms_by_rank"]
+    gathered = passes[-1]["gathered"]               # (the engine's buffers hold the last repeat)
+    launches = best["launches"]
     table = gathered.rows(sort=True)
     n_rows_table = int(table.shape[0])
-    aborts_value = eng.aborts
+    ab = torch.tensor([float(eng.aborts)], device=device)
+    if world > 1:
+        dist.all_reduce(ab)
+    aborts_value = int(ab.item())      # summed over ranks and repeats
     local_table = mid["local"]()
     per_frame = torch.bincount(local_table[:, 1].long(), minlength=K).float() if local_table.shape[0] else torch.zeros(K)
     tracks_seen = [float(v) for v in per_frame.cpu().tolist()]
@@ -494,11 +508,14 @@ def run_moyolo(args):
                          "tracks_carried_max": max(tracks_seen) if tracks_seen else 0, "track_rows_gathered": n_rows_table,
                          "host_binding": host_binding, "e2e_median_ms_by_rank": e2e_by_rank,
                          "frame_loop_ms_by_rank": frames_ms_by_rank,
+                         "value_repeats": value_reps, "value_ms_per_repeat": value_ms_all,
+                         "value_spread": round((max(value_ms_all) - min(value_ms_all)) / ms_total, 4),
                          "final_gather_ms": round(ms_gather, 3), "gather": "one all_gather_into_tensor, fixed capacity "
                          f"{gather_cap} rows per rank, merged by offset on the device, no host sync",
                          "launcher": "moyolo_b200.sharding.run_sharded (LPT assignment, lock-step groups)",
                          "parallelism": f"sequence-sharded x{world}", "cuda_graphs_precaptured": n_graphs,
-                         "host_pipeline": "frame t+1 submitted while frame t runs (speculative padded size)",
+                         "host_pipeline": f"host enqueues up to {args.host_lag} frames ahead of the newest result it has read "
+                                          "(speculative padded size, device-side abort + re-run)",
                          "speculation_aborts": int(aborts_value), "e2e_host_checksum": round(host_checksum, 3),
                          "e2e_repeats": reps, "e2e_ms_per_repeat": [round(x, 3) for x in e2e_ms],
                          "l2": f"inputs larger than L2: {K} distinct frame buffers of {feat_bytes / 1e6:.1f} MB cycled "

@@ -217,14 +217,24 @@ class _FramePlan:
 class TrackEngine:
     """Lock-step tracker for `n_seq` independent sequences on one GPU."""
 
-    DEPTH = 4  # host result ring (frames in flight <= 2)
+    DEPTH = 4  # host result ring = host_lag + 2 (set per instance)
 
     def __init__(self, sd, spec: DecoderSpec, shapes, device, precision: str = "bf16", n_detect: int = 300,
                  n_seq: int = 1, score_thresh=0.4, filter_thresh=0.5, miss_tolerance=5, iou_thresh=0.8,
                  weights: Optional[DecoderWeights] = None, cap: int = 512, bucket: int = 64, margin: int = 32,
                  use_graphs: bool = True, table_rows: int = 1 << 18, branches: bool = True, selector=None,
                  value_ahead: Optional[bool] = None, gather_probe: Optional[ops.GatherProbe] = None,
-                 cluster_decoder: Optional[bool] = None, static_tracks: Optional[int] = None, on_full: str = "raise"):
+                 cluster_decoder: Optional[bool] = None, static_tracks: Optional[int] = None, on_full: str = "raise",
+                 host_lag: int = 2):
+        # host_lag: how many frames the enqueueing host may run ahead of the newest frame whose results it has read
+        # (>= 2). The device side is unchanged (two input / value slots, frame t's copy waits for frame t-2); a larger
+        # lag only lets the host queue more launches, so a host stall shorter than (host_lag - 1) frame times no
+        # longer drains the device queue. The speculative padded size then has to cover host_lag - 1 frames of births
+        # (margin per stale frame); a wrong guess is re-run as before.
+        if host_lag < 2:
+            raise ValueError("host_lag must be >= 2")
+        self.host_lag = int(host_lag)
+        self.DEPTH = self.host_lag + 2
         # Fixed-size query memory (SURVEY.md 8 f2; the stated purpose of MOTR/models/fsqm.py:8-10): with
         # `static_tracks=N` every sequence owns N track slots and EVERY frame runs with the same N + n_detect rows per
         # sequence -- one CUDA graph serves all frames, the host never needs the track counts to size a launch (no
@@ -337,7 +347,6 @@ class TrackEngine:
             e.record(self._main)
         torch.cuda.synchronize(dev)
         self._native = use_graphs and os.environ.get("MOYOLO_NATIVE_SUBMIT", "1") != "0"
-        self._keep = [None, None]            # inputs of the two newest frames (alive until their copies ran)
         self._h_info_np = self._h_info.numpy()
         self._host_reset()
 
@@ -647,7 +656,6 @@ class TrackEngine:
         d.out_dst[0] = self._h_info[h].data_ptr()
         d.out_dst[1] = self._h_rows[h].data_ptr()
         d.n_outputs = 2 if want_rows else 1
-        self._keep[slot] = (feats, det_embed, det_refer)
         _lib.check(_lib.lib().moyolo_frame_submit(ctypes.byref(d)))
         self.launches += p.n_launch + (1 if self._vp_ahead else 0) + (self._pre_launches if self._sel_ahead else 0)
         self._last_plan = p
@@ -669,7 +677,7 @@ class TrackEngine:
             self._plan(self._static_rows, 1)
             return len(self._plans)
         lo = self.n_seq * self.n_detect
-        hi = self.n_seq * (self.n_detect + max_tracks_per_seq) + self.margin
+        hi = self.n_seq * (self.n_detect + max_tracks_per_seq) + self.margin * (self.host_lag - 1)
         r = self._round(lo)
         while r <= self._round(hi):
             self._plan(r, 0)
@@ -821,7 +829,10 @@ class TrackEngine:
         self.aborts += 1
         for rec in redo:
             rows = sum(self._T) + self.n_seq * self.n_detect
+            if self.host_lag > 2:   # the two input slots have moved on to later frames: load this frame's inputs again
+                self._load_inputs(rec["frame"] % 2, *rec["keep"], rec["frame"], False)
             new = self._launch(rec["frame"], self._round(rows), rec["want_rows"])
+            new["keep"] = rec["keep"]
             self._inflight.append(new)
             self._harvest(rec["frame"], block=True)
 
@@ -832,23 +843,25 @@ class TrackEngine:
         boxes. With a `selector` the three arguments are instead the neck's channels-last maps
         [n_seq, H_l, W_l, C_l] of the three pyramid levels (GEMM dtype). Unless sync_inputs is set the tensors must be complete when submit() is called (their copy
         runs on the engine's copy stream, which is then not ordered after the caller's stream), and they
-        must not be modified until the frame after next has been submitted. Returns the frame index for
-        `collect`."""
+        must not be modified until `host_lag` (default 2) more frames have been submitted. Returns the frame index
+        for `collect`."""
         t = self._next
-        self._harvest(t - 2, block=True)    # at most two frames in flight
+        self._harvest(t - self.host_lag, block=True)    # at most host_lag frames in flight
         self._harvest(t - 1, block=False)   # use the newest counts if they are already here
         if self._static_rows is not None:   # fixed-size query memory: the same launch for every frame
             rows_pad = self._static_rows
         else:
             rows = sum(self._T) + self.n_seq * self.n_detect
-            exact = self._known == t - 1
-            rows_pad = self._round(rows if exact else rows + self.margin)
+            stale = t - 1 - self._known     # frames whose births the host has not seen yet
+            rows_pad = self._round(rows + self.margin * stale)
             rows_pad = min(rows_pad, self._max_rows)
         if self._native_ok(feats, det_embed, det_refer):
-            self._inflight.append(self._submit_native(t, rows_pad, feats, det_embed, det_refer, want_rows, sync_inputs))
+            rec = self._submit_native(t, rows_pad, feats, det_embed, det_refer, want_rows, sync_inputs)
         else:
             self._load_inputs(t % 2, feats, det_embed, det_refer, t, sync_inputs)
-            self._inflight.append(self._launch(t, rows_pad, want_rows))
+            rec = self._launch(t, rows_pad, want_rows)
+        rec["keep"] = (feats, det_embed, det_refer)   # alive until the frame has finished (and for a re-run)
+        self._inflight.append(rec)
         self._next = t + 1
         self.frame_idx = self._next
         return t

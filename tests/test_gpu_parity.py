@@ -459,6 +459,20 @@ def test_pipelined_submit_equals_synchronous_steps(dev):
         assert torch.equal(table, want), margin
         assert ref.n_tracks_host() == eng.n_tracks_host()
 
+    # host running up to 6 frames ahead (host_lag, what sharding.run_sharded / bench.py use): nothing is collected
+    # in the loop, so the queue really gets that deep; with margin 0 the re-run path has to reload the inputs of
+    # aborted frames whose input slots were overwritten by later frames
+    for margin, bucket in ((0, 8), (32, 64)):
+        eng = TrackEngine(sd, spec, shapes, dev, "bf16", nd, S, weights=W, margin=margin, bucket=bucket, host_lag=6)
+        eng.set_seq_ids([5, 9])
+        for t in range(n_frames):
+            eng.submit(*batches[t], want_rows=False)
+        table = eng.track_table().clone().cpu()
+        if margin == 0:
+            assert eng.aborts > 0, "the deep-queue re-run path was not exercised"
+        assert torch.equal(table, want), ("host_lag 6", margin)
+        assert ref.n_tracks_host() == eng.n_tracks_host()
+
 
 def test_frame_assign_compact_equals_two_step(dev):
     """moyolo_frame_assign_compact + moyolo_track_suppress_batched (the frame path: ID assignment fused with the
