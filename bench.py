@@ -509,6 +509,7 @@ def run_moyolo(args):
                          "host_binding": host_binding, "e2e_median_ms_by_rank": e2e_by_rank,
                          "frame_loop_ms_by_rank": frames_ms_by_rank,
                          "value_repeats": value_reps, "value_ms_per_repeat": value_ms_all,
+                         "frame_loop_ms_by_rank_per_repeat": [p["frame_loop_ms_by_rank"] for p in passes],
                          "value_spread": round((max(value_ms_all) - min(value_ms_all)) / ms_total, 4),
                          "final_gather_ms": round(ms_gather, 3), "gather": "one all_gather_into_tensor, fixed capacity "
                          f"{gather_cap} rows per rank, merged by offset on the device, no host sync",

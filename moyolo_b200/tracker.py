@@ -361,6 +361,7 @@ class TrackEngine:
     def _host_reset(self):
         self._T = [0] * self.n_seq          # exact track counts after frame `_known`
         self._known = -1                    # newest frame whose counts the host has read
+        self._growth: List[int] = []        # net track growth of the last harvested frames
         self._next = 0                      # next frame index to submit
         self._inflight: List[dict] = []     # submitted, not yet harvested (oldest first)
         self._T_before: Dict[int, List[int]] = {0: [0] * self.n_seq}  # frame -> track counts it started with
@@ -814,6 +815,8 @@ class TrackEngine:
                                    f"{rec['frame']}; the surplus tracks lost their identity. Construct TrackEngine with "
                                    "a larger cap and re-run the sequence")
             self._inflight.pop(0)
+            grown = int(info[:self.n_seq].sum()) - sum(self._T)
+            self._growth = (self._growth + [grown])[-8:]   # net births of the last frames: sizes the speculation
             self._T = info[:self.n_seq].tolist()
             self._known = rec["frame"]
             self._T_before[rec["frame"] + 1] = list(self._T)
@@ -853,7 +856,10 @@ class TrackEngine:
         else:
             rows = sum(self._T) + self.n_seq * self.n_detect
             stale = t - 1 - self._known     # frames whose births the host has not seen yet
-            rows_pad = self._round(rows + self.margin * stale)
+            # per stale frame: the largest net growth of the last 8 frames + 4, at most `margin` (a wrong guess is
+            # only slower, never wrong: the device aborts the frame and it is re-run with the exact size)
+            per = self.margin if len(self._growth) < 3 else min(self.margin, max(self._growth) + 4)
+            rows_pad = self._round(rows + max(per, 0) * stale)
             rows_pad = min(rows_pad, self._max_rows)
         if self._native_ok(feats, det_embed, det_refer):
             rec = self._submit_native(t, rows_pad, feats, det_embed, det_refer, want_rows, sync_inputs)
