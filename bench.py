@@ -65,7 +65,7 @@ def parse():
     ap.add_argument("--cpu-frames", type=int, default=12, help="frames of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-tracks", type=int, default=160, help="pre-capture frame graphs up to this many tracks/seq")
-    ap.add_argument("--host-lag", type=int, default=6, help="frames the enqueueing host may run ahead (TrackEngine host_lag)")
+    ap.add_argument("--host-lag", type=int, default=2, help="frames the enqueueing host may run ahead (TrackEngine host_lag)")
     ap.add_argument("--no-selection", action="store_true", help="skip the query-selection (f1) leg")
     ap.add_argument("--check-table", action="store_true",
                     help="rank 0 re-runs every sequence of the job on one GPU and compares it with the gathered table")
