@@ -94,6 +94,14 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def wait_first(self, timeout: float = 15.0):
+        """Block until the first sample has arrived: nvidia-smi's start-up enumerates every GPU of the box through the
+        driver, which stalls running work on ALL of them for a few hundred ms (seen as 5-25 % slower first timed
+        regions on random ranks at N=8); the periodic samples afterwards do not."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
@@ -286,6 +294,7 @@ def run_moyolo(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first()
     # the enqueue loop runs ~10 us ahead of the device per launch: a generation-2 garbage collection in the middle of
     # a 20-frame region is a millisecond stall on one rank (seen as 10-20 % outliers at N=8). Freeze what exists and
     # keep the collector off while timing, as a serving loop would.
