@@ -152,3 +152,65 @@ def test_per_frame_reset_gives_shipped_semantics_and_writers(dev, tmp_path):
     assert n == len(lines) and (tmp_path / "seq0.txt").read_text().splitlines()[0] == lines[0].rstrip("\n")
     per_frame = R.save_txt_lines(table, 640, 640, save_conf=True)
     assert sorted(per_frame) == sorted({int(v) for v in table[:, 1].tolist()})
+
+
+def _tiny5_batches(dev, S, n_frames, nd):
+    from moyolo_b200 import synthetic as syn
+    spec, shapes, sd, plant = syn.tracking_workload("tiny5", 7)
+    gens = [syn.PlantedSequenceGenerator(syn.SequenceSpec("tiny", n_frames, nd, 1 + s, shapes=shapes), spec, plant)
+            for s in range(S)]
+    frames = [[tuple(t.clone() for t in g.next_frame()) for _ in range(n_frames)] for g in gens]
+    batches = [tuple(torch.stack([frames[s][t][k] for s in range(S)]).to(dev) for k in range(3)) for t in range(n_frames)]
+    return spec, shapes, sd, batches
+
+
+def test_partial_reset_keeps_other_sequences_aligned(dev):
+    """reset(seq) in the middle of a pipelined run (a new video starts in one lock-step slot, val.py:288-291): the
+    reset slot continues exactly like a fresh engine from that frame on (IDs from 0), the other slot is not
+    disturbed, and collect() keeps slicing both sequences' rows at the right offsets (`_T_before`)."""
+    from moyolo_b200.tracker import DecoderWeights, TrackEngine
+    nd, S, n_frames, cut = 48, 2, 10, 5
+    spec, shapes, sd, batches = _tiny5_batches(dev, S, n_frames, nd)
+    W = DecoderWeights(sd, spec, dev, "bf16")
+
+    def run(reset_at=None, start=0):
+        eng = TrackEngine(sd, spec, shapes, dev, "bf16", nd, S, weights=W)
+        rows = {}
+        for t in range(start, n_frames):
+            if t == reset_at:
+                eng.reset(0)
+            f = eng.submit(*batches[t], want_rows=True)
+            if f > 0:
+                rows[t - 1] = [{k: v.clone() for k, v in o.items()} for o in eng.collect(f - 1)]
+        rows[n_frames - 1] = [{k: v.clone() for k, v in o.items()} for o in eng.collect(n_frames - 1 - start)]
+        return rows
+
+    plain, with_reset, fresh = run(), run(reset_at=cut), run(start=cut)
+    assert plain[cut - 1][0]["ids"].shape[0] > nd, "slot 0 carried no track before the reset"
+    for t in range(n_frames):
+        for k in ("ids", "boxes", "scores", "labels"):
+            assert torch.equal(with_reset[t][1][k], plain[t][1][k]), ("untouched slot", t, k)
+            if t < cut:
+                assert torch.equal(with_reset[t][0][k], plain[t][0][k]), ("before the reset", t, k)
+            elif k in ("ids", "labels"):
+                assert torch.equal(with_reset[t][0][k], fresh[t][0][k]), ("after the reset", t, k)
+            else:   # (the other slot carries tracks here and none in the fresh run: same values, other row offsets)
+                assert torch.allclose(with_reset[t][0][k], fresh[t][0][k], atol=1e-2), ("after the reset", t, k)
+    assert with_reset[cut][0]["ids"].shape[0] == nd and int(with_reset[cut][0]["ids"].max()) >= 0
+
+
+def test_track_capacity_overflow_is_reported(dev):
+    """More live tracks than `cap` in the dynamic engine: the reference has no such limit, so the engine must say so
+    instead of silently dropping identities (kCtrlTrackOverflow)."""
+    from moyolo_b200.tracker import TrackEngine
+    nd, n_frames = 48, 10
+    spec, shapes, sd, batches = _tiny5_batches(dev, 1, n_frames, nd)
+    ok = TrackEngine(sd, spec, shapes, dev, "bf16", nd, 1)
+    for b in batches:
+        ok.submit(*b, want_rows=False)
+    assert max(ok.n_tracks_host()) > 8
+    eng = TrackEngine(sd, spec, shapes, dev, "bf16", nd, 1, cap=8)
+    with pytest.raises(RuntimeError, match="cap=8"):
+        for b in batches:
+            eng.submit(*b, want_rows=False)
+        eng.drain()
