@@ -104,6 +104,18 @@ int moyolo_msda_sampled_forward(const void* value, int value_dtype, int64_t valu
                                 int64_t rows, const int32_t* row_offsets, void* out,
                                 int64_t out_row_stride, moyolo_stream_t stream);
 
+/* moyolo_msda_fused_forward on a HEAD-MAJOR value tensor [B, H, Lv, head_dim] (strides in elements: batch, head,
+ * position): the x0 / x1 bilinear corners of a sampling point are one contiguous 2 * head_dim segment. Experimental
+ * (bf16, 8 heads x 32, 3 levels x 4 points); same arithmetic and results as the channel-last entry point. */
+int moyolo_msda_fused_forward_headmajor(const void* value, int value_dtype, int64_t value_batch_stride,
+                                        int64_t value_head_stride, int64_t value_pos_stride,
+                                        const int32_t* shapes_hw_host, int n_levels, int batch, int64_t len_v,
+                                        int n_heads, int head_dim, int n_points, const float* offsets,
+                                        int64_t offsets_row_stride, const float* logits, int64_t logits_row_stride,
+                                        const float* refer, int ref_levels, int ref_dim, int softmax_mode, int64_t rows,
+                                        const int32_t* row_offsets, void* out, int64_t out_row_stride,
+                                        moyolo_stream_t stream);
+
 /* Fused mode with the sampling_offsets | attention_weights projection inside the gather kernel
  * (transformer.py:268-285 in ONE launch): offsets|logits = xq . w_offlog^T + b_offlog is computed per
  * (8 rows, head) CTA on mma.sync and never leaves shared memory.

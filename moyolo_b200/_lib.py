@@ -69,6 +69,8 @@ SIGNATURES = {
                                           _p, _p, _p]),
     "moyolo_msda_fused_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _l, _p, _i, _i, _i,
                                        _l, _p, _p, _l, _p]),
+    "moyolo_msda_fused_forward_headmajor": (_i, [_p, _i, _l, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _l, _p, _i, _i,
+                                                 _i, _l, _p, _p, _l, _p]),
     "moyolo_msda_proj_fused_forward": (_i, [_p, _i, _l, _l, _p, _i, _i, _l, _i, _i, _i, _p, _l, _p, _p, _p, _i, _i, _i,
                                             _l, _p, _p, _l, _p]),
     "moyolo_linear": (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _i, _p, _i, _p]),

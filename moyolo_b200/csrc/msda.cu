@@ -33,6 +33,7 @@ struct MsdaParams {
   const void* value;
   int64_t value_batch_stride;  // elements
   int64_t value_pos_stride;    // elements
+  int64_t value_head_stride;   // elements between heads of one position (head_dim = channel-last; Lv*head_dim = head-major)
   LevelTable lv;
   int batch;
   int n_heads;
@@ -364,8 +365,9 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_pair_kernel(const 
   // ---------------- phase 2: both items' corner rows in flight, then the FMAs ----------------
   const int sg = lane / G, sub = lane % G;
   const int b = p.batch == 1 ? 0 : batch_of_row(row, p.row_offsets, p.batch, p.rows_per_batch);
+  const int64_t hs = p.value_head_stride;
   const VT* base = static_cast<const VT*>(p.value) + static_cast<int64_t>(b) * p.value_batch_stride +
-                   hp * 2 * DH + sub * CH;
+                   hp * 2 * hs + sub * CH;
   float acc[2][CH];
 #pragma unroll
   for (int h = 0; h < 2; ++h)
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_pair_kernel(const 
       for (int i = 0; i < R; ++i) {
         const int eo = s_off[h * NUp + sg + i * NSG];
         w[h][i] = s_w[h * NUp + sg + i * NSG];
-        v[h][i] = ldg128_if(base + h * DH + eo, eo >= 0);
+        v[h][i] = ldg128_if(base + h * hs + eo, eo >= 0);
       }
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -400,7 +402,7 @@ __global__ void __launch_bounds__(kGatherThreads) msda_gather_pair_kernel(const 
       for (int i = 0; i < R; ++i) {
         const int eo = s_off[h * NUp + sg + i * NSG];
         w[i] = s_w[h * NUp + sg + i * NSG];
-        v[i] = ldg128_if(base + h * DH + eo, eo >= 0);
+        v[i] = ldg128_if(base + h * hs + eo, eo >= 0);
       }
 #pragma unroll
       for (int i = 0; i < R; ++i) accumulate(acc[h], v[i], w[i]);
@@ -768,6 +770,7 @@ static int fill_common(MsdaParams* p, const void* value, int value_dtype, int64_
   p->value = value;
   p->value_batch_stride = value_batch_stride;
   p->value_pos_stride = value_pos_stride;
+  p->value_head_stride = head_dim;
   p->batch = batch;
   p->n_heads = n_heads;
   p->n_points = n_points;
@@ -831,6 +834,40 @@ extern "C" int moyolo_msda_fused_forward(const void* value, int value_dtype, int
   p.ref_dim = ref_dim;
   p.softmax_mode = softmax_mode;
   return dispatch<true>(p, value_dtype, MOYOLO_F32, head_dim, static_cast<cudaStream_t>(stream));
+}
+
+// Head-major value layout [B, H, Lv, head_dim] (value_head_stride = Lv * head_dim, value_pos_stride = head_dim): the
+// x0 / x1 bilinear corners of a sampling point are then one contiguous 2 * head_dim segment. Experimental entry point
+// (benchmarks/headmajor_probe.py): served by the two-items-per-warp kernel only.
+extern "C" int moyolo_msda_fused_forward_headmajor(const void* value, int value_dtype, int64_t value_batch_stride,
+                                                   int64_t value_head_stride, int64_t value_pos_stride,
+                                                   const int32_t* shapes_hw_host, int n_levels, int batch, int64_t len_v,
+                                                   int n_heads, int head_dim, int n_points, const float* offsets,
+                                                   int64_t offsets_row_stride, const float* logits,
+                                                   int64_t logits_row_stride, const float* refer, int ref_levels,
+                                                   int ref_dim, int softmax_mode, int64_t rows,
+                                                   const int32_t* row_offsets, void* out, int64_t out_row_stride,
+                                                   moyolo_stream_t stream) {
+  MsdaParams p{};
+  MOYOLO_REQUIRE(value_dtype == MOYOLO_BF16 && n_heads == 8 && head_dim == 32 && n_points == 4 && n_levels == 3,
+                 MOYOLO_ERR_UNSUPPORTED, "msda_fused_forward_headmajor serves bf16, 8 heads x 32, 3 levels x 4 points");
+  int rc = fill_common(&p, value, value_dtype, value_batch_stride, static_cast<int64_t>(n_heads) * head_dim, shapes_hw_host,
+                       n_levels, batch, len_v, n_heads, head_dim, n_points, rows, row_offsets, out, out_row_stride);
+  if (rc != MOYOLO_OK) return rc;
+  MOYOLO_REQUIRE(offsets && logits && refer && (ref_dim == 2 || ref_dim == 4) && (ref_levels == 1 || ref_levels == n_levels),
+                 MOYOLO_ERR_BAD_ARG, "msda_fused_forward_headmajor: bad offsets/logits/refer arguments");
+  MOYOLO_REQUIRE(aligned16(value) && aligned16(out) && (value_pos_stride * 2) % 16 == 0 && (value_head_stride * 2) % 16 == 0 &&
+                     (value_batch_stride * 2) % 16 == 0 && (out_row_stride * 2) % 16 == 0 &&
+                     (reinterpret_cast<uintptr_t>(offsets) & 7u) == 0 && offsets_row_stride % 2 == 0 &&
+                     (reinterpret_cast<uintptr_t>(refer) & (ref_dim == 4 ? 15u : 7u)) == 0,
+                 MOYOLO_ERR_ALIGNMENT, "msda_fused_forward_headmajor: operands must be 16-byte aligned");
+  MOYOLO_REQUIRE(len_v * value_pos_stride < INT32_MAX - 4096, MOYOLO_ERR_UNSUPPORTED, "tensor too large for 32-bit offsets");
+  p.value_pos_stride = value_pos_stride;
+  p.value_head_stride = value_head_stride;
+  p.offsets = offsets; p.offsets_row_stride = offsets_row_stride; p.logits = logits; p.logits_row_stride = logits_row_stride;
+  p.refer = refer; p.ref_levels = ref_levels; p.ref_dim = ref_dim; p.softmax_mode = softmax_mode;
+  if (rows == 0) return MOYOLO_OK;
+  return launch_pair<__nv_bfloat16, 4, 3>(p, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int moyolo_msda_proj_fused_forward(const void* value, int value_dtype, int64_t value_batch_stride,

@@ -122,6 +122,27 @@ def msda_sampled_backward(value: torch.Tensor, shapes, loc: torch.Tensor, weight
     return grad_value, grad_loc, grad_w
 
 
+def msda_fused_headmajor(value_hm: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch.Tensor, refer: torch.Tensor,
+                         n_points: int, softmax_mode: int = _lib.SOFTMAX, row_offsets: Optional[torch.Tensor] = None,
+                         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`msda_fused` on a head-major value tensor [B, H, Lv, Dh] (experimental layout: the x0 / x1 corners of a
+    sampling point are contiguous; benchmarks/headmajor_probe.py). bf16, 8 heads x 32, 3 levels x 4 points."""
+    _cuda(value_hm, offsets, logits, refer)
+    B, H, Lv, Dh = value_hm.shape
+    if value_hm.stride(3) != 1:
+        raise ValueError("value must be [B, H, Lv, Dh] with contiguous channels")
+    R = offsets.shape[0]
+    arr, L = _shapes_arr(shapes)
+    refer = refer.contiguous()
+    if out is None:
+        out = torch.empty(R, H * Dh, dtype=value_hm.dtype, device=value_hm.device)
+    _lib.check(_lib.lib().moyolo_msda_fused_forward_headmajor(
+        value_hm.data_ptr(), _dt(value_hm), value_hm.stride(0), value_hm.stride(1), value_hm.stride(2), arr, L, B, Lv, H, Dh,
+        n_points, offsets.data_ptr(), offsets.stride(0), logits.data_ptr(), logits.stride(0), refer.data_ptr(),
+        refer.shape[1], refer.shape[2], softmax_mode, R, _ptr(row_offsets), out.data_ptr(), out.stride(0), _stream()))
+    return out
+
+
 def msda_fused(value: torch.Tensor, shapes, offsets: torch.Tensor, logits: torch.Tensor, refer: torch.Tensor,
                n_heads: int, n_points: int, batch: int, softmax_mode: int = _lib.SOFTMAX,
                row_offsets: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,

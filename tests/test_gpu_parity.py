@@ -860,3 +860,24 @@ def test_masked_layers_and_decoders_vs_reference_golden(dev, precision):
     with pytest.raises(NotImplementedError):
         layer(q.to(dev), refer[:, :, 0].to(dev), feats.to(dev), [list(x) for x in syn.PYRAMIDS["tiny"]], None,
               torch.zeros(8, 8, 8, dtype=torch.bool, device=dev), qpos.to(dev))
+
+
+def test_headmajor_gather_bit_equal(dev):
+    """moyolo_msda_fused_forward_headmajor (value stored [B, H, Lv, 32]; profiles/r02_experiments/gather_head_major.md)
+    runs the same arithmetic as the channel-last entry point: bit-identical output, incl. ragged batches."""
+    m, ops, syn, mg, tp = _mods()
+    shapes = [list(s) for s in syn.PYRAMIDS["MOT17"]]
+    Lv = syn.level_sizes(shapes)
+    H, D, L, P, B = 8, 32, 3, 4, 3
+    g = torch.Generator().manual_seed(5)
+    allv = torch.randn(B, Lv, 2 * H * D, generator=g).to(dev).to(torch.bfloat16)
+    v_cl = allv[:, :, H * D:]
+    v_hm = v_cl.reshape(B, Lv, H, D).permute(0, 2, 1, 3).contiguous()
+    row_offsets = torch.tensor([0, 400, 401, 1100], dtype=torch.int32, device=dev)
+    R = 1100
+    offsets = torch.randn(R, H * L * P * 2, generator=g).to(dev) * 3
+    logits = torch.randn(R, H * L * P, generator=g).to(dev)
+    refer = torch.cat([torch.rand(R, 1, 2, generator=g), torch.rand(R, 1, 2, generator=g) * 0.4], -1).to(dev)
+    a = ops.msda_fused(v_cl, shapes, offsets, logits, refer, H, P, B, row_offsets=row_offsets)
+    b = ops.msda_fused_headmajor(v_hm, shapes, offsets, logits, refer, P, row_offsets=row_offsets)
+    assert torch.equal(a, b) and float(a.float().abs().max()) > 0
