@@ -43,7 +43,7 @@ def bind_host_to_gpu(local_rank: int, local_world: int = 1) -> Optional[str]:
             if local & cpus and n_nodes > 1:
                 cpus &= local
                 what.append(f"numa node {node}")
-    except (OSError, ValueError, AttributeError, RuntimeError):
+    except Exception:   # no CUDA device / no sysfs topology: keep the whole affinity mask
         pass
     if local_world > 1:
         order = sorted(cpus)

@@ -116,3 +116,27 @@ def test_gather_single_process_sorts_rows():
     out = sharding.gather_track_rows(rows)
     assert out.count() == 3 and torch.equal(out.rows(), rows)          # single process: untouched, no sort
     assert out.rows(sort=True)[:, :2].tolist() == [[0, 1], [0, 5], [1, 2]]
+
+
+def test_bind_host_to_gpu_partitions_the_cores():
+    """sharding.bind_host_to_gpu: every local rank gets its own equal slice of the allowed cores (best effort; no GPU
+    topology on this box, so only the per-rank split applies), and a single rank is left alone."""
+    import os
+    from moyolo_b200 import sharding
+    if not hasattr(os, "sched_getaffinity"):
+        pytest.skip("no sched_getaffinity")
+    before = os.sched_getaffinity(0)
+    try:
+        assert sharding.bind_host_to_gpu(0, 1) is None and os.sched_getaffinity(0) == before
+        if len(before) < 4:
+            pytest.skip("needs >= 4 cores")
+        seen = []
+        for r in range(2):
+            os.sched_setaffinity(0, before)
+            what = sharding.bind_host_to_gpu(r, 2)
+            assert what and "cpus" in what
+            seen.append(os.sched_getaffinity(0))
+        assert seen[0].isdisjoint(seen[1]) and len(seen[0]) == len(seen[1]) == len(before) // 2
+        assert (seen[0] | seen[1]) <= before
+    finally:
+        os.sched_setaffinity(0, before)
