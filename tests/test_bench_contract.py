@@ -36,3 +36,19 @@ def test_reference_arm_other_ranks_are_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout.strip() == ""
+
+
+def test_both_arms_describe_the_same_config():
+    """The driver compares the `config` objects of the two arms for equality: both come from bench.workload_config and
+    depend only on the workload flags (run-specific details live in `run_info`)."""
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from moyolo_b200 import synthetic as syn
+    for wl in ("MOT17", "DanceTrack", "KITTI"):
+        shapes = [list(s) for s in syn.PYRAMIDS[wl]]
+        a = bench.workload_config(argparse.Namespace(workload=wl, n_detect=300, seqs_per_gpu=1, precision="bf16"), shapes)
+        b = bench.workload_config(argparse.Namespace(workload=wl, n_detect=300, seqs_per_gpu=4, precision="fp32"), shapes)
+        assert a == b and "workload" in a and "model" not in a
