@@ -438,7 +438,8 @@ def run_moyolo(args):
         if tf.exists():
             traffic = json.loads(tf.read_text()).get(f"{args.workload}_S{S}_{args.precision}")
         kname = ("msda_gather_proj_kernel<4,3> (gather with the offsets|logits projection fused in)" if pf else
-                 ("msda_gather_pair_kernel<bf16,4,3>" if S * args.n_detect >= 1024 else "msda_gather_kernel<bf16,32,fused>"))
+                 (f"msda_gather_pair_kernel<{args.precision},4,3>" if S * args.n_detect >= 1024 else
+                  f"msda_gather_kernel<{args.precision},32,fused>"))
         roof = {"bound": "hbm", "kernel": kname, "achieved": round(ach, 1),
                 "peak": peak, "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic,
